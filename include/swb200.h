@@ -1,0 +1,96 @@
+/*
+ * swb200.h -- C ABI of the B200-native Smith-Waterman scoring engine.
+ *
+ * This is the drop-in boundary for the alignment path of bmwoolf/mini_parallel.  The
+ * reference exposes no FFI; its seam is one Rust function:
+ *
+ *     pub fn gpu_align(seq1: &str, seq2: &str, device: &GpuDevice) -> Result<i32, String>
+ *                                                     smith_waterman/src/aligner.rs:410
+ *
+ * Every entry point below cites the reference item it replaces.  Conventions:
+ *   - return 0 = Ok, non-zero = Err; the message (the Result<_, String> text) is in
+ *     swb_last_error() (thread-local);
+ *   - inputs are borrowed for the duration of the call, outputs are caller-allocated;
+ *   - a swb_ctx is used from one thread at a time (the reference serialises on one
+ *     queue behind a Mutex, gpu.rs:13-14, :97-115); distinct contexts are independent;
+ *   - there is NO CPU fallback: without a CUDA device swb_create fails, like
+ *     main.rs:76-79 / :160-163;
+ *   - i indexes s1 / the read (rows), j indexes s2 / the window (columns), as
+ *     seq1[i] / seq2[j] in smith_waterman.cl:114.  Coordinates are 0-based, inclusive;
+ *     (-1,-1) when the score is 0.  Tie-break: max score, then smallest i, then smallest j
+ *     (first maximum in a row-major scan; the reference has no coordinates).
+ */
+#ifndef SWB200_H
+#define SWB200_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct swb_ctx swb_ctx;                                   /* opaque: device, streams, pinned + device arenas */
+typedef struct { int32_t score; int32_t end_i; int32_t end_j; } swb_result;
+typedef struct { int32_t match, mismatch, gap; } swb_params;      /* smith_waterman.cl:5-7: {2,-1,-2}; only these are accepted */
+
+/* Device probe: replaces gpu::is_gpu_available / get_gpu_devices (gpu.rs:33-94). */
+int  swb_device_count(void);
+/* name / memory / max work-group size of a device: the GpuDevice struct, gpu.rs:17-23. */
+int  swb_device_info(int device_id, char* name, size_t name_cap, double* memory_gb, int* max_work_group_size);
+
+/* Context: replaces get_opencl_context/init_opencl (gpu.rs:97-132).  One device per context. */
+int  swb_create(swb_ctx** out, int device_id, const swb_params* params /* NULL = reference constants */);
+void swb_destroy(swb_ctx*);
+
+/* One pair, full Smith-Waterman (the recurrence of smith_waterman.cl:114-125, global max + end cell). */
+int  swb_score_pair(swb_ctx*, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, swb_result* out);
+
+/* A batch of independent pairs, HOST buffers (ASCII bytes, CSR offsets with n_pairs+1 entries).
+ * H2D, packing, scoring and D2H all happen inside the call.  This is what a chunk of reads from
+ * process_fastq_file_in_chunks (aligner.rs:107-178) is handed to instead of one gpu_align per chunk. */
+int  swb_score_batch(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off,
+                     const uint8_t* r_bytes, const uint64_t* r_off,
+                     uint64_t n_pairs, swb_result* out);
+
+/* Same, DEVICE-resident inputs and outputs (pointers from cudaMalloc / a torch tensor's data_ptr);
+ * runs on the context's stream, returns after the work is enqueued; swb_sync() waits. */
+int  swb_score_batch_device(swb_ctx*, const uint8_t* d_q_bytes, const uint64_t* d_q_off, uint64_t q_total_bytes,
+                            const uint8_t* d_r_bytes, const uint64_t* d_r_off, uint64_t r_total_bytes,
+                            uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out);
+int  swb_sync(swb_ctx*);
+
+/* The two literal behaviours of the reference, for comparison:
+ *   swb_ref_compat_align : what gpu_align returns today -- kernel smith_waterman_align
+ *                          (smith_waterman.cl:11-71) under the host geometry aligner.rs:422-424,
+ *                          result buffer zero-initialised;
+ *   swb_last_row_max     : the reduction of the never-launched smith_waterman_detailed
+ *                          (smith_waterman.cl:130-134): max over the last row only. */
+int  swb_ref_compat_align(swb_ctx*, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,
+                          uint32_t dev_max_work_group, int32_t* out);
+int  swb_last_row_max(swb_ctx*, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, int32_t* out);
+
+/* 2-bit packing stage on its own (A,C,G,T -> 2 bits, 16 bases per 32-bit word; one flag bit per word
+ * for "contains a byte outside ACGT").  Host buffers in, host buffers out; used by tests and bench. */
+int  swb_pack2bit(swb_ctx*, const uint8_t* bytes, uint64_t n, uint32_t* packed_words /* ceil(n/16) */,
+                  uint32_t* nonacgt_bitmap /* ceil(ceil(n/16)/32) */);
+
+/* Synthetic workload generator on the device (counter RNG splitmix64, seeds 0xB200 /
+ * 0xB201; distribution 0 = related reads, 1 = unrelated).  Fills ASCII bytes + offsets for pairs
+ * [first_pair, first_pair + n_pairs) of shape read_len x window_len.  Device pointers. */
+int  swb_synth_device(swb_ctx*, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len,
+                      int distribution, uint8_t* d_q_bytes, uint64_t* d_q_off, uint8_t* d_r_bytes, uint64_t* d_r_off);
+
+/* Per-stage device times of the last swb_score_batch* call on this context, CUDA events on the
+ * context's stream (ms): [0] pack, [1] short-read kernel, [2] generic kernel, [3] total device span,
+ * [4] h2d, [5] d2h.  Also the number of kernels launched by that call. */
+int  swb_last_timings(swb_ctx*, float* ms /* 6 */, int* kernels_launched);
+/* Pairs routed to each path by the last call: [0] short int16x2 path, [1] generic 32-bit path. */
+int  swb_last_routing(swb_ctx*, uint64_t* counts /* 2 */);
+
+void*       swb_stream(swb_ctx*);            /* the cudaStream_t the context launches on */
+const char* swb_last_error(void);
+const char* swb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

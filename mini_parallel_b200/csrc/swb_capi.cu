@@ -1,0 +1,375 @@
+// swb_capi.cu -- the C ABI of include/swb200.h: context, device arenas, the batch
+// pipeline (H2D -> pack -> classify -> short/generic kernels -> D2H) and the compat modes.
+// No CPU fallback lives here: without a CUDA device swb_create() fails (main.rs:76-79).
+#include "swb_kernels.cuh"
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <cstdio>
+
+namespace swb {
+int launch_generic_single(const BatchView& b, int32_t* last_row_out, cudaStream_t st);
+}
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+  return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return 1; }
+    cap = want; return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct swb_ctx {
+  int device = 0, sm_count = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[8] = {};
+  DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, generic_list, counters, out, scratch, misc;
+  float last_ms[6] = {0, 0, 0, 0, 0, 0};
+  int last_kernels = 0;
+  uint64_t last_routing[2] = {0, 0};
+  bool timings_pending = false, host_path = false;
+  int variant = 1;
+};
+
+extern "C" {
+
+const char* swb_last_error(void) { return g_err.c_str(); }
+const char* swb_version(void) { return "swb200 0.1 (sm_100a)"; }
+
+int swb_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int swb_device_info(int device_id, char* name, size_t name_cap, double* memory_gb, int* max_wg)
+{
+  cudaDeviceProp p;
+  CUDA_TRY(cudaGetDeviceProperties(&p, device_id));
+  if (name && name_cap) { std::strncpy(name, p.name, name_cap - 1); name[name_cap - 1] = 0; }
+  if (memory_gb) *memory_gb = (double)p.totalGlobalMem / (1024.0 * 1024.0 * 1024.0);
+  if (max_wg) *max_wg = p.maxThreadsPerBlock;
+  return 0;
+}
+
+int swb_create(swb_ctx** out, int device_id, const swb_params* params)
+{
+  if (!out) return fail("swb_create: null out pointer");
+  *out = nullptr;
+  if (params && (params->match != swb::kMatch || params->mismatch != swb::kMismatch || params->gap != swb::kGap))
+    return fail("swb_create: only the reference's constants {2,-1,-2} (smith_waterman.cl:5-7) are supported");
+  int n = swb_device_count();
+  if (n <= 0) return fail("error: gpu acceleration is required and no compatible gpu was found");   // main.rs:161
+  if (device_id < 0 || device_id >= n) return fail("swb_create: no such device");
+  CUDA_TRY(cudaSetDevice(device_id));
+  swb_ctx* c = new swb_ctx();
+  c->device = device_id;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device_id) != cudaSuccess) { delete c; return fail("cudaGetDeviceProperties failed"); }
+  c->sm_count = p.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
+  for (auto& e : c->ev) cudaEventCreate(&e);
+  if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 3;
+  *out = c;
+  return 0;
+}
+
+void swb_destroy(swb_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  for (DevBuf* b : {&c->q_bytes, &c->r_bytes, &c->q_off, &c->r_off, &c->q_pk, &c->r_pk, &c->q_bad, &c->r_bad,
+                    &c->short_list, &c->generic_list, &c->counters, &c->out, &c->scratch, &c->misc}) b->release();
+  for (auto& e : c->ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->st);
+  delete c;
+}
+
+void* swb_stream(swb_ctx* c) { return c ? (void*)c->st : nullptr; }
+int   swb_set_short_variant(swb_ctx* c, int v) { if (!c) return fail("null ctx"); c->variant = v & 3; return 0; }
+
+int swb_sync(swb_ctx* c)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// ---- the device pipeline: everything after the inputs are resident in HBM ----
+static int run_device_pipeline(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
+                               const uint8_t* d_r, const uint64_t* d_ro, uint64_t r_total,
+                               uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out)
+{
+  (void)max_q_len;
+  if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
+  const uint64_t qw = (q_total + 15) / 16, rw = (r_total + 15) / 16;
+  if (c->q_pk.reserve(qw * 4 + 64) || c->r_pk.reserve(rw * 4 + 64) ||
+      c->q_bad.reserve((qw + 31) / 32 * 4 + 64) || c->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
+      c->short_list.reserve(n_pairs * 4 + 64) || c->generic_list.reserve(n_pairs * 4 + 64) ||
+      c->counters.reserve(sizeof(swb::Counters))) return 1;
+  // generic kernel: persistent grid, one boundary row of max_r_len ints per resident warp
+  int ctas = c->sm_count * 4;
+  const uint64_t stride = ((uint64_t)max_r_len + 32) & ~31ull;
+  while (ctas > 1 && (uint64_t)ctas * 4 * stride * 4 > (2ull << 30)) ctas /= 2;
+  if (c->scratch.reserve((uint64_t)ctas * 4 * stride * 4)) return 1;
+
+  swb::BatchView b;
+  b.q_bytes = d_q; b.q_off = d_qo; b.r_bytes = d_r; b.r_off = d_ro;
+  b.q_pk = c->q_pk.as<uint32_t>(); b.q_bad = c->q_bad.as<uint32_t>();
+  b.r_pk = c->r_pk.as<uint32_t>(); b.r_bad = c->r_bad.as<uint32_t>();
+  b.n_pairs = n_pairs;
+  b.short_list = c->short_list.as<uint32_t>(); b.generic_list = c->generic_list.as<uint32_t>();
+  b.counters = c->counters.as<swb::Counters>(); b.out = d_out;
+  b.scratch = c->scratch.as<int32_t>(); b.scratch_stride = stride;
+
+  int k = 0;
+  cudaStream_t st = c->st;
+  CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(swb::Counters), st));
+  CUDA_TRY(cudaEventRecord(c->ev[0], st));
+  k += swb::launch_pack2bit(d_q, q_total, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
+  k += swb::launch_pack2bit(d_r, r_total, c->r_pk.as<uint32_t>(), c->r_bad.as<uint32_t>(), st);
+  k += swb::launch_classify(b, st);
+  CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  const uint32_t wcap = std::min<uint32_t>(std::max<uint32_t>(max_r_len, 1), swb::kShortMaxWindow);
+  k += swb::launch_short(b, wcap, c->variant, c->sm_count, st);
+  CUDA_TRY(cudaEventRecord(c->ev[2], st));
+  {
+    // launch_generic uses sm_count*4 CTAs; honour the scratch clamp
+    swb::BatchView bg = b;
+    k += swb::launch_generic(bg, ctas / 4 > 0 ? ctas / 4 : 1, 0, st);
+  }
+  CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  CUDA_TRY(cudaGetLastError());
+  c->last_kernels = k;
+  c->timings_pending = true;
+  return 0;
+}
+
+int swb_score_batch_device(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
+                           const uint8_t* d_r, const uint64_t* d_ro, uint64_t r_total,
+                           uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->host_path = false;
+  if (n_pairs == 0) { c->last_kernels = 0; c->timings_pending = false; return 0; }
+  return run_device_pipeline(c, d_q, d_qo, q_total, d_r, d_ro, r_total, n_pairs, max_q_len, max_r_len, d_out);
+}
+
+int swb_score_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro,
+                    uint64_t n_pairs, swb_result* out)
+{
+  if (!c) return fail("null ctx");
+  if (n_pairs == 0) return 0;
+  if (!qo || !ro || !out) return fail("swb_score_batch: null pointer");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t q_total = qo[n_pairs] - qo[0], r_total = ro[n_pairs] - ro[0];
+  if (qo[0] != 0 || ro[0] != 0) return fail("swb_score_batch: offsets must start at 0");
+  uint32_t max_q = 0, max_r = 0;
+  for (uint64_t k = 0; k < n_pairs; ++k) {
+    if (qo[k + 1] < qo[k] || ro[k + 1] < ro[k]) return fail("swb_score_batch: offsets must be non-decreasing");
+    const uint64_t a = qo[k + 1] - qo[k], b = ro[k + 1] - ro[k];
+    if (a > 0x7fffffffull || b > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
+    max_q = std::max<uint32_t>(max_q, (uint32_t)a); max_r = std::max<uint32_t>(max_r, (uint32_t)b);
+  }
+  if (c->q_bytes.reserve(q_total + 64) || c->r_bytes.reserve(r_total + 64) ||
+      c->q_off.reserve((n_pairs + 1) * 8) || c->r_off.reserve((n_pairs + 1) * 8) ||
+      c->out.reserve(n_pairs * sizeof(swb_result))) return 1;
+  cudaStream_t st = c->st;
+  CUDA_TRY(cudaEventRecord(c->ev[4], st));
+  if (q_total) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, q_total, cudaMemcpyHostToDevice, st));
+  if (r_total) CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, r, r_total, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->q_off.p, qo, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->r_off.p, ro, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(c->ev[5], st));
+  if (run_device_pipeline(c, c->q_bytes.as<uint8_t>(), c->q_off.as<uint64_t>(), q_total,
+                          c->r_bytes.as<uint8_t>(), c->r_off.as<uint64_t>(), r_total,
+                          n_pairs, max_q, max_r, c->out.as<swb_result>())) return 1;
+  CUDA_TRY(cudaEventRecord(c->ev[6], st));
+  CUDA_TRY(cudaMemcpyAsync(out, c->out.p, n_pairs * sizeof(swb_result), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(c->ev[7], st));
+  c->host_path = true;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int swb_score_pair(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, swb_result* out)
+{
+  if (!out) return fail("swb_score_pair: null out");
+  const uint64_t qo[2] = {0, n1}, ro[2] = {0, n2};
+  return swb_score_batch(c, s1, qo, s2, ro, 1, out);
+}
+
+int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (c->timings_pending) {
+    CUDA_TRY(cudaStreamSynchronize(c->st));
+    cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->last_ms[2], c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[3]);
+    c->last_ms[4] = c->last_ms[5] = 0;
+    if (c->host_path) {
+      cudaEventElapsedTime(&c->last_ms[4], c->ev[4], c->ev[5]);
+      cudaEventElapsedTime(&c->last_ms[5], c->ev[6], c->ev[7]);
+    }
+    swb::Counters h;
+    CUDA_TRY(cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    c->last_routing[0] = h.n_short; c->last_routing[1] = h.n_generic;
+    c->timings_pending = false;
+  }
+  if (ms) std::memcpy(ms, c->last_ms, sizeof(c->last_ms));
+  if (kernels) *kernels = c->last_kernels;
+  return 0;
+}
+
+int swb_last_routing(swb_ctx* c, uint64_t* counts)
+{
+  if (!c || !counts) return fail("null pointer");
+  if (swb_last_timings(c, nullptr, nullptr)) return 1;
+  counts[0] = c->last_routing[0]; counts[1] = c->last_routing[1];
+  return 0;
+}
+
+int swb_ref_compat_align(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,
+                         uint32_t dev_max_wg, int32_t* out)
+{
+  if (!c || !out) return fail("null pointer");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t len = std::min(n1, n2);                           // aligner.rs:412
+  if (len == 0) { *out = 0; return 0; }                            // aligner.rs:413-416
+  if (dev_max_wg == 0) return fail("swb_ref_compat_align: work-group size must be positive");
+  const uint32_t wgs = std::min<uint32_t>(dev_max_wg, 1024);       // aligner.rs:422, gpu.rs:9
+  const uint64_t groups = std::min<uint64_t>((len + wgs - 1) / wgs, 1000000ull);   // aligner.rs:423-424
+  if (len > 1000000ull * 1024ull)                                  // aligner.rs:436-456 (work-item limit)
+    return fail("Sequence too large (" + std::to_string(len) + " bytes), max allowed: 1024000000 bytes");
+  if (c->q_bytes.reserve(n1 + 64) || c->r_bytes.reserve(n2 + 64) || c->misc.reserve(64)) return 1;
+  cudaStream_t st = c->st;
+  CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, s1, n1, cudaMemcpyHostToDevice, st));   // full buffers, aligner.rs:478-492
+  CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, s2, n2, cudaMemcpyHostToDevice, st));
+  swb::launch_ref_compat(c->q_bytes.as<uint8_t>(), c->r_bytes.as<uint8_t>(), len, wgs, groups, c->misc.as<int32_t>(), st);
+  CUDA_TRY(cudaMemcpyAsync(out, c->misc.p, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int swb_last_row_max(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, int32_t* out)
+{
+  if (!c || !out) return fail("null pointer");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (n1 == 0 || n2 == 0) { *out = 0; return 0; }
+  if (n1 > 0x7fffffffull || n2 > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
+  const uint64_t stride = (n2 + 32) & ~31ull;
+  if (c->q_bytes.reserve(n1 + 64) || c->r_bytes.reserve(n2 + 64) || c->q_off.reserve(16) || c->r_off.reserve(16) ||
+      c->out.reserve(sizeof(swb_result)) || c->generic_list.reserve(64) || c->counters.reserve(sizeof(swb::Counters)) ||
+      c->scratch.reserve(stride * 4) || c->misc.reserve(64)) return 1;
+  cudaStream_t st = c->st;
+  const uint64_t qo[2] = {0, n1}, ro[2] = {0, n2};
+  CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, s1, n1, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, s2, n2, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->q_off.p, qo, 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->r_off.p, ro, 16, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));          // qo/ro live on this stack frame
+  swb::BatchView b{};
+  b.q_bytes = c->q_bytes.as<uint8_t>(); b.q_off = c->q_off.as<uint64_t>();
+  b.r_bytes = c->r_bytes.as<uint8_t>(); b.r_off = c->r_off.as<uint64_t>();
+  b.n_pairs = 1; b.generic_list = c->generic_list.as<uint32_t>(); b.counters = c->counters.as<swb::Counters>();
+  b.out = c->out.as<swb_result>(); b.scratch = c->scratch.as<int32_t>(); b.scratch_stride = stride;
+  swb::launch_generic_single(b, c->misc.as<int32_t>(), st);
+  CUDA_TRY(cudaMemcpyAsync(out, c->misc.p, 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int swb_pack2bit(swb_ctx* c, const uint8_t* bytes, uint64_t n, uint32_t* packed_words, uint32_t* bitmap)
+{
+  if (!c) return fail("null ctx");
+  if (n == 0) return 0;
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t nw = (n + 15) / 16, nb = (nw + 31) / 32;
+  if (c->q_bytes.reserve(n + 64) || c->q_pk.reserve(nw * 4 + 64) || c->q_bad.reserve(nb * 4 + 64)) return 1;
+  cudaStream_t st = c->st;
+  CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, bytes, n, cudaMemcpyHostToDevice, st));
+  swb::launch_pack2bit(c->q_bytes.as<uint8_t>(), n, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
+  CUDA_TRY(cudaMemcpyAsync(packed_words, c->q_pk.p, nw * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(bitmap, c->q_bad.p, nb * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// pack stage alone on device-resident bytes (bench: HBM roofline of the packing kernel)
+int swb_pack2bit_device(swb_ctx* c, const uint8_t* d_bytes, uint64_t n, uint32_t* d_words, uint32_t* d_bitmap)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  swb::launch_pack2bit(d_bytes, n, d_words, d_bitmap, c->st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int swb_synth_device(swb_ctx* c, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len,
+                     int distribution, uint8_t* d_q, uint64_t* d_qo, uint8_t* d_r, uint64_t* d_ro)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  swb::launch_synth(first_pair, n_pairs, read_len, window_len, distribution, d_q, d_qo, d_r, d_ro, c->st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// raw device / pinned memory for callers without a CUDA runtime of their own (CLI, ctypes tests)
+int swb_malloc_device(swb_ctx* c, uint64_t bytes, void** out)
+{
+  if (!c || !out) return fail("null pointer");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+}
+int swb_free_device(swb_ctx* c, void* p) { if (c) cudaSetDevice(c->device); cudaFree(p); return 0; }
+int swb_malloc_pinned(uint64_t bytes, void** out)
+{
+  if (!out) return fail("null pointer");
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+int swb_free_pinned(void* p) { cudaFreeHost(p); return 0; }
+int swb_memcpy_d2h(swb_ctx* c, void* dst, const void* src, uint64_t bytes)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  return 0;
+}
+int swb_memcpy_h2d(swb_ctx* c, void* dst, const void* src, uint64_t bytes)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->st));
+  CUDA_TRY(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+}  // extern "C"

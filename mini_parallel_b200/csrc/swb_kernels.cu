@@ -1,0 +1,596 @@
+// swb_kernels.cu -- hand-written sm_100a kernels of the Smith-Waterman scoring engine.
+//
+// Scoring function (the reference's, smith_waterman/src/smith_waterman.cl):
+//   s(i,j) = seq1[i]==seq2[j] ? +2 : -1          (:5-6, :114, raw byte equality)
+//   H[i][j] = max(0, H[i-1][j-1]+s, H[i][j-1]-2, H[i-1][j]-2)   (:7, :116-125, zero borders)
+// Output per pair: max H and the first cell (row-major) that reaches it.
+//
+// Kernels
+//   pack2bit_kernel   ASCII -> 2 bits/base, 128-bit loads, HBM-bound (1.25 B/base algorithmic)
+//   classify_kernel   routes each pair: empty / short (int16x2 DPX kernel) / generic (32-bit)
+//   sw_short_kernel   inter-task kernel for reads <= 160 bp: a group of G lanes owns TWO pairs,
+//                     packed hi/lo in int16x2 words, updated with DPX VIADDMNMX / VIMNMX3
+//   sw_generic_kernel one warp per pair, 32-bit, any length / any bytes (anti-diagonal wavefront,
+//                     boundary column through warp shuffles, row bands through a scratch row)
+//   ref_compat_kernel the reference's LIVE kernel semantics (smith_waterman.cl:11-71)
+//   synth_*           counter-RNG synthetic reads/windows
+#include "swb_kernels.cuh"
+
+namespace swb {
+
+// =====================================================================================
+// 2-bit packing.  code = (byte >> 1) & 3 : A->0 C->1 T->2 G->3 (any bijection works, only
+// equality matters).  A word is flagged when any of its bytes is not exactly A/C/G/T,
+// because the reference compares raw bytes (cl:114): 'a' != 'A', 'N' == 'N'.
+// =====================================================================================
+__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t& bad)
+{
+  const uint32_t c0 = (x >> 1) & 0x01010101u, c1 = (x >> 2) & 0x01010101u;
+  const uint32_t is2 = c1 & ~c0;
+  const uint32_t canon = 0x41414141u + 2u * c0 + 4u * c1 + 15u * is2;   // A,C,G,T rebuilt from the code
+  bad |= x ^ canon;
+  uint32_t t = (x >> 1) & 0x03030303u;
+  t |= t >> 6;
+  return (t & 0xFu) | ((t >> 12) & 0xF0u);
+}
+
+__global__ void __launch_bounds__(256)
+pack2bit_kernel(const uint8_t* __restrict__ bytes, uint64_t n, uint32_t* __restrict__ words,
+                uint32_t* __restrict__ bitmap)
+{
+  const uint64_t n_words = (n + 15) >> 4;
+  const uint64_t n_round = (n_words + 31) & ~uint64_t(31);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
+    uint32_t word = 0, bad = 0;
+    if (w < n_words) {
+      const uint64_t base = w << 4;
+      uint4 v;
+      if (base + 16 <= n) {
+        v = __ldg(reinterpret_cast<const uint4*>(bytes + base));        // 128-bit coalesced load
+      } else {                                                          // ragged tail: pad with 'A'
+        uint32_t t[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
+        for (uint64_t k = base; k < n; ++k) {
+          const uint32_t sh = (uint32_t)((k - base) & 3) * 8;
+          t[(k - base) >> 2] = (t[(k - base) >> 2] & ~(0xFFu << sh)) | ((uint32_t)bytes[k] << sh);
+        }
+        v = make_uint4(t[0], t[1], t[2], t[3]);
+      }
+      word = pack4(v.x, bad) | (pack4(v.y, bad) << 8) | (pack4(v.z, bad) << 16) | (pack4(v.w, bad) << 24);
+      words[w] = word;
+    }
+    const uint32_t ballot = __ballot_sync(0xffffffffu, bad != 0);
+    if ((threadIdx.x & 31) == 0 && w < n_words) bitmap[w >> 5] = ballot;
+  }
+}
+
+int launch_pack2bit(const uint8_t* bytes, uint64_t n, uint32_t* words, uint32_t* bitmap, cudaStream_t st)
+{
+  if (n == 0) return 0;
+  const uint64_t n_words = (n + 15) >> 4;
+  uint64_t blocks = (n_words + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;          // grid-stride: a multiple of the SM count
+  pack2bit_kernel<<<(unsigned)blocks, 256, 0, st>>>(bytes, n, words, bitmap);
+  return 1;
+}
+
+__device__ __forceinline__ uint32_t code_at(const uint32_t* __restrict__ pk, uint64_t pos)
+{
+  return (__ldg(pk + (pos >> 4)) >> (2u * (uint32_t)(pos & 15))) & 3u;
+}
+
+// any flagged 16-base word overlapping [lo, hi) ?
+__device__ __forceinline__ bool range_flagged(const uint32_t* __restrict__ bitmap, uint64_t lo, uint64_t hi)
+{
+  if (hi <= lo) return false;
+  const uint64_t w0 = lo >> 4, w1 = (hi - 1) >> 4;        // inclusive word range
+  for (uint64_t bw = w0 >> 5; bw <= (w1 >> 5); ++bw) {
+    uint32_t bits = __ldg(bitmap + bw);
+    const uint64_t first = bw << 5;
+    if (first < w0) bits &= ~0u << (uint32_t)(w0 - first);
+    if (first + 31 > w1) bits &= ~0u >> (uint32_t)(first + 31 - w1);
+    if (bits) return true;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256)
+classify_kernel(BatchView b)
+{
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t cls = 0xFF, m = 0;
+  if (k < b.n_pairs) {
+    const uint64_t q0 = b.q_off[k], q1 = b.q_off[k + 1], r0 = b.r_off[k], r1 = b.r_off[k + 1];
+    const uint64_t n = q1 - q0; const uint64_t mm = r1 - r0;
+    if (n == 0 || mm == 0) {                               // aligner.rs:413-416: empty input scores 0
+      cls = CLASS_EMPTY;
+      b.out[k] = swb_result{0, -1, -1};
+    } else if (n <= kShortMaxRead && mm <= kShortMaxWindow &&
+               !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1)) {
+      cls = CLASS_SHORT; m = (uint32_t)mm;
+    } else {
+      cls = CLASS_GENERIC;
+    }
+  }
+  // warp-aggregated append to the two work lists
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t ms = __ballot_sync(0xffffffffu, cls == CLASS_SHORT);
+  const uint32_t mg = __ballot_sync(0xffffffffu, cls == CLASS_GENERIC);
+  uint32_t base_s = 0, base_g = 0;
+  if (lane == 0) {
+    if (ms) base_s = atomicAdd(&b.counters->n_short, __popc(ms));
+    if (mg) base_g = atomicAdd(&b.counters->n_generic, __popc(mg));
+  }
+  base_s = __shfl_sync(0xffffffffu, base_s, 0);
+  base_g = __shfl_sync(0xffffffffu, base_g, 0);
+  const uint32_t below = (1u << lane) - 1;
+  if (cls == CLASS_SHORT)   b.short_list[base_s + __popc(ms & below)] = (uint32_t)k;
+  if (cls == CLASS_GENERIC) b.generic_list[base_g + __popc(mg & below)] = (uint32_t)k;
+  uint32_t wm = m;
+  for (int o = 16; o; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+  if (lane == 0 && wm) atomicMax(&b.counters->max_short_window, wm);
+}
+
+int launch_classify(const BatchView& b, cudaStream_t st)
+{
+  if (b.n_pairs == 0) return 0;
+  classify_kernel<<<(unsigned)((b.n_pairs + 255) / 256), 256, 0, st>>>(b);
+  return 1;
+}
+
+// =====================================================================================
+// Inter-task int16x2 kernel (reads <= G*K rows).
+//
+// Work decomposition.  A group of G lanes owns two pairs at once: pair A in the high
+// int16 half of every score word, pair B in the low half (identical control flow, no
+// dependency between the halves).  Lane L holds K consecutive rows i = K*L+m, m<K.  At
+// step t slot m computes cell (i, j = t - i): all K*G cells of a step lie on ONE
+// anti-diagonal, so the K cells of a lane are independent (ILP = K) and the row above
+// lane L's first row arrives from lane L-1 with one SHFL per step.
+//
+// Arithmetic.  Stored value  V = 64 * (H + 2*tau),  tau = step inside the current block
+// of BLOCK steps.  With that bias the gap additions disappear:
+//     H = max(0, D+s, U-2, L-2)      <=>     V = max(V_D + 64*(s+4), V_U, V_L, floor)
+// where floor = 64*2*tau is the image of H = 0.  Two DPX instructions per cell pair:
+//     t = VIADDMNMX.S16x2(V_D, sub, V_U);   V = VIMNMX3.S16x2(t, V_L, floor)
+// sub = {384,192} (match/mismatch) comes from a 64-entry shared-memory table indexed by
+// XOR of the 3-bit base codes of both pairs (one LOP3 + one LDS).  Every BLOCK steps all
+// values are rebased by -128*BLOCK so they stay inside int16 (max 64*(2*160+2*59) = 28032).
+//
+// End cell.  Per row, cur = max(cur, V + e) with e = tag - floor, tag = BLOCK-1-tau: the
+// low 6 bits carry the (inverted) step of the first occurrence of the row maximum inside
+// the block, the high bits carry 64*H.  At block end the K row trackers are folded into one
+// 32-bit key per pair  H<<21 | (255-i)<<13 | (8191-NPAD-j)  whose maximum is exactly
+// (max H, then min i, then min j).
+// =====================================================================================
+struct ShortArgs {
+  const uint32_t* q_pk; const uint64_t* q_off;
+  const uint32_t* r_pk; const uint64_t* r_off;
+  const uint32_t* list; const uint32_t* n_list;     // device-side count of listed pairs
+  swb_result* out;
+  uint32_t w_pad;          // columns processed per pair (multiple of K, >= longest window)
+  uint32_t wbuf_stride;    // bytes of shared memory per group
+};
+
+constexpr uint32_t CODE_QPAD = 5, CODE_WPAD = 6;
+
+template <int G, int K, bool SPLIT>
+__global__ void __launch_bounds__(128)
+sw_short_kernel(ShortArgs a)
+{
+  static_assert(K % 2 == 0, "K must be even (in-place double buffering)");
+  static_assert(32 % G == 0, "G must divide the warp");
+  constexpr int NPAD  = G * K;
+  constexpr int BLOCK = (62 / K) * K;                   // steps between rebases, multiple of K, <= 62
+  constexpr uint32_t REBASE = (uint32_t)(128 * BLOCK) * 0x00010001u;
+  constexpr int GPW = 32 / G;                           // groups per warp
+
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(256) uint32_t lut[64];           // 256-aligned: table address | index == address + index
+  if (threadIdx.x < 64) {
+    const uint32_t xa = threadIdx.x >> 3, xb = threadIdx.x & 7;
+    lut[threadIdx.x] = ((xa == 0 ? 384u : 192u) << 16) | (xb == 0 ? 384u : 192u);
+  }
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t g = lane / G, L = lane % G;
+  const uint32_t gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (g * G));
+  const uint32_t n_list = *a.n_list;
+  const uint32_t n_pp = (n_list + 1) >> 1;
+  const uint32_t pp = (blockIdx.x * 4 + warp) * GPW + g;
+  if (pp >= n_pp) return;                               // whole group idle (shuffles are group-masked)
+
+  const uint32_t pA = a.list[2 * pp];
+  const bool hasB = (2 * pp + 1) < n_list;
+  const uint32_t pB = hasB ? a.list[2 * pp + 1] : pA;
+  const uint64_t qA0 = a.q_off[pA], qB0 = a.q_off[pB], rA0 = a.r_off[pA], rB0 = a.r_off[pB];
+  const uint32_t nA = (uint32_t)(a.q_off[pA + 1] - qA0), nB = (uint32_t)(a.q_off[pB + 1] - qB0);
+  const uint32_t mA = (uint32_t)(a.r_off[pA + 1] - rA0), mB = (uint32_t)(a.r_off[pB + 1] - rB0);
+
+  // ---- stage the combined window stream of both pairs in shared memory ----
+  uint8_t* wbuf = smem + (size_t)(warp * GPW + g) * a.wbuf_stride;
+  const uint32_t n_iters = (NPAD + a.w_pad + K - 1) / K;
+  const uint32_t wlen = NPAD + n_iters * K;             // indices touched: [K, NPAD + steps)
+  for (uint32_t x = L; x < wlen; x += G) {
+    const int32_t j = (int32_t)x - NPAD;
+    const uint32_t ca = (j >= 0 && (uint32_t)j < mA) ? code_at(a.r_pk, rA0 + j) : CODE_WPAD;
+    const uint32_t cb = (j >= 0 && (uint32_t)j < mB) ? code_at(a.r_pk, rB0 + j) : CODE_WPAD;
+    wbuf[x] = (uint8_t)(((ca << 3) | cb) << 2);
+  }
+  // ---- query codes of this lane's K rows ----
+  const uint32_t lut_addr = (uint32_t)__cvta_generic_to_shared(lut);
+  uint32_t Q[K];
+#pragma unroll
+  for (int m = 0; m < K; ++m) {
+    const uint32_t i = K * L + m;
+    const uint32_t ca = i < nA ? code_at(a.q_pk, qA0 + i) : CODE_QPAD;
+    const uint32_t cb = i < nB ? code_at(a.q_pk, qB0 + i) : CODE_QPAD;
+    Q[m] = lut_addr | (((ca << 3) | cb) << 2);          // XOR with a window byte yields the LDS address itself
+  }
+  __syncwarp(gmask);
+
+  uint32_t A[K], B[K], W[K], cur[K];
+#pragma unroll
+  for (int m = 0; m < K; ++m) {
+    A[m] = 0xFF00FF00u;            // image of H=0 two steps before tau=0  (-256)
+    B[m] = 0xFF80FF80u;            // image of H=0 one step before tau=0   (-128)
+    W[m] = ((CODE_WPAD << 3) | CODE_WPAD) << 2;
+    cur[m] = 0;
+  }
+  uint32_t recA = 0, recB = 0;     // best key of pair A (hi half) / pair B (lo half)
+  uint32_t floor_ = 0, fm1 = 0xFF80FF80u, upPrev = 0xFF00FF00u;
+  uint32_t e = SPLIT ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
+  const uint8_t* wp = wbuf + (NPAD - K * L);
+  int32_t blockStart = 0;
+  int bit = 0;
+
+  auto block_end = [&]() {
+    // fold the K row trackers of this block into the two per-pair keys, then rebase
+    const int32_t P0 = (int32_t)(((255u - K * L) << 13) + K * L) + (8192 - NPAD - BLOCK - blockStart);
+#pragma unroll
+    for (int m = 0; m < K; ++m) {
+      const int32_t Pm = P0 - 8191 * m;
+      const uint32_t hi = cur[m] >> 16, lo = cur[m] & 0xFFFFu;
+      const uint32_t kh = hi * 32768u - (hi & 63u) * 32767u + (uint32_t)Pm;
+      const uint32_t kl = lo * 32768u - (lo & 63u) * 32767u + (uint32_t)Pm;
+      recA = max(recA, kh);
+      recB = max(recB, kl);
+      cur[m] = 0;
+      A[m] = __vsub2(A[m], REBASE);
+      B[m] = __vsub2(B[m], REBASE);
+    }
+    upPrev = __vsub2(upPrev, REBASE);
+    floor_ = 0; fm1 = 0xFF80FF80u;
+    e = SPLIT ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
+    blockStart += BLOCK;
+  };
+
+  for (uint32_t it = 0; it < n_iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      W[u] = wp[u];
+      uint32_t up = __shfl_up_sync(gmask, (u & 1) ? A[K - 1] : B[K - 1], 1, G);
+      if (L == 0) up = fm1;                     // row -1: image of H = 0 at the previous step
+#pragma unroll
+      for (int m = K - 1; m >= 0; --m) {
+        const uint32_t x = Q[m] ^ W[(u - m + K) % K];
+        uint32_t sub;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sub) : "r"(x));
+        uint32_t d, uu, l;
+        if (u & 1) { d = m ? B[m - 1] : upPrev; uu = m ? A[m - 1] : up; l = A[m]; }
+        else       { d = m ? A[m - 1] : upPrev; uu = m ? B[m - 1] : up; l = B[m]; }
+        const uint32_t t1 = __viaddmax_s16x2(d, sub, uu);
+        const uint32_t h  = __vimax3_s16x2(t1, l, floor_);
+        if (u & 1) B[m] = h; else A[m] = h;
+        if (SPLIT) cur[m] = __vmaxs2(cur[m], h + e);
+        else       cur[m] = __viaddmax_s16x2(h, e, cur[m]);
+      }
+      upPrev = up;
+      fm1 = floor_;
+      floor_ += 0x00800080u;
+      e -= SPLIT ? 129u * 65537u : 0u;
+      if (!SPLIT) e = __vsub2(e, 0x00810081u);
+    }
+    wp += K;
+    if (++bit == BLOCK / K) { bit = 0; block_end(); }
+  }
+  if (bit) block_end();
+
+#pragma unroll
+  for (int o = G / 2; o; o >>= 1) {
+    recA = max(recA, __shfl_xor_sync(gmask, recA, o, G));
+    recB = max(recB, __shfl_xor_sync(gmask, recB, o, G));
+  }
+  if (L == 0) {
+    const uint32_t sA = recA >> 21, sB = recB >> 21;
+    swb_result ra{0, -1, -1}, rb{0, -1, -1};
+    if (sA) ra = swb_result{(int32_t)sA, 255 - (int32_t)((recA >> 13) & 255u), 8191 - NPAD - (int32_t)(recA & 8191u)};
+    if (sB) rb = swb_result{(int32_t)sB, 255 - (int32_t)((recB >> 13) & 255u), 8191 - NPAD - (int32_t)(recB & 8191u)};
+    a.out[pA] = ra;
+    if (hasB) a.out[pB] = rb;
+  }
+}
+
+template <int G, int K, bool SPLIT>
+static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t st)
+{
+  constexpr int NPAD = G * K, GPW = 32 / G;
+  ShortArgs a;
+  a.q_pk = b.q_pk; a.q_off = b.q_off; a.r_pk = b.r_pk; a.r_off = b.r_off;
+  a.list = b.short_list; a.n_list = &b.counters->n_short; a.out = b.out;
+  a.w_pad = (window_cap + K - 1) / K * K;
+  const uint32_t n_iters = (NPAD + a.w_pad + K - 1) / K;
+  a.wbuf_stride = (NPAD + n_iters * K + 15) & ~15u;
+  const size_t smem = (size_t)a.wbuf_stride * 4 * GPW;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(sw_short_kernel<G, K, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  // the grid covers the worst case (every pair short); surplus groups read n_short and leave
+  const uint64_t n_pp = (b.n_pairs + 1) / 2;
+  const uint64_t blocks = (n_pp + 4 * GPW - 1) / (4 * GPW);
+  sw_short_kernel<G, K, SPLIT><<<(unsigned)blocks, 128, smem, st>>>(a);
+  return 1;
+}
+
+size_t short_smem_bytes(uint32_t window_cap, int variant)
+{
+  const int G = (variant & 1) ? 16 : 8, K = (variant & 1) ? 10 : 20;
+  const uint32_t NPAD = G * K;
+  const uint32_t w_pad = (window_cap + K - 1) / K * K;
+  const uint32_t n_iters = (NPAD + w_pad + K - 1) / K;
+  return (size_t)((NPAD + n_iters * K + 15) & ~15u) * 4 * (32 / G);
+}
+
+// variant bit0: 0 = G8/K20, 1 = G16/K10 ; bit1: split tracking (VIADD + VIMNMX) instead of VIADDMNMX
+int launch_short(const BatchView& b, uint32_t window_cap, int variant, int /*sm_count*/, cudaStream_t st)
+{
+  if (b.n_pairs == 0) return 0;
+  switch (variant & 3) {
+    case 0: return launch_short_t<8, 20, false>(b, window_cap, st);
+    case 1: return launch_short_t<16, 10, false>(b, window_cap, st);
+    case 2: return launch_short_t<8, 20, true>(b, window_cap, st);
+    default: return launch_short_t<16, 10, true>(b, window_cap, st);
+  }
+}
+
+// =====================================================================================
+// Generic 32-bit kernel: one warp per pair, any length, any bytes (raw byte equality).
+// Anti-diagonal wavefront: lane L holds KG rows of a 32*KG-row band, slot m of lane L
+// computes cell (i, j = t - (KG*L+m)) at step t; the row above a lane's first row comes
+// from lane L-1 by SHFL; the last row of a band is parked in a scratch row in global
+// memory and becomes the top boundary of the next band.  Tracking is exact and explicit:
+// per row (score, first column), folded per band with strict '>' in ascending row order.
+// =====================================================================================
+constexpr int KG = 8;
+constexpr int BAND = 32 * KG;
+
+__global__ void __launch_bounds__(128)
+sw_generic_kernel(BatchView b, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list_ptr,
+                  int32_t* __restrict__ last_row_out)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int32_t* scratch = b.scratch + (uint64_t)warp_global * b.scratch_stride;
+  const uint32_t n_list = *n_list_ptr;
+
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(&b.counters->generic_cursor, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_list) break;
+    const uint32_t p = list[item];
+    const uint8_t* __restrict__ q = b.q_bytes + b.q_off[p];
+    const uint8_t* __restrict__ r = b.r_bytes + b.r_off[p];
+    const uint64_t n1 = b.q_off[p + 1] - b.q_off[p];
+    const uint64_t n2 = b.r_off[p + 1] - b.r_off[p];
+
+    int32_t gbest = 0; int64_t gi = -1, gj = -1; int32_t lastrow = 0;
+    const uint64_t n_bands = (n1 + BAND - 1) / BAND;
+    for (uint64_t band = 0; band < n_bands; ++band) {
+      const uint64_t row0 = band * BAND + (uint64_t)KG * lane;
+      int32_t qv[KG], A[KG], B[KG], W[KG], best[KG]; int64_t bt[KG];
+#pragma unroll
+      for (int m = 0; m < KG; ++m) {
+        qv[m] = (row0 + m < n1) ? (int32_t)q[row0 + m] : 0x100;     // sentinel never equals a byte
+        A[m] = 0; B[m] = 0; W[m] = 0x200; best[m] = 0; bt[m] = 0;
+      }
+      int32_t upPrev = 0;
+      const uint64_t steps = (n2 + BAND - 1 + KG - 1) / KG * KG;
+      for (uint64_t t0 = 0; t0 < steps; t0 += KG) {
+#pragma unroll
+        for (int u = 0; u < KG; ++u) {
+          const uint64_t t = t0 + u;
+          const int64_t jc = (int64_t)t - (int64_t)(KG * lane);     // column of this lane's slot 0
+          W[u] = (jc >= 0 && (uint64_t)jc < n2) ? (int32_t)__ldg(r + jc) : 0x200;
+          int32_t up = __shfl_up_sync(0xffffffffu, (u & 1) ? A[KG - 1] : B[KG - 1], 1);
+          if (lane == 0) up = (band > 0 && t < n2) ? __ldcg(scratch + t) : 0;
+#pragma unroll
+          for (int m = KG - 1; m >= 0; --m) {
+            const int32_t s = (qv[m] == W[(u - m + KG) % KG]) ? kMatch : kMismatch;
+            int32_t d, uu, l;
+            if (u & 1) { d = m ? B[m - 1] : upPrev; uu = m ? A[m - 1] : up; l = A[m]; }
+            else       { d = m ? A[m - 1] : upPrev; uu = m ? B[m - 1] : up; l = B[m]; }
+            const int32_t x = max(uu, l) + kGap;
+            int32_t h = __viaddmax_s32_relu(d, s, x);
+            // cells left of column 0 / right of the last column must stay neutral
+            const int64_t j = (int64_t)t - (int64_t)(KG * lane + m);
+            if (j < 0 || (uint64_t)j >= n2) h = 0;
+            if (u & 1) B[m] = h; else A[m] = h;
+            if (h > best[m]) { best[m] = h; bt[m] = j; }
+          }
+          // park the band's last row for the next band
+          if (lane == 31) {
+            const int64_t j = (int64_t)t - (int64_t)(BAND - 1);
+            if (j >= 0 && (uint64_t)j < n2) scratch[j] = (u & 1) ? B[KG - 1] : A[KG - 1];
+          }
+          upPrev = up;
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < KG; ++m) {
+        if (best[m] > gbest) { gbest = best[m]; gi = (int64_t)(row0 + m); gj = bt[m]; }
+        if (row0 + m == n1 - 1) lastrow = best[m];
+      }
+      __syncwarp();
+    }
+    // warp reduction: max score, then min i, then min j
+    int32_t lr = lastrow;
+    for (int o = 16; o; o >>= 1) {
+      const int32_t os = __shfl_xor_sync(0xffffffffu, gbest, o);
+      const int64_t oi = __shfl_xor_sync(0xffffffffu, gi, o), oj = __shfl_xor_sync(0xffffffffu, gj, o);
+      if (os > gbest || (os == gbest && os > 0 && (oi < gi || (oi == gi && oj < gj)))) { gbest = os; gi = oi; gj = oj; }
+      lr = max(lr, __shfl_xor_sync(0xffffffffu, lr, o));
+    }
+    if (lane == 0) {
+      b.out[p] = gbest > 0 ? swb_result{gbest, (int32_t)gi, (int32_t)gj} : swb_result{0, -1, -1};
+      if (last_row_out) last_row_out[item] = lr;
+    }
+    __syncwarp();
+  }
+}
+
+int generic_warps_per_sm() { return 16; }
+
+int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cudaStream_t st)
+{
+  // persistent grid: 4 CTAs x 4 warps per SM, work-stealing over the generic list
+  sw_generic_kernel<<<sm_count * 4, 128, 0, st>>>(b, b.generic_list, &b.counters->n_generic, nullptr);
+  return 1;
+}
+
+__global__ void single_pair_setup_kernel(Counters* c, uint32_t* list)
+{
+  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; list[0] = 0;
+}
+
+int launch_last_row_max(const uint8_t*, uint64_t, const uint8_t*, uint64_t, int32_t*, int32_t*, cudaStream_t)
+{
+  return 0;   // served by sw_generic_kernel's last_row_out (see swb_capi.cu)
+}
+
+// exposed for the C API: run the generic kernel on a prepared single-pair view
+int launch_generic_single(const BatchView& b, int32_t* last_row_out, cudaStream_t st)
+{
+  single_pair_setup_kernel<<<1, 1, 0, st>>>(b.counters, b.generic_list);
+  sw_generic_kernel<<<1, 32, 0, st>>>(b, b.generic_list, &b.counters->n_generic, last_row_out);
+  return 2;
+}
+
+// =====================================================================================
+// The reference's LIVE kernel, restated for CUDA (smith_waterman.cl:11-71): work-group g
+// owns [g*chunk, min((g+1)*chunk, L)), work-item lid walks it with stride wgs keeping a
+// clamped running sum of +2/-1; the maximum over everything lands in *result.
+// =====================================================================================
+__global__ void ref_compat_kernel(const uint8_t* __restrict__ s1, const uint8_t* __restrict__ s2,
+                                  uint64_t len, uint64_t chunk, int32_t* result)
+{
+  __shared__ int32_t wmax[32];
+  const uint64_t start = (uint64_t)blockIdx.x * chunk;                 // cl:27
+  int32_t mx = 0, curv = 0;
+  if (start < len) {                                                   // cl:30-32
+    const uint64_t end = min(start + chunk, len);                      // cl:28
+    for (uint64_t i = start + threadIdx.x; i < end; i += blockDim.x) { // cl:39
+      const int32_t s = (s1[i] == s2[i]) ? kMatch : kMismatch;         // cl:43-47
+      curv = max(curv + s, 0);                                         // cl:50
+      mx = max(mx, curv);                                              // cl:51
+    }
+  }
+  for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int32_t v = (threadIdx.x < (blockDim.x + 31) / 32) ? wmax[threadIdx.x] : 0;
+    for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) atomicMax(result, v);                        // cl:68-70
+  }
+}
+
+int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32_t wgs, uint64_t groups,
+                      int32_t* result, cudaStream_t st)
+{
+  cudaMemsetAsync(result, 0, sizeof(int32_t), st);
+  if (len == 0) return 0;
+  const uint64_t chunk = (len + groups - 1) / groups;                  // cl:26
+  ref_compat_kernel<<<(unsigned)groups, wgs, 0, st>>>(s1, s2, len, chunk, result);
+  return 1;
+}
+
+// =====================================================================================
+// Synthetic workload.  Counter RNG: the k-th draw of stream `seed` for pair
+// p is splitmix64 evaluated at state  (seed ^ p*0x9E3779B97F4A7C15) + (k+1)*0x9E3779B97F4A7C15.
+// Windows: iid ACGT, 32 bases per draw of stream 0xB200.  Reads, distribution 0 (related):
+// cut from the window at offset o = draw(0xB201,0) % (W-n+1), then per read base i one draw
+// x = draw(0xB201, 1+i):  x%1000 == 0 -> 1-base insertion (random base, cursor stays),
+// x%1000 == 1 -> 1-base deletion (cursor skips one), and (x>>10)%100 == 0 -> substitution.
+// Distribution 1 (unrelated): read base i = 2 bits of draw(0xB201, 1 + i/32).
+// =====================================================================================
+__host__ __device__ __forceinline__ uint64_t splitmix_at(uint64_t seed, uint64_t p, uint64_t k)
+{
+  uint64_t z = (seed ^ (p * 0x9E3779B97F4A7C15ull)) + (k + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ uint32_t window_code(uint64_t p, uint32_t j)
+{
+  return (uint32_t)(splitmix_at(0xB200ull, p, j >> 5) >> (2 * (j & 31))) & 3u;
+}
+
+__global__ void synth_window_kernel(uint64_t first_pair, uint64_t n_pairs, uint32_t wlen,
+                                    uint8_t* __restrict__ r_bytes, uint64_t* __restrict__ r_off)
+{
+  const uint64_t total = n_pairs * wlen;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
+    const uint64_t k = x / wlen; const uint32_t j = (uint32_t)(x - k * wlen);
+    r_bytes[x] = "ACGT"[window_code(first_pair + k, j)];
+  }
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_pairs; k += stride) r_off[k] = k * wlen;
+}
+
+__global__ void synth_read_kernel(uint64_t first_pair, uint64_t n_pairs, uint32_t rlen, uint32_t wlen, int dist,
+                                  uint8_t* __restrict__ q_bytes, uint64_t* __restrict__ q_off)
+{
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_pairs; k += stride) {
+    q_off[k] = k * rlen;
+    if (k == n_pairs) break;
+    const uint64_t p = first_pair + k;
+    uint8_t* dst = q_bytes + k * rlen;
+    if (dist == 1) {
+      for (uint32_t i = 0; i < rlen; ++i)
+        dst[i] = "ACGT"[(uint32_t)(splitmix_at(0xB201ull, p, 1 + (i >> 5)) >> (2 * (i & 31))) & 3u];
+    } else {
+      const uint32_t span = wlen >= rlen ? wlen - rlen + 1 : 1;
+      uint32_t c = (uint32_t)(splitmix_at(0xB201ull, p, 0) % span);
+      for (uint32_t i = 0; i < rlen; ++i) {
+        const uint64_t x = splitmix_at(0xB201ull, p, 1 + i);
+        const uint32_t ev = (uint32_t)(x % 1000u);
+        uint32_t code;
+        if (ev == 0) {
+          code = (uint32_t)(x >> 32) & 3u;                       // insertion: cursor stays
+        } else {
+          if (ev == 1) ++c;                                      // deletion: skip one window base
+          code = c < wlen ? window_code(p, c) : ((uint32_t)(x >> 34) & 3u);
+          ++c;
+          if ((uint32_t)((x >> 10) % 100u) == 0) code = (code + 1u + (uint32_t)((x >> 20) % 3u)) & 3u;
+        }
+        dst[i] = "ACGT"[code];
+      }
+    }
+  }
+}
+
+int launch_synth(uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len, int distribution,
+                 uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, cudaStream_t st)
+{
+  synth_window_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, window_len, r_bytes, r_off);
+  synth_read_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, read_len, window_len, distribution, q_bytes, q_off);
+  return 2;
+}
+
+}  // namespace swb

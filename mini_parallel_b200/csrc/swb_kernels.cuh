@@ -1,0 +1,54 @@
+// swb_kernels.cuh -- device-side interface of the Smith-Waterman engine (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/swb200.h"
+
+namespace swb {
+
+// Scoring constants: smith_waterman.cl:5-7.
+constexpr int kMatch = 2, kMismatch = -1, kGap = -2;
+
+// ---- routing classes written by classify_pairs ----
+enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2 };
+
+// Limits of the int16x2 inter-task kernel (see sw_short_kernel).
+constexpr uint32_t kShortMaxRead   = 160;    // rows held by one lane group (G x K)
+constexpr uint32_t kShortMaxWindow = 4096;   // columns staged in shared memory per group
+
+struct Counters {             // device-resident, zeroed per batch
+  uint32_t n_short;           // pairs routed to the int16x2 kernel
+  uint32_t n_generic;         // pairs routed to the 32-bit kernel
+  uint32_t max_short_window;  // longest window among the short pairs
+  uint32_t generic_cursor;    // work-stealing cursor of the generic kernel
+};
+
+struct BatchView {            // everything the kernels need about one batch (device pointers)
+  const uint8_t*  q_bytes;  const uint64_t* q_off;     // ASCII reads, CSR offsets (n_pairs+1)
+  const uint8_t*  r_bytes;  const uint64_t* r_off;     // ASCII windows
+  const uint32_t* q_pk;     const uint32_t* q_bad;     // 2-bit packed reads  + non-ACGT bitmap (1 bit / 16-base word)
+  const uint32_t* r_pk;     const uint32_t* r_bad;     // 2-bit packed windows + bitmap
+  uint64_t        n_pairs;
+  uint32_t*       short_list;   // pair ids, n_short entries
+  uint32_t*       generic_list; // pair ids, n_generic entries
+  Counters*       counters;
+  swb_result*     out;
+  int32_t*        scratch;      // generic kernel: one boundary row per resident warp
+  uint64_t        scratch_stride;
+};
+
+// launchers (all asynchronous on `st`); each returns the number of kernels it launched
+int launch_pack2bit(const uint8_t* bytes, uint64_t n, uint32_t* words, uint32_t* bitmap, cudaStream_t st);
+int launch_classify(const BatchView& b, cudaStream_t st);
+int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st);
+int launch_generic(const BatchView& b, int sm_count, int warps_resident, cudaStream_t st);
+int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32_t wgs, uint64_t groups,
+                      int32_t* result, cudaStream_t st);
+int launch_last_row_max(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,
+                        int32_t* rows /* 2*(n2+1) */, int32_t* result, cudaStream_t st);
+int launch_synth(uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len, int distribution,
+                 uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, cudaStream_t st);
+int generic_warps_per_sm();
+size_t short_smem_bytes(uint32_t window_cap, int variant);
+
+}  // namespace swb

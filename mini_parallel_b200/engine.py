@@ -1,0 +1,169 @@
+"""Engine: one swb_ctx (one GPU).  Host-side convenience over the C ABI; all compute is in libswb200.so."""
+import ctypes
+
+import numpy as np
+
+from ._lib import RESULT_DTYPE, SwbResult, load_library
+
+
+class SwbError(RuntimeError):
+    """Mirrors the Err(String) arm of the reference's Result<i32, String> (aligner.rs:410)."""
+
+
+def device_count():
+    return int(load_library().swb_device_count())
+
+
+def _as_bytes_array(x):
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.uint8:
+            raise TypeError("byte arrays must be uint8")
+        return np.ascontiguousarray(x)
+    if isinstance(x, str):
+        x = x.encode("utf-8")
+    return np.frombuffer(bytes(x), dtype=np.uint8)
+
+
+def to_csr(seqs):
+    """list of bytes/str -> (uint8 concatenation, uint64 offsets)."""
+    arrs = [_as_bytes_array(s) for s in seqs]
+    off = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    if arrs:
+        off[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)
+    data = np.concatenate(arrs) if arrs and off[-1] > 0 else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(data, dtype=np.uint8), off
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        if self._lib.swb_create(ctypes.byref(h), int(device), None) != 0:
+            raise SwbError(self._err())
+        self._h = h
+        self.device = int(device)
+
+    def _err(self):
+        return self._lib.swb_last_error().decode("utf-8", "replace")
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SwbError(self._err())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.swb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- scoring ----
+    def score_pair(self, s1, s2):
+        a, b = _as_bytes_array(s1), _as_bytes_array(s2)
+        res = SwbResult()
+        self._check(self._lib.swb_score_pair(self._h, a.ctypes.data, a.size, b.ctypes.data, b.size, ctypes.byref(res)))
+        return int(res.score), int(res.end_i), int(res.end_j)
+
+    def score_batch_csr(self, q_bytes, q_off, r_bytes, r_off):
+        q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8)
+        r_bytes = np.ascontiguousarray(r_bytes, dtype=np.uint8)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        r_off = np.ascontiguousarray(r_off, dtype=np.uint64)
+        n = q_off.size - 1
+        if r_off.size - 1 != n:
+            raise ValueError("q_off and r_off must describe the same number of pairs")
+        out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
+        if n > 0:
+            self._check(self._lib.swb_score_batch(self._h, q_bytes.ctypes.data, q_off.ctypes.data,
+                                                  r_bytes.ctypes.data, r_off.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def score_batch(self, reads, windows):
+        q, qo = to_csr(reads)
+        r, ro = to_csr(windows)
+        return self.score_batch_csr(q, qo, r, ro)
+
+    def score_batch_device(self, d_q, d_qo, q_total, d_r, d_ro, r_total, n_pairs, max_q_len, max_r_len, d_out):
+        """All pointers are device addresses (ints).  Asynchronous on the engine's stream."""
+        self._check(self._lib.swb_score_batch_device(self._h, d_q, d_qo, q_total, d_r, d_ro, r_total,
+                                                     n_pairs, max_q_len, max_r_len, d_out))
+
+    def sync(self):
+        self._check(self._lib.swb_sync(self._h))
+
+    # ---- the reference's two literal behaviours ----
+    def ref_compat_align(self, s1, s2, dev_max_work_group=1024):
+        a, b = _as_bytes_array(s1), _as_bytes_array(s2)
+        out = ctypes.c_int32()
+        self._check(self._lib.swb_ref_compat_align(self._h, a.ctypes.data, a.size, b.ctypes.data, b.size,
+                                                   dev_max_work_group, ctypes.byref(out)))
+        return int(out.value)
+
+    def last_row_max(self, s1, s2):
+        a, b = _as_bytes_array(s1), _as_bytes_array(s2)
+        out = ctypes.c_int32()
+        self._check(self._lib.swb_last_row_max(self._h, a.ctypes.data, a.size, b.ctypes.data, b.size, ctypes.byref(out)))
+        return int(out.value)
+
+    # ---- stages ----
+    def pack2bit(self, data):
+        a = _as_bytes_array(data)
+        nw = (a.size + 15) // 16
+        words = np.zeros(nw, dtype=np.uint32)
+        bitmap = np.zeros((nw + 31) // 32, dtype=np.uint32)
+        if a.size:
+            self._check(self._lib.swb_pack2bit(self._h, a.ctypes.data, a.size, words.ctypes.data, bitmap.ctypes.data))
+        return words, bitmap
+
+    def pack2bit_device(self, d_bytes, n, d_words, d_bitmap):
+        self._check(self._lib.swb_pack2bit_device(self._h, d_bytes, n, d_words, d_bitmap))
+
+    def synth_device(self, first_pair, n_pairs, read_len, window_len, distribution, d_q, d_qo, d_r, d_ro):
+        self._check(self._lib.swb_synth_device(self._h, first_pair, n_pairs, read_len, window_len, distribution,
+                                               d_q, d_qo, d_r, d_ro))
+
+    def set_short_variant(self, v):
+        self._check(self._lib.swb_set_short_variant(self._h, int(v)))
+
+    def last_timings(self):
+        ms = (ctypes.c_float * 6)()
+        k = ctypes.c_int()
+        self._check(self._lib.swb_last_timings(self._h, ms, ctypes.byref(k)))
+        names = ("pack_classify_ms", "short_ms", "generic_ms", "device_ms", "h2d_ms", "d2h_ms")
+        d = {n: float(v) for n, v in zip(names, ms)}
+        d["kernels"] = int(k.value)
+        return d
+
+    def last_routing(self):
+        c = (ctypes.c_uint64 * 2)()
+        self._check(self._lib.swb_last_routing(self._h, c))
+        return {"short": int(c[0]), "generic": int(c[1])}
+
+    @property
+    def stream(self):
+        return self._lib.swb_stream(self._h)
+
+    # ---- raw memory (for callers without torch) ----
+    def malloc_device(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self._lib.swb_malloc_device(self._h, int(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def free_device(self, p):
+        self._lib.swb_free_device(self._h, p)
+
+    def d2h(self, dst_array, d_src, nbytes):
+        self._check(self._lib.swb_memcpy_d2h(self._h, dst_array.ctypes.data, d_src, int(nbytes)))
+
+    def h2d(self, d_dst, src_array, nbytes):
+        self._check(self._lib.swb_memcpy_h2d(self._h, d_dst, src_array.ctypes.data, int(nbytes)))
