@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Smith-Waterman scoring path (BASELINE.json metric:
+GCUPS and reads/s on 150 bp reads, 1/2/4/8 B200, beside the CPU SIMD path).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle SIMD port, all host cores)
+
+Workload (config.workload): BASELINE.json configs[1] -- 1,000,000 synthetic 150 bp reads, each against its own
+500 bp window, on ONE B200; with N GPUs every rank scores its own 1 M-pair shard of the same counter-RNG stream
+(weak scaling, no data-path collective: pairs are independent).  One step = one pass of the hot
+path (2-bit pack + classify + int16x2 DPX kernel + generic kernel) over the whole batch.
+
+  value   : whole-job GCUPS with the ASCII inputs already resident in HBM when the timed region starts
+  e2e     : the same through swb_score_batch with HOST (pinned) buffers: H2D + kernels + D2H inside the region
+  roofline: the short-read kernel against the DPX integer-issue roofline; second object for
+            the HBM-bound packing kernel
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+READ_LEN, WINDOW_LEN = 150, 500
+DPX_INSTR_PER_CLK_PER_SM_FALLBACK = 64.0     # measured: profiles/issue_rate_r01.json
+INT_ISSUE_PER_CELL = 2.0                     # 4 thread-instructions per int16x2 cell pair
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d.get("hbm_gbs", 6650.0)), "sm_max_mhz": float(d.get("sm_max_mhz", 1965.0)), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+def load_issue_rate():
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True) if os.path.isdir(os.path.join(ROOT, "profiles")) else []:
+        if name.startswith("issue_rate_") and name.endswith(".json"):
+            try:
+                d = json.load(open(os.path.join(ROOT, "profiles", name)))
+                return float(d["rates"]["viaddmnmx_s16x2"]["thread_instr_per_clk_per_sm"]), name
+            except Exception:
+                pass
+    return DPX_INSTR_PER_CLK_PER_SM_FALLBACK, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_simd_gcups(first_pair, n_pairs, dist, threads, budget_s):
+    """Times the oracle's CPU SIMD port on a bounded sample of the workload; returns (gcups, pairs_done, seconds)."""
+    import oracle_lib as ol
+    from mini_parallel_b200 import synth
+    chunk = 100_000
+    done, spent = 0, 0.0
+    while done < n_pairs and spent < budget_s:
+        m = min(chunk, n_pairs - done)
+        q, qo, r, ro = synth.make_pairs(first_pair + done, m, READ_LEN, WINDOW_LEN, dist)
+        t0 = time.perf_counter()
+        ol.batch(q, qo, r, ro, threads=threads, simd=True)
+        spent += time.perf_counter() - t0
+        done += m
+    return done * READ_LEN * WINDOW_LEN / spent / 1e9, done, spent
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference has no CPU scoring path and cannot be built here (no
+    Rust / OpenCL); the arm times this repo's CPU port of the same scoring function (oracle/sw_simd.c,
+    bit-exact with the oracle) on all host cores, on a bounded sample of the same workload per step."""
+    if rank != 0:
+        return
+    import oracle_lib as ol
+    threads = os.cpu_count() or 1
+    sample_pairs = args.ref_pairs
+    for _ in range(args.warmup):
+        cpu_simd_gcups(0, min(sample_pairs, 50_000), args.dist, threads, 1e9)
+    t_total, pairs_total = 0.0, 0
+    for s in range(args.steps):
+        _, done, spent = cpu_simd_gcups(0, sample_pairs, args.dist, threads, 1e9)
+        t_total += spent
+        pairs_total += done
+    gcups = pairs_total * READ_LEN * WINDOW_LEN / t_total / 1e9
+    line = {
+        "impl": "reference", "metric": "GCUPS", "value": round(gcups, 3), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(1e3 * t_total / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16", "data": "synthetic",
+        "reads_per_s": round(pairs_total / t_total, 1),
+        "config": {"workload": f"BASELINE.json configs[1]: 150 bp reads x 500 bp windows, synthetic related reads (dist {args.dist}); "
+                               f"CPU arm scores a bounded sample of {sample_pairs} pairs per step", "pairs_per_step": sample_pairs,
+                   "read_len": READ_LEN, "window_len": WINDOW_LEN},
+        "cpu_baseline": {"value": round(gcups, 3), "unit": "GCUPS", "cores": threads, "kind": "port", "isa": ol.simd_isa(),
+                         "sample": f"{sample_pairs} pairs x {args.steps} steps of the config-2 stream (pairs 0..{sample_pairs - 1})"},
+        "e2e": {"value": round(gcups, 3), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per step")
+    ap.add_argument("--dist", type=int, default=0, help="0 = related reads, 1 = unrelated")
+    ap.add_argument("--ref-pairs", type=int, default=200_000, help="pairs per step of the CPU arm")
+    ap.add_argument("--cpu-budget-s", type=float, default=12.0)
+    ap.add_argument("--variant", type=int, default=-1)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import mini_parallel_b200 as mp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    warmup = max(args.warmup, 3)
+    n, rl, wl = args.pairs, READ_LEN, WINDOW_LEN
+    first_pair = rank * n                                  # this rank's shard of the counter-RNG stream
+    eng = mp.Engine(local_rank)
+    if args.variant >= 0:
+        eng.set_short_variant(args.variant)
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local_rank))
+
+    # ---- device-resident inputs (ASCII, as a FASTQ chunk would arrive) ----
+    dev = torch.device("cuda", local_rank)
+    d_q = torch.empty(n * rl, dtype=torch.uint8, device=dev)
+    d_r = torch.empty(n * wl, dtype=torch.uint8, device=dev)
+    d_qo = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_ro = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    d_out = torch.empty(n * 3, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    eng.synth_device(first_pair, n, rl, wl, args.dist, d_q.data_ptr(), d_qo.data_ptr(), d_r.data_ptr(), d_ro.data_ptr())
+    eng.sync()
+
+    def step_device():
+        eng.score_batch_device(d_q.data_ptr(), d_qo.data_ptr(), n * rl, d_r.data_ptr(), d_ro.data_ptr(), n * wl, n, rl, wl,
+                               d_out.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- timed region 1: device-resident ----
+    for _ in range(warmup):
+        step_device()
+    eng.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    short_ms, pack_ms, generic_ms, launches = [], [], [], 0
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+            t = eng.last_timings()                          # CUDA events around each kernel, on the launching stream
+            short_ms.append(t["short_ms"]); pack_ms.append(t["pack_classify_ms"]); generic_ms.append(t["generic_ms"])
+            launches += t["kernels"]
+        e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    routing = eng.last_routing()
+
+    # ---- timed region 2: end to end through the host API (pinned host buffers) ----
+    h_q = torch.empty(n * rl, dtype=torch.uint8).pin_memory()
+    h_r = torch.empty(n * wl, dtype=torch.uint8).pin_memory()
+    h_qo = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+    h_ro = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+    h_out = torch.empty(n * 3, dtype=torch.int32).pin_memory()
+    h_q.copy_(d_q); h_r.copy_(d_r); h_qo.copy_(d_qo); h_ro.copy_(d_ro)
+    torch.cuda.synchronize()
+    lib = mp.load_library()
+
+    def step_host():
+        rc = lib.swb_score_batch(eng._h, h_q.data_ptr(), h_qo.data_ptr(), h_r.data_ptr(), h_ro.data_ptr(), n, h_out.data_ptr())
+        if rc != 0:
+            raise RuntimeError(lib.swb_last_error().decode())
+
+    for _ in range(2):
+        step_host()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        g0.record(stream)
+        for _ in range(e2e_steps):
+            step_host()
+        g1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(g0.elapsed_time(g1))
+    host_same = bool(torch.equal(h_out.to(dev), d_out))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cells_step = float(n) * rl * wl
+    gcups = world * cells_step * args.steps / (ms_total * 1e-3) / 1e9
+    e2e_gcups = world * cells_step * e2e_steps / (e2e_ms * 1e-3) / 1e9
+    peaks = load_peaks()
+    rate, rate_src = load_issue_rate()
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    peak_gcups = sms * peaks["sm_max_mhz"] * 1e6 * rate / INT_ISSUE_PER_CELL / 1e9
+    k_ms = statistics.mean(short_ms)
+    k_gcups = cells_step / (k_ms * 1e-3) / 1e9
+    p_ms = statistics.mean(pack_ms)
+    pack_bytes = 1.25 * n * (rl + wl)                      # 1 B read + 0.25 B written per base
+    cpu_val, cpu_pairs, cpu_s = cpu_simd_gcups(0, min(n, 1_000_000), args.dist, os.cpu_count() or 1, args.cpu_budget_s)
+    import oracle_lib as ol
+
+    line = {
+        "metric": "GCUPS", "value": round(gcups, 2), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16", "data": "synthetic",
+        "reads_per_s": round(world * n * args.steps / (ms_total * 1e-3), 1),
+        "config": {"workload": "BASELINE.json configs[1]: 1M synthetic 150bp reads vs 500bp windows per GPU (inter-task int16x2 DPX kernel), "
+                               "related reads (1% subst, 0.1% ins, 0.1% del)" if args.dist == 0 else
+                               "BASELINE.json configs[1] shape, unrelated reads",
+                   "pairs_per_gpu": n, "read_len": rl, "window_len": wl, "distribution": args.dist, "sharding": f"{world} x independent shard",
+                   "l2_policy": f"inputs larger than L2 ({(n * (rl + wl)) >> 20} MiB ASCII per step vs 126 MB L2)",
+                   "short_variant": args.variant, "routing": routing, "host_path_equals_device_path": host_same},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_gcups, 2), "unit": "GCUPS", "reads_per_s": round(world * n * e2e_steps / (e2e_ms * 1e-3), 1),
+                "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
+                "h2d_bytes_per_step": int(h_q.numel() + h_r.numel() + 8 * (h_qo.numel() + h_ro.numel())),
+                "d2h_bytes_per_step": int(4 * h_out.numel())},
+        "roofline": {"bound": "int_issue", "kernel": "sw_short_kernel", "achieved": round(k_gcups, 1), "peak": round(peak_gcups, 1),
+                     "unit": "GCUPS", "frac": round(k_gcups / peak_gcups, 4), "traffic": None,
+                     "kernel_ms": round(k_ms, 4), "kernel_share_of_step": round(k_ms / (ms_total / args.steps), 4),
+                     "peak_is": f"{sms} SMs x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} MEASURED_PEAKS.json) x {rate:.2f} DPX s16x2 "
+                                f"thread-instr/clk/SM (measured, {rate_src}) / {INT_ISSUE_PER_CELL} instr per cell"},
+        "roofline_pack": {"bound": "hbm", "kernel": "pack2bit_kernel x2 + classify_kernel", "achieved": round(pack_bytes / (p_ms * 1e-3) / 1e9, 1),
+                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(pack_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                          "kernel_ms": round(p_ms, 4), "traffic": None, "peak_is": f"{peaks['source']} copy bandwidth"},
+        "cpu_baseline": {"value": round(cpu_val, 3), "unit": "GCUPS", "cores": os.cpu_count() or 1, "kind": "port", "isa": ol.simd_isa(),
+                         "sample": f"first {cpu_pairs} pairs of the same workload, {cpu_s:.1f} s of CPU time (oracle/sw_simd.c)"},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -86,6 +86,23 @@ int  swb_last_timings(swb_ctx*, float* ms /* 6 */, int* kernels_launched);
 /* Pairs routed to each path by the last call: [0] short int16x2 path, [1] generic 32-bit path. */
 int  swb_last_routing(swb_ctx*, uint64_t* counts /* 2 */);
 
+/* The packing stage alone on device-resident bytes (bench: HBM roofline of the packing kernel). */
+int  swb_pack2bit_device(swb_ctx*, const uint8_t* d_bytes, uint64_t n, uint32_t* d_words, uint32_t* d_bitmap);
+
+/* Tuning knob: which instantiation of the short-read kernel runs (bit0: 0 = 8 lanes x 20 rows, 1 = 16 lanes x
+ * 10 rows per group; bit1: split end-cell tracking).  All variants return identical results. */
+int  swb_set_short_variant(swb_ctx*, int variant);
+
+/* Raw device / pinned-host memory and copies for hosts without a CUDA runtime of their own (the CLI, the
+ * ctypes tests, a Rust caller).  Replaces ocl::Buffer creation in gpu_align (aligner.rs:466-499);
+ * USE_PINNED_MEMORY (aligner.rs:466-475) maps to swb_malloc_pinned. */
+int  swb_malloc_device(swb_ctx*, uint64_t bytes, void** out);
+int  swb_free_device(swb_ctx*, void* p);
+int  swb_malloc_pinned(uint64_t bytes, void** out);
+int  swb_free_pinned(void* p);
+int  swb_memcpy_h2d(swb_ctx*, void* d_dst, const void* h_src, uint64_t bytes);
+int  swb_memcpy_d2h(swb_ctx*, void* h_dst, const void* d_src, uint64_t bytes);
+
 void*       swb_stream(swb_ctx*);            /* the cudaStream_t the context launches on */
 const char* swb_last_error(void);
 const char* swb_version(void);

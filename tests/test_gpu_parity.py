@@ -1,0 +1,238 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libswb200.so), against the CPU
+oracle on the same inputs.  Bit-exact: scores and end coordinates are integers."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import mini_parallel_b200 as mp
+from mini_parallel_b200 import synth
+from mini_parallel_b200.engine import to_csr
+
+pytestmark = pytest.mark.gpu
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sw_vectors.json")))["vectors"]
+ALL_VARIANTS = (0, 1, 2, 3)
+
+
+def _rand(rng, n, alphabet=b"ACGT"):
+    al = np.frombuffer(alphabet, dtype=np.uint8)
+    return al[rng.integers(0, al.size, n)]
+
+
+def _pairs(rng, n, rl, wl, related=True, alphabet=b"ACGT", mut=0.03):
+    reads, wins = [], []
+    for _ in range(n):
+        n1, n2 = int(rng.integers(rl[0], rl[1] + 1)), int(rng.integers(wl[0], wl[1] + 1))
+        w = _rand(rng, n2, alphabet)
+        if related and n2 >= n1 > 0:
+            o = int(rng.integers(0, n2 - n1 + 1))
+            r = w[o:o + n1].copy()
+            m = rng.random(n1) < mut
+            r[m] = _rand(rng, int(m.sum()), alphabet)
+        else:
+            r = _rand(rng, n1, alphabet)
+        reads.append(r)
+        wins.append(w)
+    return reads, wins
+
+
+def _assert_parity(engine, reads, wins, threads=8):
+    q, qo = to_csr(reads)
+    r, ro = to_csr(wins)
+    got = engine.score_batch_csr(q, qo, r, ro)
+    exp = ol.batch(q, qo, r, ro, threads=threads, simd=False)
+    bad = np.nonzero(got != exp)[0]
+    assert bad.size == 0, f"{bad.size} pairs differ, first: pair {bad[0]} got {got[bad[0]]} expected {exp[bad[0]]}"
+    return got
+
+
+@pytest.mark.parametrize("v", GOLD, ids=[v["name"] for v in GOLD])
+def test_golden_vectors(engine, v):
+    a, b = v["seq1"].encode("latin1"), v["seq2"].encode("latin1")
+    assert engine.score_pair(a, b) == (v["score"], v["end_i"], v["end_j"])
+    assert engine.last_row_max(a, b) == v["last_row_max"]
+    assert engine.ref_compat_align(a, b, 1024) == v["ref_compat_1024"]
+    assert engine.ref_compat_align(a, b, 256) == v["ref_compat_256"]
+
+
+def test_golden_vectors_as_one_batch(engine):
+    reads = [v["seq1"].encode("latin1") for v in GOLD]
+    wins = [v["seq2"].encode("latin1") for v in GOLD]
+    for variant in ALL_VARIANTS:
+        engine.set_short_variant(variant)
+        got = engine.score_batch(reads, wins)
+        for g, v in zip(got, GOLD):
+            assert (int(g["score"]), int(g["end_i"]), int(g["end_j"])) == (v["score"], v["end_i"], v["end_j"]), v["name"]
+    engine.set_short_variant(1)
+
+
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
+def test_short_path_uniform_150x500(engine, variant):
+    rng = np.random.default_rng(100 + variant)
+    engine.set_short_variant(variant)
+    _assert_parity(engine, *_pairs(rng, 4001, (150, 150), (500, 500)))           # odd count: last group holds one pair
+    assert engine.last_routing() == {"short": 4001, "generic": 0}
+    _assert_parity(engine, *_pairs(rng, 2000, (150, 150), (500, 500), related=False))
+    engine.set_short_variant(1)
+
+
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
+def test_short_path_ragged_lengths(engine, variant):
+    rng = np.random.default_rng(200 + variant)
+    engine.set_short_variant(variant)
+    _assert_parity(engine, *_pairs(rng, 6000, (1, 160), (1, 900)))
+    _assert_parity(engine, *_pairs(rng, 1500, (140, 160), (1, 60), related=False))   # window shorter than the read
+    engine.set_short_variant(1)
+
+
+@pytest.mark.parametrize("variant", ALL_VARIANTS)
+def test_short_path_many_way_ties(engine, variant):
+    """Homopolymers and short repeats: every tie-break decision (min i, then min j) is exercised."""
+    rng = np.random.default_rng(300 + variant)
+    engine.set_short_variant(variant)
+    _assert_parity(engine, *_pairs(rng, 1500, (1, 160), (1, 400), alphabet=b"A"))
+    _assert_parity(engine, *_pairs(rng, 1500, (1, 160), (1, 400), related=False, alphabet=b"AC"))
+    reads = [b"ACG" * 50] * 64 + [b"AT" * 80] * 64
+    wins = [b"ACG" * 160] * 64 + [b"TA" * 250] * 64
+    _assert_parity(engine, reads, wins)
+    engine.set_short_variant(1)
+
+
+def test_short_path_window_limits(engine):
+    rng = np.random.default_rng(400)
+    _assert_parity(engine, *_pairs(rng, 64, (150, 160), (4000, 4096)))               # longest window the short path takes
+    assert engine.last_routing()["generic"] == 0
+    _assert_parity(engine, *_pairs(rng, 16, (150, 160), (4097, 4200)))               # one past: generic path
+    assert engine.last_routing()["short"] == 0
+
+
+def test_generic_path_bytes_and_lengths(engine):
+    rng = np.random.default_rng(500)
+    _assert_parity(engine, *_pairs(rng, 1500, (1, 200), (1, 600), alphabet=b"ACGTN"))          # N == N matches (cl:114)
+    _assert_parity(engine, *_pairs(rng, 400, (10, 150), (10, 500), alphabet=b"ACGTacgt"))       # case-sensitive
+    _assert_parity(engine, *_pairs(rng, 100, (161, 900), (200, 3000)))                          # multi-band reads
+    _assert_parity(engine, *_pairs(rng, 50, (255, 258), (255, 258)))                            # band boundary 256
+    _assert_parity(engine, *_pairs(rng, 8, (2000, 2100), (5000, 5100)))
+    reads = [bytes(rng.integers(0, 256, 200, dtype=np.uint8)) for _ in range(64)]               # arbitrary bytes
+    wins = [bytes(rng.integers(0, 256, 300, dtype=np.uint8)) for _ in range(64)]
+    _assert_parity(engine, reads, wins)
+
+
+def test_mixed_batch_routing_and_empties(engine):
+    rng = np.random.default_rng(600)
+    r1, w1 = _pairs(rng, 300, (100, 160), (200, 600))
+    r2, w2 = _pairs(rng, 60, (161, 400), (200, 900))
+    r3, w3 = _pairs(rng, 40, (50, 150), (100, 400), alphabet=b"ACGTN")
+    reads = r1 + r2 + r3 + [b"", b"ACGT", b""]
+    wins = w1 + w2 + w3 + [b"ACGT", b"", b""]
+    order = rng.permutation(len(reads))
+    reads = [reads[k] for k in order]
+    wins = [wins[k] for k in order]
+    got = _assert_parity(engine, reads, wins)
+    routing = engine.last_routing()
+    assert routing["short"] + routing["generic"] == len(reads) - 3
+    assert routing["short"] >= 250 and routing["generic"] >= 60
+    for k, (a, b) in enumerate(zip(reads, wins)):
+        if len(a) == 0 or len(b) == 0:
+            assert tuple(got[k]) == (0, -1, -1)                                                 # aligner.rs:413-416
+
+
+def test_long_identical_pair_needs_32bit(engine):
+    rng = np.random.default_rng(700)
+    s = bytes(_rand(rng, 16500))
+    assert engine.score_pair(s, s) == (33000, 16499, 16499)
+
+
+def test_long_pair_10k(engine):
+    """Config 4 shape (10 kb x 10 kb), a few pairs: the oracle needs ~0.3 s per pair."""
+    rng = np.random.default_rng(701)
+    _assert_parity(engine, *_pairs(rng, 3, (10000, 10000), (10000, 10000), mut=0.1), threads=3)
+
+
+def test_results_do_not_depend_on_batch_composition(engine):
+    rng = np.random.default_rng(800)
+    reads, wins = _pairs(rng, 999, (1, 160), (1, 700))
+    whole = engine.score_batch(reads, wins)
+    perm = rng.permutation(len(reads))
+    shuffled = engine.score_batch([reads[k] for k in perm], [wins[k] for k in perm])
+    assert np.array_equal(whole[perm], shuffled)
+    parts = np.concatenate([engine.score_batch(reads[a:a + 100], wins[a:a + 100]) for a in range(0, 999, 100)])
+    assert np.array_equal(whole, parts)
+    again = engine.score_batch(reads, wins)
+    assert np.array_equal(whole, again)                                                         # idempotent
+
+
+def test_pack2bit_matches_numpy(engine):
+    rng = np.random.default_rng(900)
+    for n in (1, 15, 16, 17, 511, 512, 513, 100003):
+        data = _rand(rng, n, b"ACGT").copy()
+        if n > 40:
+            data[rng.integers(0, n, 5)] = ord("N")
+            data[rng.integers(0, n)] = ord("a")
+        words, bitmap = engine.pack2bit(data)
+        codes = (data >> 1) & 3
+        pad = np.zeros((-n) % 16, dtype=np.uint8)
+        c = np.concatenate([codes, pad]).reshape(-1, 16).astype(np.uint32)
+        exp_words = (c << (2 * np.arange(16, dtype=np.uint32))[None, :]).sum(axis=1).astype(np.uint32)
+        assert np.array_equal(words, exp_words)
+        okb = np.isin(data, np.frombuffer(b"ACGT", dtype=np.uint8))
+        bad_word = ~np.concatenate([okb, np.ones((-n) % 16, dtype=bool)]).reshape(-1, 16).all(axis=1)
+        got_bad = ((bitmap[np.arange(words.size) // 32] >> (np.arange(words.size) % 32).astype(np.uint32)) & 1).astype(bool)
+        assert np.array_equal(got_bad, bad_word)
+
+
+@pytest.mark.parametrize("dist", [0, 1])
+def test_device_generator_matches_host_twin(engine, dist):
+    n, rl, wl = 777, 150, 500
+    dq, dqo = engine.malloc_device(n * rl), engine.malloc_device((n + 1) * 8)
+    dr, dro = engine.malloc_device(n * wl), engine.malloc_device((n + 1) * 8)
+    try:
+        engine.synth_device(12345, n, rl, wl, dist, dq, dqo, dr, dro)
+        engine.sync()
+        q = np.zeros(n * rl, dtype=np.uint8); r = np.zeros(n * wl, dtype=np.uint8)
+        qo = np.zeros(n + 1, dtype=np.uint64); ro = np.zeros(n + 1, dtype=np.uint64)
+        engine.d2h(q, dq, q.nbytes); engine.d2h(r, dr, r.nbytes); engine.d2h(qo, dqo, qo.nbytes); engine.d2h(ro, dro, ro.nbytes)
+    finally:
+        for p in (dq, dqo, dr, dro):
+            engine.free_device(p)
+    eq, eqo, er, ero = synth.make_pairs(12345, n, rl, wl, dist)
+    assert np.array_equal(qo, eqo) and np.array_equal(ro, ero)
+    assert np.array_equal(r, er)
+    assert np.array_equal(q, eq)
+
+
+def test_config2_full_size_device_resident(engine):
+    """BASELINE.json configs[1] at full size (1 M pairs, 150 x 500), inputs generated and kept in HBM.
+    Checked through size-independent properties plus a 30 k-pair sample against the SIMD oracle."""
+    n, rl, wl = 1_000_000, 150, 500
+    dq, dqo = engine.malloc_device(n * rl), engine.malloc_device((n + 1) * 8)
+    dr, dro = engine.malloc_device(n * wl), engine.malloc_device((n + 1) * 8)
+    dout = engine.malloc_device(n * 12)
+    try:
+        engine.synth_device(0, n, rl, wl, 0, dq, dqo, dr, dro)
+        engine.score_batch_device(dq, dqo, n * rl, dr, dro, n * wl, n, rl, wl, dout)
+        engine.sync()
+        out = np.zeros(n, dtype=mp.RESULT_DTYPE)
+        engine.d2h(out, dout, out.nbytes)
+        assert engine.last_routing() == {"short": n, "generic": 0}
+        assert out["score"].min() > 200 and out["score"].max() <= 2 * rl            # related reads score high
+        assert np.all(out["end_i"] < rl) and np.all(out["end_j"] < wl) and np.all(out["end_i"] >= 0)
+        m = 30_000
+        q = np.zeros(m * rl, dtype=np.uint8); r = np.zeros(m * wl, dtype=np.uint8)
+        engine.d2h(q, dq, q.nbytes); engine.d2h(r, dr, r.nbytes)
+        qo = np.arange(m + 1, dtype=np.uint64) * rl; ro = np.arange(m + 1, dtype=np.uint64) * wl
+        exp = ol.batch(q, qo, r, ro, threads=os.cpu_count() or 8, simd=True)
+        assert np.array_equal(out[:m], exp)
+        # sharded == whole: score the second half alone (what a second rank would do) and compare
+        h = n // 2
+        engine.synth_device(h, n - h, rl, wl, 0, dq, dqo, dr, dro)
+        engine.score_batch_device(dq, dqo, (n - h) * rl, dr, dro, (n - h) * wl, n - h, rl, wl, dout)
+        engine.sync()
+        half = np.zeros(n - h, dtype=mp.RESULT_DTYPE)
+        engine.d2h(half, dout, half.nbytes)
+        assert np.array_equal(half, out[h:])
+    finally:
+        for p in (dq, dqo, dr, dro, dout):
+            engine.free_device(p)
