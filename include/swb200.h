@@ -51,6 +51,15 @@ int  swb_score_batch(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off,
                      const uint8_t* r_bytes, const uint64_t* r_off,
                      uint64_t n_pairs, swb_result* out);
 
+/* Reads against windows of a DEVICE-RESIDENT reference (north_star: windows must not stream over PCIe).
+ * swb_set_reference uploads and 2-bit-packs the reference once; each call then ships only the reads plus one
+ * (start,len) per read.  Window k is reference[win_start[k], win_start[k]+win_len[k]).  The reference has no
+ * read-vs-reference notion (it self-compares a chunk, aligner.rs:270-274); this is the pairing the
+ * --full-wgs driver uses here. */
+int  swb_set_reference(swb_ctx*, const uint8_t* ref_bytes, uint64_t n);
+int  swb_score_batch_vs_reference(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off, uint64_t n_pairs,
+                                  const uint64_t* win_start, const uint32_t* win_len, swb_result* out);
+
 /* Same, DEVICE-resident inputs and outputs (pointers from cudaMalloc / a torch tensor's data_ptr);
  * runs on the context's stream, returns after the work is enqueued; swb_sync() waits. */
 int  swb_score_batch_device(swb_ctx*, const uint8_t* d_q_bytes, const uint64_t* d_q_off, uint64_t q_total_bytes,

@@ -29,6 +29,8 @@ SIGNATURES = {
     "swb_score_batch": (_int, [_vp, _u8p, _vp, _u8p, _vp, _u64, _vp]),
     "swb_score_batch_device": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, _u64, _u32, _u32, _vp]),
     "swb_sync": (_int, [_vp]),
+    "swb_set_reference": (_int, [_vp, _u8p, _u64]),
+    "swb_score_batch_vs_reference": (_int, [_vp, _u8p, _vp, _u64, _vp, _vp, _vp]),
     "swb_ref_compat_align": (_int, [_vp, _u8p, _u64, _u8p, _u64, _u32, ctypes.POINTER(ctypes.c_int32)]),
     "swb_last_row_max": (_int, [_vp, _u8p, _u64, _u8p, _u64, ctypes.POINTER(ctypes.c_int32)]),
     "swb_pack2bit": (_int, [_vp, _u8p, _u64, _vp, _vp]),

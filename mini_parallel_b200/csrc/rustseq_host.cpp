@@ -1,0 +1,660 @@
+// rustseq_host.cpp -- C++ mirror of the reference's Rust host side for the alignment path
+// (smith_waterman/src/aligner.rs, gpu.rs, main.rs).  See include/rustseq_host.h.  All scoring goes
+// through the C ABI of swb200.h; there is no CPU scoring code in this file.
+#include "../../include/rustseq_host.h"
+#include <zlib.h>
+#include <algorithm>
+#include <cerrno>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+
+bool ref_compat_mode()
+{
+  const char* m = std::getenv("SWB_GPU_ALIGN_MODE");
+  return m && std::string(m) == "ref_compat";
+}
+
+// ---- process-wide context per device: the OPENCL_CONTEXT singleton of gpu.rs:13-14, :97-115 ----
+std::mutex g_ctx_mu;
+swb_ctx* g_ctx[64] = {};
+
+swb_ctx* context_for(int ordinal)
+{
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (ordinal < 0 || ordinal >= 64) { g_err = "Failed to get GPU context: bad device ordinal"; return nullptr; }
+  if (!g_ctx[ordinal]) {
+    swb_ctx* c = nullptr;
+    if (swb_create(&c, ordinal, nullptr) != 0) { g_err = std::string("Failed to get GPU context: ") + swb_last_error(); return nullptr; }
+    g_ctx[ordinal] = c;
+  }
+  return g_ctx[ordinal];
+}
+
+// ---- Rust's str::parse::<usize>() and its ParseIntError texts (aligner.rs:13-14) ----
+int parse_usize(const std::string& s, uint64_t* out, std::string* why)
+{
+  size_t i = 0;
+  if (s.empty()) { *why = "cannot parse integer from empty string"; return 1; }
+  if (s[0] == '+') { i = 1; if (s.size() == 1) { *why = "invalid digit found in string"; return 1; } }
+  uint64_t v = 0;
+  for (; i < s.size(); ++i) {
+    if (s[i] < '0' || s[i] > '9') { *why = "invalid digit found in string"; return 1; }
+    const uint64_t d = (uint64_t)(s[i] - '0');
+    if (v > (UINT64_MAX - d) / 10) { *why = "number too large to fit in target type"; return 1; }
+    v = v * 10 + d;
+  }
+  *out = v;
+  return 0;
+}
+
+bool valid_utf8(const uint8_t* p, size_t n)
+{
+  size_t i = 0;
+  while (i < n) {
+    const uint8_t c = p[i];
+    if (c < 0x80) { ++i; continue; }
+    int extra; uint32_t cp;
+    if ((c & 0xE0) == 0xC0) { extra = 1; cp = c & 0x1F; }
+    else if ((c & 0xF0) == 0xE0) { extra = 2; cp = c & 0x0F; }
+    else if ((c & 0xF8) == 0xF0) { extra = 3; cp = c & 0x07; }
+    else return false;
+    if (i + (size_t)extra >= n) return false;
+    for (int k = 1; k <= extra; ++k) { if ((p[i + k] & 0xC0) != 0x80) return false; cp = (cp << 6) | (p[i + k] & 0x3F); }
+    if ((extra == 1 && cp < 0x80) || (extra == 2 && cp < 0x800) || (extra == 3 && cp < 0x10000) || cp > 0x10FFFF ||
+        (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+    i += extra + 1;
+  }
+  return true;
+}
+
+// ---- streaming FASTQ reader: the body of process_fastq_file_in_chunks (aligner.rs:107-178), pull style ----
+class FastqReader {
+ public:
+  ~FastqReader() { close(); }
+  int open(const std::string& path)
+  {
+    path_ = path;
+    const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;   // aligner.rs:109
+    if (gz) {
+      gz_ = gzopen(path.c_str(), "rb");            // in-process inflate instead of a `zcat` child (aligner.rs:111-120)
+      if (!gz_) return fail("Failed to open file " + path + ": " + std::strerror(errno));
+      gzbuffer(gz_, 1 << 20);
+    } else {
+      fp_ = std::fopen(path.c_str(), "rb");        // aligner.rs:123-125
+      if (!fp_) return fail("Failed to open file " + path + ": " + std::strerror(errno));
+    }
+    buf_.resize(4 << 20);
+    return 0;
+  }
+  void close() { if (gz_) gzclose(gz_); if (fp_) std::fclose(fp_); gz_ = nullptr; fp_ = nullptr; }
+
+  // Appends up to max_reads sequence lines (and at most max_bases bases, 0 = no cap) to bases/offs.
+  // Returns 0 ok, 1 error; *eof set when the input is exhausted.
+  int next_chunk(uint64_t max_reads, uint64_t max_bases, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs, bool* eof)
+  {
+    bases.clear(); offs.clear(); offs.push_back(0);
+    *eof = false;
+    for (;;) {
+      // consume complete lines in the buffer
+      while (pos_ < len_) {
+        const uint8_t* start = buf_.data() + pos_;
+        const uint8_t* nl = (const uint8_t*)std::memchr(start, '\n', len_ - pos_);
+        if (!nl) break;
+        size_t n = (size_t)(nl - start);
+        pos_ += n + 1;
+        if (handle_line(start, n, bases, offs)) return 1;
+        if (chunk_full(max_reads, max_bases, bases, offs)) return 0;
+      }
+      // refill, keeping the partial line
+      if (pos_ > 0) { std::memmove(buf_.data(), buf_.data() + pos_, len_ - pos_); len_ -= pos_; pos_ = 0; }
+      if (len_ == buf_.size()) buf_.resize(buf_.size() * 2);
+      long got = 0;
+      if (!at_eof_) {
+        got = gz_ ? gzread(gz_, buf_.data() + len_, (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30))
+                  : (long)std::fread(buf_.data() + len_, 1, buf_.size() - len_, fp_);
+        if (got < 0) return fail("Failed to read " + path_ + ": gzip stream error");
+        if (got == 0) at_eof_ = true;
+        len_ += (size_t)got;
+      }
+      if (at_eof_ && got == 0) {
+        if (len_ > pos_) {                         // final line without a newline: BufRead::lines() yields it
+          const size_t n = len_ - pos_;
+          std::vector<uint8_t> last(buf_.begin() + pos_, buf_.begin() + pos_ + n);
+          pos_ = len_ = 0;
+          if (handle_line(last.data(), n, bases, offs)) return 1;
+          if (chunk_full(max_reads, max_bases, bases, offs)) return 0;
+        }
+        *eof = true;
+        return 0;
+      }
+    }
+  }
+  uint64_t line_count = 0, total_reads = 0, error_count = 0;
+
+ private:
+  bool chunk_full(uint64_t max_reads, uint64_t max_bases, const std::vector<uint8_t>& bases, const std::vector<uint64_t>& offs) const
+  {
+    const uint64_t n = offs.size() - 1;
+    if (n == 0) return false;
+    return n >= max_reads || (max_bases && bases.size() >= max_bases);   // aligner.rs:143 (+ GPU_CHUNK_SIZE_BASES)
+  }
+  int handle_line(const uint8_t* p, size_t n, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs)
+  {
+    if (n && p[n - 1] == '\r') --n;                // lines() strips "\r\n" too
+    if (!valid_utf8(p, n)) {                       // lines() yields Err for invalid UTF-8 (aligner.rs:155-163)
+      ++error_count;
+      if (error_count <= 5) std::printf("    Warning: Error reading line %llu: stream did not contain valid UTF-8\n", (unsigned long long)line_count);
+      if (error_count > 10) return fail("Too many read errors (>10), stopping at line " + std::to_string(line_count));
+      return 0;
+    }
+    ++line_count;                                  // aligner.rs:136
+    if (line_count % 4 == 2) {                     // aligner.rs:138: the sequence line of a 4-line record
+      bases.insert(bases.end(), p, p + n);
+      offs.push_back(bases.size());
+      ++total_reads;
+    }
+    if (line_count % 1000000 == 0)                 // aligner.rs:151-153
+      std::printf("    Debug: Read %llu lines, found %llu reads, current chunk size: %llu\n", (unsigned long long)line_count,
+                  (unsigned long long)total_reads, (unsigned long long)(offs.size() - 1));
+    return 0;
+  }
+  std::string path_;
+  gzFile gz_ = nullptr; FILE* fp_ = nullptr;
+  std::vector<uint8_t> buf_;
+  size_t pos_ = 0, len_ = 0;
+  bool at_eof_ = false;
+};
+
+uint64_t splitmix64(uint64_t x)
+{
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+std::string env_or(const char* k, const char* dflt) { const char* v = std::getenv(k); return v ? v : dflt; }
+
+std::vector<std::string> wgs_files()
+{
+  // aligner.rs:184-204
+  const std::string dir = env_or("WGS_DATA_DIR", "/path/to/wgs/data"), sample = env_or("WGS_SAMPLE_ID", "SAMPLE_ID");
+  uint64_t lanes = 8, rpl = 2; std::string why;
+  if (parse_usize(env_or("WGS_LANES", "8"), &lanes, &why)) lanes = 8;
+  if (parse_usize(env_or("WGS_READS_PER_LANE", "2"), &rpl, &why)) rpl = 2;
+  std::vector<std::string> files;
+  for (uint64_t lane = 1; lane <= lanes; ++lane)
+    for (uint64_t read = 1; read <= rpl; ++read) {
+      char name[64];
+      std::snprintf(name, sizeof name, "_L%03llu_R%llu_001.fastq.gz", (unsigned long long)lane, (unsigned long long)read);
+      files.push_back(dir + "/" + sample + name);
+    }
+  return files;
+}
+
+std::string base_name(const std::string& p) { const size_t k = p.rfind('/'); return k == std::string::npos ? p : p.substr(k + 1); }
+
+// ---- the reference genome the --full-wgs reads are scored against (this engine's pairing rule) ----
+int load_reference(std::vector<uint8_t>& ref)
+{
+  const char* path = std::getenv("WGS_REFERENCE");
+  if (path && *path) {
+    gzFile g = gzopen(path, "rb");
+    if (!g) return fail(std::string("Failed to open file ") + path + ": " + std::strerror(errno));
+    std::vector<uint8_t> buf(4 << 20);
+    bool header = false, line_start = true;
+    for (;;) {
+      const int got = gzread(g, buf.data(), (unsigned)buf.size());
+      if (got < 0) { gzclose(g); return fail(std::string("Failed to read ") + path); }
+      if (got == 0) break;
+      for (int k = 0; k < got; ++k) {
+        const uint8_t c = buf[k];
+        if (line_start && c == '>') header = true;
+        line_start = (c == '\n');
+        if (c == '\n') { header = false; continue; }
+        if (!header && c != '\r') ref.push_back(c);
+      }
+    }
+    gzclose(g);
+    if (ref.empty()) return fail(std::string("WGS_REFERENCE ") + path + " holds no bases");
+    return 0;
+  }
+  uint64_t n = 16000000; std::string why;
+  if (parse_usize(env_or("WGS_SYNTH_REFERENCE_BASES", "16000000"), &n, &why) || n == 0) n = 16000000;
+  ref.resize(n);
+  for (uint64_t k = 0; k < n; k += 32) {
+    uint64_t x = splitmix64(0xB2F0ull + (k >> 5));
+    for (uint64_t j = k; j < std::min(n, k + 32); ++j, x >>= 2) ref[j] = (uint8_t)"ACGT"[x & 3];
+  }
+  return 0;
+}
+
+struct FileOutcome { int rc = 0; std::string err; rsm_alignment_result res{}; };
+
+// One file of the --full-wgs loop (aligner.rs:261-339) on one device.
+void process_one_file(size_t index, size_t total, const std::string& file, uint64_t chunk_reads, uint64_t chunk_bases,
+                      const rsm_gpu_device* dev, swb_ctx* ctx, uint64_t ref_len, uint32_t window_len, bool compat, FileOutcome* out)
+{
+  std::printf("Processing file %zu/%zu: %s\n", index + 1, total, base_name(file).c_str());
+  std::printf("    Using chunk size: %llu reads \n", (unsigned long long)chunk_reads);
+  const auto t0 = std::chrono::steady_clock::now();
+  int64_t total_score = 0; uint64_t processed_chunks = 0, total_bases = 0, total_reads = 0;
+  FastqReader rd;
+  int rc = rd.open(file);
+  std::vector<uint8_t> bases; std::vector<uint64_t> offs, wstart; std::vector<uint32_t> wlen; std::vector<swb_result> res;
+  bool eof = false;
+  while (rc == 0 && !eof) {
+    rc = rd.next_chunk(chunk_reads ? chunk_reads : 1, chunk_bases, bases, offs, &eof);
+    const uint64_t n = offs.size() - 1;
+    if (rc != 0 || n == 0) break;
+    int crc = 0; int64_t chunk_score = 0;
+    if (compat) {                                                   // aligner.rs:270-276: concat + self-align
+      int32_t s = 0;
+      crc = rsm_gpu_align_chunk_self(bases.data(), bases.size(), dev, &s);
+      chunk_score = s;
+    } else {                                                        // reads against windows of the resident reference
+      wstart.resize(n); wlen.resize(n); res.resize(n);
+      const uint32_t w = (uint32_t)std::min<uint64_t>(window_len, ref_len);
+      for (uint64_t k = 0; k < n; ++k) {
+        const uint64_t g = ((uint64_t)index << 40) + total_reads + k;
+        wstart[k] = splitmix64(g ^ 0xB202ull) % (ref_len - w + 1);
+        wlen[k] = w;
+      }
+      crc = swb_score_batch_vs_reference(ctx, bases.data(), offs.data(), n, wstart.data(), wlen.data(), res.data());
+      if (crc) g_err = swb_last_error();
+      for (uint64_t k = 0; k < n && !crc; ++k) chunk_score += res[k].score;
+    }
+    total_bases += bases.size(); total_reads += n;
+    if (crc == 0) {
+      total_score += chunk_score; ++processed_chunks;
+      if (processed_chunks % 10 == 0)                               // aligner.rs:278-282
+        std::printf("    Processed %llu chunks (%llu reads), current score: %lld\n", (unsigned long long)processed_chunks,
+                    (unsigned long long)n, (long long)total_score);
+    } else {
+      std::printf("    Warning: Failed to align chunk %llu: %s\n", (unsigned long long)processed_chunks, g_err.c_str());   // aligner.rs:284-286
+    }
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (rc == 0) {
+    const uint64_t cr = chunk_reads ? chunk_reads : 1;
+    std::printf("    Processed %llu total reads in %llu chunks\n", (unsigned long long)rd.total_reads, (unsigned long long)((rd.total_reads + cr - 1) / cr));
+    std::printf("    Total lines read: %llu\n", (unsigned long long)rd.line_count);
+    std::printf("  File %zu complete: Score=%lld, Bases=%llu, Time: %.2f s \n", index + 1, (long long)total_score, (unsigned long long)total_bases, secs);
+  } else {
+    std::printf("  File %zu failed: %s\n", index + 1, g_err.c_str());
+    out->rc = 1; out->err = "File " + std::to_string(index + 1) + " failed: " + g_err;
+  }
+  out->res.score64 = total_score; out->res.score = (int32_t)total_score;
+  out->res.processing_time_ms = std::floor(secs * 1000.0);            // as_millis() as f64
+  std::snprintf(out->res.gpu_device, sizeof out->res.gpu_device, "%s", dev->name);
+  out->res.total_reads = total_reads; out->res.total_bases = total_bases;
+}
+
+void load_dotenv()
+{
+  // dotenv::dotenv().ok() (main.rs:50): KEY=VALUE lines of ./.env, existing variables win
+  FILE* f = std::fopen(".env", "r");
+  if (!f) return;
+  char line[4096];
+  while (std::fgets(line, sizeof line, f)) {
+    std::string s(line);
+    while (!s.empty() && (s.back() == '\n' || s.back() == '\r' || s.back() == ' ')) s.pop_back();
+    size_t a = 0; while (a < s.size() && (s[a] == ' ' || s[a] == '\t')) ++a;
+    if (a >= s.size() || s[a] == '#') continue;
+    if (s.compare(a, 7, "export ") == 0) a += 7;
+    const size_t eq = s.find('=', a);
+    if (eq == std::string::npos) continue;
+    std::string k = s.substr(a, eq - a), v = s.substr(eq + 1);
+    while (!k.empty() && k.back() == ' ') k.pop_back();
+    if (v.size() >= 2 && ((v.front() == '"' && v.back() == '"') || (v.front() == '\'' && v.back() == '\''))) v = v.substr(1, v.size() - 2);
+    setenv(k.c_str(), v.c_str(), 0);
+  }
+  std::fclose(f);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rsm_last_error(void) { return g_err.c_str(); }
+
+int rsm_is_gpu_available(void) { return swb_device_count() > 0 ? 1 : 0; }
+
+int rsm_get_gpu_devices(rsm_gpu_device* out, int cap)
+{
+  const int n = swb_device_count();
+  for (int i = 0; i < n && i < cap; ++i) {
+    double gb = 0; int wg = 1024;
+    std::memset(&out[i], 0, sizeof out[i]);
+    if (swb_device_info(i, out[i].name, sizeof out[i].name, &gb, &wg) != 0) std::snprintf(out[i].name, sizeof out[i].name, "Unknown");
+    out[i].memory_gb = (float)gb; out[i].max_work_group_size = (uint64_t)wg; out[i].ordinal = i;
+  }
+  return n;
+}
+
+int rsm_get_chunk_size_reads(uint64_t* out)
+{
+  const char* v = std::getenv("GPU_CHUNK_SIZE_READS");
+  if (!v) return fail("GPU_CHUNK_SIZE_READS not set in .env file");                                  // aligner.rs:11
+  std::string why;
+  if (parse_usize(v, out, &why)) return fail(std::string("Invalid GPU_CHUNK_SIZE_READS value '") + v + "': " + why);   // aligner.rs:14
+  return 0;
+}
+
+int rsm_get_chunk_size_bases(uint64_t* out)
+{
+  *out = 0;
+  const char* v = std::getenv("GPU_CHUNK_SIZE_BASES");
+  if (!v) return 0;
+  std::string why;
+  if (parse_usize(v, out, &why)) return fail(std::string("Invalid GPU_CHUNK_SIZE_BASES value '") + v + "': " + why);
+  return 0;
+}
+
+int rsm_process_fastq_file_in_chunks(const char* filepath, uint64_t chunk_size_reads, rsm_chunk_fn processor, void* user)
+{
+  uint64_t max_bases = 0;
+  if (rsm_get_chunk_size_bases(&max_bases)) return 1;
+  FastqReader rd;
+  if (rd.open(filepath)) return 1;
+  std::vector<uint8_t> bases; std::vector<uint64_t> offs;
+  bool eof = false;
+  while (!eof) {
+    if (rd.next_chunk(chunk_size_reads ? chunk_size_reads : 1, max_bases, bases, offs, &eof)) return 1;
+    if (offs.size() > 1 && processor(user, bases.data(), offs.data(), offs.size() - 1) != 0) return 1;   // processor(&chunk)?
+  }
+  const uint64_t cr = chunk_size_reads ? chunk_size_reads : 1;
+  std::printf("    Processed %llu total reads in %llu chunks\n", (unsigned long long)rd.total_reads, (unsigned long long)((rd.total_reads + cr - 1) / cr));
+  std::printf("    Total lines read: %llu\n", (unsigned long long)rd.line_count);
+  if (rd.error_count) std::printf("    Total read errors: %llu\n", (unsigned long long)rd.error_count);
+  return 0;
+}
+
+static int count_cb(void* user, const uint8_t*, const uint64_t* offs, uint64_t n) { *(uint64_t*)user += offs[n]; return 0; }
+
+int rsm_count_bases_in_fastq(const char* filepath, uint64_t* out)
+{
+  uint64_t chunk = 0;
+  if (rsm_get_chunk_size_reads(&chunk)) return 1;                    // aligner.rs:538
+  *out = 0;
+  return rsm_process_fastq_file_in_chunks(filepath, chunk, count_cb, out);
+}
+
+int rsm_gpu_align_ex(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, const rsm_gpu_device* dev, swb_result* out)
+{
+  out->score = 0; out->end_i = -1; out->end_j = -1;
+  const uint64_t len = std::min(n1, n2);
+  if (len == 0) return 0;                                            // aligner.rs:413-416
+  swb_ctx* c = context_for(dev ? dev->ordinal : 0);
+  if (!c) return 1;
+  if (ref_compat_mode()) {
+    int32_t v = 0;
+    const uint32_t wg = dev ? (uint32_t)std::min<uint64_t>(dev->max_work_group_size, 0xffffffffull) : 1024u;
+    if (swb_ref_compat_align(c, s1, n1, s2, n2, wg, &v)) return fail(swb_last_error());
+    out->score = v;
+    return 0;
+  }
+  // the size guard of aligner.rs:436-456, restated for a quadratic kernel: bound the DP cells of one call
+  uint64_t max_cells = 400000000000ull; std::string why;
+  if (const char* v = std::getenv("SWB_MAX_CELLS")) parse_usize(v, &max_cells, &why);
+  if ((long double)n1 * (long double)n2 > (long double)max_cells)
+    return fail("Sequence too large (" + std::to_string(len) + " bytes): " + std::to_string(n1) + " x " + std::to_string(n2) +
+                " DP cells exceed SWB_MAX_CELLS=" + std::to_string(max_cells));
+  if (swb_score_pair(c, s1, n1, s2, n2, out)) return fail(swb_last_error());
+  return 0;
+}
+
+int rsm_gpu_align(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, const rsm_gpu_device* dev, int32_t* score)
+{
+  swb_result r;
+  if (rsm_gpu_align_ex(s1, n1, s2, n2, dev, &r)) return 1;
+  *score = r.score;
+  return 0;
+}
+
+int rsm_gpu_align_chunk_self(const uint8_t* chunk, uint64_t n, const rsm_gpu_device* dev, int32_t* score)
+{
+  if (n < 1000) { *score = 0; return 0; }                            // aligner.rs:366-368
+  return rsm_gpu_align(chunk, n, chunk, n, dev, score);              // aligner.rs:372
+}
+
+int rsm_gpu_align_pair(const char* file1, const char* file2, const rsm_gpu_device* dev, rsm_alignment_result* out)
+{
+  uint64_t bases1 = 0, bases2 = 0, chunk = 0, chunk_bases = 0;
+  if (rsm_count_bases_in_fastq(file1, &bases1) || rsm_count_bases_in_fastq(file2, &bases2)) return 1;   // aligner.rs:378-379
+  std::printf("Loaded %llu bases from %s\n", (unsigned long long)bases1, file1);
+  std::printf("Loaded %llu bases from %s\n", (unsigned long long)bases2, file2);
+  if (rsm_get_chunk_size_reads(&chunk) || rsm_get_chunk_size_bases(&chunk_bases)) return 1;
+  const auto t0 = std::chrono::steady_clock::now();
+  int64_t total = 0; uint64_t reads = 0;
+  std::vector<uint8_t> b1, b2; std::vector<uint64_t> o1, o2;
+  if (ref_compat_mode()) {
+    // aligner.rs:390-398 literally: every chunk of file1 against every chunk of file2 (file2 re-read each time)
+    FastqReader r1; if (r1.open(file1)) return 1;
+    bool eof1 = false;
+    while (!eof1) {
+      if (r1.next_chunk(chunk ? chunk : 1, chunk_bases, b1, o1, &eof1)) return 1;
+      if (o1.size() <= 1) continue;
+      FastqReader r2; if (r2.open(file2)) return 1;
+      bool eof2 = false;
+      while (!eof2) {
+        if (r2.next_chunk(chunk ? chunk : 1, chunk_bases, b2, o2, &eof2)) return 1;
+        if (o2.size() <= 1) continue;
+        int32_t s = 0;
+        if (rsm_gpu_align(b1.data(), b1.size(), b2.data(), b2.size(), dev, &s)) return 1;
+        total += s;
+      }
+      reads += o1.size() - 1;
+    }
+  } else {
+    // Smith-Waterman mode: read k of file1 against read k of file2 (mates), one batch per chunk
+    swb_ctx* c = context_for(dev ? dev->ordinal : 0);
+    if (!c) return 1;
+    FastqReader r1, r2; if (r1.open(file1) || r2.open(file2)) return 1;
+    bool eof1 = false, eof2 = false; std::vector<swb_result> res;
+    while (!eof1 && !eof2) {
+      if (r1.next_chunk(chunk ? chunk : 1, 0, b1, o1, &eof1) || r2.next_chunk(chunk ? chunk : 1, 0, b2, o2, &eof2)) return 1;
+      const uint64_t n = std::min(o1.size(), o2.size()) - 1;
+      if (n == 0) break;
+      res.resize(n);
+      if (swb_score_batch(c, b1.data(), o1.data(), b2.data(), o2.data(), n, res.data())) return fail(swb_last_error());
+      for (uint64_t k = 0; k < n; ++k) total += res[k].score;
+      reads += n;
+    }
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  std::memset(out, 0, sizeof *out);
+  out->score64 = total; out->score = (int32_t)total; out->processing_time_ms = std::floor(secs * 1000.0);
+  std::snprintf(out->gpu_device, sizeof out->gpu_device, "%s", dev ? dev->name : "");
+  out->total_reads = reads; out->total_bases = bases1 + bases2;
+  return 0;
+}
+
+int rsm_wgs_file_list(char* buf, size_t cap, int* n_files)
+{
+  const auto files = wgs_files();
+  std::string all;
+  for (const auto& f : files) { all += f; all += '\n'; }
+  if (n_files) *n_files = (int)files.size();
+  if (buf && cap) { std::snprintf(buf, cap, "%s", all.c_str()); }
+  return all.size() + 1 > cap ? 1 : 0;
+}
+
+int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_result* out, int cap, int* n_out)
+{
+  const auto files = wgs_files();
+  const size_t total = files.size();
+  uint64_t chunk = 0, chunk_bases = 0;
+  if (rsm_get_chunk_size_reads(&chunk) || rsm_get_chunk_size_bases(&chunk_bases)) return 1;        // aligner.rs:207
+  const bool compat = ref_compat_mode();
+  std::printf("==========================================\n");
+  std::printf("GPU PROCESSING STARTING\n");
+  std::printf("==========================================\n");
+  std::printf("GPU_CHUNK_SIZE_READS: %llu (from .env)\n", (unsigned long long)chunk);
+  std::printf("Score mode: %s\n", compat ? "ref_compat (reference's live kernel)" : "sw (Smith-Waterman, reads vs reference windows)");
+  std::printf("Processing %zu files (your complete genome)...\n", total);
+  std::printf("==========================================\n");
+
+  // devices: the one handed in first, then every other visible GPU (files shard over GPUs)
+  rsm_gpu_device devs[64];
+  int nd = rsm_get_gpu_devices(devs, 64);
+  if (nd <= 0) return fail("No GPU devices found");
+  uint64_t want = (uint64_t)nd; std::string why;
+  if (const char* v = std::getenv("SWB_NUM_DEVICES")) if (!parse_usize(v, &want, &why) && want >= 1 && want < (uint64_t)nd) nd = (int)want;
+  if (compat) nd = 1;
+  std::vector<int> order;
+  const int first = device ? device->ordinal : 0;
+  order.push_back(first);
+  for (int d = 0; d < nd; ++d) if (d != first && (int)order.size() < nd) order.push_back(d);
+
+  std::vector<uint8_t> ref; uint32_t window_len = 500;
+  if (!compat) {
+    if (load_reference(ref)) return 1;
+    uint64_t w = 500; if (!parse_usize(env_or("WGS_WINDOW_LEN", "500"), &w, &why) && w >= 1) window_len = (uint32_t)std::min<uint64_t>(w, ref.size());
+    std::printf("Reference: %zu bases, window %u bp, %zu GPU(s)\n", ref.size(), window_len, order.size());
+  }
+  std::vector<FileOutcome> outcomes(total);
+  std::vector<std::thread> workers;
+  std::vector<std::string> werr(order.size());
+  for (size_t w = 0; w < order.size(); ++w) {
+    workers.emplace_back([&, w]() {
+      const int ord = order[w];
+      swb_ctx* ctx = context_for(ord);
+      if (!ctx) { werr[w] = g_err; return; }
+      if (!compat && swb_set_reference(ctx, ref.data(), ref.size())) { werr[w] = swb_last_error(); return; }
+      for (size_t i = w; i < total; i += order.size()) {
+        process_one_file(i, total, files[i], chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, compat, &outcomes[i]);
+        if (outcomes[i].rc) return;                               // aligner.rs:336: a failed file aborts the run
+      }
+    });
+  }
+  for (auto& t : workers) t.join();
+  for (const auto& e : werr) if (!e.empty()) return fail(e);
+  int n = 0;
+  for (size_t i = 0; i < total; ++i) {
+    if (outcomes[i].rc) return fail(outcomes[i].err);
+    if (n < cap) out[n] = outcomes[i].res;
+    ++n;
+  }
+  if (n_out) *n_out = n;
+  return 0;
+}
+
+static void usage()
+{
+  std::printf("High-performance sequence alignment for genome-scale data\n\nUsage: rustseq_mini [OPTIONS]\n\nOptions:\n"
+              "  -1, --seq1 <SEQ1>              first sequence or file path\n"
+              "  -2, --seq2 <SEQ2>              second sequence or file path\n"
+              "  -f, --files                    treat inputs as file paths instead of direct sequences\n"
+              "  -c, --chunk-size <CHUNK_SIZE>  chunk size in MB for large sequences [default: 1]\n"
+              "  -g, --gpu                      use GPU acceleration if available\n"
+              "  -n, --num-files <NUM_FILES>    number of files to process (for multi-file mode)\n"
+              "  -t, --test-wgs                 test mode: read WGS files from USB drive\n"
+              "      --full-wgs                 process full WGS dataset from all 16 files\n"
+              "  -h, --help                     Print help\n");
+}
+
+int rsm_main(int argc, char** argv)
+{
+  load_dotenv();                                                     // main.rs:50
+  std::string seq1, seq2; bool has1 = false, has2 = false, files = false, gpu = false, test_wgs = false, full_wgs = false;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    auto value = [&](const char* name, std::string* dst) -> int {
+      const size_t eq = a.find('=');
+      if (a.rfind("--", 0) == 0 && eq != std::string::npos) { *dst = a.substr(eq + 1); return 0; }
+      if (i + 1 >= argc) { std::fprintf(stderr, "error: a value is required for '%s' but none was supplied\n", name); return 2; }
+      *dst = argv[++i]; return 0;
+    };
+    std::string tmp;
+    if (a == "-1" || a == "--seq1" || a.rfind("--seq1=", 0) == 0) { if (value("--seq1 <SEQ1>", &seq1)) return 2; has1 = true; }
+    else if (a == "-2" || a == "--seq2" || a.rfind("--seq2=", 0) == 0) { if (value("--seq2 <SEQ2>", &seq2)) return 2; has2 = true; }
+    else if (a == "-f" || a == "--files") files = true;
+    else if (a == "-g" || a == "--gpu") gpu = true;
+    else if (a == "-t" || a == "--test-wgs") test_wgs = true;
+    else if (a == "--full-wgs") full_wgs = true;
+    else if (a == "-c" || a == "--chunk-size" || a.rfind("--chunk-size=", 0) == 0) { if (value("--chunk-size <CHUNK_SIZE>", &tmp)) return 2; }   // parsed, unused (main.rs:27-29)
+    else if (a == "-n" || a == "--num-files" || a.rfind("--num-files=", 0) == 0) { if (value("--num-files <NUM_FILES>", &tmp)) return 2; }      // parsed, unused (main.rs:35-37)
+    else if (a == "-h" || a == "--help") { usage(); return 0; }
+    else { std::fprintf(stderr, "error: unexpected argument '%s' found\n\nUsage: rustseq_mini [OPTIONS]\n", a.c_str()); return 2; }
+  }
+
+  if (full_wgs) {                                                    // main.rs:72-125
+    std::printf("Processing FULL WGS dataset from all 16 files...\n");
+    if (!gpu || !rsm_is_gpu_available()) {
+      std::fprintf(stderr, "error: gpu acceleration is required for full WGS processing\n");   // main.rs:77
+      return 1;
+    }
+    rsm_gpu_device devs[64];
+    const int nd = rsm_get_gpu_devices(devs, 64);
+    std::printf("GPU acceleration enabled\n");
+    for (int d = 0; d < nd && d < 64; ++d) std::printf("  Found GPU: %s (%g GB)\n", devs[d].name, devs[d].memory_gb);
+    std::vector<rsm_alignment_result> res(4096);
+    int n = 0;
+    if (rsm_process_full_wgs_dataset(&devs[0], res.data(), (int)res.size(), &n)) {
+      std::fprintf(stderr, "Full WGS processing error: %s\n", rsm_last_error());               // main.rs:115
+      return 1;
+    }
+    std::printf("\nFULL WGS PROCESSING COMPLETE!\n==========================================\n");
+    std::printf("Total files processed: %d\n", n);
+    double ms = 0; uint64_t reads = 0, bases = 0;
+    for (int i = 0; i < n; ++i) { ms += res[i].processing_time_ms; reads += res[i].total_reads; bases += res[i].total_bases; }
+    std::printf("Total reads processed: %llu\nTotal base pairs: %llu\n", (unsigned long long)reads, (unsigned long long)bases);
+    std::printf("Total processing time: %.2f seconds\n", ms / 1000.0);
+    for (int i = 0; i < n; ++i) std::printf("File %d: Score=%lld, Time=%.2fs\n", i + 1, (long long)res[i].score64, res[i].processing_time_ms / 1000.0);
+    return 0;
+  }
+
+  if (test_wgs) {                                                    // main.rs:127-153: counts bases, needs no GPU
+    std::printf("Testing WGS file reading from configured directory...\n");
+    const std::string dir = env_or("WGS_DATA_DIR", "/path/to/wgs/data"), sample = env_or("WGS_SAMPLE_ID", "SAMPLE_ID");
+    for (const char* suffix : {"_L001_R1_001.fastq.gz", "_L001_R2_001.fastq.gz"}) {
+      const std::string file = sample + suffix, full = dir + "/" + file;
+      std::printf("Testing: %s\n", full.c_str());
+      uint64_t bases = 0;
+      if (rsm_count_bases_in_fastq(full.c_str(), &bases) == 0) std::printf("Successfully counted %llu bases in %s\n", (unsigned long long)bases, file.c_str());
+      else std::printf("Error counting bases in %s: %s\n", file.c_str(), rsm_last_error());
+    }
+    return 0;
+  }
+
+  if (!has1) { std::fprintf(stderr, "--seq1 is required when not in test mode\n"); return 101; }   // .expect() panic, main.rs:156
+  if (!has2) { std::fprintf(stderr, "--seq2 is required when not in test mode\n"); return 101; }   // main.rs:157
+  if (!gpu || !rsm_is_gpu_available()) {
+    std::fprintf(stderr, "error: gpu acceleration is required and no compatible gpu was found\n");   // main.rs:161
+    return 1;
+  }
+  std::printf("GPU acceleration enabled\n");
+  rsm_gpu_device devs[64];
+  const int nd = rsm_get_gpu_devices(devs, 64);
+  for (int d = 0; d < nd && d < 64; ++d) std::printf("  Found GPU: %s (%g GB)\n", devs[d].name, devs[d].memory_gb);
+  if (files) {                                                       // main.rs:170-182
+    rsm_alignment_result r;
+    if (rsm_gpu_align_pair(seq1.c_str(), seq2.c_str(), &devs[0], &r)) { std::fprintf(stderr, "GPU alignment error: %s\n", rsm_last_error()); return 1; }
+    std::printf("GPU Alignment Result:\n  Score: %lld\n  Processing time: %.2f ms\n  GPU device: %s\n", (long long)r.score64, r.processing_time_ms, r.gpu_device);
+  } else {                                                           // main.rs:183-190
+    swb_result r;
+    if (rsm_gpu_align_ex((const uint8_t*)seq1.data(), seq1.size(), (const uint8_t*)seq2.data(), seq2.size(), &devs[0], &r)) {
+      std::fprintf(stderr, "GPU alignment error: %s\n", rsm_last_error());
+      return 1;
+    }
+    std::printf("GPU Alignment score: %d\n", r.score);
+    if (!ref_compat_mode()) std::printf("  End cell: (%d, %d)\n", r.end_i, r.end_j);
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -38,6 +38,8 @@ struct swb_ctx {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8] = {};
   DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, generic_list, counters, out, scratch, misc;
+  DevBuf ref_bytes, ref_pk, ref_bad, win_beg, win_end;   // device-resident reference (swb_set_reference)
+  uint64_t ref_len = 0;
   float last_ms[6] = {0, 0, 0, 0, 0, 0};
   int last_kernels = 0;
   uint64_t last_routing[2] = {0, 0};
@@ -95,7 +97,8 @@ void swb_destroy(swb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   for (DevBuf* b : {&c->q_bytes, &c->r_bytes, &c->q_off, &c->r_off, &c->q_pk, &c->r_pk, &c->q_bad, &c->r_bad,
-                    &c->short_list, &c->generic_list, &c->counters, &c->out, &c->scratch, &c->misc}) b->release();
+                    &c->short_list, &c->generic_list, &c->counters, &c->out, &c->scratch, &c->misc,
+                    &c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->win_beg, &c->win_end}) b->release();
   for (auto& e : c->ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->st);
   delete c;
@@ -113,13 +116,16 @@ int swb_sync(swb_ctx* c)
 }
 
 // ---- the device pipeline: everything after the inputs are resident in HBM ----
+// Windows are either CSR ranges of d_r (d_rend == d_rbeg + 1, packed here) or ranges of the resident,
+// already packed reference (ref_windows).
 static int run_device_pipeline(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
-                               const uint8_t* d_r, const uint64_t* d_ro, uint64_t r_total,
+                               const uint8_t* d_r, const uint64_t* d_rbeg, const uint64_t* d_rend, uint64_t r_total,
+                               bool ref_windows,
                                uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out)
 {
   (void)max_q_len;
   if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
-  const uint64_t qw = (q_total + 15) / 16, rw = (r_total + 15) / 16;
+  const uint64_t qw = (q_total + 15) / 16, rw = ref_windows ? 0 : (r_total + 15) / 16;
   if (c->q_pk.reserve(qw * 4 + 64) || c->r_pk.reserve(rw * 4 + 64) ||
       c->q_bad.reserve((qw + 31) / 32 * 4 + 64) || c->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
       c->short_list.reserve(n_pairs * 4 + 64) || c->generic_list.reserve(n_pairs * 4 + 64) ||
@@ -131,9 +137,10 @@ static int run_device_pipeline(swb_ctx* c, const uint8_t* d_q, const uint64_t* d
   if (c->scratch.reserve((uint64_t)ctas * 4 * stride * 4)) return 1;
 
   swb::BatchView b;
-  b.q_bytes = d_q; b.q_off = d_qo; b.r_bytes = d_r; b.r_off = d_ro;
+  b.q_bytes = d_q; b.q_beg = d_qo; b.q_end = d_qo + 1; b.r_bytes = d_r; b.r_beg = d_rbeg; b.r_end = d_rend;
   b.q_pk = c->q_pk.as<uint32_t>(); b.q_bad = c->q_bad.as<uint32_t>();
-  b.r_pk = c->r_pk.as<uint32_t>(); b.r_bad = c->r_bad.as<uint32_t>();
+  b.r_pk = ref_windows ? c->ref_pk.as<uint32_t>() : c->r_pk.as<uint32_t>();
+  b.r_bad = ref_windows ? c->ref_bad.as<uint32_t>() : c->r_bad.as<uint32_t>();
   b.n_pairs = n_pairs;
   b.short_list = c->short_list.as<uint32_t>(); b.generic_list = c->generic_list.as<uint32_t>();
   b.counters = c->counters.as<swb::Counters>(); b.out = d_out;
@@ -144,7 +151,7 @@ static int run_device_pipeline(swb_ctx* c, const uint8_t* d_q, const uint64_t* d
   CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(swb::Counters), st));
   CUDA_TRY(cudaEventRecord(c->ev[0], st));
   k += swb::launch_pack2bit(d_q, q_total, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
-  k += swb::launch_pack2bit(d_r, r_total, c->r_pk.as<uint32_t>(), c->r_bad.as<uint32_t>(), st);
+  if (!ref_windows) k += swb::launch_pack2bit(d_r, r_total, c->r_pk.as<uint32_t>(), c->r_bad.as<uint32_t>(), st);
   k += swb::launch_classify(b, st);
   CUDA_TRY(cudaEventRecord(c->ev[1], st));
   const uint32_t wcap = std::min<uint32_t>(std::max<uint32_t>(max_r_len, 1), swb::kShortMaxWindow);
@@ -170,7 +177,7 @@ int swb_score_batch_device(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo,
   CUDA_TRY(cudaSetDevice(c->device));
   c->host_path = false;
   if (n_pairs == 0) { c->last_kernels = 0; c->timings_pending = false; return 0; }
-  return run_device_pipeline(c, d_q, d_qo, q_total, d_r, d_ro, r_total, n_pairs, max_q_len, max_r_len, d_out);
+  return run_device_pipeline(c, d_q, d_qo, q_total, d_r, d_ro, d_ro + 1, r_total, false, n_pairs, max_q_len, max_r_len, d_out);
 }
 
 int swb_score_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro,
@@ -200,13 +207,68 @@ int swb_score_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint
   CUDA_TRY(cudaMemcpyAsync(c->r_off.p, ro, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaEventRecord(c->ev[5], st));
   if (run_device_pipeline(c, c->q_bytes.as<uint8_t>(), c->q_off.as<uint64_t>(), q_total,
-                          c->r_bytes.as<uint8_t>(), c->r_off.as<uint64_t>(), r_total,
+                          c->r_bytes.as<uint8_t>(), c->r_off.as<uint64_t>(), c->r_off.as<uint64_t>() + 1, r_total, false,
                           n_pairs, max_q, max_r, c->out.as<swb_result>())) return 1;
   CUDA_TRY(cudaEventRecord(c->ev[6], st));
   CUDA_TRY(cudaMemcpyAsync(out, c->out.p, n_pairs * sizeof(swb_result), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(c->ev[7], st));
   c->host_path = true;
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- reads against windows of a device-resident reference ----
+int swb_set_reference(swb_ctx* c, const uint8_t* ref, uint64_t n)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const uint64_t nw = (n + 15) / 16;
+  if (c->ref_bytes.reserve(n + 64) || c->ref_pk.reserve(nw * 4 + 64) || c->ref_bad.reserve((nw + 31) / 32 * 4 + 64)) return 1;
+  cudaStream_t st = c->st;
+  if (n) CUDA_TRY(cudaMemcpyAsync(c->ref_bytes.p, ref, n, cudaMemcpyHostToDevice, st));
+  swb::launch_pack2bit(c->ref_bytes.as<uint8_t>(), n, c->ref_pk.as<uint32_t>(), c->ref_bad.as<uint32_t>(), st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  c->ref_len = n;
+  return 0;
+}
+
+int swb_score_batch_vs_reference(swb_ctx* c, const uint8_t* q, const uint64_t* qo, uint64_t n_pairs,
+                                 const uint64_t* win_start, const uint32_t* win_len, swb_result* out)
+{
+  if (!c) return fail("null ctx");
+  if (n_pairs == 0) return 0;
+  if (!qo || !win_start || !win_len || !out) return fail("swb_score_batch_vs_reference: null pointer");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (qo[0] != 0) return fail("swb_score_batch_vs_reference: offsets must start at 0");
+  const uint64_t q_total = qo[n_pairs];
+  uint32_t max_q = 0, max_r = 0;
+  std::vector<uint64_t> wend(n_pairs);
+  for (uint64_t k = 0; k < n_pairs; ++k) {
+    if (qo[k + 1] < qo[k]) return fail("swb_score_batch_vs_reference: offsets must be non-decreasing");
+    if (win_start[k] + win_len[k] > c->ref_len) return fail("swb_score_batch_vs_reference: window outside the reference");
+    const uint64_t a = qo[k + 1] - qo[k];
+    if (a > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
+    max_q = std::max<uint32_t>(max_q, (uint32_t)a); max_r = std::max<uint32_t>(max_r, win_len[k]);
+    wend[k] = win_start[k] + win_len[k];
+  }
+  if (c->q_bytes.reserve(q_total + 64) || c->q_off.reserve((n_pairs + 1) * 8) || c->win_beg.reserve(n_pairs * 8) ||
+      c->win_end.reserve(n_pairs * 8) || c->out.reserve(n_pairs * sizeof(swb_result))) return 1;
+  cudaStream_t st = c->st;
+  CUDA_TRY(cudaEventRecord(c->ev[4], st));
+  if (q_total) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, q_total, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->q_off.p, qo, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->win_beg.p, win_start, n_pairs * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->win_end.p, wend.data(), n_pairs * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(c->ev[5], st));
+  if (run_device_pipeline(c, c->q_bytes.as<uint8_t>(), c->q_off.as<uint64_t>(), q_total,
+                          c->ref_bytes.as<uint8_t>(), c->win_beg.as<uint64_t>(), c->win_end.as<uint64_t>(), 0, true,
+                          n_pairs, max_q, max_r, c->out.as<swb_result>())) return 1;
+  CUDA_TRY(cudaEventRecord(c->ev[6], st));
+  CUDA_TRY(cudaMemcpyAsync(out, c->out.p, n_pairs * sizeof(swb_result), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(c->ev[7], st));
+  c->host_path = true;
+  CUDA_TRY(cudaStreamSynchronize(st));      // also keeps wend alive until the copy is done
   return 0;
 }
 
@@ -291,8 +353,8 @@ int swb_last_row_max(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* 
   CUDA_TRY(cudaMemcpyAsync(c->r_off.p, ro, 16, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaStreamSynchronize(st));          // qo/ro live on this stack frame
   swb::BatchView b{};
-  b.q_bytes = c->q_bytes.as<uint8_t>(); b.q_off = c->q_off.as<uint64_t>();
-  b.r_bytes = c->r_bytes.as<uint8_t>(); b.r_off = c->r_off.as<uint64_t>();
+  b.q_bytes = c->q_bytes.as<uint8_t>(); b.q_beg = c->q_off.as<uint64_t>(); b.q_end = b.q_beg + 1;
+  b.r_bytes = c->r_bytes.as<uint8_t>(); b.r_beg = c->r_off.as<uint64_t>(); b.r_end = b.r_beg + 1;
   b.n_pairs = 1; b.generic_list = c->generic_list.as<uint32_t>(); b.counters = c->counters.as<swb::Counters>();
   b.out = c->out.as<swb_result>(); b.scratch = c->scratch.as<int32_t>(); b.scratch_stride = stride;
   swb::launch_generic_single(b, c->misc.as<int32_t>(), st);

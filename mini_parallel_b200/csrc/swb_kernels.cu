@@ -100,7 +100,7 @@ classify_kernel(BatchView b)
   const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t cls = 0xFF, m = 0;
   if (k < b.n_pairs) {
-    const uint64_t q0 = b.q_off[k], q1 = b.q_off[k + 1], r0 = b.r_off[k], r1 = b.r_off[k + 1];
+    const uint64_t q0 = b.q_beg[k], q1 = b.q_end[k], r0 = b.r_beg[k], r1 = b.r_end[k];
     const uint64_t n = q1 - q0; const uint64_t mm = r1 - r0;
     if (n == 0 || mm == 0) {                               // aligner.rs:413-416: empty input scores 0
       cls = CLASS_EMPTY;
@@ -164,8 +164,8 @@ int launch_classify(const BatchView& b, cudaStream_t st)
 // (max H, then min i, then min j).
 // =====================================================================================
 struct ShortArgs {
-  const uint32_t* q_pk; const uint64_t* q_off;
-  const uint32_t* r_pk; const uint64_t* r_off;
+  const uint32_t* q_pk; const uint64_t* q_beg; const uint64_t* q_end;
+  const uint32_t* r_pk; const uint64_t* r_beg; const uint64_t* r_end;
   const uint32_t* list; const uint32_t* n_list;     // device-side count of listed pairs
   swb_result* out;
   uint32_t w_pad;          // columns processed per pair (multiple of K, >= longest window)
@@ -204,9 +204,9 @@ sw_short_kernel(ShortArgs a)
   const uint32_t pA = a.list[2 * pp];
   const bool hasB = (2 * pp + 1) < n_list;
   const uint32_t pB = hasB ? a.list[2 * pp + 1] : pA;
-  const uint64_t qA0 = a.q_off[pA], qB0 = a.q_off[pB], rA0 = a.r_off[pA], rB0 = a.r_off[pB];
-  const uint32_t nA = (uint32_t)(a.q_off[pA + 1] - qA0), nB = (uint32_t)(a.q_off[pB + 1] - qB0);
-  const uint32_t mA = (uint32_t)(a.r_off[pA + 1] - rA0), mB = (uint32_t)(a.r_off[pB + 1] - rB0);
+  const uint64_t qA0 = a.q_beg[pA], qB0 = a.q_beg[pB], rA0 = a.r_beg[pA], rB0 = a.r_beg[pB];
+  const uint32_t nA = (uint32_t)(a.q_end[pA] - qA0), nB = (uint32_t)(a.q_end[pB] - qB0);
+  const uint32_t mA = (uint32_t)(a.r_end[pA] - rA0), mB = (uint32_t)(a.r_end[pB] - rB0);
 
   // ---- stage the combined window stream of both pairs in shared memory ----
   uint8_t* wbuf = smem + (size_t)(warp * GPW + g) * a.wbuf_stride;
@@ -317,7 +317,7 @@ static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t 
 {
   constexpr int NPAD = G * K, GPW = 32 / G;
   ShortArgs a;
-  a.q_pk = b.q_pk; a.q_off = b.q_off; a.r_pk = b.r_pk; a.r_off = b.r_off;
+  a.q_pk = b.q_pk; a.q_beg = b.q_beg; a.q_end = b.q_end; a.r_pk = b.r_pk; a.r_beg = b.r_beg; a.r_end = b.r_end;
   a.list = b.short_list; a.n_list = &b.counters->n_short; a.out = b.out;
   a.w_pad = (window_cap + K - 1) / K * K;
   const uint32_t n_iters = (NPAD + a.w_pad + K - 1) / K;
@@ -382,10 +382,10 @@ sw_generic_kernel(BatchView b, const uint32_t* __restrict__ list, const uint32_t
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_list) break;
     const uint32_t p = list[item];
-    const uint8_t* __restrict__ q = b.q_bytes + b.q_off[p];
-    const uint8_t* __restrict__ r = b.r_bytes + b.r_off[p];
-    const uint64_t n1 = b.q_off[p + 1] - b.q_off[p];
-    const uint64_t n2 = b.r_off[p + 1] - b.r_off[p];
+    const uint8_t* __restrict__ q = b.q_bytes + b.q_beg[p];
+    const uint8_t* __restrict__ r = b.r_bytes + b.r_beg[p];
+    const uint64_t n1 = b.q_end[p] - b.q_beg[p];
+    const uint64_t n2 = b.r_end[p] - b.r_beg[p];
 
     int32_t gbest = 0; int64_t gi = -1, gj = -1; int32_t lastrow = 0;
     const uint64_t n_bands = (n1 + BAND - 1) / BAND;

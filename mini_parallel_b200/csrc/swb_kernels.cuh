@@ -24,8 +24,10 @@ struct Counters {             // device-resident, zeroed per batch
 };
 
 struct BatchView {            // everything the kernels need about one batch (device pointers)
-  const uint8_t*  q_bytes;  const uint64_t* q_off;     // ASCII reads, CSR offsets (n_pairs+1)
-  const uint8_t*  r_bytes;  const uint64_t* r_off;     // ASCII windows
+  // ASCII reads / windows.  Sequence p occupies bytes [beg[p], end[p]).  For CSR offsets end == beg + 1; for
+  // windows cut from a device-resident reference beg/end are independent arrays (windows may overlap).
+  const uint8_t*  q_bytes;  const uint64_t* q_beg;  const uint64_t* q_end;
+  const uint8_t*  r_bytes;  const uint64_t* r_beg;  const uint64_t* r_end;
   const uint32_t* q_pk;     const uint32_t* q_bad;     // 2-bit packed reads  + non-ACGT bitmap (1 bit / 16-base word)
   const uint32_t* r_pk;     const uint32_t* r_bad;     // 2-bit packed windows + bitmap
   uint64_t        n_pairs;

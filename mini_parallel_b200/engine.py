@@ -93,6 +93,22 @@ class Engine:
         r, ro = to_csr(windows)
         return self.score_batch_csr(q, qo, r, ro)
 
+    def set_reference(self, ref):
+        a = _as_bytes_array(ref)
+        self._check(self._lib.swb_set_reference(self._h, a.ctypes.data, a.size))
+
+    def score_batch_vs_reference(self, q_bytes, q_off, win_start, win_len):
+        q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        win_start = np.ascontiguousarray(win_start, dtype=np.uint64)
+        win_len = np.ascontiguousarray(win_len, dtype=np.uint32)
+        n = q_off.size - 1
+        out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
+        if n > 0:
+            self._check(self._lib.swb_score_batch_vs_reference(self._h, q_bytes.ctypes.data, q_off.ctypes.data, n,
+                                                               win_start.ctypes.data, win_len.ctypes.data, out.ctypes.data))
+        return out
+
     def score_batch_device(self, d_q, d_qo, q_total, d_r, d_ro, r_total, n_pairs, max_q_len, max_r_len, d_out):
         """All pointers are device addresses (ints).  Asynchronous on the engine's stream."""
         self._check(self._lib.swb_score_batch_device(self._h, d_q, d_qo, q_total, d_r, d_ro, r_total,

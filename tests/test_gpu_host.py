@@ -1,0 +1,162 @@
+"""GPU tests of the host mirror: the reference's entry points (gpu_align & callers, the WGS driver, the CLI)
+driven end to end on a B200, results checked against the oracle."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from mini_parallel_b200 import aligner
+from mini_parallel_b200.engine import to_csr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "build", "rustseq_mini")
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def _fastq(path, reads):
+    with gzip.open(path, "wb") as f:
+        for k, r in enumerate(reads):
+            f.write(b"@r%d\n%s\n+\n%s\n" % (k, r, b"I" * len(r)))
+
+
+@pytest.fixture
+def device():
+    devs = aligner.get_gpu_devices()
+    assert devs and aligner.is_gpu_available()
+    return devs[0]
+
+
+def test_gpu_align_sw_and_compat_modes(device, monkeypatch):
+    rng = np.random.default_rng(1)
+    monkeypatch.delenv("SWB_GPU_ALIGN_MODE", raising=False)
+    assert device.max_work_group_size == 1024 and device.memory_gb > 100
+    for _ in range(20):
+        a = bytes(ACGT[rng.integers(0, 4, int(rng.integers(1, 400)))])
+        b = bytes(ACGT[rng.integers(0, 4, int(rng.integers(1, 900)))])
+        assert aligner.gpu_align_ex(a, b, device) == ol.sw_linear(a, b)
+        assert aligner.gpu_align(a, b, device) == ol.sw_linear(a, b)[0]
+    assert aligner.gpu_align(b"", b"ACGT", device) == 0                               # aligner.rs:413-416
+    monkeypatch.setenv("SWB_GPU_ALIGN_MODE", "ref_compat")
+    for _ in range(20):
+        a = bytes(ACGT[rng.integers(0, 4, int(rng.integers(1, 5000)))])
+        b = bytes(ACGT[rng.integers(0, 4, int(rng.integers(1, 5000)))])
+        assert aligner.gpu_align(a, b, device) == ol.ref_compat_align(a, b, 1024)
+    chunk = bytes(ACGT[rng.integers(0, 4, 1500)])
+    assert aligner.gpu_align_chunk_self(chunk, device) == 2                            # what --full-wgs sums today
+    assert aligner.gpu_align_chunk_self(chunk[:999], device) == 0                      # aligner.rs:366-368
+    monkeypatch.delenv("SWB_GPU_ALIGN_MODE")
+    assert aligner.gpu_align_chunk_self(chunk, device) == 3000                         # true SW of a sequence with itself
+    monkeypatch.setenv("SWB_MAX_CELLS", "1000")
+    with pytest.raises(aligner.AlignerError, match="Sequence too large"):
+        aligner.gpu_align(chunk, chunk, device)
+
+
+def test_gpu_align_pair_files(tmp_path, device, monkeypatch):
+    rng = np.random.default_rng(2)
+    r1 = [bytes(ACGT[rng.integers(0, 4, 150)]) for _ in range(57)]
+    r2 = [bytes(ACGT[rng.integers(0, 4, 150)]) for _ in range(57)]
+    _fastq(tmp_path / "a.fastq.gz", r1)
+    _fastq(tmp_path / "b.fastq.gz", r2)
+    monkeypatch.setenv("GPU_CHUNK_SIZE_READS", "10")
+    monkeypatch.delenv("SWB_GPU_ALIGN_MODE", raising=False)
+    res = aligner.gpu_align_pair(tmp_path / "a.fastq.gz", tmp_path / "b.fastq.gz", device)
+    assert res.score64 == sum(ol.sw_linear(a, b)[0] for a, b in zip(r1, r2))
+    assert res.total_reads == 57 and res.total_bases == 2 * 57 * 150
+    assert res.gpu_device.decode().startswith("NVIDIA")
+    monkeypatch.setenv("SWB_GPU_ALIGN_MODE", "ref_compat")                              # aligner.rs:390-398: chunks x chunks
+    res = aligner.gpu_align_pair(tmp_path / "a.fastq.gz", tmp_path / "b.fastq.gz", device)
+    c1 = [b"".join(r1[k:k + 10]) for k in range(0, 57, 10)]
+    c2 = [b"".join(r2[k:k + 10]) for k in range(0, 57, 10)]
+    assert res.score64 == sum(ol.ref_compat_align(x, y, 1024) for x in c1 for y in c2)
+
+
+def _make_lanes(tmp_path, lanes, reads_per_file, rng):
+    files = {}
+    for lane in range(1, lanes + 1):
+        for rd in (1, 2):
+            reads = [bytes(ACGT[rng.integers(0, 4, 150)]) for _ in range(reads_per_file)]
+            name = f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"
+            _fastq(tmp_path / name, reads)
+            files[name] = reads
+    return files
+
+
+def test_full_wgs_driver_both_modes(tmp_path, device, monkeypatch):
+    rng = np.random.default_rng(3)
+    files = _make_lanes(tmp_path, 2, 45, rng)
+    for k, v in dict(WGS_DATA_DIR=str(tmp_path), WGS_SAMPLE_ID="SYN", WGS_LANES="2", WGS_READS_PER_LANE="2",
+                     GPU_CHUNK_SIZE_READS="20", WGS_SYNTH_REFERENCE_BASES="200000", WGS_WINDOW_LEN="500").items():
+        monkeypatch.setenv(k, v)
+    # --- reference-compatible mode: per chunk concat + self compat-align => 2 per chunk of >= 1000 bases ---
+    monkeypatch.setenv("SWB_GPU_ALIGN_MODE", "ref_compat")
+    res = aligner.process_full_wgs_dataset(device)
+    assert len(res) == 4
+    for r in res:
+        assert r.score64 == 2 * 3 and r.total_reads == 45 and r.total_bases == 45 * 150   # chunks of 20,20,5 reads
+    # --- Smith-Waterman mode: every read against its window of the (synthetic) resident reference ---
+    monkeypatch.delenv("SWB_GPU_ALIGN_MODE")
+    res = aligner.process_full_wgs_dataset(device)
+    assert len(res) == 4
+
+    def splitmix(x):
+        m = (1 << 64) - 1
+        x = (x + 0x9E3779B97F4A7C15) & m
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & m
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & m
+        return x ^ (x >> 31)
+    n_ref = 200000
+    ref = bytearray(n_ref)
+    for k in range(0, n_ref, 32):
+        x = splitmix(0xB2F0 + (k >> 5))
+        for j in range(k, min(n_ref, k + 32)):
+            ref[j] = b"ACGT"[x & 3]
+            x >>= 2
+    names = sorted(files)                                   # L001_R1, L001_R2, L002_R1, L002_R2 = the driver's order
+    for fi, name in enumerate(names):
+        exp = 0
+        for k, read in enumerate(files[name]):
+            start = splitmix(((fi << 40) + k) ^ 0xB202) % (n_ref - 500 + 1)
+            exp += ol.sw_linear(read, bytes(ref[start:start + 500]))[0]
+        assert res[fi].score64 == exp, name
+        assert res[fi].total_reads == 45
+
+
+def test_cli_on_gpu(tmp_path):
+    env = {k: v for k, v in os.environ.items() if k != "SWB_GPU_ALIGN_MODE"}
+    r = subprocess.run([CLI, "-1", "TGTTACGG", "-2", "GGTTGACTA", "--gpu"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "GPU acceleration enabled" in r.stdout and "Found GPU: NVIDIA" in r.stdout
+    assert "GPU Alignment score: 8" in r.stdout and "End cell: (5, 6)" in r.stdout
+    env["SWB_GPU_ALIGN_MODE"] = "ref_compat"
+    r = subprocess.run([CLI, "--seq1", "TGTTACGG", "--seq2=GGTTGACTA", "-g"], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and "GPU Alignment score: 2" in r.stdout                  # what the reference prints today
+
+
+def test_reads_vs_resident_reference(engine):
+    rng = np.random.default_rng(5)
+    ref = ACGT[rng.integers(0, 4, 50_000)]
+    ref[1000:1010] = ord("N")
+    engine.set_reference(ref)
+    n = 3000
+    starts = rng.integers(0, 50_000 - 600, n).astype(np.uint64)
+    lens = rng.integers(300, 600, n).astype(np.uint32)
+    reads = []
+    for k in range(n):
+        w = ref[int(starts[k]):int(starts[k]) + int(lens[k])]
+        o = int(rng.integers(0, 150))
+        r = w[o:o + 150].copy()
+        m = rng.random(r.size) < 0.02
+        r[m] = ACGT[rng.integers(0, 4, int(m.sum()))]
+        reads.append(r)
+    q, qo = to_csr(reads)
+    got = engine.score_batch_vs_reference(q, qo, starts, lens)
+    wins = [ref[int(s):int(s) + int(l)] for s, l in zip(starts, lens)]
+    r, ro = to_csr(wins)
+    exp = ol.batch(q, qo, r, ro, threads=8)
+    assert np.array_equal(got, exp)
+    routing = engine.last_routing()
+    assert routing["generic"] > 0 and routing["short"] > 2000                          # windows over the N stretch go generic

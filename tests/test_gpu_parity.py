@@ -133,7 +133,7 @@ def test_mixed_batch_routing_and_empties(engine):
     got = _assert_parity(engine, reads, wins)
     routing = engine.last_routing()
     assert routing["short"] + routing["generic"] == len(reads) - 3
-    assert routing["short"] >= 250 and routing["generic"] >= 60
+    assert routing["short"] >= 200 and routing["generic"] >= 100   # N-flags are per 16-base word: neighbours of an N read may go generic too
     for k, (a, b) in enumerate(zip(reads, wins)):
         if len(a) == 0 or len(b) == 0:
             assert tuple(got[k]) == (0, -1, -1)                                                 # aligner.rs:413-416
