@@ -96,7 +96,7 @@ def test_full_wgs_driver_both_modes(tmp_path, device, monkeypatch):
     res = aligner.process_full_wgs_dataset(device)
     assert len(res) == 4
     for r in res:
-        assert r.score64 == 2 * 3 and r.total_reads == 45 and r.total_bases == 45 * 150   # chunks of 20,20,5 reads
+        assert r.score64 == 2 * 2 and r.total_reads == 45 and r.total_bases == 45 * 150   # chunks of 20,20,5 reads; the 750-base tail is skipped (aligner.rs:366)
     # --- Smith-Waterman mode: every read against its window of the (synthetic) resident reference ---
     monkeypatch.delenv("SWB_GPU_ALIGN_MODE")
     res = aligner.process_full_wgs_dataset(device)
