@@ -37,7 +37,7 @@ struct swb_ctx {
   int device = 0, sm_count = 0;
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8] = {};
-  DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, generic_list, counters, out, scratch, misc;
+  DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, short_desc, generic_list, counters, out, scratch, misc;
   DevBuf ref_bytes, ref_pk, ref_bad, win_beg, win_end;   // device-resident reference (swb_set_reference)
   uint64_t ref_len = 0;
   float last_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -86,7 +86,7 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   c->sm_count = p.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
   for (auto& e : c->ev) cudaEventCreate(&e);
-  if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 3;
+  if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 7;
   *out = c;
   return 0;
 }
@@ -97,7 +97,7 @@ void swb_destroy(swb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   for (DevBuf* b : {&c->q_bytes, &c->r_bytes, &c->q_off, &c->r_off, &c->q_pk, &c->r_pk, &c->q_bad, &c->r_bad,
-                    &c->short_list, &c->generic_list, &c->counters, &c->out, &c->scratch, &c->misc,
+                    &c->short_list, &c->short_desc, &c->generic_list, &c->counters, &c->out, &c->scratch, &c->misc,
                     &c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->win_beg, &c->win_end}) b->release();
   for (auto& e : c->ev) cudaEventDestroy(e);
   cudaStreamDestroy(c->st);
@@ -105,7 +105,7 @@ void swb_destroy(swb_ctx* c)
 }
 
 void* swb_stream(swb_ctx* c) { return c ? (void*)c->st : nullptr; }
-int   swb_set_short_variant(swb_ctx* c, int v) { if (!c) return fail("null ctx"); c->variant = v & 3; return 0; }
+int   swb_set_short_variant(swb_ctx* c, int v) { if (!c) return fail("null ctx"); c->variant = v & 7; return 0; }
 
 int swb_sync(swb_ctx* c)
 {
@@ -128,7 +128,7 @@ static int run_device_pipeline(swb_ctx* c, const uint8_t* d_q, const uint64_t* d
   const uint64_t qw = (q_total + 15) / 16, rw = ref_windows ? 0 : (r_total + 15) / 16;
   if (c->q_pk.reserve(qw * 4 + 64) || c->r_pk.reserve(rw * 4 + 64) ||
       c->q_bad.reserve((qw + 31) / 32 * 4 + 64) || c->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
-      c->short_list.reserve(n_pairs * 4 + 64) || c->generic_list.reserve(n_pairs * 4 + 64) ||
+      c->short_list.reserve(n_pairs * 4 + 64) || c->short_desc.reserve(n_pairs * sizeof(swb::ShortDesc) + 64) || c->generic_list.reserve(n_pairs * 4 + 64) ||
       c->counters.reserve(sizeof(swb::Counters))) return 1;
   // generic kernel: persistent grid, one boundary row of max_r_len ints per resident warp
   int ctas = c->sm_count * 4;
@@ -142,7 +142,7 @@ static int run_device_pipeline(swb_ctx* c, const uint8_t* d_q, const uint64_t* d
   b.r_pk = ref_windows ? c->ref_pk.as<uint32_t>() : c->r_pk.as<uint32_t>();
   b.r_bad = ref_windows ? c->ref_bad.as<uint32_t>() : c->r_bad.as<uint32_t>();
   b.n_pairs = n_pairs;
-  b.short_list = c->short_list.as<uint32_t>(); b.generic_list = c->generic_list.as<uint32_t>();
+  b.short_list = c->short_list.as<uint32_t>(); b.short_desc = c->short_desc.as<swb::ShortDesc>(); b.generic_list = c->generic_list.as<uint32_t>();
   b.counters = c->counters.as<swb::Counters>(); b.out = d_out;
   b.scratch = c->scratch.as<int32_t>(); b.scratch_stride = stride;
 

@@ -124,7 +124,14 @@ classify_kernel(BatchView b)
   base_s = __shfl_sync(0xffffffffu, base_s, 0);
   base_g = __shfl_sync(0xffffffffu, base_g, 0);
   const uint32_t below = (1u << lane) - 1;
-  if (cls == CLASS_SHORT)   b.short_list[base_s + __popc(ms & below)] = (uint32_t)k;
+  if (cls == CLASS_SHORT) {
+    const uint32_t slot = base_s + __popc(ms & below);
+    b.short_list[slot] = (uint32_t)k;
+    const uint64_t q0 = b.q_beg[k], r0 = b.r_beg[k];
+    uint4* d = reinterpret_cast<uint4*>(b.short_desc + slot);
+    d[0] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)r0, (uint32_t)(r0 >> 32));
+    d[1] = make_uint4((uint32_t)(b.q_end[k] - q0), m, (uint32_t)k, 0u);
+  }
   if (cls == CLASS_GENERIC) b.generic_list[base_g + __popc(mg & below)] = (uint32_t)k;
   uint32_t wm = m;
   for (int o = 16; o; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
@@ -344,16 +351,297 @@ size_t short_smem_bytes(uint32_t window_cap, int variant)
   return (size_t)((NPAD + n_iters * K + 15) & ~15u) * 4 * (32 / G);
 }
 
-// variant bit0: 0 = G8/K20, 1 = G16/K10 ; bit1: split tracking (VIADD + VIMNMX) instead of VIADDMNMX
-int launch_short(const BatchView& b, uint32_t window_cap, int variant, int /*sm_count*/, cudaStream_t st)
+template <int G, int K, int MINB> static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st);
+
+// variant 4..6: streaming kernel; else bit0: 0 = G8/K20, 1 = G16/K10 ; bit1: split tracking (VIADD + VIMNMX) instead of VIADDMNMX
+int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st)
 {
   if (b.n_pairs == 0) return 0;
+  if ((variant & 7) == 4) return launch_stream_t<8, 20, 4>(b, sm_count, st);
+  if ((variant & 7) == 5) return launch_stream_t<16, 10, 5>(b, sm_count, st);
+  if ((variant & 7) == 6) return launch_stream_t<8, 20, 3>(b, sm_count, st);
   switch (variant & 3) {
     case 0: return launch_short_t<8, 20, false>(b, window_cap, st);
     case 1: return launch_short_t<16, 10, false>(b, window_cap, st);
     case 2: return launch_short_t<8, 20, true>(b, window_cap, st);
     default: return launch_short_t<16, 10, true>(b, window_cap, st);
   }
+}
+
+// =====================================================================================
+// Streaming inter-task kernel (sw_stream_kernel): same cell arithmetic as sw_short_kernel,
+// three changes that remove its structural losses.
+//
+// 1. Pairs STREAM through a lane group.  The anti-diagonal wavefront of sw_short_kernel pays
+//    G*K fill/drain steps per pair (160 of 660 at 150x500).  Here a group owns a run of pair
+//    couples whose windows are laid end to end on one column stream with a fixed stride of
+//    Wp columns per pair (Wp = window cap + K-1 rounded up to K, pad columns never match).
+//    Lane L switches to the next pair when its slot 0 reaches that pair's column 0 -- K steps
+//    after lane L-1 did -- so the wavefront never drains: one fill/drain per RUN of pairs.
+//    At its switch a lane folds its row trackers, reloads its K query codes and resets its
+//    K cells to the image of H=0; the K-1 slots that are still on pad columns compute zeros.
+//    A lane of the old pair reads zeros (not junk) from the lane above once that one has
+//    switched; it only does so on pad columns, whose values are never the maximum.
+// 2. The window stream lives in a small per-group RING in shared memory (4*G*K entries),
+//    refilled G*K columns at a time, so shared memory no longer grows with the window
+//    length and the staging cost is spread over the run.
+// 3. The substitution table is indexed by an ADD (IMAD on the idle FMA pipe, the ALU pipe is
+//    the one that saturates) instead of a LOP3, and replicated per lane so that the LDS of a
+//    warp never has a bank conflict: entry(idx) of lane l sits at lut + 128*idx + 4*l,
+//    idx = 9*a + b with a = (3 - q_code_A) + w_code_A in 0..8 (match iff a == 3; pad codes are
+//    4 on both sides so a pad never matches), b likewise for pair B.
+//
+// Work distribution: persistent grid (a multiple of the SM count), group g scores the pair
+// couples g, g+NG, g+2NG, ... of the short list (NG = groups in the grid).
+// =====================================================================================
+struct StreamArgs {
+  const uint32_t* q_pk; const uint32_t* r_pk;
+  const ShortDesc* desc; const Counters* counters;
+  swb_result* out;
+};
+
+// 2-bit codes of bases [pos, pos+32) of a packed array, code k in bits 2k..2k+1
+__device__ __forceinline__ uint64_t codes32(const uint32_t* __restrict__ pk, uint64_t pos)
+{
+  const uint32_t* w = pk + (pos >> 4);
+  const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);   // arenas carry 64 B of slack
+  const uint32_t sh = 2u * (uint32_t)(pos & 15);
+  return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+__device__ __forceinline__ ShortDesc load_desc(const ShortDesc* __restrict__ d)
+{
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(d)), b = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+  ShortDesc r;
+  r.q0 = (uint64_t)a.x | ((uint64_t)a.y << 32); r.r0 = (uint64_t)a.z | ((uint64_t)a.w << 32);
+  r.n = b.x; r.m = b.y; r.pair = b.z; r.pad = b.w;
+  return r;
+}
+
+constexpr int kLutEntries = 81;
+constexpr int kLutBytes = kLutEntries * 128;
+
+template <int G, int K, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+sw_stream_kernel(StreamArgs a)
+{
+  static_assert(K % 2 == 0 && K <= 32, "K even, at most 32 codes per 64-bit code word");
+  static_assert(32 % G == 0, "G must divide the warp");
+  constexpr int NPAD  = G * K;
+  constexpr int BLOCK = (62 / K) * K;
+  constexpr int IPB   = BLOCK / K;                       // iterations per block
+  constexpr uint32_t REBASE = (uint32_t)(128 * BLOCK) * 0x00010001u;
+  constexpr int GPW = 32 / G;
+  constexpr int RSLOTS = 4 * G;                          // ring = RSLOTS slots of K columns
+  constexpr int RING = RSLOTS * K;                       // uint16 entries
+  constexpr int GSTRIDE = RING * 2 + (G == 8 ? 4 : 64);  // bytes between group rings: keeps the groups of a warp on distinct banks
+  constexpr uint32_t WPADV = (9u * 4u + 4u) << 7;        // ring value of a pad column
+
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t* lut = reinterpret_cast<uint32_t*>(smem);
+  for (uint32_t x = threadIdx.x; x < kLutEntries * 32; x += blockDim.x) {
+    const uint32_t idx = x >> 5, ia = idx / 9, ib = idx % 9;
+    lut[x] = ((ia == 3 ? 384u : 192u) << 16) | (ib == 3 ? 384u : 192u);
+  }
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t g = lane / G, L = lane % G;
+  const uint32_t n_list = a.counters->n_short;
+  const uint32_t n_pp = (n_list + 1) >> 1;
+  const uint32_t NG = gridDim.x * 4 * GPW;
+  const uint32_t gidx0 = (blockIdx.x * 4 + warp) * GPW, gidx = gidx0 + g;
+  if (gidx0 >= n_pp) return;                             // no pair couple for any group of this warp
+  const uint32_t myN   = gidx < n_pp ? (n_pp - 1 - gidx) / NG + 1 : 0;
+  const uint32_t warpN = (n_pp - 1 - gidx0) / NG + 1;    // the warp's first group has the longest run
+  uint32_t Wp = (a.counters->max_short_window + 2 * K - 2) / K * K;
+  if (Wp < NPAD + K) Wp = NPAD + K;                      // at most two pairs in flight per group
+  const uint32_t ipp = Wp / K;                           // iterations per pair
+
+  uint16_t* ring = reinterpret_cast<uint16_t*>(smem + kLutBytes + (size_t)(warp * GPW + g) * GSTRIDE);
+  const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + 4u * lane;
+
+  // ---- producer side of the ring: columns [k*NPAD + L*K, +K) of the stream per call ----
+  uint32_t stg_n = 0, stg_j = L * K;
+  auto stage = [&](uint32_t slot) {
+    uint64_t cA = 0, cB = 0; int32_t vA = 0, vB = 0;
+    if (stg_n < myN) {
+      const uint32_t pp = gidx + stg_n * NG;
+      const ShortDesc dA = load_desc(a.desc + 2 * (uint64_t)pp);
+      vA = (int32_t)dA.m - (int32_t)stg_j;
+      if (vA > 0) cA = codes32(a.r_pk, dA.r0 + stg_j);
+      if (2 * pp + 1 < n_list) {
+        const ShortDesc dB = load_desc(a.desc + 2 * (uint64_t)pp + 1);
+        vB = (int32_t)dB.m - (int32_t)stg_j;
+        if (vB > 0) cB = codes32(a.r_pk, dB.r0 + stg_j);
+      }
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * K);
+#pragma unroll
+    for (int x = 0; x < K; x += 2) {
+      const uint32_t a0 = x < vA ? (uint32_t)(cA >> (2 * x)) & 3u : 4u, a1 = x + 1 < vA ? (uint32_t)(cA >> (2 * x + 2)) & 3u : 4u;
+      const uint32_t b0 = x < vB ? (uint32_t)(cB >> (2 * x)) & 3u : 4u, b1 = x + 1 < vB ? (uint32_t)(cB >> (2 * x + 2)) & 3u : 4u;
+      dst[x >> 1] = ((9u * a0 + b0) << 7) | ((9u * a1 + b1) << 23);
+    }
+    stg_j += NPAD;
+    if (stg_j >= Wp) { stg_j -= Wp; ++stg_n; }
+  };
+
+  // ---- query codes of this lane's K rows for the lane's pair number n ----
+  uint32_t Q[K];
+  auto load_query = [&](uint32_t n) {
+    uint64_t cA = 0, cB = 0; int32_t vA = 0, vB = 0;
+    if (n < myN) {
+      const uint32_t pp = gidx + n * NG;
+      const ShortDesc dA = load_desc(a.desc + 2 * (uint64_t)pp);
+      vA = (int32_t)dA.n - (int32_t)(K * L);
+      if (vA > 0) cA = codes32(a.q_pk, dA.q0 + K * L);
+      if (2 * pp + 1 < n_list) {
+        const ShortDesc dB = load_desc(a.desc + 2 * (uint64_t)pp + 1);
+        vB = (int32_t)dB.n - (int32_t)(K * L);
+        if (vB > 0) cB = codes32(a.q_pk, dB.q0 + K * L);
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < K; ++m) {
+      const uint32_t qa = m < vA ? 3u - ((uint32_t)(cA >> (2 * m)) & 3u) : 4u;
+      const uint32_t qb = m < vB ? 3u - ((uint32_t)(cB >> (2 * m)) & 3u) : 4u;
+      Q[m] = lut_lane + ((9u * qa + qb) << 7);
+    }
+  };
+
+  // ---- prologue: pad columns [-NPAD, 0), stream chunk 0, query of pair 0 ----
+  {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ring + L * K);
+#pragma unroll
+    for (int x = 0; x < K / 2; ++x) dst[x] = WPADV | (WPADV << 16);
+  }
+  stage(G + L);
+  load_query(0);
+  __syncwarp();
+
+  uint32_t A[K], B[K], W[K], cur[K];
+#pragma unroll
+  for (int m = 0; m < K; ++m) { A[m] = 0xFF00FF00u; B[m] = 0xFF80FF80u; W[m] = WPADV; cur[m] = 0; }
+  uint32_t recA = 0, recB = 0, prevA = 0, prevB = 0;
+  uint32_t floor_ = 0, fm1 = 0xFF80FF80u, upPrev = 0xFF00FF00u;
+  uint32_t e = (uint32_t)(BLOCK - 1) * 0x00010001u;
+  int32_t blockStart = 0;
+  int32_t pairBase = 0;                                  // first stream column of the lane's current pair
+  uint32_t lane_n = 0, fin_n = 0;
+  uint32_t sw_it = ipp + L, fin_it = ipp + G - 1, stage_it = 0, stage_k = 1;
+  int bit = 0;
+
+  // fold the K row trackers into the two per-pair keys  H<<21 | (255-i)<<13 | (8191-NPAD-j)
+  auto fold = [&]() {
+    const int32_t P0 = (int32_t)(((255u - K * L) << 13) + K * L) + (8192 - NPAD - BLOCK - blockStart) + pairBase;
+#pragma unroll
+    for (int m = 0; m < K; ++m) {
+      const int32_t Pm = P0 - 8191 * m;
+      const uint32_t hi = cur[m] >> 16, lo = cur[m] & 0xFFFFu;
+      const uint32_t kh = hi * 32768u - (hi & 63u) * 32767u + (uint32_t)Pm;
+      const uint32_t kl = lo * 32768u - (lo & 63u) * 32767u + (uint32_t)Pm;
+      recA = max(recA, kh);
+      recB = max(recB, kl);
+      cur[m] = 0;
+    }
+  };
+
+  const uint32_t n_iters = warpN * ipp + G;
+  for (uint32_t it = 0; it < n_iters; ++it) {
+    // ---- events at the iteration boundary ----
+    if (bit == IPB) {                                    // block end (all lanes): fold, rebase
+      bit = 0;
+      fold();
+#pragma unroll
+      for (int m = 0; m < K; ++m) { A[m] = __vsub2(A[m], REBASE); B[m] = __vsub2(B[m], REBASE); }
+      upPrev = __vsub2(upPrev, REBASE);
+      floor_ = 0; fm1 = 0xFF80FF80u;
+      e = (uint32_t)(BLOCK - 1) * 0x00010001u;
+      blockStart += BLOCK;
+    }
+    if (it == stage_it) {                                // refill the ring one chunk ahead (all lanes)
+      stage((stage_k * G + G + L) & (RSLOTS - 1));
+      ++stage_k; stage_it += G;
+      __syncwarp();
+    }
+    if (it == sw_it) {                                   // this lane moves on to its next pair
+      fold();
+      prevA = recA; prevB = recB; recA = 0; recB = 0;
+      ++lane_n; pairBase += (int32_t)Wp; sw_it += ipp;
+      load_query(lane_n);
+      const uint32_t z2 = __vsub2(floor_, 0x01000100u);
+#pragma unroll
+      for (int m = 0; m < K; ++m) { A[m] = z2; B[m] = fm1; }
+    }
+    if (it == fin_it) {                                  // every lane of the group has left pair fin_n (all lanes)
+      uint32_t ka = prevA, kb = prevB;
+#pragma unroll
+      for (int o = G / 2; o; o >>= 1) {
+        ka = max(ka, __shfl_xor_sync(0xffffffffu, ka, o, G));
+        kb = max(kb, __shfl_xor_sync(0xffffffffu, kb, o, G));
+      }
+      if (L == 0 && fin_n < myN) {
+        const uint32_t pp = gidx + fin_n * NG;
+        const uint32_t sA = ka >> 21, sB = kb >> 21;
+        swb_result ra{0, -1, -1}, rb{0, -1, -1};
+        if (sA) ra = swb_result{(int32_t)sA, 255 - (int32_t)((ka >> 13) & 255u), 8191 - NPAD - (int32_t)(ka & 8191u)};
+        if (sB) rb = swb_result{(int32_t)sB, 255 - (int32_t)((kb >> 13) & 255u), 8191 - NPAD - (int32_t)(kb & 8191u)};
+        a.out[a.desc[2 * (uint64_t)pp].pair] = ra;
+        if (2 * pp + 1 < n_list) a.out[a.desc[2 * (uint64_t)pp + 1].pair] = rb;
+      }
+      ++fin_n; fin_it += ipp;
+    }
+    ++bit;
+
+    // ---- K steps of the wavefront ----
+    const uint16_t* wp = ring + ((it + G - L) & (RSLOTS - 1)) * K;
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      W[u] = wp[u];
+      uint32_t up = __shfl_up_sync(0xffffffffu, (u & 1) ? A[K - 1] : B[K - 1], 1, G);
+      if (L == 0) up = fm1;
+#pragma unroll
+      for (int m = K - 1; m >= 0; --m) {
+        const uint32_t x = Q[m] + W[(u - m + K) % K];
+        uint32_t sub;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(sub) : "r"(x));
+        uint32_t d, uu, l;
+        if (u & 1) { d = m ? B[m - 1] : upPrev; uu = m ? A[m - 1] : up; l = A[m]; }
+        else       { d = m ? A[m - 1] : upPrev; uu = m ? B[m - 1] : up; l = B[m]; }
+        const uint32_t t1 = __viaddmax_s16x2(d, sub, uu);
+        const uint32_t h  = __vimax3_s16x2(t1, l, floor_);
+        if (u & 1) B[m] = h; else A[m] = h;
+        cur[m] = __viaddmax_s16x2(h, e, cur[m]);
+      }
+      upPrev = up;
+      fm1 = floor_;
+      floor_ += 0x00800080u;
+      e = __vsub2(e, 0x00810081u);
+    }
+  }
+}
+
+template <int G, int K, int MINB>
+static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
+{
+  constexpr int GPW = 32 / G;
+  constexpr int GSTRIDE = 4 * G * K * 2 + (G == 8 ? 4 : 64);
+  StreamArgs a;
+  a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.desc = b.short_desc; a.counters = b.counters; a.out = b.out;
+  const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(sw_stream_kernel<G, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  // persistent grid: MINB CTAs per SM; never more groups than pair couples in the worst case
+  const uint64_t n_pp = (b.n_pairs + 1) / 2;
+  uint64_t blocks = (uint64_t)sm_count * MINB;
+  const uint64_t need = (n_pp + 4 * GPW - 1) / (4 * GPW);
+  if (blocks > need) blocks = need;
+  sw_stream_kernel<G, K, MINB><<<(unsigned)blocks, 128, smem, st>>>(a);
+  return 1;
 }
 
 // =====================================================================================

@@ -23,6 +23,12 @@ struct Counters {             // device-resident, zeroed per batch
   uint32_t generic_cursor;    // work-stealing cursor of the generic kernel
 };
 
+struct ShortDesc {            // one entry per short-listed pair, written by classify_kernel (32 B, 16-aligned)
+  uint64_t q0, r0;            // first base of the read / of the window (base coordinates of the packed arrays)
+  uint32_t n, m;              // read length, window length
+  uint32_t pair, pad;         // index of the pair in the batch
+};
+
 struct BatchView {            // everything the kernels need about one batch (device pointers)
   // ASCII reads / windows.  Sequence p occupies bytes [beg[p], end[p]).  For CSR offsets end == beg + 1; for
   // windows cut from a device-resident reference beg/end are independent arrays (windows may overlap).
@@ -32,6 +38,7 @@ struct BatchView {            // everything the kernels need about one batch (de
   const uint32_t* r_pk;     const uint32_t* r_bad;     // 2-bit packed windows + bitmap
   uint64_t        n_pairs;
   uint32_t*       short_list;   // pair ids, n_short entries
+  ShortDesc*      short_desc;   // descriptors, same order as short_list
   uint32_t*       generic_list; // pair ids, n_generic entries
   Counters*       counters;
   swb_result*     out;

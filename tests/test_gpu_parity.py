@@ -13,7 +13,7 @@ from mini_parallel_b200.engine import to_csr
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sw_vectors.json")))["vectors"]
-ALL_VARIANTS = (0, 1, 2, 3)
+ALL_VARIANTS = (0, 1, 2, 3, 4, 5, 6)
 
 
 def _rand(rng, n, alphabet=b"ACGT"):
