@@ -44,7 +44,7 @@ struct swb_ctx {
   int last_kernels = 0;
   uint64_t last_routing[2] = {0, 0};
   bool timings_pending = false, host_path = false;
-  int variant = 1;
+  int variant = 4;
 };
 
 extern "C" {

@@ -357,7 +357,7 @@ template <int G, int K, int MINB> static int launch_stream_t(const BatchView& b,
 int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st)
 {
   if (b.n_pairs == 0) return 0;
-  if ((variant & 7) == 4) return launch_stream_t<8, 20, 4>(b, sm_count, st);
+  if ((variant & 7) == 4) return launch_stream_t<16, 10, 4>(b, sm_count, st);
   if ((variant & 7) == 5) return launch_stream_t<16, 10, 5>(b, sm_count, st);
   if ((variant & 7) == 6) return launch_stream_t<8, 20, 3>(b, sm_count, st);
   switch (variant & 3) {
@@ -394,6 +394,12 @@ int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_co
 // Work distribution: persistent grid (a multiple of the SM count), group g scores the pair
 // couples g, g+NG, g+2NG, ... of the short list (NG = groups in the grid).
 // =====================================================================================
+// The groups of a warp read their rings at the same phase; skew the ring bases so that their
+// bank sets are disjoint (lane stride is K*2 bytes: G=8,K=20 -> banks {0,10,20,30,8,18,28,6}+c,
+// translates by 0,1,16,17 words are disjoint; G=16,K=10 -> 16 distinct banks, translate by 16).
+__device__ __forceinline__ uint32_t ring_skew(uint32_t g) { return (g & 1u) * 4u + (g >> 1) * 64u; }
+template <int G> __device__ __forceinline__ uint32_t ring_skew_t(uint32_t g) { return G == 16 ? g * 64u : ring_skew(g); }
+
 struct StreamArgs {
   const uint32_t* q_pk; const uint32_t* r_pk;
   const ShortDesc* desc; const Counters* counters;
@@ -434,7 +440,7 @@ sw_stream_kernel(StreamArgs a)
   constexpr int GPW = 32 / G;
   constexpr int RSLOTS = 4 * G;                          // ring = RSLOTS slots of K columns
   constexpr int RING = RSLOTS * K;                       // uint16 entries
-  constexpr int GSTRIDE = RING * 2 + (G == 8 ? 4 : 64);  // bytes between group rings: keeps the groups of a warp on distinct banks
+  constexpr int GSTRIDE = RING * 2 + 128;                // bytes between group rings (a multiple of 128, room for ring_skew)
   constexpr uint32_t WPADV = (9u * 4u + 4u) << 7;        // ring value of a pad column
 
   extern __shared__ __align__(16) uint8_t smem[];
@@ -458,8 +464,12 @@ sw_stream_kernel(StreamArgs a)
   if (Wp < NPAD + K) Wp = NPAD + K;                      // at most two pairs in flight per group
   const uint32_t ipp = Wp / K;                           // iterations per pair
 
-  uint16_t* ring = reinterpret_cast<uint16_t*>(smem + kLutBytes + (size_t)(warp * GPW + g) * GSTRIDE);
+  uint16_t* ring = reinterpret_cast<uint16_t*>(smem + kLutBytes + (size_t)(warp * GPW + g) * GSTRIDE + ring_skew_t<G>(g));
   const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + 4u * lane;
+  // per-thread scratch (word m of thread t at [m*128 + t]: conflict-free): the query codes prepared for the
+  // lane's NEXT pair, and the row trackers a lane parks at its switch until the group folds them together
+  uint32_t* qnext = reinterpret_cast<uint32_t*>(smem + kLutBytes + (size_t)4 * GPW * GSTRIDE) + threadIdx.x;
+  uint32_t* csave = qnext + K * 128;
 
   // ---- producer side of the ring: columns [k*NPAD + L*K, +K) of the stream per call ----
   uint32_t stg_n = 0, stg_j = L * K;
@@ -489,7 +499,7 @@ sw_stream_kernel(StreamArgs a)
 
   // ---- query codes of this lane's K rows for the lane's pair number n ----
   uint32_t Q[K];
-  auto load_query = [&](uint32_t n) {
+  auto load_query = [&](uint32_t n, bool to_regs) {
     uint64_t cA = 0, cB = 0; int32_t vA = 0, vB = 0;
     if (n < myN) {
       const uint32_t pp = gidx + n * NG;
@@ -506,7 +516,8 @@ sw_stream_kernel(StreamArgs a)
     for (int m = 0; m < K; ++m) {
       const uint32_t qa = m < vA ? 3u - ((uint32_t)(cA >> (2 * m)) & 3u) : 4u;
       const uint32_t qb = m < vB ? 3u - ((uint32_t)(cB >> (2 * m)) & 3u) : 4u;
-      Q[m] = lut_lane + ((9u * qa + qb) << 7);
+      const uint32_t v = lut_lane + ((9u * qa + qb) << 7);
+      if (to_regs) Q[m] = v; else qnext[m * 128] = v;
     }
   };
 
@@ -517,7 +528,8 @@ sw_stream_kernel(StreamArgs a)
     for (int x = 0; x < K / 2; ++x) dst[x] = WPADV | (WPADV << 16);
   }
   stage(G + L);
-  load_query(0);
+  load_query(0, true);
+  load_query(1, false);
   __syncwarp();
 
   uint32_t A[K], B[K], W[K], cur[K];
@@ -528,33 +540,30 @@ sw_stream_kernel(StreamArgs a)
   uint32_t e = (uint32_t)(BLOCK - 1) * 0x00010001u;
   int32_t blockStart = 0;
   int32_t pairBase = 0;                                  // first stream column of the lane's current pair
-  uint32_t lane_n = 0, fin_n = 0;
+  uint32_t fin_n = 0;
   uint32_t sw_it = ipp + L, fin_it = ipp + G - 1, stage_it = 0, stage_k = 1;
   int bit = 0;
 
   // fold the K row trackers into the two per-pair keys  H<<21 | (255-i)<<13 | (8191-NPAD-j)
-  auto fold = [&]() {
-    const int32_t P0 = (int32_t)(((255u - K * L) << 13) + K * L) + (8192 - NPAD - BLOCK - blockStart) + pairBase;
-#pragma unroll
-    for (int m = 0; m < K; ++m) {
-      const int32_t Pm = P0 - 8191 * m;
-      const uint32_t hi = cur[m] >> 16, lo = cur[m] & 0xFFFFu;
-      const uint32_t kh = hi * 32768u - (hi & 63u) * 32767u + (uint32_t)Pm;
-      const uint32_t kl = lo * 32768u - (lo & 63u) * 32767u + (uint32_t)Pm;
-      recA = max(recA, kh);
-      recB = max(recB, kl);
-      cur[m] = 0;
-    }
+  auto fold_word = [&](uint32_t c, int32_t Pm, uint32_t& ra, uint32_t& rb) {
+    const uint32_t hi = c >> 16, lo = c & 0xFFFFu;
+    ra = max(ra, hi * 32768u - (hi & 63u) * 32767u + (uint32_t)Pm);
+    rb = max(rb, lo * 32768u - (lo & 63u) * 32767u + (uint32_t)Pm);
   };
+  const int32_t Pconst = (int32_t)(((255u - K * L) << 13) + K * L) + (8192 - NPAD - BLOCK);
 
   const uint32_t n_iters = warpN * ipp + G;
   for (uint32_t it = 0; it < n_iters; ++it) {
     // ---- events at the iteration boundary ----
     if (bit == IPB) {                                    // block end (all lanes): fold, rebase
       bit = 0;
-      fold();
+      const int32_t P0 = Pconst - blockStart + pairBase;
 #pragma unroll
-      for (int m = 0; m < K; ++m) { A[m] = __vsub2(A[m], REBASE); B[m] = __vsub2(B[m], REBASE); }
+      for (int m = 0; m < K; ++m) {
+        fold_word(cur[m], P0 - 8191 * m, recA, recB);
+        cur[m] = 0;
+        A[m] = __vsub2(A[m], REBASE); B[m] = __vsub2(B[m], REBASE);
+      }
       upPrev = __vsub2(upPrev, REBASE);
       floor_ = 0; fm1 = 0xFF80FF80u;
       e = (uint32_t)(BLOCK - 1) * 0x00010001u;
@@ -565,16 +574,26 @@ sw_stream_kernel(StreamArgs a)
       ++stage_k; stage_it += G;
       __syncwarp();
     }
-    if (it == sw_it) {                                   // this lane moves on to its next pair
-      fold();
-      prevA = recA; prevB = recB; recA = 0; recB = 0;
-      ++lane_n; pairBase += (int32_t)Wp; sw_it += ipp;
-      load_query(lane_n);
+    if (it == sw_it) {                                   // this lane moves on to its next pair (one lane per group:
+      prevA = recA; prevB = recB; recA = 0; recB = 0;    //  divergent, so it only parks / fetches / resets)
+      pairBase += (int32_t)Wp; sw_it += ipp;
       const uint32_t z2 = __vsub2(floor_, 0x01000100u);
 #pragma unroll
-      for (int m = 0; m < K; ++m) { A[m] = z2; B[m] = fm1; }
+      for (int m = 0; m < K; ++m) {
+        csave[m * 128] = cur[m]; cur[m] = 0;
+        Q[m] = qnext[m * 128];
+        A[m] = z2; B[m] = fm1;
+      }
     }
     if (it == fin_it) {                                  // every lane of the group has left pair fin_n (all lanes)
+      // fold the trackers each lane parked at its switch (iteration fin_it - (G-1) + L, after that
+      // boundary's block end) into the keys of pair fin_n
+      {
+        const uint32_t it_sw = it - (G - 1) + L;
+        const int32_t P0 = Pconst - (int32_t)(it_sw / IPB) * BLOCK + (int32_t)(fin_n * Wp);
+#pragma unroll
+        for (int m = 0; m < K; ++m) fold_word(csave[m * 128], P0 - 8191 * m, prevA, prevB);
+      }
       uint32_t ka = prevA, kb = prevB;
 #pragma unroll
       for (int o = G / 2; o; o >>= 1) {
@@ -590,6 +609,7 @@ sw_stream_kernel(StreamArgs a)
         a.out[a.desc[2 * (uint64_t)pp].pair] = ra;
         if (2 * pp + 1 < n_list) a.out[a.desc[2 * (uint64_t)pp + 1].pair] = rb;
       }
+      load_query(fin_n + 2, false);                      // every lane has consumed the codes of pair fin_n+1
       ++fin_n; fin_it += ipp;
     }
     ++bit;
@@ -626,10 +646,10 @@ template <int G, int K, int MINB>
 static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
 {
   constexpr int GPW = 32 / G;
-  constexpr int GSTRIDE = 4 * G * K * 2 + (G == 8 ? 4 : 64);
+  constexpr int GSTRIDE = 4 * G * K * 2 + 128;
   StreamArgs a;
   a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.desc = b.short_desc; a.counters = b.counters; a.out = b.out;
-  const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW;
+  const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(sw_stream_kernel<G, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

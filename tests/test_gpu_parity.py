@@ -65,7 +65,7 @@ def test_golden_vectors_as_one_batch(engine):
         got = engine.score_batch(reads, wins)
         for g, v in zip(got, GOLD):
             assert (int(g["score"]), int(g["end_i"]), int(g["end_j"])) == (v["score"], v["end_i"], v["end_j"]), v["name"]
-    engine.set_short_variant(1)
+    engine.set_short_variant(4)
 
 
 @pytest.mark.parametrize("variant", ALL_VARIANTS)
@@ -75,7 +75,7 @@ def test_short_path_uniform_150x500(engine, variant):
     _assert_parity(engine, *_pairs(rng, 4001, (150, 150), (500, 500)))           # odd count: last group holds one pair
     assert engine.last_routing() == {"short": 4001, "generic": 0}
     _assert_parity(engine, *_pairs(rng, 2000, (150, 150), (500, 500), related=False))
-    engine.set_short_variant(1)
+    engine.set_short_variant(4)
 
 
 @pytest.mark.parametrize("variant", ALL_VARIANTS)
@@ -84,7 +84,7 @@ def test_short_path_ragged_lengths(engine, variant):
     engine.set_short_variant(variant)
     _assert_parity(engine, *_pairs(rng, 6000, (1, 160), (1, 900)))
     _assert_parity(engine, *_pairs(rng, 1500, (140, 160), (1, 60), related=False))   # window shorter than the read
-    engine.set_short_variant(1)
+    engine.set_short_variant(4)
 
 
 @pytest.mark.parametrize("variant", ALL_VARIANTS)
@@ -97,7 +97,7 @@ def test_short_path_many_way_ties(engine, variant):
     reads = [b"ACG" * 50] * 64 + [b"AT" * 80] * 64
     wins = [b"ACG" * 160] * 64 + [b"TA" * 250] * 64
     _assert_parity(engine, reads, wins)
-    engine.set_short_variant(1)
+    engine.set_short_variant(4)
 
 
 def test_short_path_window_limits(engine):
