@@ -98,9 +98,17 @@ int  swb_last_routing(swb_ctx*, uint64_t* counts /* 2 */);
 /* The packing stage alone on device-resident bytes (bench: HBM roofline of the packing kernel). */
 int  swb_pack2bit_device(swb_ctx*, const uint8_t* d_bytes, uint64_t n, uint32_t* d_words, uint32_t* d_bitmap);
 
-/* Tuning knob: which instantiation of the short-read kernel runs (bit0: 0 = 8 lanes x 20 rows, 1 = 16 lanes x
- * 10 rows per group; bit1: split end-cell tracking).  All variants return identical results. */
+/* Tuning knob: which instantiation of the short-read kernel runs.  4 (default), 5, 6: the streaming kernel
+ * (16 lanes x 10 rows at 4 or 5 CTAs/SM, 8 lanes x 20 rows); 0..3: the one-couple-per-group kernel (bit0: 0 = 8 lanes
+ * x 20 rows, 1 = 16 lanes x 10 rows; bit1: split end-cell tracking).  All variants return identical results. */
 int  swb_set_short_variant(swb_ctx*, int variant);
+
+/* Host batches (swb_score_batch, swb_score_batch_vs_reference) are cut into chunks of about chunk_bytes of ASCII
+ * input (at least min_chunk_pairs pairs each) that are pipelined over three CUDA streams: H2D of one chunk, the
+ * kernels of the previous one and D2H of the one before overlap (north_star: "streams it H2D on multiple CUDA
+ * streams").  Defaults: 64 MiB, 16384 pairs; SWB_CHUNK_MB overrides the first.  Pass pinned host memory
+ * (swb_malloc_pinned) for the copies to be asynchronous. */
+int  swb_set_chunking(swb_ctx*, uint64_t chunk_bytes, uint64_t min_chunk_pairs);
 
 /* Raw device / pinned-host memory and copies for hosts without a CUDA runtime of their own (the CLI, the
  * ctypes tests, a Rust caller).  Replaces ocl::Buffer creation in gpu_align (aligner.rs:466-499);

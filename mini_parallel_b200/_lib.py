@@ -39,6 +39,7 @@ SIGNATURES = {
     "swb_last_timings": (_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_int)]),
     "swb_last_routing": (_int, [_vp, ctypes.POINTER(_u64)]),
     "swb_set_short_variant": (_int, [_vp, _int]),
+    "swb_set_chunking": (_int, [_vp, _u64, _u64]),
     "swb_stream": (_vp, [_vp]),
     "swb_last_error": (ctypes.c_char_p, []),
     "swb_version": (ctypes.c_char_p, []),

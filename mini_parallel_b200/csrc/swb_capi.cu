@@ -12,6 +12,7 @@
 namespace swb {
 int launch_generic_single(const BatchView& b, int32_t* last_row_out, cudaStream_t st);
 }
+#include <array>
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) { g_err = m; return 1; }
@@ -33,13 +34,34 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct swb_ctx {
-  int device = 0, sm_count = 0;
+// One pipeline lane = one CUDA stream + the arenas of one batch (or one chunk of a host batch) in flight.
+struct Lane {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8] = {};
   DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, short_desc, generic_list, counters, out, scratch, misc;
-  DevBuf ref_bytes, ref_pk, ref_bad, win_beg, win_end;   // device-resident reference (swb_set_reference)
+  DevBuf win_beg, win_end, win_len;
+  void release_all() {
+    for (DevBuf* b : {&q_bytes, &r_bytes, &q_off, &r_off, &q_pk, &r_pk, &q_bad, &r_bad, &short_list, &short_desc,
+                      &generic_list, &counters, &out, &scratch, &misc, &win_beg, &win_end, &win_len}) b->release();
+  }
+};
+
+constexpr int kLanes = 3;                  // chunks of a host batch in flight: H2D / kernels / D2H overlap
+
+struct ChunkEvents { cudaEvent_t ev[8]; };
+
+struct swb_ctx : Lane {                    // lane 0 is the context itself (device-resident API, single-pair calls)
+  int device = 0, sm_count = 0;
+  Lane extra[kLanes - 1];
+  Lane* lane(int i) { return i == 0 ? static_cast<Lane*>(this) : &extra[i - 1]; }
+  DevBuf ref_bytes, ref_pk, ref_bad;       // device-resident reference (swb_set_reference)
   uint64_t ref_len = 0;
+  std::vector<ChunkEvents> chunk_ev;       // host path: one event set per chunk of the last call
+  swb::Counters* h_counters = nullptr;     // pinned, one slot per chunk
+  size_t h_counters_cap = 0;
+  size_t last_chunks = 0;
+  uint64_t chunk_bytes = 64ull << 20;      // ASCII bytes per chunk of a host batch (SWB_CHUNK_MB, swb_set_chunking)
+  uint64_t min_chunk_pairs = 16384;
   float last_ms[6] = {0, 0, 0, 0, 0, 0};
   int last_kernels = 0;
   uint64_t last_routing[2] = {0, 0};
@@ -84,9 +106,13 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device_id) != cudaSuccess) { delete c; return fail("cudaGetDeviceProperties failed"); }
   c->sm_count = p.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
-  for (auto& e : c->ev) cudaEventCreate(&e);
+  for (int i = 0; i < kLanes; ++i) {
+    Lane* l = c->lane(i);
+    if (cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
+    for (auto& e : l->ev) cudaEventCreate(&e);
+  }
   if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 7;
+  if (const char* v = std::getenv("SWB_CHUNK_MB")) { const long mb = std::atol(v); if (mb > 0) c->chunk_bytes = (uint64_t)mb << 20; }
   *out = c;
   return 0;
 }
@@ -95,77 +121,83 @@ void swb_destroy(swb_ctx* c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->st);
-  for (DevBuf* b : {&c->q_bytes, &c->r_bytes, &c->q_off, &c->r_off, &c->q_pk, &c->r_pk, &c->q_bad, &c->r_bad,
-                    &c->short_list, &c->short_desc, &c->generic_list, &c->counters, &c->out, &c->scratch, &c->misc,
-                    &c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->win_beg, &c->win_end}) b->release();
-  for (auto& e : c->ev) cudaEventDestroy(e);
-  cudaStreamDestroy(c->st);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < kLanes; ++i) {
+    Lane* l = c->lane(i);
+    l->release_all();
+    for (auto& e : l->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(l->st);
+  }
+  for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad}) b->release();
+  for (auto& ce : c->chunk_ev) for (auto& e : ce.ev) cudaEventDestroy(e);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
 }
 
 void* swb_stream(swb_ctx* c) { return c ? (void*)c->st : nullptr; }
 int   swb_set_short_variant(swb_ctx* c, int v) { if (!c) return fail("null ctx"); c->variant = v & 7; return 0; }
 
+int swb_set_chunking(swb_ctx* c, uint64_t chunk_bytes, uint64_t min_chunk_pairs)
+{
+  if (!c) return fail("null ctx");
+  if (chunk_bytes == 0 || min_chunk_pairs == 0) return fail("swb_set_chunking: sizes must be positive");
+  c->chunk_bytes = chunk_bytes; c->min_chunk_pairs = min_chunk_pairs;
+  return 0;
+}
+
 int swb_sync(swb_ctx* c)
 {
   if (!c) return fail("null ctx");
   CUDA_TRY(cudaSetDevice(c->device));
-  CUDA_TRY(cudaStreamSynchronize(c->st));
+  for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamSynchronize(c->lane(i)->st));
   return 0;
 }
 
 // ---- the device pipeline: everything after the inputs are resident in HBM ----
-// Windows are either CSR ranges of d_r (d_rend == d_rbeg + 1, packed here) or ranges of the resident,
-// already packed reference (ref_windows).
-static int run_device_pipeline(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
+// Runs on lane `l` (its stream, its arenas), events into `ev` (8 of them).  Windows are either CSR ranges of d_r
+// (d_rend == d_rbeg + 1, packed here) or ranges of the resident, already packed reference (ref_windows).
+static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
                                const uint8_t* d_r, const uint64_t* d_rbeg, const uint64_t* d_rend, uint64_t r_total,
-                               bool ref_windows,
-                               uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out)
+                               bool ref_windows, uint64_t n_pairs, uint32_t max_r_len, swb_result* d_out, int* kernels)
 {
-  (void)max_q_len;
   if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
   const uint64_t qw = (q_total + 15) / 16, rw = ref_windows ? 0 : (r_total + 15) / 16;
-  if (c->q_pk.reserve(qw * 4 + 64) || c->r_pk.reserve(rw * 4 + 64) ||
-      c->q_bad.reserve((qw + 31) / 32 * 4 + 64) || c->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
-      c->short_list.reserve(n_pairs * 4 + 64) || c->short_desc.reserve(n_pairs * sizeof(swb::ShortDesc) + 64) || c->generic_list.reserve(n_pairs * 4 + 64) ||
-      c->counters.reserve(sizeof(swb::Counters))) return 1;
+  if (l->q_pk.reserve(qw * 4 + 64) || l->r_pk.reserve(rw * 4 + 64) ||
+      l->q_bad.reserve((qw + 31) / 32 * 4 + 64) || l->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
+      l->short_list.reserve(n_pairs * 4 + 64) || l->short_desc.reserve(n_pairs * sizeof(swb::ShortDesc) + 64) ||
+      l->generic_list.reserve(n_pairs * 4 + 64) || l->counters.reserve(sizeof(swb::Counters))) return 1;
   // generic kernel: persistent grid, one boundary row of max_r_len ints per resident warp
   int ctas = c->sm_count * 4;
   const uint64_t stride = ((uint64_t)max_r_len + 32) & ~31ull;
   while (ctas > 1 && (uint64_t)ctas * 4 * stride * 4 > (2ull << 30)) ctas /= 2;
-  if (c->scratch.reserve((uint64_t)ctas * 4 * stride * 4)) return 1;
+  if (l->scratch.reserve((uint64_t)ctas * 4 * stride * 4)) return 1;
 
   swb::BatchView b;
   b.q_bytes = d_q; b.q_beg = d_qo; b.q_end = d_qo + 1; b.r_bytes = d_r; b.r_beg = d_rbeg; b.r_end = d_rend;
-  b.q_pk = c->q_pk.as<uint32_t>(); b.q_bad = c->q_bad.as<uint32_t>();
-  b.r_pk = ref_windows ? c->ref_pk.as<uint32_t>() : c->r_pk.as<uint32_t>();
-  b.r_bad = ref_windows ? c->ref_bad.as<uint32_t>() : c->r_bad.as<uint32_t>();
+  b.q_pk = l->q_pk.as<uint32_t>(); b.q_bad = l->q_bad.as<uint32_t>();
+  b.r_pk = ref_windows ? c->ref_pk.as<uint32_t>() : l->r_pk.as<uint32_t>();
+  b.r_bad = ref_windows ? c->ref_bad.as<uint32_t>() : l->r_bad.as<uint32_t>();
   b.n_pairs = n_pairs;
-  b.short_list = c->short_list.as<uint32_t>(); b.short_desc = c->short_desc.as<swb::ShortDesc>(); b.generic_list = c->generic_list.as<uint32_t>();
-  b.counters = c->counters.as<swb::Counters>(); b.out = d_out;
-  b.scratch = c->scratch.as<int32_t>(); b.scratch_stride = stride;
+  b.short_list = l->short_list.as<uint32_t>(); b.short_desc = l->short_desc.as<swb::ShortDesc>();
+  b.generic_list = l->generic_list.as<uint32_t>();
+  b.counters = l->counters.as<swb::Counters>(); b.out = d_out;
+  b.scratch = l->scratch.as<int32_t>(); b.scratch_stride = stride;
 
   int k = 0;
-  cudaStream_t st = c->st;
-  CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, sizeof(swb::Counters), st));
-  CUDA_TRY(cudaEventRecord(c->ev[0], st));
-  k += swb::launch_pack2bit(d_q, q_total, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
-  if (!ref_windows) k += swb::launch_pack2bit(d_r, r_total, c->r_pk.as<uint32_t>(), c->r_bad.as<uint32_t>(), st);
+  cudaStream_t st = l->st;
+  CUDA_TRY(cudaMemsetAsync(l->counters.p, 0, sizeof(swb::Counters), st));
+  CUDA_TRY(cudaEventRecord(ev[0], st));
+  k += swb::launch_pack2bit(d_q, q_total, l->q_pk.as<uint32_t>(), l->q_bad.as<uint32_t>(), st);
+  if (!ref_windows) k += swb::launch_pack2bit(d_r, r_total, l->r_pk.as<uint32_t>(), l->r_bad.as<uint32_t>(), st);
   k += swb::launch_classify(b, st);
-  CUDA_TRY(cudaEventRecord(c->ev[1], st));
+  CUDA_TRY(cudaEventRecord(ev[1], st));
   const uint32_t wcap = std::min<uint32_t>(std::max<uint32_t>(max_r_len, 1), swb::kShortMaxWindow);
   k += swb::launch_short(b, wcap, c->variant, c->sm_count, st);
-  CUDA_TRY(cudaEventRecord(c->ev[2], st));
-  {
-    // launch_generic uses sm_count*4 CTAs; honour the scratch clamp
-    swb::BatchView bg = b;
-    k += swb::launch_generic(bg, ctas / 4 > 0 ? ctas / 4 : 1, 0, st);
-  }
-  CUDA_TRY(cudaEventRecord(c->ev[3], st));
+  CUDA_TRY(cudaEventRecord(ev[2], st));
+  k += swb::launch_generic(b, ctas / 4 > 0 ? ctas / 4 : 1, 0, st);
+  CUDA_TRY(cudaEventRecord(ev[3], st));
   CUDA_TRY(cudaGetLastError());
-  c->last_kernels = k;
-  c->timings_pending = true;
+  *kernels += k;
   return 0;
 }
 
@@ -173,11 +205,111 @@ int swb_score_batch_device(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo,
                            const uint8_t* d_r, const uint64_t* d_ro, uint64_t r_total,
                            uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out)
 {
+  (void)max_q_len;
   if (!c) return fail("null ctx");
   CUDA_TRY(cudaSetDevice(c->device));
   c->host_path = false;
-  if (n_pairs == 0) { c->last_kernels = 0; c->timings_pending = false; return 0; }
-  return run_device_pipeline(c, d_q, d_qo, q_total, d_r, d_ro, d_ro + 1, r_total, false, n_pairs, max_q_len, max_r_len, d_out);
+  c->last_kernels = 0; c->last_chunks = 0;
+  if (n_pairs == 0) { c->timings_pending = false; return 0; }
+  if (run_device_pipeline(c, c, c->ev, d_q, d_qo, q_total, d_r, d_ro, d_ro + 1, r_total, false, n_pairs, max_r_len, d_out,
+                          &c->last_kernels)) return 1;
+  c->timings_pending = true;
+  return 0;
+}
+
+// ---- host batches: chunks of pairs pipelined over kLanes streams ----
+// Chunk k runs on lane k % kLanes: H2D of its bytes and offsets, offset rebase, the device pipeline, D2H of its
+// results.  While one lane computes, the next lane's H2D and the previous lane's D2H are in flight (one copy
+// engine per direction), so a large batch costs max(PCIe, kernels) instead of their sum.
+static int ensure_chunk_slots(swb_ctx* c, size_t n_chunks)
+{
+  while (c->chunk_ev.size() < n_chunks) {
+    ChunkEvents ce;
+    for (auto& e : ce.ev) CUDA_TRY(cudaEventCreate(&e));
+    c->chunk_ev.push_back(ce);
+  }
+  if (c->h_counters_cap < n_chunks) {
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    c->h_counters = nullptr; c->h_counters_cap = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_counters, sizeof(swb::Counters) * (n_chunks + 16), cudaHostAllocDefault));
+    c->h_counters_cap = n_chunks + 16;
+  }
+  return 0;
+}
+
+static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const uint64_t* qo,
+                            const uint8_t* r, const uint64_t* ro,                     /* CSR windows, or */
+                            const uint64_t* win_start, const uint32_t* win_len,       /* windows of the resident reference */
+                            uint64_t n_pairs, swb_result* out)
+{
+  const bool ref_windows = (r == nullptr && ro == nullptr);
+  if (qo[0] != 0 || (!ref_windows && ro[0] != 0)) return fail(std::string(who) + ": offsets must start at 0");
+  const uint64_t bytes_total = qo[n_pairs] + (ref_windows ? 0 : ro[n_pairs]);
+  uint64_t n_chunks = std::max<uint64_t>(1, (bytes_total + c->chunk_bytes - 1) / c->chunk_bytes);
+  uint64_t per = (n_pairs + n_chunks - 1) / n_chunks;
+  per = std::max<uint64_t>(per, std::min<uint64_t>(n_pairs, c->min_chunk_pairs));
+  n_chunks = (n_pairs + per - 1) / per;
+  if (ensure_chunk_slots(c, n_chunks)) return 1;
+  c->last_kernels = 0;
+
+  for (uint64_t ch = 0; ch < n_chunks; ++ch) {
+    const uint64_t p0 = ch * per, p1 = std::min(n_pairs, p0 + per), n = p1 - p0;
+    Lane* l = c->lane((int)(ch % kLanes));
+    cudaEvent_t* ev = c->chunk_ev[ch].ev;
+    cudaStream_t st = l->st;
+    uint32_t max_r = 0;
+    for (uint64_t k = p0; k < p1; ++k) {                      // validation + longest window of this chunk
+      if (qo[k + 1] < qo[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
+      if (qo[k + 1] - qo[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
+      if (ref_windows) {
+        if (win_start[k] + win_len[k] > c->ref_len) return fail(std::string(who) + ": window outside the reference");
+        max_r = std::max<uint32_t>(max_r, win_len[k]);
+      } else {
+        if (ro[k + 1] < ro[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
+        if (ro[k + 1] - ro[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
+        max_r = std::max<uint32_t>(max_r, (uint32_t)(ro[k + 1] - ro[k]));
+      }
+    }
+    const uint64_t qb = qo[p1] - qo[p0], rb = ref_windows ? 0 : ro[p1] - ro[p0];
+    if (l->q_bytes.reserve(qb + 64) || l->q_off.reserve((n + 1) * 8) || l->out.reserve(n * sizeof(swb_result))) return 1;
+    if (ref_windows) { if (l->win_beg.reserve(n * 8) || l->win_end.reserve(n * 8) || l->win_len.reserve(n * 4)) return 1; }
+    else             { if (l->r_bytes.reserve(rb + 64) || l->r_off.reserve((n + 1) * 8)) return 1; }
+
+    CUDA_TRY(cudaEventRecord(ev[4], st));
+    if (qb) CUDA_TRY(cudaMemcpyAsync(l->q_bytes.p, q + qo[p0], qb, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(l->q_off.p, qo + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    int k = 0;
+    if (ref_windows) {
+      CUDA_TRY(cudaMemcpyAsync(l->win_beg.p, win_start + p0, n * 8, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(l->win_len.p, win_len + p0, n * 4, cudaMemcpyHostToDevice, st));
+      k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], nullptr, 0, 0,
+                                     l->win_beg.as<uint64_t>(), l->win_len.as<uint32_t>(), l->win_end.as<uint64_t>(), n, st);
+    } else {
+      if (rb) CUDA_TRY(cudaMemcpyAsync(l->r_bytes.p, r + ro[p0], rb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(l->r_off.p, ro + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+      k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], l->r_off.as<uint64_t>(), n + 1, ro[p0],
+                                     nullptr, nullptr, nullptr, 0, st);
+    }
+    CUDA_TRY(cudaEventRecord(ev[5], st));
+    c->last_kernels += k;
+    if (ref_windows) {
+      if (run_device_pipeline(c, l, ev, l->q_bytes.as<uint8_t>(), l->q_off.as<uint64_t>(), qb, c->ref_bytes.as<uint8_t>(),
+                              l->win_beg.as<uint64_t>(), l->win_end.as<uint64_t>(), 0, true, n, max_r, l->out.as<swb_result>(),
+                              &c->last_kernels)) return 1;
+    } else {
+      if (run_device_pipeline(c, l, ev, l->q_bytes.as<uint8_t>(), l->q_off.as<uint64_t>(), qb, l->r_bytes.as<uint8_t>(),
+                              l->r_off.as<uint64_t>(), l->r_off.as<uint64_t>() + 1, rb, false, n, max_r, l->out.as<swb_result>(),
+                              &c->last_kernels)) return 1;
+    }
+    CUDA_TRY(cudaEventRecord(ev[6], st));
+    CUDA_TRY(cudaMemcpyAsync(out + p0, l->out.p, n * sizeof(swb_result), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters + ch, l->counters.p, sizeof(swb::Counters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(ev[7], st));
+  }
+  for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamSynchronize(c->lane(i)->st));
+  CUDA_TRY(cudaGetLastError());
+  c->host_path = true; c->last_chunks = (size_t)n_chunks; c->timings_pending = true;
+  return 0;
 }
 
 int swb_score_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro,
@@ -187,34 +319,8 @@ int swb_score_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint
   if (n_pairs == 0) return 0;
   if (!qo || !ro || !out) return fail("swb_score_batch: null pointer");
   CUDA_TRY(cudaSetDevice(c->device));
-  const uint64_t q_total = qo[n_pairs] - qo[0], r_total = ro[n_pairs] - ro[0];
-  if (qo[0] != 0 || ro[0] != 0) return fail("swb_score_batch: offsets must start at 0");
-  uint32_t max_q = 0, max_r = 0;
-  for (uint64_t k = 0; k < n_pairs; ++k) {
-    if (qo[k + 1] < qo[k] || ro[k + 1] < ro[k]) return fail("swb_score_batch: offsets must be non-decreasing");
-    const uint64_t a = qo[k + 1] - qo[k], b = ro[k + 1] - ro[k];
-    if (a > 0x7fffffffull || b > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
-    max_q = std::max<uint32_t>(max_q, (uint32_t)a); max_r = std::max<uint32_t>(max_r, (uint32_t)b);
-  }
-  if (c->q_bytes.reserve(q_total + 64) || c->r_bytes.reserve(r_total + 64) ||
-      c->q_off.reserve((n_pairs + 1) * 8) || c->r_off.reserve((n_pairs + 1) * 8) ||
-      c->out.reserve(n_pairs * sizeof(swb_result))) return 1;
-  cudaStream_t st = c->st;
-  CUDA_TRY(cudaEventRecord(c->ev[4], st));
-  if (q_total) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, q_total, cudaMemcpyHostToDevice, st));
-  if (r_total) CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, r, r_total, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(c->q_off.p, qo, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(c->r_off.p, ro, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaEventRecord(c->ev[5], st));
-  if (run_device_pipeline(c, c->q_bytes.as<uint8_t>(), c->q_off.as<uint64_t>(), q_total,
-                          c->r_bytes.as<uint8_t>(), c->r_off.as<uint64_t>(), c->r_off.as<uint64_t>() + 1, r_total, false,
-                          n_pairs, max_q, max_r, c->out.as<swb_result>())) return 1;
-  CUDA_TRY(cudaEventRecord(c->ev[6], st));
-  CUDA_TRY(cudaMemcpyAsync(out, c->out.p, n_pairs * sizeof(swb_result), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaEventRecord(c->ev[7], st));
-  c->host_path = true;
-  CUDA_TRY(cudaStreamSynchronize(st));
-  return 0;
+  static const uint8_t empty = 0;
+  return score_host_batch(c, "swb_score_batch", q ? q : &empty, qo, r ? r : &empty, ro, nullptr, nullptr, n_pairs, out);
 }
 
 // ---- reads against windows of a device-resident reference ----
@@ -240,36 +346,8 @@ int swb_score_batch_vs_reference(swb_ctx* c, const uint8_t* q, const uint64_t* q
   if (n_pairs == 0) return 0;
   if (!qo || !win_start || !win_len || !out) return fail("swb_score_batch_vs_reference: null pointer");
   CUDA_TRY(cudaSetDevice(c->device));
-  if (qo[0] != 0) return fail("swb_score_batch_vs_reference: offsets must start at 0");
-  const uint64_t q_total = qo[n_pairs];
-  uint32_t max_q = 0, max_r = 0;
-  std::vector<uint64_t> wend(n_pairs);
-  for (uint64_t k = 0; k < n_pairs; ++k) {
-    if (qo[k + 1] < qo[k]) return fail("swb_score_batch_vs_reference: offsets must be non-decreasing");
-    if (win_start[k] + win_len[k] > c->ref_len) return fail("swb_score_batch_vs_reference: window outside the reference");
-    const uint64_t a = qo[k + 1] - qo[k];
-    if (a > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
-    max_q = std::max<uint32_t>(max_q, (uint32_t)a); max_r = std::max<uint32_t>(max_r, win_len[k]);
-    wend[k] = win_start[k] + win_len[k];
-  }
-  if (c->q_bytes.reserve(q_total + 64) || c->q_off.reserve((n_pairs + 1) * 8) || c->win_beg.reserve(n_pairs * 8) ||
-      c->win_end.reserve(n_pairs * 8) || c->out.reserve(n_pairs * sizeof(swb_result))) return 1;
-  cudaStream_t st = c->st;
-  CUDA_TRY(cudaEventRecord(c->ev[4], st));
-  if (q_total) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, q_total, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(c->q_off.p, qo, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(c->win_beg.p, win_start, n_pairs * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(c->win_end.p, wend.data(), n_pairs * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaEventRecord(c->ev[5], st));
-  if (run_device_pipeline(c, c->q_bytes.as<uint8_t>(), c->q_off.as<uint64_t>(), q_total,
-                          c->ref_bytes.as<uint8_t>(), c->win_beg.as<uint64_t>(), c->win_end.as<uint64_t>(), 0, true,
-                          n_pairs, max_q, max_r, c->out.as<swb_result>())) return 1;
-  CUDA_TRY(cudaEventRecord(c->ev[6], st));
-  CUDA_TRY(cudaMemcpyAsync(out, c->out.p, n_pairs * sizeof(swb_result), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaEventRecord(c->ev[7], st));
-  c->host_path = true;
-  CUDA_TRY(cudaStreamSynchronize(st));      // also keeps wend alive until the copy is done
-  return 0;
+  static const uint8_t empty = 0;
+  return score_host_batch(c, "swb_score_batch_vs_reference", q ? q : &empty, qo, nullptr, nullptr, win_start, win_len, n_pairs, out);
 }
 
 int swb_score_pair(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, swb_result* out)
@@ -284,19 +362,38 @@ int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
   if (!c) return fail("null ctx");
   CUDA_TRY(cudaSetDevice(c->device));
   if (c->timings_pending) {
-    CUDA_TRY(cudaStreamSynchronize(c->st));
-    cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
-    cudaEventElapsedTime(&c->last_ms[2], c->ev[2], c->ev[3]);
-    cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[3]);
-    c->last_ms[4] = c->last_ms[5] = 0;
-    if (c->host_path) {
-      cudaEventElapsedTime(&c->last_ms[4], c->ev[4], c->ev[5]);
-      cudaEventElapsedTime(&c->last_ms[5], c->ev[6], c->ev[7]);
+    for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamSynchronize(c->lane(i)->st));
+    for (float& v : c->last_ms) v = 0;
+    c->last_routing[0] = c->last_routing[1] = 0;
+    if (!c->host_path) {
+      cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+      cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
+      cudaEventElapsedTime(&c->last_ms[2], c->ev[2], c->ev[3]);
+      cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[3]);
+      swb::Counters h;
+      CUDA_TRY(cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+      c->last_routing[0] = h.n_short; c->last_routing[1] = h.n_generic;
+    } else {
+      // sums over the chunks of the call (chunks overlap in time, so [3] is the span first event -> last event)
+      for (size_t ch = 0; ch < c->last_chunks; ++ch) {
+        cudaEvent_t* ev = c->chunk_ev[ch].ev;
+        float t;
+        cudaEventElapsedTime(&t, ev[0], ev[1]); c->last_ms[0] += t;
+        cudaEventElapsedTime(&t, ev[1], ev[2]); c->last_ms[1] += t;
+        cudaEventElapsedTime(&t, ev[2], ev[3]); c->last_ms[2] += t;
+        cudaEventElapsedTime(&t, ev[4], ev[5]); c->last_ms[4] += t;
+        cudaEventElapsedTime(&t, ev[6], ev[7]); c->last_ms[5] += t;
+        c->last_routing[0] += c->h_counters[ch].n_short; c->last_routing[1] += c->h_counters[ch].n_generic;
+      }
+      if (c->last_chunks) {
+        float span = 0;
+        for (size_t ch = 0; ch < c->last_chunks; ++ch) {      // lanes finish out of order: take the latest end
+          float t; cudaEventElapsedTime(&t, c->chunk_ev[0].ev[4], c->chunk_ev[ch].ev[7]);
+          span = std::max(span, t);
+        }
+        c->last_ms[3] = span;
+      }
     }
-    swb::Counters h;
-    CUDA_TRY(cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
-    c->last_routing[0] = h.n_short; c->last_routing[1] = h.n_generic;
     c->timings_pending = false;
   }
   if (ms) std::memcpy(ms, c->last_ms, sizeof(c->last_ms));

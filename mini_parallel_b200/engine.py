@@ -151,6 +151,10 @@ class Engine:
     def set_short_variant(self, v):
         self._check(self._lib.swb_set_short_variant(self._h, int(v)))
 
+    def set_chunking(self, chunk_bytes, min_chunk_pairs=16384):
+        """Chunk size of the pipelined host path (swb_set_chunking)."""
+        self._check(self._lib.swb_set_chunking(self._h, int(chunk_bytes), int(min_chunk_pairs)))
+
     def last_timings(self):
         ms = (ctypes.c_float * 6)()
         k = ctypes.c_int()

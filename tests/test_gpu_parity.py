@@ -236,3 +236,51 @@ def test_config2_full_size_device_resident(engine):
     finally:
         for p in (dq, dqo, dr, dro, dout):
             engine.free_device(p)
+
+
+def test_host_path_is_chunked_over_streams_and_stays_exact(engine):
+    """swb_score_batch cuts a host batch into chunks pipelined over three streams; every chunk boundary
+    (offset rebase, result placement, routing sums) must be invisible in the results."""
+    rng = np.random.default_rng(900)
+    reads, wins = _pairs(rng, 5000, (1, 160), (1, 700))
+    reads[17] = b""                                               # empty read inside a chunk
+    wins[4099] = b""                                              # empty window at a chunk boundary (1024-pair chunks)
+    reads[2048] = b"ACGTN" * 30                                   # generic path inside a chunk
+    q, qo = to_csr(reads)
+    r, ro = to_csr(wins)
+    exp = ol.batch(q, qo, r, ro, threads=8, simd=False)
+    try:
+        for chunk_bytes, min_pairs in ((1 << 14, 1), (1 << 16, 1024), (1 << 20, 999), (64 << 20, 16384)):
+            engine.set_chunking(chunk_bytes, min_pairs)
+            got = engine.score_batch_csr(q, qo, r, ro)
+            assert np.array_equal(got, exp), (chunk_bytes, min_pairs)
+            rt = engine.last_routing()
+            assert rt["short"] + rt["generic"] == 4998, rt      # the two empty pairs are routed nowhere
+            assert rt["generic"] >= 1
+    finally:
+        engine.set_chunking(64 << 20, 16384)
+
+
+def test_reference_windows_chunked(engine):
+    rng = np.random.default_rng(901)
+    ref = _rand(rng, 200_000)
+    n = 6000
+    start = rng.integers(0, 200_000 - 600, n).astype(np.uint64)
+    wlen = rng.integers(1, 600, n).astype(np.uint32)
+    reads = []
+    for k in range(n):
+        o = int(start[k]) + int(rng.integers(0, max(1, int(wlen[k]) - 100)))
+        rd = ref[o:o + int(rng.integers(1, 160))].copy()
+        reads.append(rd)
+    q, qo = to_csr(reads)
+    wins = [ref[int(s):int(s) + int(l)] for s, l in zip(start, wlen)]
+    r, ro = to_csr(wins)
+    exp = ol.batch(q, qo, r, ro, threads=8, simd=False)
+    engine.set_reference(ref)
+    try:
+        for chunk_bytes, min_pairs in ((1 << 15, 1), (64 << 20, 16384)):
+            engine.set_chunking(chunk_bytes, min_pairs)
+            got = engine.score_batch_vs_reference(q, qo, start, wlen)
+            assert np.array_equal(got, exp), (chunk_bytes, min_pairs)
+    finally:
+        engine.set_chunking(64 << 20, 16384)
