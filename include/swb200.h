@@ -92,8 +92,9 @@ int  swb_synth_device(swb_ctx*, uint64_t first_pair, uint64_t n_pairs, uint32_t 
  * context's stream (ms): [0] pack, [1] short-read kernel, [2] generic kernel, [3] total device span,
  * [4] h2d, [5] d2h.  Also the number of kernels launched by that call. */
 int  swb_last_timings(swb_ctx*, float* ms /* 6 */, int* kernels_launched);
-/* Pairs routed to each path by the last call: [0] short int16x2 path, [1] generic 32-bit path. */
-int  swb_last_routing(swb_ctx*, uint64_t* counts /* 2 */);
+/* Pairs routed to each path by the last call: [0] short-read int16x2 kernel, [1] generic 32-bit byte-compare kernel
+ * (any bytes, any length), [2] long-pair 32-bit banded wavefront kernel (ACGT-only pairs beyond the short limits). */
+int  swb_last_routing(swb_ctx*, uint64_t* counts /* 3 */);
 
 /* The packing stage alone on device-resident bytes (bench: HBM roofline of the packing kernel). */
 int  swb_pack2bit_device(swb_ctx*, const uint8_t* d_bytes, uint64_t n, uint32_t* d_words, uint32_t* d_bitmap);

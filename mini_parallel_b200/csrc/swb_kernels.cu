@@ -108,6 +108,9 @@ classify_kernel(BatchView b)
     } else if (n <= kShortMaxRead && mm <= kShortMaxWindow &&
                !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1)) {
       cls = CLASS_SHORT; m = (uint32_t)mm;
+    } else if (n <= kLongMaxLen && mm <= kLongMaxLen &&
+               !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1)) {
+      cls = CLASS_LONG;
     } else {
       cls = CLASS_GENERIC;
     }
@@ -116,13 +119,16 @@ classify_kernel(BatchView b)
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t ms = __ballot_sync(0xffffffffu, cls == CLASS_SHORT);
   const uint32_t mg = __ballot_sync(0xffffffffu, cls == CLASS_GENERIC);
-  uint32_t base_s = 0, base_g = 0;
+  const uint32_t ml = __ballot_sync(0xffffffffu, cls == CLASS_LONG);
+  uint32_t base_s = 0, base_g = 0, base_l = 0;
   if (lane == 0) {
     if (ms) base_s = atomicAdd(&b.counters->n_short, __popc(ms));
     if (mg) base_g = atomicAdd(&b.counters->n_generic, __popc(mg));
+    if (ml) base_l = atomicAdd(&b.counters->n_long, __popc(ml));
   }
   base_s = __shfl_sync(0xffffffffu, base_s, 0);
   base_g = __shfl_sync(0xffffffffu, base_g, 0);
+  base_l = __shfl_sync(0xffffffffu, base_l, 0);
   const uint32_t below = (1u << lane) - 1;
   if (cls == CLASS_SHORT) {
     const uint32_t slot = base_s + __popc(ms & below);
@@ -133,6 +139,7 @@ classify_kernel(BatchView b)
     d[1] = make_uint4((uint32_t)(b.q_end[k] - q0), m, (uint32_t)k, 0u);
   }
   if (cls == CLASS_GENERIC) b.generic_list[base_g + __popc(mg & below)] = (uint32_t)k;
+  if (cls == CLASS_LONG)    b.long_list[base_l + __popc(ml & below)] = (uint32_t)k;
   uint32_t wm = m;
   for (int o = 16; o; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
   if (lane == 0 && wm) atomicMax(&b.counters->max_short_window, wm);
@@ -692,6 +699,317 @@ static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
 }
 
 // =====================================================================================
+// Long-pair kernel (sw_long_kernel): intra-task anti-diagonal wavefront, one warp per pair,
+// 32-bit cells, for ACGT-only pairs that the int16x2 kernel cannot take (reads > 160 rows,
+// windows > 4096 columns, 10 kb x 10 kb pairs).  Same cell arithmetic as the streaming kernel
+// with 32-bit DPX (VIADDMNMX / VIMNMX3), one pair per word:  V = 256*(H + 2*tau), 8 tag bits,
+// blocks of up to 254 steps, sub = {1536, 768} from a 9-entry per-lane table (idx = (3-q) + w).
+//
+// The read is cut into BANDS of 32*K rows.  The bands of a pair -- and then the next pair the warp
+// steals -- stream through the warp exactly like pairs stream through a group in
+// sw_stream_kernel: lane L enters the next band K steps after lane L-1, so the wavefront of
+// a 10 kb x 10 kb pair (32 bands) fills and drains once, not 32 times.  The last row of a band
+// leaves lane 31 one value per step into a per-warp scratch row in global memory (unbiased);
+// the ring refill of the next band loads it back next to the window codes, and lane 0 reads it as
+// its "row above" (zero for the first band).  A band's column stride is at least 3 wavefronts
+// (3*32*K) so the stored value is always older than the refill that needs it.
+// =====================================================================================
+struct LongArgs {
+  const uint32_t* q_pk; const uint32_t* r_pk;
+  const uint64_t* q_beg; const uint64_t* q_end; const uint64_t* r_beg; const uint64_t* r_end;
+  const uint32_t* list; Counters* counters;
+  swb_result* out; int32_t* scratch; uint64_t scratch_stride;
+};
+
+struct LongJob {                     // one band of one pair (uniform per warp, lives in shared memory)
+  uint64_t q0, r0;                   // first base of the band's rows / of the window
+  uint32_t rows, n2;                 // valid rows in this band (<= 32*K; 0 = dummy job), window length
+  uint32_t row0;                     // first row of the band inside the read
+  uint32_t pair;                     // pair index in the batch
+  uint32_t base_it;                  // iteration at which lane 0 enters the job (stream column = base_it*K)
+  uint32_t ipp;                      // iterations per job (column stride / K)
+  uint32_t first, last;              // first / last band of its pair
+};
+
+
+template <int K, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+sw_long_kernel(LongArgs a)
+{
+  static_assert(K % 2 == 0 && K <= 32, "K even, at most 32 codes per 64-bit code word");
+  constexpr int G = 32;
+  constexpr int NPAD  = G * K;
+  constexpr int TB = 8;                                  // tag bits
+  constexpr int BLOCK = (254 / K) * K;
+  constexpr int IPB   = BLOCK / K;
+  constexpr uint32_t SC = 1u << TB;                      // value scale
+  constexpr uint32_t REBASE = 2u * SC * BLOCK;
+  constexpr int RSLOTS = 4 * G;
+  constexpr int RING = RSLOTS * K;
+  constexpr uint32_t WPADV = 4u << 7;
+  constexpr uint32_t NOEVENT = 0xFFFFFFFFu;
+  constexpr uint64_t M21 = (1ull << 21) - 1;
+  constexpr int JT = 8;                                  // live job table entries
+
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint32_t* lut = reinterpret_cast<uint32_t*>(smem);     // 9 entries x 32 lanes
+  for (uint32_t x = threadIdx.x; x < 9 * 32; x += blockDim.x) lut[x] = ((x >> 5) == 3) ? 6u * SC : 3u * SC;
+  __syncthreads();
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, L = lane;
+  constexpr size_t WARP_BYTES = (size_t)RING * 2 + (size_t)RING * 4 + JT * sizeof(LongJob);
+  uint8_t* wbase = smem + 9 * 128 + warp * WARP_BYTES;
+  uint32_t* bring = reinterpret_cast<uint32_t*>(wbase);                       // boundary row values per stream column
+  uint16_t* ring  = reinterpret_cast<uint16_t*>(wbase + (size_t)RING * 4);    // window codes per stream column
+  LongJob*  jobs  = reinterpret_cast<LongJob*>(wbase + (size_t)RING * 6);
+  uint32_t* qnext = reinterpret_cast<uint32_t*>(smem + 9 * 128 + 4 * WARP_BYTES) + threadIdx.x;
+  uint32_t* csave = qnext + K * 128;
+  const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + 4u * lane;
+  int32_t* scratch = a.scratch + (uint64_t)(blockIdx.x * 4 + warp) * a.scratch_stride;
+  const uint32_t n_list = a.counters->n_long;
+
+  // ---- job creation (uniform): next band of the current pair, else steal the next pair ----
+  uint32_t created = 0, next_base_it = 0;                // jobs created so far, base_it of the next one
+  uint32_t cp_pair = 0, cp_n1 = 0, cp_n2 = 0, cp_row = 0; uint64_t cp_q0 = 0, cp_r0 = 0;   // pair being cut into bands
+  bool cp_live = false, exhausted = false;
+  uint32_t first_dummy = NOEVENT;
+  auto create_job = [&]() {
+    if (!cp_live && !exhausted) {
+      uint32_t item = 0;
+      if (lane == 0) item = atomicAdd(&a.counters->long_cursor, 1u);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item < n_list) {
+        cp_pair = a.list[item];
+        cp_q0 = a.q_beg[cp_pair]; cp_r0 = a.r_beg[cp_pair];
+        cp_n1 = (uint32_t)(a.q_end[cp_pair] - cp_q0); cp_n2 = (uint32_t)(a.r_end[cp_pair] - cp_r0);
+        cp_row = 0; cp_live = true;
+      } else {
+        exhausted = true;
+      }
+    }
+    LongJob j;
+    if (cp_live) {
+      j.q0 = cp_q0 + cp_row; j.r0 = cp_r0; j.n2 = cp_n2; j.row0 = cp_row; j.pair = cp_pair;
+      j.rows = min(cp_n1 - cp_row, (uint32_t)NPAD);
+      j.first = cp_row == 0; j.last = cp_row + NPAD >= cp_n1;
+      uint32_t wp = (cp_n2 + 2 * K - 2) / K * K;
+      if (wp < 3 * NPAD + K) wp = 3 * NPAD + K;
+      j.ipp = wp / K;
+      cp_row += NPAD;
+      if (j.last) cp_live = false;
+    } else {
+      if (first_dummy == NOEVENT) first_dummy = created;
+      j.q0 = 0; j.r0 = 0; j.n2 = 0; j.row0 = 0; j.pair = 0; j.rows = 0; j.first = 1; j.last = 1; j.ipp = 3 * G + 1;
+    }
+    j.base_it = next_base_it;
+    next_base_it += j.ipp;
+    if (lane == 0) jobs[created % JT] = j;
+    ++created;
+    __syncwarp();
+  };
+
+  // ---- ring refill: columns [k*NPAD + L*K, +K) of the stream: window codes + boundary values ----
+  uint32_t stg_job = 0;                                  // job the lane's next refill piece belongs to
+  auto stage = [&](uint32_t chunk) {
+    const uint32_t it0 = chunk * G + L;                  // the piece starts at stream column it0*K
+    while (it0 >= jobs[stg_job % JT].base_it + jobs[stg_job % JT].ipp) ++stg_job;
+    const LongJob j = jobs[stg_job % JT];
+    const uint32_t col0 = (it0 - j.base_it) * K;
+    const int32_t v = j.rows ? (int32_t)j.n2 - (int32_t)col0 : 0;       // valid columns in this piece
+    uint64_t cw = 0;
+    if (v > 0) cw = codes32(a.r_pk, j.r0 + col0);
+    const uint32_t slot = (chunk * G + G + L) & (RSLOTS - 1);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * K);
+    uint32_t* bdst = bring + slot * K;
+    const bool has_above = v > 0 && !j.first;
+#pragma unroll
+    for (int x = 0; x < K; x += 2) {
+      const uint32_t w0 = x < v ? (uint32_t)(cw >> (2 * x)) & 3u : 4u, w1 = x + 1 < v ? (uint32_t)(cw >> (2 * x + 2)) & 3u : 4u;
+      dst[x >> 1] = (w0 << 7) | (w1 << 23);
+      bdst[x]     = (has_above && x < v)     ? (uint32_t)__ldcg(scratch + col0 + x)     : 0u;
+      bdst[x + 1] = (has_above && x + 1 < v) ? (uint32_t)__ldcg(scratch + col0 + x + 1) : 0u;
+    }
+  };
+
+  // ---- query codes of the lane's K rows in job jn, parked in shared memory until the lane switches ----
+  uint32_t Q[K];
+  auto load_query = [&](uint32_t jn, bool to_regs) {
+    const LongJob j = jobs[jn % JT];
+    const int32_t v = (int32_t)j.rows - (int32_t)(K * L);
+    uint64_t cq = 0;
+    if (v > 0) cq = codes32(a.q_pk, j.q0 + K * L);
+#pragma unroll
+    for (int m = 0; m < K; ++m) {
+      const uint32_t qc = m < v ? 3u - ((uint32_t)(cq >> (2 * m)) & 3u) : 4u;
+      const uint32_t val = lut_lane + (qc << 7);
+      if (to_regs) Q[m] = val; else qnext[m * 128] = val;
+    }
+  };
+
+  // ---- prologue ----
+  create_job(); create_job(); create_job();
+  if (jobs[0].rows == 0) return;                         // nothing to steal for this warp
+  {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ring + L * K);
+#pragma unroll
+    for (int x = 0; x < K / 2; ++x) dst[x] = WPADV | (WPADV << 16);
+#pragma unroll
+    for (int x = 0; x < K; ++x) bring[L * K + x] = 0;
+  }
+  stage(0);
+  load_query(0, true);
+  load_query(1, false);
+  __syncwarp();
+
+  uint32_t A[K], B[K], W[K], cur[K];
+#pragma unroll
+  for (int m = 0; m < K; ++m) { A[m] = 0u - 4u * SC; B[m] = 0u - 2u * SC; W[m] = WPADV; cur[m] = 0; }
+  uint64_t rec = 0, prev = 0, pair_best = 0;
+  uint32_t floor_ = 0, fm1 = 0u - 2u * SC, upPrev = 0u - 4u * SC;
+  uint32_t e = (uint32_t)(BLOCK - 1);
+  int32_t blockStart = 0;
+  uint32_t head = 0, tail = 0, ljob = 0;                 // job of lane 0 / of lane 31 (uniform), of this lane
+  uint32_t it_head = jobs[1].base_it, sw_it = jobs[1].base_it + L, fin_it = jobs[1].base_it + (G - 1);
+  uint32_t stage_it = 0, stage_k = 1;
+  // per-lane context of the job the lane is in: key offset and what lane 31 stores
+  int32_t jobCol = 0;                                    // stream column of the job's column 0
+  uint32_t rowBase = K * L;                              // absolute row of slot 0
+  uint32_t store_n2 = jobs[0].last ? 0u : jobs[0].n2;    // lane 31: columns to park for the next band
+  int bit = 0;
+
+  // key = H << 42 | (M21 - i) << 21 | (M21 - NPAD - j)
+  auto fold_word = [&](uint32_t c, uint32_t i, int32_t tcol, uint64_t& r) {
+    const uint32_t H = c >> TB, tag = c & (SC - 1);
+    const int32_t j = tcol - (int32_t)tag;               // tcol = column of this slot at tag 0
+    const uint64_t key = ((uint64_t)H << 42) | ((M21 - i) << 21) | (uint64_t)(uint32_t)((int32_t)M21 - NPAD - j);
+    r = max(r, key);
+  };
+
+  for (uint32_t it = 0;; ++it) {
+    // ---- events at the iteration boundary ----
+    if (bit == IPB) {                                    // block end (all lanes)
+      bit = 0;
+      const int32_t tcol = blockStart + (BLOCK - 1) - (int32_t)(K * L) - jobCol;
+#pragma unroll
+      for (int m = 0; m < K; ++m) {
+        fold_word(cur[m], rowBase + m, tcol - m, rec);
+        cur[m] = 0;
+        A[m] -= REBASE; B[m] -= REBASE;
+      }
+      upPrev -= REBASE;
+      floor_ = 0; fm1 = 0u - 2u * SC;
+      e = (uint32_t)(BLOCK - 1);
+      blockStart += BLOCK;
+    }
+    if (it == stage_it) {                                // refill the ring one chunk ahead (all lanes)
+      stage(stage_k);
+      ++stage_k; stage_it += G;
+      __syncwarp();
+    }
+    if (it + 1 == it_head) load_query(head + 1, false);  // every lane has taken the codes of job `head` (all lanes)
+    if (it == it_head) {                                 // lane 0 enters job head+1: look one more job ahead (all lanes)
+      ++head;
+      create_job();
+      it_head = jobs[(head + 1) % JT].base_it;
+    }
+    if (it == sw_it) {                                   // this lane enters its next job (one lane: park / fetch / reset)
+      ++ljob;
+      const LongJob j = jobs[ljob % JT];
+      prev = rec; rec = 0;
+      jobCol = (int32_t)(j.base_it * K); rowBase = j.row0 + K * L;
+      store_n2 = j.last ? 0u : j.n2;
+      sw_it = jobs[(ljob + 1) % JT].base_it + L;         // jobs are created two ahead of lane 0
+      const uint32_t z2 = floor_ - 4u * SC;
+#pragma unroll
+      for (int m = 0; m < K; ++m) {
+        csave[m * 128] = cur[m]; cur[m] = 0;
+        Q[m] = qnext[m * 128];
+        A[m] = z2; B[m] = fm1;
+      }
+    }
+    if (it == fin_it) {                                  // every lane has left job `tail` (all lanes)
+      const LongJob j = jobs[tail % JT];
+      {
+        const uint32_t it_sw = it - (G - 1) + L;         // the iteration at which this lane parked its trackers
+        const int32_t tcol = (int32_t)(it_sw / IPB) * BLOCK + (BLOCK - 1) - (int32_t)(K * L) - (int32_t)(j.base_it * K);
+#pragma unroll
+        for (int m = 0; m < K; ++m) fold_word(csave[m * 128], j.row0 + K * L + m, tcol - m, prev);
+      }
+      uint64_t k = prev;
+#pragma unroll
+      for (int o = 16; o; o >>= 1) k = max(k, __shfl_xor_sync(0xffffffffu, k, o));
+      pair_best = j.first ? k : max(pair_best, k);
+      if (j.last && j.rows && lane == 0) {
+        const uint32_t sc = (uint32_t)(pair_best >> 42);
+        swb_result r{0, -1, -1};
+        if (sc) r = swb_result{(int32_t)sc, (int32_t)(M21 - ((pair_best >> 21) & M21)), (int32_t)M21 - NPAD - (int32_t)(pair_best & M21)};
+        a.out[j.pair] = r;
+      }
+      ++tail;
+      if (tail == first_dummy) break;                    // every real job of this warp is written
+      fin_it = jobs[(tail + 1) % JT].base_it + (G - 1);
+    }
+    ++bit;
+
+    // ---- K steps of the wavefront ----
+    const uint32_t slot = (it + G - L) & (RSLOTS - 1);
+    const uint16_t* wp = ring + slot * K;
+    const uint32_t* bp = bring + ((it + G) & (RSLOTS - 1)) * K;     // lane 0's columns
+    const int32_t scol = (int32_t)(it * K) - (NPAD - 1) - jobCol;   // column of lane 31's last slot at step 0
+#pragma unroll
+    for (int u = 0; u < K; ++u) {
+      W[u] = wp[u];
+      uint32_t up = __shfl_up_sync(0xffffffffu, (u & 1) ? A[K - 1] : B[K - 1], 1);
+      if (L == 0) up = bp[u] + fm1;
+#pragma unroll
+      for (int m = K - 1; m >= 0; --m) {
+        const uint32_t x = Q[m] + W[(u - m + K) % K];
+        uint32_t sub;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(sub) : "r"(x));
+        uint32_t d, uu, l;
+        if (u & 1) { d = m ? B[m - 1] : upPrev; uu = m ? A[m - 1] : up; l = A[m]; }
+        else       { d = m ? A[m - 1] : upPrev; uu = m ? B[m - 1] : up; l = B[m]; }
+        const uint32_t t1 = (uint32_t)__viaddmax_s32((int32_t)d, (int32_t)sub, (int32_t)uu);
+        const uint32_t h  = (uint32_t)__vimax3_s32((int32_t)t1, (int32_t)l, (int32_t)floor_);
+        if (u & 1) B[m] = h; else A[m] = h;
+        cur[m] = (uint32_t)__viaddmax_s32((int32_t)h, (int32_t)e, (int32_t)cur[m]);
+      }
+      if (L == G - 1 && (uint32_t)(scol + u) < store_n2)
+        scratch[scol + u] = (int32_t)(((u & 1) ? B[K - 1] : A[K - 1]) - floor_);
+      upPrev = up;
+      fm1 = floor_;
+      floor_ += 2u * SC;
+      e -= 2u * SC + 1u;
+    }
+  }
+}
+
+template <int K, int MINB>
+static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
+{
+  LongArgs a;
+  a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.q_beg = b.q_beg; a.q_end = b.q_end; a.r_beg = b.r_beg; a.r_end = b.r_end;
+  a.list = b.long_list; a.counters = b.counters; a.out = b.out; a.scratch = b.scratch; a.scratch_stride = b.scratch_stride;
+  constexpr size_t RING = 4 * 32 * K;
+  const size_t smem = 9 * 128 + 4 * (RING * 6 + 8 * sizeof(LongJob)) + (size_t)2 * K * 128 * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(sw_long_kernel<K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  sw_long_kernel<K, MINB><<<ctas, 128, smem, st>>>(a);
+  return 1;
+}
+
+int long_ctas_per_sm() { return 4; }
+
+// persistent grid (ctas = a multiple of the SM count unless the scratch clamp reduced it), work-stealing over the long list
+int launch_long(const BatchView& b, int ctas, cudaStream_t st)
+{
+  return launch_long_t<10, 4>(b, ctas, st);
+}
+
+// =====================================================================================
 // Generic 32-bit kernel: one warp per pair, any length, any bytes (raw byte equality).
 // Anti-diagonal wavefront: lane L holds KG rows of a 32*KG-row band, slot m of lane L
 // computes cell (i, j = t - (KG*L+m)) at step t; the row above a lane's first row comes
@@ -798,7 +1116,7 @@ int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cud
 
 __global__ void single_pair_setup_kernel(Counters* c, uint32_t* list)
 {
-  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; list[0] = 0;
+  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; list[0] = 0;
 }
 
 int launch_last_row_max(const uint8_t*, uint64_t, const uint8_t*, uint64_t, int32_t*, int32_t*, cudaStream_t)

@@ -10,17 +10,21 @@ namespace swb {
 constexpr int kMatch = 2, kMismatch = -1, kGap = -2;
 
 // ---- routing classes written by classify_pairs ----
-enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2 };
+enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2, CLASS_LONG = 3 };
 
 // Limits of the int16x2 inter-task kernel (see sw_short_kernel).
 constexpr uint32_t kShortMaxRead   = 160;    // rows held by one lane group (G x K)
 constexpr uint32_t kShortMaxWindow = 4096;   // columns staged in shared memory per group
+constexpr uint32_t kLongMaxLen = (1u << 20) - 4096;   // rows / columns the 64-bit end-cell key of sw_long_kernel can hold
 
 struct Counters {             // device-resident, zeroed per batch
   uint32_t n_short;           // pairs routed to the int16x2 kernel
   uint32_t n_generic;         // pairs routed to the 32-bit kernel
   uint32_t max_short_window;  // longest window among the short pairs
   uint32_t generic_cursor;    // work-stealing cursor of the generic kernel
+  uint32_t n_long;            // ACGT-only pairs too long for the int16x2 kernel: 32-bit banded wavefront kernel
+  uint32_t long_cursor;       // work-stealing cursor of the long kernel
+  uint32_t pad[2];
 };
 
 struct ShortDesc {            // one entry per short-listed pair, written by classify_kernel (32 B, 16-aligned)
@@ -40,6 +44,7 @@ struct BatchView {            // everything the kernels need about one batch (de
   uint32_t*       short_list;   // pair ids, n_short entries
   ShortDesc*      short_desc;   // descriptors, same order as short_list
   uint32_t*       generic_list; // pair ids, n_generic entries
+  uint32_t*       long_list;    // pair ids, n_long entries
   Counters*       counters;
   swb_result*     out;
   int32_t*        scratch;      // generic kernel: one boundary row per resident warp
@@ -53,6 +58,7 @@ int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_
                          const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st);
 int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st);
 int launch_generic(const BatchView& b, int sm_count, int warps_resident, cudaStream_t st);
+int launch_long(const BatchView& b, int ctas, cudaStream_t st);
 int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32_t wgs, uint64_t groups,
                       int32_t* result, cudaStream_t st);
 int launch_last_row_max(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,

@@ -165,9 +165,9 @@ class Engine:
         return d
 
     def last_routing(self):
-        c = (ctypes.c_uint64 * 2)()
+        c = (ctypes.c_uint64 * 3)()
         self._check(self._lib.swb_last_routing(self._h, c))
-        return {"short": int(c[0]), "generic": int(c[1])}
+        return {"short": int(c[0]), "generic": int(c[1]), "long": int(c[2])}
 
     @property
     def stream(self):

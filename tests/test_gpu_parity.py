@@ -73,7 +73,7 @@ def test_short_path_uniform_150x500(engine, variant):
     rng = np.random.default_rng(100 + variant)
     engine.set_short_variant(variant)
     _assert_parity(engine, *_pairs(rng, 4001, (150, 150), (500, 500)))           # odd count: last group holds one pair
-    assert engine.last_routing() == {"short": 4001, "generic": 0}
+    assert engine.last_routing() == {"short": 4001, "generic": 0, "long": 0}
     _assert_parity(engine, *_pairs(rng, 2000, (150, 150), (500, 500), related=False))
     engine.set_short_variant(4)
 
@@ -104,8 +104,8 @@ def test_short_path_window_limits(engine):
     rng = np.random.default_rng(400)
     _assert_parity(engine, *_pairs(rng, 64, (150, 160), (4000, 4096)))               # longest window the short path takes
     assert engine.last_routing()["generic"] == 0
-    _assert_parity(engine, *_pairs(rng, 16, (150, 160), (4097, 4200)))               # one past: generic path
-    assert engine.last_routing()["short"] == 0
+    _assert_parity(engine, *_pairs(rng, 16, (150, 160), (4097, 4200)))               # one past: long-pair kernel
+    assert engine.last_routing() == {"short": 0, "generic": 0, "long": 16}
 
 
 def test_generic_path_bytes_and_lengths(engine):
@@ -132,11 +132,31 @@ def test_mixed_batch_routing_and_empties(engine):
     wins = [wins[k] for k in order]
     got = _assert_parity(engine, reads, wins)
     routing = engine.last_routing()
-    assert routing["short"] + routing["generic"] == len(reads) - 3
-    assert routing["short"] >= 200 and routing["generic"] >= 100   # N-flags are per 16-base word: neighbours of an N read may go generic too
+    assert routing["short"] + routing["generic"] + routing["long"] == len(reads) - 3
+    assert routing["short"] >= 200 and routing["generic"] >= 25 and routing["long"] >= 25   # N-flags are per 16-base word: neighbours of an N read may go generic too
     for k, (a, b) in enumerate(zip(reads, wins)):
         if len(a) == 0 or len(b) == 0:
             assert tuple(got[k]) == (0, -1, -1)                                                 # aligner.rs:413-416
+
+
+def test_long_kernel_band_and_stride_edges(engine):
+    """sw_long_kernel: bands of 320 rows streamed through one warp.  Row counts around the band height, windows
+    shorter / longer than the minimum column stride (3 wavefronts), tall-and-narrow and short-and-wide pairs, many
+    pairs per warp (work stealing), ties."""
+    rng = np.random.default_rng(750)
+    _assert_parity(engine, *_pairs(rng, 40, (161, 170), (1, 400)))                  # one band, window < stride
+    assert engine.last_routing()["long"] == 40
+    _assert_parity(engine, *_pairs(rng, 60, (318, 323), (900, 1100)))               # band boundary 320, stride boundary 970
+    _assert_parity(engine, *_pairs(rng, 30, (639, 642), (950, 990)))                # two / three bands
+    _assert_parity(engine, *_pairs(rng, 12, (1500, 2500), (1, 50), related=False))  # tall and narrow
+    _assert_parity(engine, *_pairs(rng, 12, (161, 200), (6000, 9000)))              # short and wide
+    _assert_parity(engine, *_pairs(rng, 3000, (161, 700), (100, 1500)))             # more pairs than resident warps
+    assert engine.last_routing() == {"short": 0, "generic": 0, "long": 3000}
+    _assert_parity(engine, *_pairs(rng, 200, (161, 1000), (1, 1200), alphabet=b"A"))                 # all ties
+    _assert_parity(engine, *_pairs(rng, 200, (161, 1000), (1, 1200), related=False, alphabet=b"AC"))
+    reads = [b"ACG" * 400] * 8 + [b"AT" * 500] * 8
+    wins = [b"ACG" * 700] * 8 + [b"TA" * 900] * 8
+    _assert_parity(engine, reads, wins)
 
 
 def test_long_identical_pair_needs_32bit(engine):
@@ -216,7 +236,7 @@ def test_config2_full_size_device_resident(engine):
         engine.sync()
         out = np.zeros(n, dtype=mp.RESULT_DTYPE)
         engine.d2h(out, dout, out.nbytes)
-        assert engine.last_routing() == {"short": n, "generic": 0}
+        assert engine.last_routing() == {"short": n, "generic": 0, "long": 0}
         assert out["score"].min() > 200 and out["score"].max() <= 2 * rl            # related reads score high
         assert np.all(out["end_i"] < rl) and np.all(out["end_j"] < wl) and np.all(out["end_i"] >= 0)
         m = 30_000
@@ -255,7 +275,7 @@ def test_host_path_is_chunked_over_streams_and_stays_exact(engine):
             got = engine.score_batch_csr(q, qo, r, ro)
             assert np.array_equal(got, exp), (chunk_bytes, min_pairs)
             rt = engine.last_routing()
-            assert rt["short"] + rt["generic"] == 4998, rt      # the two empty pairs are routed nowhere
+            assert rt["short"] + rt["generic"] + rt["long"] == 4998, rt      # the two empty pairs are routed nowhere
             assert rt["generic"] >= 1
     finally:
         engine.set_chunking(64 << 20, 16384)
