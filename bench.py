@@ -97,6 +97,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_ncu_traffic(kernel_tag):
+    """dram read+write bytes per launch of the dominant kernel from the committed `ncu --set full` summary."""
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir), reverse=True) if os.path.isdir(pdir) else []:
+        if name.startswith(f"ncu_{kernel_tag}_") and name.endswith(".csv"):
+            tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for line in open(os.path.join(pdir, name)):
+                f = line.strip().split(",")
+                if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[1] in scale:
+                    tot += float(f[2]) * scale[f[1]]
+            if tot > 0:
+                return tot, name
+    return None, None
+
+
 def cpu_simd_gcups(first_pair, n_pairs, dist, threads, budget_s):
     """Times the oracle's CPU SIMD port on a bounded sample of the workload; returns (gcups, pairs_done, seconds)."""
     import oracle_lib as ol
@@ -156,6 +171,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=200_000, help="pairs per step of the CPU arm")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--long-pairs", type=int, default=2368, help="pairs of the auxiliary 10 kb x 10 kb measurement (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -292,6 +308,29 @@ def main():
     ref_ms = max_over_ranks(r0.elapsed_time(r1))
     ref_same = bool(torch.equal(h_out2, h_out))
 
+    # ---- auxiliary: BASELINE.json configs[3] shape (10 kb x 10 kb pairs, sw_long_kernel), one resident wave of pairs ----
+    aux_long = None
+    if args.long_pairs > 0 and rank == 0:
+        ln, ll = args.long_pairs, 10_000
+        del d_q, d_r, d_qo, d_ro
+        l_q = torch.empty(ln * ll, dtype=torch.uint8, device=dev); l_r = torch.empty(ln * ll, dtype=torch.uint8, device=dev)
+        l_qo = torch.empty(ln + 1, dtype=torch.int64, device=dev); l_ro = torch.empty(ln + 1, dtype=torch.int64, device=dev)
+        l_out = torch.empty(ln * 3, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        eng.synth_device(0, ln, ll, ll, 0, l_q.data_ptr(), l_qo.data_ptr(), l_r.data_ptr(), l_ro.data_ptr())
+        lms = []
+        for s_ in range(3):
+            eng.score_batch_device(l_q.data_ptr(), l_qo.data_ptr(), ln * ll, l_r.data_ptr(), l_ro.data_ptr(), ln * ll, ln, ll, ll,
+                                   l_out.data_ptr())
+            t = eng.last_timings()
+            if s_:
+                lms.append(t["device_ms"])
+        lcells = float(ln) * ll * ll
+        aux_long = {"workload": f"BASELINE.json configs[3] shape: {ln} pairs 10000 x 10000 (one resident wave of warps), related reads",
+                    "kernel": "sw_long_kernel (32-bit banded wavefront, one warp per pair)", "ms_per_step": round(statistics.mean(lms), 3),
+                    "gcups": round(lcells / (statistics.mean(lms) * 1e-3) / 1e9, 1), "routing": eng.last_routing(),
+                    "peak_gcups_at_4_instr_per_cell": None}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -305,6 +344,9 @@ def main():
     rate, rate_src = load_issue_rate()
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     peak_gcups = sms * peaks["sm_max_mhz"] * 1e6 * rate / INT_ISSUE_PER_CELL / 1e9
+    traffic, traffic_src = load_ncu_traffic("stream_kernel")
+    if aux_long:
+        aux_long["peak_gcups_at_4_instr_per_cell"] = round(sms * peaks["sm_max_mhz"] * 1e6 * rate / 4.0 / 1e9, 1)
     k_ms = statistics.mean(short_ms)
     k_gcups = cells_step / (k_ms * 1e-3) / 1e9
     p_ms = statistics.mean(pack_ms)
@@ -339,13 +381,16 @@ def main():
                                    "api": "swb_score_batch_vs_reference (reads from pinned host memory, windows of a reference "
                                           "uploaded once)"},
         "roofline": {"bound": "int_issue", "kernel": "sw_stream_kernel" if args.variant < 0 or args.variant >= 4 else "sw_short_kernel", "achieved": round(k_gcups, 1), "peak": round(peak_gcups, 1),
-                     "unit": "GCUPS", "frac": round(k_gcups / peak_gcups, 4), "traffic": None,
+                     "unit": "GCUPS", "frac": round(k_gcups / peak_gcups, 4),
+                     "traffic": None if traffic is None else {"dram_bytes_per_launch": int(traffic), "source": f"profiles/{traffic_src}",
+                                                              "algorithmic_bytes_per_launch": int(n * (rl / 4 + wl / 4 + 32 + 12))},
                      "kernel_ms": round(k_ms, 4), "kernel_share_of_step": round(k_ms / (ms_total / args.steps), 4),
                      "peak_is": f"{sms} SMs x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} MEASURED_PEAKS.json) x {rate:.2f} DPX s16x2 "
                                 f"thread-instr/clk/SM (measured, {rate_src}) / {INT_ISSUE_PER_CELL} instr per cell"},
         "roofline_pack": {"bound": "hbm", "kernel": "pack2bit_kernel x2 + classify_kernel", "achieved": round(pack_bytes / (p_ms * 1e-3) / 1e9, 1),
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(pack_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                           "kernel_ms": round(p_ms, 4), "traffic": None, "peak_is": f"{peaks['source']} copy bandwidth"},
+        "aux_long_pairs": aux_long,
         "cpu_baseline": {"value": round(cpu_val, 3), "unit": "GCUPS", "cores": os.cpu_count() or 1, "kind": "port", "isa": ol.simd_isa(),
                          "sample": f"first {cpu_pairs} pairs of the same workload, {cpu_s:.1f} s of CPU time (oracle/sw_simd.c)"},
     }

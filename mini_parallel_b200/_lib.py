@@ -4,7 +4,7 @@ import os
 
 import numpy as np
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libswb200.so")
+LIB_PATH = os.environ.get("SWB_LIB_OVERRIDE") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libswb200.so")   # override: timing experiments only
 
 
 class SwbResult(ctypes.Structure):

@@ -15,6 +15,11 @@
 //   ref_compat_kernel the reference's LIVE kernel semantics (smith_waterman.cl:11-71)
 //   synth_*           counter-RNG synthetic reads/windows
 #include "swb_kernels.cuh"
+#ifndef SWB_ABLATE
+#define SWB_ABLATE 0
+#endif
+#include <cstdio>
+#include <cstdlib>
 
 namespace swb {
 
@@ -657,16 +662,24 @@ sw_stream_kernel(StreamArgs a)
       if (L == 0) up = fm1;
 #pragma unroll
       for (int m = K - 1; m >= 0; --m) {
+#if SWB_ABLATE >= 1                                  /* timing experiments only: results are wrong */
+        const uint32_t sub = Q[m] ^ W[(u - m + K) % K];
+#else
         const uint32_t x = Q[m] + W[(u - m + K) % K];
         uint32_t sub;
         asm("ld.shared.u32 %0, [%1];" : "=r"(sub) : "r"(x));
+#endif
         uint32_t d, uu, l;
         if (u & 1) { d = m ? B[m - 1] : upPrev; uu = m ? A[m - 1] : up; l = A[m]; }
         else       { d = m ? A[m - 1] : upPrev; uu = m ? B[m - 1] : up; l = B[m]; }
         const uint32_t t1 = __viaddmax_s16x2(d, sub, uu);
         const uint32_t h  = __vimax3_s16x2(t1, l, floor_);
         if (u & 1) B[m] = h; else A[m] = h;
+#if SWB_ABLATE != 2
         cur[m] = __viaddmax_s16x2(h, e, cur[m]);
+#else
+        cur[m] |= h;
+#endif
       }
       upPrev = up;
       fm1 = floor_;
@@ -684,14 +697,17 @@ static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
   StreamArgs a;
   a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.desc = b.short_desc; a.counters = b.counters; a.out = b.out;
   const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int resident = 0;                               // CTAs of this kernel one SM holds (asked once)
+  if (!resident) {
     cudaFuncSetAttribute(sw_stream_kernel<G, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sw_stream_kernel<G, K, MINB>, 128, smem) != cudaSuccess || resident < 1)
+      resident = 1;
+    if (const char* v = getenv("SWB_STREAM_CTAS_PER_SM")) { const int w = atoi(v); if (w >= 1 && w <= resident) resident = w; }
+    if (getenv("SWB_DEBUG")) fprintf(stderr, "sw_stream_kernel<%d,%d,%d>: %d resident CTAs/SM, %zu B smem\n", G, K, MINB, resident, smem);
   }
-  // persistent grid: MINB CTAs per SM; never more groups than pair couples in the worst case
+  // persistent grid: every resident CTA slot of every SM; never more groups than pair couples in the worst case
   const uint64_t n_pp = (b.n_pairs + 1) / 2;
-  uint64_t blocks = (uint64_t)sm_count * MINB;
+  uint64_t blocks = (uint64_t)sm_count * resident;
   const uint64_t need = (n_pp + 4 * GPW - 1) / (4 * GPW);
   if (blocks > need) blocks = need;
   sw_stream_kernel<G, K, MINB><<<(unsigned)blocks, 128, smem, st>>>(a);
