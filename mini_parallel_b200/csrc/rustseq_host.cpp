@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -63,6 +65,11 @@ int parse_usize(const std::string& s, uint64_t* out, std::string* why)
 bool valid_utf8(const uint8_t* p, size_t n)
 {
   size_t i = 0;
+  while (i + 8 <= n) {                             // ASCII fast path, 8 bytes at a time (FASTQ lines are ASCII)
+    uint64_t w; std::memcpy(&w, p + i, 8);
+    if (w & 0x8080808080808080ull) break;
+    i += 8;
+  }
   while (i < n) {
     const uint8_t c = p[i];
     if (c < 0x80) { ++i; continue; }
@@ -79,6 +86,19 @@ bool valid_utf8(const uint8_t* p, size_t n)
   }
   return true;
 }
+
+// Host memory the GPU can copy from asynchronously (USE_PINNED_MEMORY, aligner.rs:466-475): std::vector over
+// swb_malloc_pinned.  The WGS pipeline keeps its chunk buffers in it so H2D overlaps inflate and scoring.
+template <class T> struct PinnedAlloc {
+  using value_type = T;
+  PinnedAlloc() = default;
+  template <class U> PinnedAlloc(const PinnedAlloc<U>&) {}
+  T* allocate(size_t n) { void* p = nullptr; if (swb_malloc_pinned(n * sizeof(T), &p) != 0 || !p) throw std::bad_alloc(); return (T*)p; }
+  void deallocate(T* p, size_t) { swb_free_pinned(p); }
+  template <class U> bool operator==(const PinnedAlloc<U>&) const { return true; }
+  template <class U> bool operator!=(const PinnedAlloc<U>&) const { return false; }
+};
+template <class T> using pinned_vector = std::vector<T, PinnedAlloc<T>>;
 
 // ---- streaming FASTQ reader: the body of process_fastq_file_in_chunks (aligner.rs:107-178), pull style ----
 class FastqReader {
@@ -103,7 +123,8 @@ class FastqReader {
 
   // Appends up to max_reads sequence lines (and at most max_bases bases, 0 = no cap) to bases/offs.
   // Returns 0 ok, 1 error; *eof set when the input is exhausted.
-  int next_chunk(uint64_t max_reads, uint64_t max_bases, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs, bool* eof)
+  template <class VB, class VO>
+  int next_chunk(uint64_t max_reads, uint64_t max_bases, VB& bases, VO& offs, bool* eof)
   {
     bases.clear(); offs.clear(); offs.push_back(0);
     *eof = false;
@@ -145,13 +166,15 @@ class FastqReader {
   uint64_t line_count = 0, total_reads = 0, error_count = 0;
 
  private:
-  bool chunk_full(uint64_t max_reads, uint64_t max_bases, const std::vector<uint8_t>& bases, const std::vector<uint64_t>& offs) const
+  template <class VB, class VO>
+  bool chunk_full(uint64_t max_reads, uint64_t max_bases, const VB& bases, const VO& offs) const
   {
     const uint64_t n = offs.size() - 1;
     if (n == 0) return false;
     return n >= max_reads || (max_bases && bases.size() >= max_bases);   // aligner.rs:143 (+ GPU_CHUNK_SIZE_BASES)
   }
-  int handle_line(const uint8_t* p, size_t n, std::vector<uint8_t>& bases, std::vector<uint64_t>& offs)
+  template <class VB, class VO>
+  int handle_line(const uint8_t* p, size_t n, VB& bases, VO& offs)
   {
     if (n && p[n - 1] == '\r') --n;                // lines() strips "\r\n" too
     if (!valid_utf8(p, n)) {                       // lines() yields Err for invalid UTF-8 (aligner.rs:155-163)
@@ -244,9 +267,9 @@ int load_reference(std::vector<uint8_t>& ref)
 
 struct FileOutcome { int rc = 0; std::string err; rsm_alignment_result res{}; };
 
-// One file of the --full-wgs loop (aligner.rs:261-339) on one device.
-void process_one_file(size_t index, size_t total, const std::string& file, uint64_t chunk_reads, uint64_t chunk_bases,
-                      const rsm_gpu_device* dev, swb_ctx* ctx, uint64_t ref_len, uint32_t window_len, bool compat, FileOutcome* out)
+// One file of the --full-wgs loop (aligner.rs:261-339) in ref_compat mode: sequential, concat + self-align.
+void process_one_file_compat(size_t index, size_t total, const std::string& file, uint64_t chunk_reads, uint64_t chunk_bases,
+                             const rsm_gpu_device* dev, FileOutcome* out)
 {
   std::printf("Processing file %zu/%zu: %s\n", index + 1, total, base_name(file).c_str());
   std::printf("    Using chunk size: %llu reads \n", (unsigned long long)chunk_reads);
@@ -254,32 +277,17 @@ void process_one_file(size_t index, size_t total, const std::string& file, uint6
   int64_t total_score = 0; uint64_t processed_chunks = 0, total_bases = 0, total_reads = 0;
   FastqReader rd;
   int rc = rd.open(file);
-  std::vector<uint8_t> bases; std::vector<uint64_t> offs, wstart; std::vector<uint32_t> wlen; std::vector<swb_result> res;
+  std::vector<uint8_t> bases; std::vector<uint64_t> offs;
   bool eof = false;
   while (rc == 0 && !eof) {
     rc = rd.next_chunk(chunk_reads ? chunk_reads : 1, chunk_bases, bases, offs, &eof);
     const uint64_t n = offs.size() - 1;
     if (rc != 0 || n == 0) break;
-    int crc = 0; int64_t chunk_score = 0;
-    if (compat) {                                                   // aligner.rs:270-276: concat + self-align
-      int32_t s = 0;
-      crc = rsm_gpu_align_chunk_self(bases.data(), bases.size(), dev, &s);
-      chunk_score = s;
-    } else {                                                        // reads against windows of the resident reference
-      wstart.resize(n); wlen.resize(n); res.resize(n);
-      const uint32_t w = (uint32_t)std::min<uint64_t>(window_len, ref_len);
-      for (uint64_t k = 0; k < n; ++k) {
-        const uint64_t g = ((uint64_t)index << 40) + total_reads + k;
-        wstart[k] = splitmix64(g ^ 0xB202ull) % (ref_len - w + 1);
-        wlen[k] = w;
-      }
-      crc = swb_score_batch_vs_reference(ctx, bases.data(), offs.data(), n, wstart.data(), wlen.data(), res.data());
-      if (crc) g_err = swb_last_error();
-      for (uint64_t k = 0; k < n && !crc; ++k) chunk_score += res[k].score;
-    }
+    int32_t sc = 0;
+    const int crc = rsm_gpu_align_chunk_self(bases.data(), bases.size(), dev, &sc);     // aligner.rs:270-276
     total_bases += bases.size(); total_reads += n;
     if (crc == 0) {
-      total_score += chunk_score; ++processed_chunks;
+      total_score += sc; ++processed_chunks;
       if (processed_chunks % 10 == 0)                               // aligner.rs:278-282
         std::printf("    Processed %llu chunks (%llu reads), current score: %lld\n", (unsigned long long)processed_chunks,
                     (unsigned long long)n, (long long)total_score);
@@ -298,9 +306,177 @@ void process_one_file(size_t index, size_t total, const std::string& file, uint6
     out->rc = 1; out->err = "File " + std::to_string(index + 1) + " failed: " + g_err;
   }
   out->res.score64 = total_score; out->res.score = (int32_t)total_score;
-  out->res.processing_time_ms = std::floor(secs * 1000.0);            // as_millis() as f64
+  out->res.processing_time_ms = std::floor(secs * 1000.0);
   std::snprintf(out->res.gpu_device, sizeof out->res.gpu_device, "%s", dev->name);
   out->res.total_reads = total_reads; out->res.total_bases = total_bases;
+}
+
+// ---- the --full-wgs pipeline in Smith-Waterman mode ----
+// The reference inflates with one `zcat` child, parses on the main thread and blocks on every chunk
+// (aligner.rs:111-148, :269-289, :527).  Here every file has its own inflate+parse thread that fills pinned chunk
+// buffers (reads, offsets, and the window each read is scored against); every GPU has one consumer thread that takes
+// whichever chunk of its files is ready and hands it to swb_score_batch_vs_reference, whose three stream lanes overlap
+// the chunk's H2D, kernels and D2H.  Inflate of all files, PCIe and the SMs run concurrently.
+struct WgsChunk {
+  pinned_vector<uint8_t> bases; pinned_vector<uint64_t> offs, wstart; pinned_vector<uint32_t> wlen;
+  pinned_vector<swb_result> res;
+  bool ends_chunk = true;                      // last piece of a GPU_CHUNK_SIZE_READS/BASES chunk (progress accounting)
+};
+
+// A reference-sized chunk (GPU_CHUNK_SIZE_READS can be millions of reads) moves through the pipeline in pieces of at most
+// this many reads: pinned memory stays small (page-locking is slow) and inflate, PCIe and the SMs overlap inside a chunk.
+constexpr uint64_t kWgsPieceReads = 16384;
+
+struct DeviceGate { std::mutex mu; std::condition_variable cv; };   // wakes the consumer of one GPU
+
+struct WgsFile {
+  size_t index = 0; std::string path;
+  DeviceGate* gate = nullptr;
+  std::deque<WgsChunk*> ready, spare;          // guarded by gate->mu
+  bool closed = false; int rc = 0; std::string err;
+  uint64_t total_reads = 0, line_count = 0;    // filled by the reader before it closes
+  std::vector<std::unique_ptr<WgsChunk>> pool;
+  std::chrono::steady_clock::time_point t0;
+  // consumer side
+  int64_t score = 0; uint64_t chunks = 0, bases = 0, reads = 0, chunk_reads_seen = 0;
+};
+
+void wgs_reader_thread(WgsFile* f, uint64_t chunk_reads, uint64_t chunk_bases, uint64_t ref_len, uint32_t window_len)
+{
+  FastqReader rd;
+  int rc = rd.open(f->path);
+  std::string err = rc ? g_err : "";
+  bool eof = false; uint64_t first = 0, in_chunk_reads = 0, in_chunk_bases = 0;
+  while (rc == 0 && !eof) {
+    WgsChunk* c = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(f->gate->mu);
+      f->gate->cv.wait(lk, [&] { return !f->spare.empty(); });
+      c = f->spare.front(); f->spare.pop_front();
+    }
+    try {
+      const uint64_t cr = chunk_reads ? chunk_reads : 1;
+      const uint64_t want = std::min<uint64_t>(kWgsPieceReads, cr - in_chunk_reads);
+      const uint64_t bcap = chunk_bases ? (chunk_bases > in_chunk_bases ? chunk_bases - in_chunk_bases : 1) : 0;
+      rc = rd.next_chunk(want, bcap, c->bases, c->offs, &eof);
+      if (rc) err = g_err;
+      const uint64_t n = c->offs.size() - 1;
+      in_chunk_reads += n; in_chunk_bases += c->bases.size();
+      c->ends_chunk = eof || in_chunk_reads >= cr || (chunk_bases && in_chunk_bases >= chunk_bases);   // aligner.rs:143 (+ BASES)
+      if (c->ends_chunk) { in_chunk_reads = 0; in_chunk_bases = 0; }
+      c->wstart.resize(n); c->wlen.resize(n); c->res.resize(n);
+      const uint32_t w = (uint32_t)std::min<uint64_t>(window_len, ref_len);
+      for (uint64_t k = 0; k < n; ++k) {       // this engine's pairing rule: a deterministic window per read
+        const uint64_t g = ((uint64_t)f->index << 40) + first + k;
+        c->wstart[k] = splitmix64(g ^ 0xB202ull) % (ref_len - w + 1);
+        c->wlen[k] = w;
+      }
+      first += n;
+    } catch (const std::bad_alloc&) { rc = 1; err = "out of pinned host memory"; }
+    std::lock_guard<std::mutex> lk(f->gate->mu);
+    if (rc == 0 && c->offs.size() > 1) f->ready.push_back(c); else f->spare.push_back(c);
+    f->gate->cv.notify_all();
+  }
+  std::lock_guard<std::mutex> lk(f->gate->mu);
+  f->total_reads = rd.total_reads; f->line_count = rd.line_count;
+  f->rc = rc; f->err = err; f->closed = true;
+  f->gate->cv.notify_all();
+}
+
+void wgs_finish_file(WgsFile* f, size_t total, uint64_t chunk_reads, const rsm_gpu_device* dev, FileOutcome* out)
+{
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - f->t0).count();
+  if (f->rc == 0) {
+    const uint64_t cr = chunk_reads ? chunk_reads : 1;
+    std::printf("    Processed %llu total reads in %llu chunks\n", (unsigned long long)f->total_reads, (unsigned long long)((f->total_reads + cr - 1) / cr));
+    std::printf("    Total lines read: %llu\n", (unsigned long long)f->line_count);
+    std::printf("  File %zu complete: Score=%lld, Bases=%llu, Time: %.2f s \n", f->index + 1, (long long)f->score, (unsigned long long)f->bases, secs);
+  } else {
+    std::printf("  File %zu failed: %s\n", f->index + 1, f->err.c_str());
+    out->rc = 1; out->err = "File " + std::to_string(f->index + 1) + " failed: " + f->err;
+  }
+  (void)total;
+  out->res.score64 = f->score; out->res.score = (int32_t)f->score;
+  out->res.processing_time_ms = std::floor(secs * 1000.0);            // as_millis() as f64
+  std::snprintf(out->res.gpu_device, sizeof out->res.gpu_device, "%s", dev->name);
+  out->res.total_reads = f->reads; out->res.total_bases = f->bases;
+}
+
+// All files of one GPU: readers in parallel, one consumer (this thread) scoring whatever is ready.
+void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std::string>& files, size_t total, uint64_t chunk_reads,
+                         uint64_t chunk_bases, const rsm_gpu_device* dev, swb_ctx* ctx, uint64_t ref_len, uint32_t window_len,
+                         std::vector<FileOutcome>* outcomes)
+{
+  DeviceGate gate;
+  std::vector<std::unique_ptr<WgsFile>> fs;
+  const size_t depth = 3;
+  for (size_t i : mine) {
+    auto f = std::make_unique<WgsFile>();
+    f->index = i; f->path = files[i]; f->gate = &gate; f->t0 = std::chrono::steady_clock::now();
+    for (size_t d = 0; d < depth; ++d) {
+      f->pool.push_back(std::make_unique<WgsChunk>());
+      WgsChunk* c = f->pool.back().get();
+      // one pinned allocation per buffer instead of a doubling series (page-locking is slow and serialised in the driver)
+      const uint64_t nr = std::min<uint64_t>(chunk_reads ? chunk_reads : 1, kWgsPieceReads);
+      const uint64_t nb = chunk_bases ? std::min<uint64_t>(chunk_bases + 1024, nr * 152) : nr * 152;
+      try {
+        c->bases.reserve(std::min<uint64_t>(nb, 600ull << 20)); c->offs.reserve(nr + 1); c->wstart.reserve(nr); c->wlen.reserve(nr); c->res.reserve(nr);
+      } catch (const std::bad_alloc&) {}
+      f->spare.push_back(c);
+    }
+    std::printf("Processing file %zu/%zu: %s\n", i + 1, total, base_name(files[i]).c_str());
+    std::printf("    Using chunk size: %llu reads \n", (unsigned long long)chunk_reads);
+    fs.push_back(std::move(f));
+  }
+  std::vector<std::thread> readers;
+  for (auto& f : fs) readers.emplace_back(wgs_reader_thread, f.get(), chunk_reads, chunk_bases, ref_len, window_len);
+  std::vector<WgsFile*> active;
+  for (auto& f : fs) active.push_back(f.get());
+  bool abort_run = false;
+  size_t rr = 0;
+  while (!active.empty()) {
+    WgsFile* f = nullptr; WgsChunk* c = nullptr; bool finished = false;
+    {
+      std::unique_lock<std::mutex> lk(gate.mu);
+      for (;;) {
+        for (size_t k = 0; k < active.size() && !f; ++k) {
+          WgsFile* g = active[(rr + k) % active.size()];
+          if (!g->ready.empty()) { f = g; c = g->ready.front(); g->ready.pop_front(); }
+          else if (g->closed) { f = g; finished = true; }
+        }
+        if (f) break;
+        gate.cv.wait(lk);
+      }
+      ++rr;
+    }
+    if (finished) {
+      wgs_finish_file(f, total, chunk_reads, dev, &(*outcomes)[f->index]);
+      if (f->rc) abort_run = true;                                   // aligner.rs:336: a failed file aborts the run
+      active.erase(std::find(active.begin(), active.end(), f));
+      continue;
+    }
+    const uint64_t n = c->offs.size() - 1;
+    int crc = abort_run ? 0 : swb_score_batch_vs_reference(ctx, c->bases.data(), c->offs.data(), n, c->wstart.data(), c->wlen.data(), c->res.data());
+    if (crc == 0 && !abort_run) {
+      int64_t cs = 0;
+      for (uint64_t k = 0; k < n; ++k) cs += c->res[k].score;
+      f->score += cs; f->chunk_reads_seen += n;
+      if (c->ends_chunk) {
+        ++f->chunks;
+        if (f->chunks % 10 == 0)                                     // aligner.rs:278-282
+          std::printf("    Processed %llu chunks (%llu reads), current score: %lld\n", (unsigned long long)f->chunks,
+                      (unsigned long long)f->chunk_reads_seen, (long long)f->score);
+        f->chunk_reads_seen = 0;
+      }
+    } else if (crc) {
+      std::printf("    Warning: Failed to align chunk %llu: %s\n", (unsigned long long)f->chunks, swb_last_error());   // aligner.rs:284-286
+    }
+    f->bases += c->bases.size(); f->reads += n;
+    std::lock_guard<std::mutex> lk(gate.mu);
+    f->spare.push_back(c);
+    gate.cv.notify_all();
+  }
+  for (auto& t : readers) t.join();
 }
 
 void load_dotenv()
@@ -520,6 +696,10 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   order.push_back(first);
   for (int d = 0; d < nd; ++d) if (d != first && (int)order.size() < nd) order.push_back(d);
 
+  const auto t_start = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (std::getenv("SWB_DEBUG")) std::fprintf(stderr, "[wgs] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+  };
   std::vector<uint8_t> ref; uint32_t window_len = 500;
   if (!compat) {
     if (load_reference(ref)) return 1;
@@ -532,16 +712,25 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   for (size_t w = 0; w < order.size(); ++w) {
     workers.emplace_back([&, w]() {
       const int ord = order[w];
+      if (compat) {
+        for (size_t i = w; i < total; i += order.size()) {
+          process_one_file_compat(i, total, files[i], chunk, chunk_bases, &devs[ord], &outcomes[i]);
+          if (outcomes[i].rc) return;                             // aligner.rs:336: a failed file aborts the run
+        }
+        return;
+      }
       swb_ctx* ctx = context_for(ord);
       if (!ctx) { werr[w] = g_err; return; }
-      if (!compat && swb_set_reference(ctx, ref.data(), ref.size())) { werr[w] = swb_last_error(); return; }
-      for (size_t i = w; i < total; i += order.size()) {
-        process_one_file(i, total, files[i], chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, compat, &outcomes[i]);
-        if (outcomes[i].rc) return;                               // aligner.rs:336: a failed file aborts the run
-      }
+      if (swb_set_reference(ctx, ref.data(), ref.size())) { werr[w] = swb_last_error(); return; }
+      stamp("context + reference on device");
+      std::vector<size_t> mine;
+      for (size_t i = w; i < total; i += order.size()) mine.push_back(i);
+      wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes);
     });
   }
+  stamp("reference + workers started");
   for (auto& t : workers) t.join();
+  stamp("all files done");
   for (const auto& e : werr) if (!e.empty()) return fail(e);
   int n = 0;
   for (size_t i = 0; i < total; ++i) {

@@ -125,6 +125,55 @@ def test_full_wgs_driver_both_modes(tmp_path, device, monkeypatch):
         assert res[fi].total_reads == 45
 
 
+def test_full_wgs_pipeline_pieces_and_caps(tmp_path, device, monkeypatch):
+    """The threaded --full-wgs pipeline: chunks larger than one pipeline piece (16384 reads), a GPU_CHUNK_SIZE_BASES cap,
+    ragged read lengths, one file per reader thread; per-file score totals against the SIMD oracle."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_wgs
+    rng = np.random.default_rng(33)
+    n_ref, n_reads = 300_000, 40_000
+    ref = bench_wgs.synth_reference(n_ref)
+    files = {}
+    for fi, (lane, rd) in enumerate(((1, 1), (1, 2))):
+        k = np.arange(n_reads, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            ws = bench_wgs.splitmix64(((np.uint64(fi) << np.uint64(40)) + k) ^ np.uint64(0xB202)) % np.uint64(n_ref - 500 + 1)
+        lens = rng.integers(30, 161, n_reads)
+        offs = rng.integers(0, 300, n_reads)
+        reads = []
+        for j in range(n_reads):
+            a = int(ws[j]) + int(offs[j])
+            r = ref[a:a + int(lens[j])].copy()
+            m = rng.random(r.size) < 0.02
+            r[m] = ACGT[rng.integers(0, 4, int(m.sum()))]
+            reads.append(r.tobytes())
+        name = f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"
+        with gzip.open(tmp_path / name, "wb", compresslevel=1) as f:
+            f.write(b"".join(b"@r%d\n%s\n+\n%s\n" % (j, r, b"I" * len(r)) for j, r in enumerate(reads)))
+        files[name] = (reads, ws)
+    for kk, v in dict(WGS_DATA_DIR=str(tmp_path), WGS_SAMPLE_ID="SYN", WGS_LANES="1", WGS_READS_PER_LANE="2",
+                      WGS_SYNTH_REFERENCE_BASES=str(n_ref), WGS_WINDOW_LEN="500").items():
+        monkeypatch.setenv(kk, v)
+    monkeypatch.delenv("SWB_GPU_ALIGN_MODE", raising=False)
+    exp = {}
+    for name, (reads, ws) in files.items():
+        q, qo = to_csr(reads)
+        r, ro = to_csr([ref[int(s):int(s) + 500] for s in ws])
+        exp[name] = int(ol.batch(q, qo, r, ro, threads=os.cpu_count() or 8, simd=True)["score"].astype(np.int64).sum())
+    for chunk_reads, chunk_bases in (("35000", None), ("1000000", "1000000"), ("777", None)):
+        monkeypatch.setenv("GPU_CHUNK_SIZE_READS", chunk_reads)
+        if chunk_bases:
+            monkeypatch.setenv("GPU_CHUNK_SIZE_BASES", chunk_bases)
+        else:
+            monkeypatch.delenv("GPU_CHUNK_SIZE_BASES", raising=False)
+        res = aligner.process_full_wgs_dataset(device)
+        assert len(res) == 2
+        for fi, name in enumerate(sorted(files)):
+            assert res[fi].score64 == exp[name], (name, chunk_reads, chunk_bases)
+            assert res[fi].total_reads == n_reads and res[fi].total_bases == sum(len(x) for x in files[name][0])
+
+
 def test_cli_on_gpu(tmp_path):
     env = {k: v for k, v in os.environ.items() if k != "SWB_GPU_ALIGN_MODE"}
     r = subprocess.run([CLI, "-1", "TGTTACGG", "-2", "GGTTGACTA", "--gpu"], env=env, capture_output=True, text=True)

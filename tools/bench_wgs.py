@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4], scaled: synthetic WGS lanes ({SAMPLE}_L{lane:03}_R{read}_001.fastq.gz, 150 bp reads)
+streamed end to end through build/rustseq_mini --full-wgs --gpu (inflate + parse + H2D + pack + score + D2H).
+Generates the files (reads cut from the driver's synthetic reference at the window each read is paired with,
+1 % substitutions), runs the CLI, prints one JSON line with wall-clock reads/s and GCUPS."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+import zlib
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def synth_reference(n):
+    """Same bytes as load_reference() in rustseq_host.cpp when WGS_REFERENCE is unset."""
+    k = np.arange((n + 31) // 32, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = splitmix64(np.uint64(0xB2F0) + k)
+    sh = (np.arange(32, dtype=np.uint64) * np.uint64(2))[None, :]
+    codes = ((x[:, None] >> sh) & np.uint64(3)).astype(np.uint8).reshape(-1)[:n]
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+
+
+def make_file(args):
+    path, fi, n_reads, ref_len, rl, wl, level = args
+    ref = synth_reference(ref_len)
+    co = zlib.compressobj(level, zlib.DEFLATED, 31)
+    step = 100_000
+    with open(path, "wb") as f:
+        for a in range(0, n_reads, step):
+            m = min(step, n_reads - a)
+            k = np.arange(a, a + m, dtype=np.uint64)
+            with np.errstate(over="ignore"):
+                g = (np.uint64(fi) << np.uint64(40)) + k
+                ws = splitmix64(g ^ np.uint64(0xB202)) % np.uint64(ref_len - wl + 1)
+                off = splitmix64(g ^ np.uint64(0xB203)) % np.uint64(wl - rl + 1)
+                noise = splitmix64((g[:, None] * np.uint64(257) + np.arange(rl, dtype=np.uint64)[None, :]) ^ np.uint64(0xB204))
+            idx = (ws + off)[:, None].astype(np.int64) + np.arange(rl, dtype=np.int64)[None, :]
+            reads = ref[idx]
+            sub = (noise % np.uint64(100)) == 0
+            alt = np.frombuffer(b"ACGT", dtype=np.uint8)[((noise >> np.uint64(8)) & np.uint64(3)).astype(np.uint8)]
+            reads = np.where(sub, alt, reads)
+            rec = np.empty((m, 12 + rl + 3 + rl + 1), dtype=np.uint8)
+            names = np.char.add("@", np.char.zfill(k.astype(str), 10)).astype("S11")
+            rec[:, :11] = np.frombuffer(names.tobytes(), dtype=np.uint8).reshape(m, 11)
+            rec[:, 11] = 10
+            rec[:, 12:12 + rl] = reads
+            rec[:, 12 + rl:12 + rl + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+            rec[:, 12 + rl + 3:12 + 2 * rl + 3] = ord("I")
+            rec[:, -1] = 10
+            f.write(co.compress(rec.tobytes()))
+        f.write(co.flush())
+    return os.path.getsize(path), n_reads * rec.shape[1]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads-per-file", type=int, default=250_000)
+    ap.add_argument("--lanes", type=int, default=8)
+    ap.add_argument("--chunk-reads", type=int, default=100_000)
+    ap.add_argument("--devices", type=int, default=1)
+    ap.add_argument("--ref-bases", type=int, default=16_000_000)
+    ap.add_argument("--dir", default="/tmp/synwgs")
+    ap.add_argument("--level", type=int, default=1)
+    args = ap.parse_args()
+    os.makedirs(args.dir, exist_ok=True)
+    jobs = []
+    fi = 0
+    for lane in range(1, args.lanes + 1):
+        for rd in (1, 2):
+            jobs.append((os.path.join(args.dir, f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"), fi, args.reads_per_file, args.ref_bases, 150, 500, args.level))
+            fi += 1
+    t0 = time.time()
+    with ProcessPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        sizes = list(ex.map(make_file, jobs))
+    gen_s = time.time() - t0
+    gz_bytes = sum(s[0] for s in sizes); text_bytes = sum(s[1] for s in sizes)
+    env = dict(os.environ, GPU_CHUNK_SIZE_READS=str(args.chunk_reads), WGS_DATA_DIR=args.dir, WGS_SAMPLE_ID="SYN", WGS_LANES=str(args.lanes),
+               WGS_READS_PER_LANE="2", WGS_SYNTH_REFERENCE_BASES=str(args.ref_bases), SWB_NUM_DEVICES=str(args.devices))
+    env.pop("SWB_GPU_ALIGN_MODE", None)
+    cli = os.path.join(ROOT, "build", "rustseq_mini")
+    subprocess.run([cli, "-1", "ACGT", "-2", "ACGT", "--gpu"], env=env, capture_output=True)      # warm the driver / context creation
+    t0 = time.time()
+    r = subprocess.run([cli, "--full-wgs", "--gpu"], env=env, capture_output=True, text=True)
+    wall = time.time() - t0
+    if os.environ.get("SWB_DEBUG"):
+        print(r.stderr[-3000:], file=sys.stderr)
+    if r.returncode != 0:
+        print(r.stdout[-2000:], r.stderr[-2000:], file=sys.stderr)
+        raise SystemExit("rustseq_mini --full-wgs failed")
+    scores = [int(l.split("Score=")[1].split(",")[0]) for l in r.stdout.splitlines() if "complete: Score=" in l]
+    file_s = [float(l.split("Time:")[1].split("s")[0]) for l in r.stdout.splitlines() if "complete: Score=" in l]
+    n_reads = args.reads_per_file * len(jobs)
+    print(json.dumps({
+        "workload": f"BASELINE.json configs[4] scaled: {len(jobs)} files x {args.reads_per_file} reads of 150 bp (gzip -{args.level}), each read vs a 500 bp window "
+                    f"of a {args.ref_bases} bp device-resident reference, GPU_CHUNK_SIZE_READS={args.chunk_reads}, {args.devices} GPU(s)",
+        "wall_s": round(wall, 3), "reads_per_s": round(n_reads / wall, 1), "gcups_end_to_end": round(n_reads * 150 * 500 / wall / 1e9, 1),
+        "gz_mb_per_s": round(gz_bytes / wall / 1e6, 1), "fastq_text_mb_per_s": round(text_bytes / wall / 1e6, 1),
+        "slowest_file_s": max(file_s) if file_s else None,
+        "pipeline_reads_per_s": round(n_reads / max(file_s), 1) if file_s else None,      # all files run concurrently: excludes process + CUDA context start-up
+        "pipeline_gcups": round(n_reads * 150 * 500 / max(file_s) / 1e9, 1) if file_s else None, "host_cores": os.cpu_count(), "generate_s": round(gen_s, 1),
+        "mean_score_per_read": round(sum(scores) / n_reads, 2), "files_done": len(scores)}))
+
+
+if __name__ == "__main__":
+    main()
