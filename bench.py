@@ -189,7 +189,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout at communicator creation; stdout carries exactly one JSON line
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     warmup = max(args.warmup, 3)
     n, rl, wl = args.pairs, READ_LEN, WINDOW_LEN
     first_pair = rank * n                                  # this rank's shard of the counter-RNG stream

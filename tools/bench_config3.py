@@ -30,7 +30,10 @@ def main():
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
     if world > 1:
+        saved = os.dup(1); os.dup2(2, 1)                                         # NCCL's version banner goes to stderr
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        dist.barrier(); torch.cuda.synchronize()
+        sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     dev = torch.device("cuda", lr)
     eng = mp.Engine(lr)
     rl, wl = 150, 500
