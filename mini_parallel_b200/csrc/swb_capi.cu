@@ -38,11 +38,11 @@ struct DevBuf {
 struct Lane {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8] = {};
-  DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, short_desc, generic_list, long_list, long_scratch, counters, out, scratch, misc;
+  DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, short_desc, generic_list, long_list, bytes_list, long_scratch, bytes_scratch, counters, out, scratch, misc;
   DevBuf win_beg, win_end, win_len;
   void release_all() {
     for (DevBuf* b : {&q_bytes, &r_bytes, &q_off, &r_off, &q_pk, &r_pk, &q_bad, &r_bad, &short_list, &short_desc,
-                      &generic_list, &long_list, &long_scratch, &counters, &out, &scratch, &misc, &win_beg, &win_end, &win_len}) b->release();
+                      &generic_list, &long_list, &bytes_list, &long_scratch, &bytes_scratch, &counters, &out, &scratch, &misc, &win_beg, &win_end, &win_len}) b->release();
   }
 };
 
@@ -67,6 +67,7 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   uint64_t last_routing[3] = {0, 0, 0};
   bool timings_pending = false, host_path = false;
   int variant = 4;
+  int force_bytes = 0;                     // SWB_FORCE_BYTES=1: every non-short pair through the byte-compare kernel (bench / tests)
 };
 
 extern "C" {
@@ -112,6 +113,7 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
     for (auto& e : l->ev) cudaEventCreate(&e);
   }
   if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 7;
+  if (const char* v = std::getenv("SWB_FORCE_BYTES")) c->force_bytes = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_CHUNK_MB")) { const long mb = std::atol(v); if (mb > 0) c->chunk_bytes = (uint64_t)mb << 20; }
   *out = c;
   return 0;
@@ -165,13 +167,14 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   if (l->q_pk.reserve(qw * 4 + 64) || l->r_pk.reserve(rw * 4 + 64) ||
       l->q_bad.reserve((qw + 31) / 32 * 4 + 64) || l->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
       l->short_list.reserve(n_pairs * 4 + 64) || l->short_desc.reserve(n_pairs * sizeof(swb::ShortDesc) + 64) ||
-      l->generic_list.reserve(n_pairs * 4 + 64) || l->long_list.reserve(n_pairs * 4 + 64) ||
+      l->generic_list.reserve(n_pairs * 4 + 64) || l->long_list.reserve(n_pairs * 4 + 64) || l->bytes_list.reserve(n_pairs * 4 + 64) ||
       l->counters.reserve(sizeof(swb::Counters))) return 1;
   // generic kernel: persistent grid, one boundary row of max_r_len ints per resident warp
   int ctas = c->sm_count * 4;
   const uint64_t stride = ((uint64_t)max_r_len + 32) & ~31ull;
   while (ctas > 1 && (uint64_t)ctas * 4 * stride * 4 > (2ull << 30)) ctas /= 2;
-  if (l->scratch.reserve((uint64_t)ctas * 4 * stride * 4) || l->long_scratch.reserve((uint64_t)ctas * 4 * stride * 4)) return 1;
+  if (l->scratch.reserve((uint64_t)ctas * 4 * stride * 4) || l->long_scratch.reserve((uint64_t)ctas * 4 * stride * 4) ||
+      l->bytes_scratch.reserve((uint64_t)ctas * 4 * stride * 4)) return 1;
 
   swb::BatchView b;
   b.q_bytes = d_q; b.q_beg = d_qo; b.q_end = d_qo + 1; b.r_bytes = d_r; b.r_beg = d_rbeg; b.r_end = d_rend;
@@ -180,7 +183,8 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   b.r_bad = ref_windows ? c->ref_bad.as<uint32_t>() : l->r_bad.as<uint32_t>();
   b.n_pairs = n_pairs;
   b.short_list = l->short_list.as<uint32_t>(); b.short_desc = l->short_desc.as<swb::ShortDesc>();
-  b.generic_list = l->generic_list.as<uint32_t>(); b.long_list = l->long_list.as<uint32_t>();
+  b.generic_list = l->generic_list.as<uint32_t>(); b.long_list = l->long_list.as<uint32_t>(); b.bytes_list = l->bytes_list.as<uint32_t>();
+  b.force_bytes = c->force_bytes;
   b.counters = l->counters.as<swb::Counters>(); b.out = d_out;
   b.scratch = l->scratch.as<int32_t>(); b.scratch_stride = stride;
 
@@ -200,6 +204,8 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
     swb::BatchView bl = b;
     bl.scratch = l->long_scratch.as<int32_t>();
     k += swb::launch_long(bl, ctas, st);
+    bl.scratch = l->bytes_scratch.as<int32_t>();
+    k += swb::launch_long_bytes(bl, ctas, st);
   }
   CUDA_TRY(cudaEventRecord(ev[3], st));
   CUDA_TRY(cudaGetLastError());
@@ -378,7 +384,7 @@ int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
       cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[3]);
       swb::Counters h;
       CUDA_TRY(cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
-      c->last_routing[0] = h.n_short; c->last_routing[1] = h.n_generic; c->last_routing[2] = h.n_long;
+      c->last_routing[0] = h.n_short; c->last_routing[1] = h.n_generic + h.n_bytes; c->last_routing[2] = h.n_long;
     } else {
       // sums over the chunks of the call (chunks overlap in time, so [3] is the span first event -> last event)
       for (size_t ch = 0; ch < c->last_chunks; ++ch) {
@@ -389,7 +395,7 @@ int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
         cudaEventElapsedTime(&t, ev[2], ev[3]); c->last_ms[2] += t;
         cudaEventElapsedTime(&t, ev[4], ev[5]); c->last_ms[4] += t;
         cudaEventElapsedTime(&t, ev[6], ev[7]); c->last_ms[5] += t;
-        c->last_routing[0] += c->h_counters[ch].n_short; c->last_routing[1] += c->h_counters[ch].n_generic;
+        c->last_routing[0] += c->h_counters[ch].n_short; c->last_routing[1] += c->h_counters[ch].n_generic + c->h_counters[ch].n_bytes;
         c->last_routing[2] += c->h_counters[ch].n_long;
       }
       if (c->last_chunks) {

@@ -113,9 +113,9 @@ classify_kernel(BatchView b)
     } else if (n <= kShortMaxRead && mm <= kShortMaxWindow &&
                !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1)) {
       cls = CLASS_SHORT; m = (uint32_t)mm;
-    } else if (n <= kLongMaxLen && mm <= kLongMaxLen &&
-               !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1)) {
-      cls = CLASS_LONG;
+    } else if (n <= kLongMaxLen && mm <= kLongMaxLen) {
+      const bool acgt = !b.force_bytes && !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1);
+      cls = acgt ? CLASS_LONG : CLASS_BYTES;
     } else {
       cls = CLASS_GENERIC;
     }
@@ -125,15 +125,18 @@ classify_kernel(BatchView b)
   const uint32_t ms = __ballot_sync(0xffffffffu, cls == CLASS_SHORT);
   const uint32_t mg = __ballot_sync(0xffffffffu, cls == CLASS_GENERIC);
   const uint32_t ml = __ballot_sync(0xffffffffu, cls == CLASS_LONG);
-  uint32_t base_s = 0, base_g = 0, base_l = 0;
+  const uint32_t mb = __ballot_sync(0xffffffffu, cls == CLASS_BYTES);
+  uint32_t base_s = 0, base_g = 0, base_l = 0, base_b = 0;
   if (lane == 0) {
     if (ms) base_s = atomicAdd(&b.counters->n_short, __popc(ms));
     if (mg) base_g = atomicAdd(&b.counters->n_generic, __popc(mg));
     if (ml) base_l = atomicAdd(&b.counters->n_long, __popc(ml));
+    if (mb) base_b = atomicAdd(&b.counters->n_bytes, __popc(mb));
   }
   base_s = __shfl_sync(0xffffffffu, base_s, 0);
   base_g = __shfl_sync(0xffffffffu, base_g, 0);
   base_l = __shfl_sync(0xffffffffu, base_l, 0);
+  base_b = __shfl_sync(0xffffffffu, base_b, 0);
   const uint32_t below = (1u << lane) - 1;
   if (cls == CLASS_SHORT) {
     const uint32_t slot = base_s + __popc(ms & below);
@@ -145,6 +148,7 @@ classify_kernel(BatchView b)
   }
   if (cls == CLASS_GENERIC) b.generic_list[base_g + __popc(mg & below)] = (uint32_t)k;
   if (cls == CLASS_LONG)    b.long_list[base_l + __popc(ml & below)] = (uint32_t)k;
+  if (cls == CLASS_BYTES)   b.bytes_list[base_b + __popc(mb & below)] = (uint32_t)k;
   uint32_t wm = m;
   for (int o = 16; o; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
   if (lane == 0 && wm) atomicMax(&b.counters->max_short_window, wm);
@@ -732,6 +736,7 @@ static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
 // =====================================================================================
 struct LongArgs {
   const uint32_t* q_pk; const uint32_t* r_pk;
+  const uint8_t* q_bytes; const uint8_t* r_bytes;
   const uint64_t* q_beg; const uint64_t* q_end; const uint64_t* r_beg; const uint64_t* r_end;
   const uint32_t* list; Counters* counters;
   swb_result* out; int32_t* scratch; uint64_t scratch_stride;
@@ -748,7 +753,10 @@ struct LongJob {                     // one band of one pair (uniform per warp, 
 };
 
 
-template <int K, int MINB>
+// BYTES = true is the same kernel on RAW BYTES (any alphabet: 'N' == 'N', 'a' != 'A' as in smith_waterman.cl:114): the
+// ring holds window bytes, Q the read bytes (pads 0x200 / 0x100 never compare equal) and the substitution term is
+// arithmetic instead of a table fetch -- d = q - w, sub = 6S - 3S*min(d*d, 1): three FMA-pipe IMADs and one ALU min.
+template <int K, int MINB, bool BYTES>
 __global__ void __launch_bounds__(128, MINB)
 sw_long_kernel(LongArgs a)
 {
@@ -762,7 +770,7 @@ sw_long_kernel(LongArgs a)
   constexpr uint32_t REBASE = 2u * SC * BLOCK;
   constexpr int RSLOTS = 4 * G;
   constexpr int RING = RSLOTS * K;
-  constexpr uint32_t WPADV = 4u << 7;
+  constexpr uint32_t WPADV = BYTES ? 0x200u : (4u << 7);
   constexpr uint32_t NOEVENT = 0xFFFFFFFFu;
   constexpr uint64_t M21 = (1ull << 21) - 1;
   constexpr int JT = 8;                                  // live job table entries
@@ -782,7 +790,8 @@ sw_long_kernel(LongArgs a)
   uint32_t* csave = qnext + K * 128;
   const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + 4u * lane;
   int32_t* scratch = a.scratch + (uint64_t)(blockIdx.x * 4 + warp) * a.scratch_stride;
-  const uint32_t n_list = a.counters->n_long;
+  const uint32_t n_list = BYTES ? a.counters->n_bytes : a.counters->n_long;
+  uint32_t* const cursor = BYTES ? &a.counters->bytes_cursor : &a.counters->long_cursor;
 
   // ---- job creation (uniform): next band of the current pair, else steal the next pair ----
   uint32_t created = 0, next_base_it = 0;                // jobs created so far, base_it of the next one
@@ -792,7 +801,7 @@ sw_long_kernel(LongArgs a)
   auto create_job = [&]() {
     if (!cp_live && !exhausted) {
       uint32_t item = 0;
-      if (lane == 0) item = atomicAdd(&a.counters->long_cursor, 1u);
+      if (lane == 0) item = atomicAdd(cursor, 1u);
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item < n_list) {
         cp_pair = a.list[item];
@@ -833,15 +842,21 @@ sw_long_kernel(LongArgs a)
     const uint32_t col0 = (it0 - j.base_it) * K;
     const int32_t v = j.rows ? (int32_t)j.n2 - (int32_t)col0 : 0;       // valid columns in this piece
     uint64_t cw = 0;
-    if (v > 0) cw = codes32(a.r_pk, j.r0 + col0);
+    if (!BYTES && v > 0) cw = codes32(a.r_pk, j.r0 + col0);
+    const uint8_t* wb = a.r_bytes + j.r0 + col0;
     const uint32_t slot = (chunk * G + G + L) & (RSLOTS - 1);
     uint32_t* dst = reinterpret_cast<uint32_t*>(ring + slot * K);
     uint32_t* bdst = bring + slot * K;
     const bool has_above = v > 0 && !j.first;
 #pragma unroll
     for (int x = 0; x < K; x += 2) {
-      const uint32_t w0 = x < v ? (uint32_t)(cw >> (2 * x)) & 3u : 4u, w1 = x + 1 < v ? (uint32_t)(cw >> (2 * x + 2)) & 3u : 4u;
-      dst[x >> 1] = (w0 << 7) | (w1 << 23);
+      if (BYTES) {
+        const uint32_t w0 = x < v ? (uint32_t)__ldg(wb + x) : WPADV, w1 = x + 1 < v ? (uint32_t)__ldg(wb + x + 1) : WPADV;
+        dst[x >> 1] = w0 | (w1 << 16);
+      } else {
+        const uint32_t w0 = x < v ? (uint32_t)(cw >> (2 * x)) & 3u : 4u, w1 = x + 1 < v ? (uint32_t)(cw >> (2 * x + 2)) & 3u : 4u;
+        dst[x >> 1] = (w0 << 7) | (w1 << 23);
+      }
       bdst[x]     = (has_above && x < v)     ? (uint32_t)__ldcg(scratch + col0 + x)     : 0u;
       bdst[x + 1] = (has_above && x + 1 < v) ? (uint32_t)__ldcg(scratch + col0 + x + 1) : 0u;
     }
@@ -853,11 +868,17 @@ sw_long_kernel(LongArgs a)
     const LongJob j = jobs[jn % JT];
     const int32_t v = (int32_t)j.rows - (int32_t)(K * L);
     uint64_t cq = 0;
-    if (v > 0) cq = codes32(a.q_pk, j.q0 + K * L);
+    if (!BYTES && v > 0) cq = codes32(a.q_pk, j.q0 + K * L);
+    const uint8_t* qb = a.q_bytes + j.q0 + K * L;
 #pragma unroll
     for (int m = 0; m < K; ++m) {
-      const uint32_t qc = m < v ? 3u - ((uint32_t)(cq >> (2 * m)) & 3u) : 4u;
-      const uint32_t val = lut_lane + (qc << 7);
+      uint32_t val;
+      if (BYTES) {
+        val = m < v ? (uint32_t)__ldg(qb + m) : 0x100u;
+      } else {
+        const uint32_t qc = m < v ? 3u - ((uint32_t)(cq >> (2 * m)) & 3u) : 4u;
+        val = lut_lane + (qc << 7);
+      }
       if (to_regs) Q[m] = val; else qnext[m * 128] = val;
     }
   };
@@ -979,9 +1000,14 @@ sw_long_kernel(LongArgs a)
       if (L == 0) up = bp[u] + fm1;
 #pragma unroll
       for (int m = K - 1; m >= 0; --m) {
-        const uint32_t x = Q[m] + W[(u - m + K) % K];
         uint32_t sub;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(sub) : "r"(x));
+        if (BYTES) {
+          const uint32_t dq = Q[m] - W[(u - m + K) % K];
+          sub = 6u * SC - 3u * SC * min(dq * dq, 1u);
+        } else {
+          const uint32_t x = Q[m] + W[(u - m + K) % K];
+          asm("ld.shared.u32 %0, [%1];" : "=r"(sub) : "r"(x));
+        }
         uint32_t d, uu, l;
         if (u & 1) { d = m ? B[m - 1] : upPrev; uu = m ? A[m - 1] : up; l = A[m]; }
         else       { d = m ? A[m - 1] : upPrev; uu = m ? B[m - 1] : up; l = B[m]; }
@@ -1000,29 +1026,36 @@ sw_long_kernel(LongArgs a)
   }
 }
 
-template <int K, int MINB>
+template <int K, int MINB, bool BYTES>
 static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
 {
   LongArgs a;
-  a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.q_beg = b.q_beg; a.q_end = b.q_end; a.r_beg = b.r_beg; a.r_end = b.r_end;
-  a.list = b.long_list; a.counters = b.counters; a.out = b.out; a.scratch = b.scratch; a.scratch_stride = b.scratch_stride;
+  a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.q_bytes = b.q_bytes; a.r_bytes = b.r_bytes;
+  a.q_beg = b.q_beg; a.q_end = b.q_end; a.r_beg = b.r_beg; a.r_end = b.r_end;
+  a.list = BYTES ? b.bytes_list : b.long_list; a.counters = b.counters; a.out = b.out;
+  a.scratch = b.scratch; a.scratch_stride = b.scratch_stride;
   constexpr size_t RING = 4 * 32 * K;
   const size_t smem = 9 * 128 + 4 * (RING * 6 + 8 * sizeof(LongJob)) + (size_t)2 * K * 128 * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(sw_long_kernel<K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(sw_long_kernel<K, MINB, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
-  sw_long_kernel<K, MINB><<<ctas, 128, smem, st>>>(a);
+  sw_long_kernel<K, MINB, BYTES><<<ctas, 128, smem, st>>>(a);
   return 1;
 }
 
 int long_ctas_per_sm() { return 4; }
 
-// persistent grid (ctas = a multiple of the SM count unless the scratch clamp reduced it), work-stealing over the long list
+// persistent grids (ctas = a multiple of the SM count unless the scratch clamp reduced it), work-stealing over the long /
+// the bytes list; the two launches use disjoint scratch halves
 int launch_long(const BatchView& b, int ctas, cudaStream_t st)
 {
-  return launch_long_t<10, 4>(b, ctas, st);
+  return launch_long_t<10, 4, false>(b, ctas, st);
+}
+int launch_long_bytes(const BatchView& b, int ctas, cudaStream_t st)
+{
+  return launch_long_t<10, 4, true>(b, ctas, st);
 }
 
 // =====================================================================================
@@ -1132,7 +1165,7 @@ int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cud
 
 __global__ void single_pair_setup_kernel(Counters* c, uint32_t* list)
 {
-  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; list[0] = 0;
+  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; list[0] = 0;
 }
 
 int launch_last_row_max(const uint8_t*, uint64_t, const uint8_t*, uint64_t, int32_t*, int32_t*, cudaStream_t)

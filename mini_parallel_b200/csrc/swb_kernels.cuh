@@ -10,7 +10,7 @@ namespace swb {
 constexpr int kMatch = 2, kMismatch = -1, kGap = -2;
 
 // ---- routing classes written by classify_pairs ----
-enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2, CLASS_LONG = 3 };
+enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2, CLASS_LONG = 3, CLASS_BYTES = 4 };
 
 // Limits of the int16x2 inter-task kernel (see sw_short_kernel).
 constexpr uint32_t kShortMaxRead   = 160;    // rows held by one lane group (G x K)
@@ -24,7 +24,8 @@ struct Counters {             // device-resident, zeroed per batch
   uint32_t generic_cursor;    // work-stealing cursor of the generic kernel
   uint32_t n_long;            // ACGT-only pairs too long for the int16x2 kernel: 32-bit banded wavefront kernel
   uint32_t long_cursor;       // work-stealing cursor of the long kernel
-  uint32_t pad[2];
+  uint32_t n_bytes;           // pairs touching a non-ACGT byte (any length below kLongMaxLen): the same kernel on raw bytes
+  uint32_t bytes_cursor;
 };
 
 struct ShortDesc {            // one entry per short-listed pair, written by classify_kernel (32 B, 16-aligned)
@@ -45,6 +46,8 @@ struct BatchView {            // everything the kernels need about one batch (de
   ShortDesc*      short_desc;   // descriptors, same order as short_list
   uint32_t*       generic_list; // pair ids, n_generic entries
   uint32_t*       long_list;    // pair ids, n_long entries
+  uint32_t*       bytes_list;   // pair ids, n_bytes entries
+  int             force_bytes;  // debug/bench knob: route every non-short pair to the byte-compare kernel
   Counters*       counters;
   swb_result*     out;
   int32_t*        scratch;      // generic kernel: one boundary row per resident warp
@@ -59,6 +62,7 @@ int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_
 int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st);
 int launch_generic(const BatchView& b, int sm_count, int warps_resident, cudaStream_t st);
 int launch_long(const BatchView& b, int ctas, cudaStream_t st);
+int launch_long_bytes(const BatchView& b, int ctas, cudaStream_t st);
 int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32_t wgs, uint64_t groups,
                       int32_t* result, cudaStream_t st);
 int launch_last_row_max(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,
