@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=200_000, help="pairs per step of the CPU arm")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary measurements (unrelated reads, 1 % N, configs[0] shape)")
     ap.add_argument("--long-pairs", type=int, default=2368, help="pairs of the auxiliary 10 kb x 10 kb measurement (0 = skip)")
     args = ap.parse_args()
 
@@ -202,7 +203,8 @@ def main():
             os.close(saved)
     warmup = max(args.warmup, 3)
     n, rl, wl = args.pairs, READ_LEN, WINDOW_LEN
-    first_pair = rank * n                                  # this rank's shard of the counter-RNG stream
+    from mini_parallel_b200 import sharding
+    first_pair, _ = sharding.shard_range(rank, world, world * n)   # this rank's contiguous shard of the counter-RNG stream
     eng = mp.Engine(local_rank)
     if args.variant >= 0:
         eng.set_short_variant(args.variant)
@@ -229,11 +231,7 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.reduce_scalars([x], "max")[0]
 
     # ---- timed region 1: device-resident ----
     for _ in range(warmup):
@@ -318,6 +316,39 @@ def main():
     ref_ms = max_over_ranks(r0.elapsed_time(r1))
     ref_same = bool(torch.equal(h_out2, h_out))
 
+    # ---- auxiliary device-resident measurements on rank 0 (both distributions, the 1 % N variant,
+    #      the configs[0] shape); three steps each, the first one is warm-up ----
+    aux = {}
+    if rank == 0 and not args.no_aux:
+        def timed(tag, nn, qlen, wlen, dq, dqo, dr, dro, note):
+            ms = []
+            for s_ in range(3):
+                eng.score_batch_device(dq.data_ptr(), dqo.data_ptr(), nn * qlen, dr.data_ptr(), dro.data_ptr(), nn * wlen, nn, qlen, wlen,
+                                       d_out.data_ptr())
+                t = eng.last_timings()
+                if s_:
+                    ms.append(t["device_ms"])
+            m = statistics.mean(ms)
+            aux[tag] = {"workload": note, "ms_per_step": round(m, 3), "gcups": round(float(nn) * qlen * wlen / (m * 1e-3) / 1e9, 1),
+                        "reads_per_s": round(nn / (m * 1e-3), 1), "routing": eng.last_routing()}
+        # unrelated reads (distribution U): scores ~20, stresses the floor path
+        eng.synth_device(first_pair, n, rl, wl, 1, d_q.data_ptr(), d_qo.data_ptr(), d_r.data_ptr(), d_ro.data_ptr())
+        timed("unrelated_reads", n, rl, wl, d_q, d_qo, d_r, d_ro, f"{n} pairs {rl}x{wl}, reads independent of their windows")
+        # 1 % of the reads carry one 'N': byte-compare routing (smith_waterman.cl:114 compares raw bytes)
+        eng.synth_device(first_pair, n, rl, wl, 0, d_q.data_ptr(), d_qo.data_ptr(), d_r.data_ptr(), d_ro.data_ptr())
+        eng.sync()
+        g = torch.Generator(device=dev); g.manual_seed(0xB200)
+        sel = torch.randperm(n, device=dev, generator=g)[: n // 100].to(torch.int64)
+        d_q[sel * rl + torch.randint(0, rl, (sel.numel(),), device=dev, generator=g)] = ord("N")
+        torch.cuda.synchronize()
+        timed("one_percent_N", n, rl, wl, d_q, d_qo, d_r, d_ro, f"{n} pairs {rl}x{wl}, related reads, 1 % of the reads contain one N")
+        # BASELINE.json configs[0] shape: 10 k reads against 1 kb windows
+        c1 = 10_000
+        eng.synth_device(0, c1, rl, 1000, 0, d_q.data_ptr(), d_qo.data_ptr(), d_r.data_ptr(), d_ro.data_ptr())
+        timed("config0_shape", c1, rl, 1000, d_q, d_qo, d_r, d_ro, "BASELINE.json configs[0] shape: 10000 reads of 150 bp x 1 kb windows (one small launch)")
+        eng.synth_device(first_pair, n, rl, wl, args.dist, d_q.data_ptr(), d_qo.data_ptr(), d_r.data_ptr(), d_ro.data_ptr())
+        eng.sync()
+
     # ---- auxiliary: BASELINE.json configs[3] shape (10 kb x 10 kb pairs, sw_long_kernel), one resident wave of pairs ----
     aux_long = None
     if args.long_pairs > 0 and rank == 0:
@@ -363,6 +394,11 @@ def main():
     pack_bytes = 1.25 * n * (rl + wl)                      # 1 B read + 0.25 B written per base
     cpu_val, cpu_pairs, cpu_s = cpu_simd_gcups(0, min(n, 1_000_000), args.dist, os.cpu_count() or 1, args.cpu_budget_s)
     import oracle_lib as ol
+    from mini_parallel_b200 import synth as _synth
+    sq, sqo, sr, sro = _synth.make_pairs(0, 2000, rl, wl, args.dist)
+    t0 = time.perf_counter()
+    ol.batch(sq, sqo, sr, sro, threads=1, simd=False)
+    scalar_gcups = 2000 * rl * wl / (time.perf_counter() - t0) / 1e9
 
     line = {
         "metric": "GCUPS", "value": round(gcups, 2), "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -401,7 +437,9 @@ def main():
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(pack_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
                           "kernel_ms": round(p_ms, 4), "traffic": None, "peak_is": f"{peaks['source']} copy bandwidth"},
         "aux_long_pairs": aux_long,
+        "aux": aux,
         "cpu_baseline": {"value": round(cpu_val, 3), "unit": "GCUPS", "cores": os.cpu_count() or 1, "kind": "port", "isa": ol.simd_isa(),
+                         "scalar_oracle_gcups_1_core": round(scalar_gcups, 3),
                          "sample": f"first {cpu_pairs} pairs of the same workload, {cpu_s:.1f} s of CPU time (oracle/sw_simd.c)"},
     }
     print(json.dumps(line), flush=True)

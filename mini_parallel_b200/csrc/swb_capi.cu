@@ -160,7 +160,7 @@ int swb_sync(swb_ctx* c)
 // (d_rend == d_rbeg + 1, packed here) or ranges of the resident, already packed reference (ref_windows).
 static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
                                const uint8_t* d_r, const uint64_t* d_rbeg, const uint64_t* d_rend, uint64_t r_total,
-                               bool ref_windows, uint64_t n_pairs, uint32_t max_r_len, swb_result* d_out, int* kernels)
+                               bool ref_windows, uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out, int* kernels)
 {
   if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
   const uint64_t qw = (q_total + 15) / 16, rw = ref_windows ? 0 : (r_total + 15) / 16;
@@ -203,9 +203,9 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   {
     swb::BatchView bl = b;
     bl.scratch = l->long_scratch.as<int32_t>();
-    k += swb::launch_long(bl, ctas, st);
+    k += swb::launch_long(bl, ctas, max_q_len, st);
     bl.scratch = l->bytes_scratch.as<int32_t>();
-    k += swb::launch_long_bytes(bl, ctas, st);
+    k += swb::launch_long_bytes(bl, ctas, max_q_len, st);
   }
   CUDA_TRY(cudaEventRecord(ev[3], st));
   CUDA_TRY(cudaGetLastError());
@@ -217,14 +217,13 @@ int swb_score_batch_device(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo,
                            const uint8_t* d_r, const uint64_t* d_ro, uint64_t r_total,
                            uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out)
 {
-  (void)max_q_len;
   if (!c) return fail("null ctx");
   CUDA_TRY(cudaSetDevice(c->device));
   c->host_path = false;
   c->last_kernels = 0; c->last_chunks = 0;
   if (n_pairs == 0) { c->timings_pending = false; return 0; }
-  if (run_device_pipeline(c, c, c->ev, d_q, d_qo, q_total, d_r, d_ro, d_ro + 1, r_total, false, n_pairs, max_r_len, d_out,
-                          &c->last_kernels)) return 1;
+  if (run_device_pipeline(c, c, c->ev, d_q, d_qo, q_total, d_r, d_ro, d_ro + 1, r_total, false, n_pairs,
+                          max_q_len ? max_q_len : 0xffffffffu, max_r_len, d_out, &c->last_kernels)) return 1;
   c->timings_pending = true;
   return 0;
 }
@@ -269,10 +268,11 @@ static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const
     Lane* l = c->lane((int)(ch % kLanes));
     cudaEvent_t* ev = c->chunk_ev[ch].ev;
     cudaStream_t st = l->st;
-    uint32_t max_r = 0;
-    for (uint64_t k = p0; k < p1; ++k) {                      // validation + longest window of this chunk
+    uint32_t max_r = 0, max_q = 0;
+    for (uint64_t k = p0; k < p1; ++k) {                      // validation + longest read / window of this chunk
       if (qo[k + 1] < qo[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
       if (qo[k + 1] - qo[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
+      max_q = std::max<uint32_t>(max_q, (uint32_t)(qo[k + 1] - qo[k]));
       if (ref_windows) {
         if (win_start[k] + win_len[k] > c->ref_len) return fail(std::string(who) + ": window outside the reference");
         max_r = std::max<uint32_t>(max_r, win_len[k]);
@@ -306,11 +306,11 @@ static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const
     c->last_kernels += k;
     if (ref_windows) {
       if (run_device_pipeline(c, l, ev, l->q_bytes.as<uint8_t>(), l->q_off.as<uint64_t>(), qb, c->ref_bytes.as<uint8_t>(),
-                              l->win_beg.as<uint64_t>(), l->win_end.as<uint64_t>(), 0, true, n, max_r, l->out.as<swb_result>(),
+                              l->win_beg.as<uint64_t>(), l->win_end.as<uint64_t>(), 0, true, n, max_q, max_r, l->out.as<swb_result>(),
                               &c->last_kernels)) return 1;
     } else {
       if (run_device_pipeline(c, l, ev, l->q_bytes.as<uint8_t>(), l->q_off.as<uint64_t>(), qb, l->r_bytes.as<uint8_t>(),
-                              l->r_off.as<uint64_t>(), l->r_off.as<uint64_t>() + 1, rb, false, n, max_r, l->out.as<swb_result>(),
+                              l->r_off.as<uint64_t>(), l->r_off.as<uint64_t>() + 1, rb, false, n, max_q, max_r, l->out.as<swb_result>(),
                               &c->last_kernels)) return 1;
     }
     CUDA_TRY(cudaEventRecord(ev[6], st));

@@ -773,7 +773,8 @@ sw_long_kernel(LongArgs a)
   constexpr uint32_t WPADV = BYTES ? 0x200u : (4u << 7);
   constexpr uint32_t NOEVENT = 0xFFFFFFFFu;
   constexpr uint64_t M21 = (1ull << 21) - 1;
-  constexpr int JT = 8;                                  // live job table entries
+  constexpr int JT = 16;                                 // job table entries (live: lane 31's job .. LA jobs ahead of lane 0)
+  constexpr int LA = 4;                                  // jobs created ahead of lane 0 (the ring refill runs up to 3 chunks ahead)
 
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* lut = reinterpret_cast<uint32_t*>(smem);     // 9 entries x 32 lanes
@@ -817,14 +818,18 @@ sw_long_kernel(LongArgs a)
       j.q0 = cp_q0 + cp_row; j.r0 = cp_r0; j.n2 = cp_n2; j.row0 = cp_row; j.pair = cp_pair;
       j.rows = min(cp_n1 - cp_row, (uint32_t)NPAD);
       j.first = cp_row == 0; j.last = cp_row + NPAD >= cp_n1;
+      // column stride: the window plus K-1 pad columns; a band that hands its last row to the next band (or takes one)
+      // needs three wavefronts between producer and consumer; every job needs > 32 iterations so lanes 0 and 31 are
+      // never more than one job apart
       uint32_t wp = (cp_n2 + 2 * K - 2) / K * K;
-      if (wp < 3 * NPAD + K) wp = 3 * NPAD + K;
+      const uint32_t wmin = (j.first && j.last) ? 34u * K : 3u * NPAD + K;
+      if (wp < wmin) wp = wmin;
       j.ipp = wp / K;
       cp_row += NPAD;
       if (j.last) cp_live = false;
     } else {
       if (first_dummy == NOEVENT) first_dummy = created;
-      j.q0 = 0; j.r0 = 0; j.n2 = 0; j.row0 = 0; j.pair = 0; j.rows = 0; j.first = 1; j.last = 1; j.ipp = 3 * G + 1;
+      j.q0 = 0; j.r0 = 0; j.n2 = 0; j.row0 = 0; j.pair = 0; j.rows = 0; j.first = 1; j.last = 1; j.ipp = 34;
     }
     j.base_it = next_base_it;
     next_base_it += j.ipp;
@@ -884,7 +889,8 @@ sw_long_kernel(LongArgs a)
   };
 
   // ---- prologue ----
-  create_job(); create_job(); create_job();
+#pragma unroll 1
+  for (int k = 0; k <= LA; ++k) create_job();
   if (jobs[0].rows == 0) return;                         // nothing to steal for this warp
   {
     uint32_t* dst = reinterpret_cast<uint32_t*>(ring + L * K);
@@ -955,7 +961,7 @@ sw_long_kernel(LongArgs a)
       prev = rec; rec = 0;
       jobCol = (int32_t)(j.base_it * K); rowBase = j.row0 + K * L;
       store_n2 = j.last ? 0u : j.n2;
-      sw_it = jobs[(ljob + 1) % JT].base_it + L;         // jobs are created two ahead of lane 0
+      sw_it = jobs[(ljob + 1) % JT].base_it + L;         // jobs are created LA ahead of lane 0
       const uint32_t z2 = floor_ - 4u * SC;
 #pragma unroll
       for (int m = 0; m < K; ++m) {
@@ -1035,7 +1041,7 @@ static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
   a.list = BYTES ? b.bytes_list : b.long_list; a.counters = b.counters; a.out = b.out;
   a.scratch = b.scratch; a.scratch_stride = b.scratch_stride;
   constexpr size_t RING = 4 * 32 * K;
-  const size_t smem = 9 * 128 + 4 * (RING * 6 + 8 * sizeof(LongJob)) + (size_t)2 * K * 128 * 4;
+  const size_t smem = 9 * 128 + 4 * (RING * 6 + 16 * sizeof(LongJob)) + (size_t)2 * K * 128 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(sw_long_kernel<K, MINB, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1049,13 +1055,14 @@ int long_ctas_per_sm() { return 4; }
 
 // persistent grids (ctas = a multiple of the SM count unless the scratch clamp reduced it), work-stealing over the long /
 // the bytes list; the two launches use disjoint scratch halves
-int launch_long(const BatchView& b, int ctas, cudaStream_t st)
+// max_read_len <= 192: every job is a single band, 32 x 6 rows waste fewer lanes than 32 x 10 on 150 bp reads
+int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st)
 {
-  return launch_long_t<10, 4, false>(b, ctas, st);
+  return max_read_len <= 192 ? launch_long_t<6, 4, false>(b, ctas, st) : launch_long_t<10, 4, false>(b, ctas, st);
 }
-int launch_long_bytes(const BatchView& b, int ctas, cudaStream_t st)
+int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st)
 {
-  return launch_long_t<10, 4, true>(b, ctas, st);
+  return max_read_len <= 192 ? launch_long_t<6, 4, true>(b, ctas, st) : launch_long_t<10, 4, true>(b, ctas, st);
 }
 
 // =====================================================================================

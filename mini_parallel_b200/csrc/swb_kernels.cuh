@@ -61,8 +61,8 @@ int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_
                          const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st);
 int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st);
 int launch_generic(const BatchView& b, int sm_count, int warps_resident, cudaStream_t st);
-int launch_long(const BatchView& b, int ctas, cudaStream_t st);
-int launch_long_bytes(const BatchView& b, int ctas, cudaStream_t st);
+int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st);
+int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st);
 int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32_t wgs, uint64_t groups,
                       int32_t* result, cudaStream_t st);
 int launch_last_row_max(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,
