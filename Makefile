@@ -5,7 +5,7 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 CSRC      := mini_parallel_b200/csrc
 LIB       := mini_parallel_b200/libswb200.so
 
-all: $(LIB) build/rustseq_mini build/issue_rate_bench oracle
+all: $(LIB) build/rustseq_mini build/issue_rate_bench build/cell_loop_bench oracle
 
 $(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh include/swb200.h include/rustseq_host.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
@@ -16,6 +16,10 @@ build/rustseq_mini: $(CSRC)/rustseq_mini_main.cpp $(LIB)
 	g++ -O2 -std=c++17 -o $@ $(CSRC)/rustseq_mini_main.cpp -Lmini_parallel_b200 -lswb200 -Wl,-rpath,'$$ORIGIN/../mini_parallel_b200'
 
 build/issue_rate_bench: $(CSRC)/issue_rate_bench.cu
+	mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+
+build/cell_loop_bench: $(CSRC)/cell_loop_bench.cu
 	mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 

@@ -712,6 +712,7 @@ static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
   // persistent grid: every resident CTA slot of every SM; never more groups than pair couples in the worst case
   const uint64_t n_pp = (b.n_pairs + 1) / 2;
   uint64_t blocks = (uint64_t)sm_count * resident;
+  if (const char* v = getenv("SWB_STREAM_GRID")) { const long w = atol(v); if (w >= 1) blocks = (uint64_t)w; }
   const uint64_t need = (n_pp + 4 * GPW - 1) / (4 * GPW);
   if (blocks > need) blocks = need;
   sw_stream_kernel<G, K, MINB><<<(unsigned)blocks, 128, smem, st>>>(a);
