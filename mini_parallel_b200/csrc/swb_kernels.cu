@@ -373,10 +373,11 @@ static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t 
   const uint32_t n_iters = (NPAD + a.w_pad + K - 1) / K;
   a.wbuf_stride = (NPAD + n_iters * K + 15) & ~15u;
   const size_t smem = (size_t)a.wbuf_stride * 4 * GPW;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                         // function attributes are per device
+  int dev_id = 0; cudaGetDevice(&dev_id);
+  if (!attr_set[dev_id & 63]) {
     cudaFuncSetAttribute(sw_short_kernel<G, K, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
+    attr_set[dev_id & 63] = true;
   }
   // the grid covers the worst case (every pair short); surplus groups read n_short and leave
   const uint64_t n_pp = (b.n_pairs + 1) / 2;
@@ -701,7 +702,9 @@ static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
   StreamArgs a;
   a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.desc = b.short_desc; a.counters = b.counters; a.out = b.out;
   const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4;
-  static int resident = 0;                               // CTAs of this kernel one SM holds (asked once)
+  static int resident_by_device[64] = {};                // CTAs of this kernel one SM holds (asked once per device)
+  int dev_id = 0; cudaGetDevice(&dev_id);
+  int& resident = resident_by_device[dev_id & 63];
   if (!resident) {
     cudaFuncSetAttribute(sw_stream_kernel<G, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sw_stream_kernel<G, K, MINB>, 128, smem) != cudaSuccess || resident < 1)
@@ -1043,10 +1046,11 @@ static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
   a.scratch = b.scratch; a.scratch_stride = b.scratch_stride;
   constexpr size_t RING = 4 * 32 * K;
   const size_t smem = 9 * 128 + 4 * (RING * 6 + 16 * sizeof(LongJob)) + (size_t)2 * K * 128 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};                         // function attributes are per device
+  int dev_id = 0; cudaGetDevice(&dev_id);
+  if (!attr_set[dev_id & 63]) {
     cudaFuncSetAttribute(sw_long_kernel<K, MINB, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
+    attr_set[dev_id & 63] = true;
   }
   sw_long_kernel<K, MINB, BYTES><<<ctas, 128, smem, st>>>(a);
   return 1;
