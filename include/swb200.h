@@ -107,7 +107,7 @@ int  swb_set_short_variant(swb_ctx*, int variant);
 /* Host batches (swb_score_batch, swb_score_batch_vs_reference) are cut into chunks of about chunk_bytes of ASCII
  * input (at least min_chunk_pairs pairs each) that are pipelined over three CUDA streams: H2D of one chunk, the
  * kernels of the previous one and D2H of the one before overlap (north_star: "streams it H2D on multiple CUDA
- * streams").  Defaults: 64 MiB, 16384 pairs; SWB_CHUNK_MB overrides the first.  Pass pinned host memory
+ * streams").  Defaults: 32 MiB (16 MiB when only reads travel), 16384 pairs; SWB_CHUNK_MB overrides the first.  Pass pinned host memory
  * (swb_malloc_pinned) for the copies to be asynchronous. */
 int  swb_set_chunking(swb_ctx*, uint64_t chunk_bytes, uint64_t min_chunk_pairs);
 

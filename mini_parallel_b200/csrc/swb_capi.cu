@@ -60,7 +60,8 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   swb::Counters* h_counters = nullptr;     // pinned, one slot per chunk
   size_t h_counters_cap = 0;
   size_t last_chunks = 0;
-  uint64_t chunk_bytes = 64ull << 20;      // ASCII bytes per chunk of a host batch (SWB_CHUNK_MB, swb_set_chunking)
+  uint64_t chunk_bytes = 32ull << 20;      // ASCII bytes per chunk of a host batch (SWB_CHUNK_MB, swb_set_chunking); half of it
+                                           // when only reads travel (windows of the resident reference): measured optima on B200
   uint64_t min_chunk_pairs = 16384;
   float last_ms[6] = {0, 0, 0, 0, 0, 0};
   int last_kernels = 0;
@@ -256,7 +257,8 @@ static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const
   const bool ref_windows = (r == nullptr && ro == nullptr);
   if (qo[0] != 0 || (!ref_windows && ro[0] != 0)) return fail(std::string(who) + ": offsets must start at 0");
   const uint64_t bytes_total = qo[n_pairs] + (ref_windows ? 0 : ro[n_pairs]);
-  uint64_t n_chunks = std::max<uint64_t>(1, (bytes_total + c->chunk_bytes - 1) / c->chunk_bytes);
+  const uint64_t cb = ref_windows ? std::max<uint64_t>(c->chunk_bytes / 2, 1) : c->chunk_bytes;
+  uint64_t n_chunks = std::max<uint64_t>(1, (bytes_total + cb - 1) / cb);
   uint64_t per = (n_pairs + n_chunks - 1) / n_chunks;
   per = std::max<uint64_t>(per, std::min<uint64_t>(n_pairs, c->min_chunk_pairs));
   n_chunks = (n_pairs + per - 1) / per;

@@ -278,7 +278,7 @@ def test_host_path_is_chunked_over_streams_and_stays_exact(engine):
             assert rt["short"] + rt["generic"] + rt["long"] == 4998, rt      # the two empty pairs are routed nowhere
             assert rt["generic"] >= 1
     finally:
-        engine.set_chunking(64 << 20, 16384)
+        engine.set_chunking(32 << 20, 16384)
 
 
 def test_reference_windows_chunked(engine):
@@ -303,4 +303,42 @@ def test_reference_windows_chunked(engine):
             got = engine.score_batch_vs_reference(q, qo, start, wlen)
             assert np.array_equal(got, exp), (chunk_bytes, min_pairs)
     finally:
-        engine.set_chunking(64 << 20, 16384)
+        engine.set_chunking(32 << 20, 16384)
+
+
+def test_config4_full_size_long_pairs(engine):
+    """BASELINE.json configs[3] at full size: 10 000 pairs of 10 kb x 10 kb (1e12 cells) through sw_long_kernel,
+    inputs generated and kept in HBM.  Checked through size-independent properties -- an identical pair scores 2n and ends
+    in the last cell, the score is symmetric in its arguments, bounds -- plus three pairs against the oracle."""
+    n, L = 10_000, 10_000
+    dq, dqo = engine.malloc_device(n * L), engine.malloc_device((n + 1) * 8)
+    dr, dro = engine.malloc_device(n * L), engine.malloc_device((n + 1) * 8)
+    dout = engine.malloc_device(n * 12)
+    try:
+        engine.synth_device(0, n, L, L, 0, dq, dqo, dr, dro)            # related: read = window with ~1.2 % edits
+        engine.score_batch_device(dq, dqo, n * L, dr, dro, n * L, n, L, L, dout)
+        engine.sync()
+        out = np.zeros(n, dtype=mp.RESULT_DTYPE)
+        engine.d2h(out, dout, out.nbytes)
+        assert engine.last_routing() == {"short": 0, "generic": 0, "long": n}
+        assert out["score"].min() > 18_000 and out["score"].max() <= 2 * L
+        assert np.all(out["end_i"] < L) and np.all(out["end_j"] < L) and np.all(out["end_i"] > 9_000)
+        q = np.zeros(3 * L, dtype=np.uint8); r = np.zeros(3 * L, dtype=np.uint8)
+        engine.d2h(q, dq, q.nbytes); engine.d2h(r, dr, r.nbytes)
+        for k in range(3):
+            assert tuple(out[k]) == ol.sw_linear(q[k * L:(k + 1) * L].tobytes(), r[k * L:(k + 1) * L].tobytes())
+        # symmetry: swapping reads and windows leaves every score unchanged (coordinates follow the tie-break, not checked)
+        engine.score_batch_device(dr, dro, n * L, dq, dqo, n * L, n, L, L, dout)
+        engine.sync()
+        swapped = np.zeros(n, dtype=mp.RESULT_DTYPE)
+        engine.d2h(swapped, dout, swapped.nbytes)
+        assert np.array_equal(swapped["score"], out["score"])
+        # identity: every window against itself scores 2n and ends in the last cell
+        engine.score_batch_device(dr, dro, n * L, dr, dro, n * L, n, L, L, dout)
+        engine.sync()
+        ident = np.zeros(n, dtype=mp.RESULT_DTYPE)
+        engine.d2h(ident, dout, ident.nbytes)
+        assert np.all(ident["score"] == 2 * L) and np.all(ident["end_i"] == L - 1) and np.all(ident["end_j"] == L - 1)
+    finally:
+        for p in (dq, dqo, dr, dro, dout):
+            engine.free_device(p)
