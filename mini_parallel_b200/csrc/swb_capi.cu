@@ -249,10 +249,10 @@ static int ensure_chunk_slots(swb_ctx* c, size_t n_chunks)
   return 0;
 }
 
-static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const uint64_t* qo,
-                            const uint8_t* r, const uint64_t* ro,                     /* CSR windows, or */
-                            const uint64_t* win_start, const uint32_t* win_len,       /* windows of the resident reference */
-                            uint64_t n_pairs, swb_result* out)
+static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* q, const uint64_t* qo,
+                                   const uint8_t* r, const uint64_t* ro,                     /* CSR windows, or */
+                                   const uint64_t* win_start, const uint32_t* win_len,       /* windows of the resident reference */
+                                   uint64_t n_pairs, swb_result* out)
 {
   const bool ref_windows = (r == nullptr && ro == nullptr);
   if (qo[0] != 0 || (!ref_windows && ro[0] != 0)) return fail(std::string(who) + ": offsets must start at 0");
@@ -324,6 +324,22 @@ static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const
   CUDA_TRY(cudaGetLastError());
   c->host_path = true; c->last_chunks = (size_t)n_chunks; c->timings_pending = true;
   return 0;
+}
+
+static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro,
+                            const uint64_t* win_start, const uint32_t* win_len, uint64_t n_pairs, swb_result* out)
+{
+  const int rc = score_host_batch_enqueue(c, who, q, qo, r, ro, win_start, win_len, n_pairs, out);
+  if (rc != 0) {
+    // an error after some chunks were enqueued: the caller's buffers are borrowed for the call only, so nothing may
+    // still be reading or writing them when we return
+    const std::string keep = g_err;
+    for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(c->lane(i)->st);
+    cudaGetLastError();
+    c->timings_pending = false;
+    g_err = keep;
+  }
+  return rc;
 }
 
 int swb_score_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro,

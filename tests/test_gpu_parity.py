@@ -342,3 +342,22 @@ def test_config4_full_size_long_pairs(engine):
     finally:
         for p in (dq, dqo, dr, dro, dout):
             engine.free_device(p)
+
+
+def test_error_in_a_later_chunk_leaves_the_engine_usable(engine):
+    """A malformed offset found while chunk 3 is being validated aborts the call after chunks 0-2 were enqueued; the call
+    must drain them (inputs are borrowed for the call only) and the context must keep working."""
+    rng = np.random.default_rng(950)
+    reads, wins = _pairs(rng, 4000, (100, 160), (200, 600))
+    q, qo = to_csr(reads)
+    r, ro = to_csr(wins)
+    bad = qo.copy()
+    bad[3500] = bad[3499] - 1                                     # non-monotone offset inside the last chunk
+    try:
+        engine.set_chunking(1 << 17, 1000)
+        with pytest.raises(mp.SwbError, match="non-decreasing"):
+            engine.score_batch_csr(q, bad, r, ro)
+        got = engine.score_batch_csr(q, qo, r, ro)
+        assert np.array_equal(got, ol.batch(q, qo, r, ro, threads=8, simd=True))
+    finally:
+        engine.set_chunking(32 << 20, 16384)
