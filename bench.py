@@ -256,6 +256,21 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     routing = eng.last_routing()
 
+    # ---- the packing kernel alone (HBM roofline of pack2bit_kernel; classify and launch gaps excluded) ----
+    pk_words = torch.empty((n * wl + 15) // 16 + 16, dtype=torch.int32, device=dev)
+    pk_bits = torch.empty(pk_words.numel() // 32 + 16, dtype=torch.int32, device=dev)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            eng.pack2bit_device(d_r.data_ptr(), n * wl, pk_words.data_ptr(), pk_bits.data_ptr())
+        p0.record(stream)
+        for _ in range(10):
+            eng.pack2bit_device(d_r.data_ptr(), n * wl, pk_words.data_ptr(), pk_bits.data_ptr())
+        p1.record(stream)
+    torch.cuda.synchronize()
+    pack_alone_ms = p0.elapsed_time(p1) / 10
+    del pk_words, pk_bits
+
     # ---- timed region 2: end to end through the host API (pinned host buffers) ----
     h_q = torch.empty(n * rl, dtype=torch.uint8).pin_memory()
     h_r = torch.empty(n * wl, dtype=torch.uint8).pin_memory()
@@ -435,7 +450,11 @@ def main():
                                 f"thread-instr/clk/SM (measured, {rate_src}) / {INT_ISSUE_PER_CELL} instr per cell"},
         "roofline_pack": {"bound": "hbm", "kernel": "pack2bit_kernel x2 + classify_kernel", "achieved": round(pack_bytes / (p_ms * 1e-3) / 1e9, 1),
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(pack_bytes / (p_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
-                          "kernel_ms": round(p_ms, 4), "traffic": None, "peak_is": f"{peaks['source']} copy bandwidth"},
+                          "kernel_ms": round(p_ms, 4), "traffic": None, "peak_is": f"{peaks['source']} copy bandwidth",
+                          "pack2bit_kernel_alone": {"bytes": int(1.25 * n * wl), "ms": round(pack_alone_ms, 4),
+                                                    "achieved": round(1.25 * n * wl / (pack_alone_ms * 1e-3) / 1e9, 1),
+                                                    "frac": round(1.25 * n * wl / (pack_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4),
+                                                    "what": "the window array of the step (500 MB in, 125 MB out), 10 back-to-back launches"}},
         "aux_long_pairs": aux_long,
         "aux": aux,
         "cpu_baseline": {"value": round(cpu_val, 3), "unit": "GCUPS", "cores": os.cpu_count() or 1, "kind": "port", "isa": ol.simd_isa(),

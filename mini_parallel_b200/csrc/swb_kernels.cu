@@ -39,33 +39,47 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t& bad)
   return (t & 0xFu) | ((t >> 12) & 0xF0u);
 }
 
+// One warp packs UNROLL groups of 32 words (512 bases each) per iteration: every lane issues UNROLL independent
+// 128-bit loads before it touches the first result, which is what keeps enough bytes in flight for HBM3e.
+constexpr int kPackUnroll = 4;
+
+__device__ __forceinline__ uint4 pack_load(const uint8_t* __restrict__ bytes, uint64_t n, uint64_t w)
+{
+  const uint64_t base = w << 4;
+  if (base + 16 <= n) return __ldcs(reinterpret_cast<const uint4*>(bytes + base));    // streamed once: 128-bit, evict-first
+  uint32_t t[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};                 // ragged tail: pad with 'A'
+  for (uint64_t k = base; k < n; ++k) {
+    const uint32_t sh = (uint32_t)((k - base) & 3) * 8;
+    t[(k - base) >> 2] = (t[(k - base) >> 2] & ~(0xFFu << sh)) | ((uint32_t)bytes[k] << sh);
+  }
+  return make_uint4(t[0], t[1], t[2], t[3]);
+}
+
 __global__ void __launch_bounds__(256)
 pack2bit_kernel(const uint8_t* __restrict__ bytes, uint64_t n, uint32_t* __restrict__ words,
                 uint32_t* __restrict__ bitmap)
 {
   const uint64_t n_words = (n + 15) >> 4;
-  const uint64_t n_round = (n_words + 31) & ~uint64_t(31);
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_round; w += stride) {
-    uint32_t word = 0, bad = 0;
-    if (w < n_words) {
-      const uint64_t base = w << 4;
-      uint4 v;
-      if (base + 16 <= n) {
-        v = __ldg(reinterpret_cast<const uint4*>(bytes + base));        // 128-bit coalesced load
-      } else {                                                          // ragged tail: pad with 'A'
-        uint32_t t[4] = {0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u};
-        for (uint64_t k = base; k < n; ++k) {
-          const uint32_t sh = (uint32_t)((k - base) & 3) * 8;
-          t[(k - base) >> 2] = (t[(k - base) >> 2] & ~(0xFFu << sh)) | ((uint32_t)bytes[k] << sh);
-        }
-        v = make_uint4(t[0], t[1], t[2], t[3]);
-      }
-      word = pack4(v.x, bad) | (pack4(v.y, bad) << 8) | (pack4(v.z, bad) << 16) | (pack4(v.w, bad) << 24);
-      words[w] = word;
+  const uint64_t n_groups = (n_words + 31) >> 5;                       // 32 words = one bitmap word
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t g0 = warp * kPackUnroll; g0 < n_groups; g0 += n_warps * kPackUnroll) {
+    uint4 v[kPackUnroll];
+#pragma unroll
+    for (int u = 0; u < kPackUnroll; ++u) {
+      const uint64_t w = ((g0 + u) << 5) + lane;
+      v[u] = w < n_words ? pack_load(bytes, n, w) : make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
     }
-    const uint32_t ballot = __ballot_sync(0xffffffffu, bad != 0);
-    if ((threadIdx.x & 31) == 0 && w < n_words) bitmap[w >> 5] = ballot;
+#pragma unroll
+    for (int u = 0; u < kPackUnroll; ++u) {
+      const uint64_t w = ((g0 + u) << 5) + lane;
+      uint32_t bad = 0;
+      const uint32_t word = pack4(v[u].x, bad) | (pack4(v[u].y, bad) << 8) | (pack4(v[u].z, bad) << 16) | (pack4(v[u].w, bad) << 24);
+      if (w < n_words) words[w] = word;
+      const uint32_t ballot = __ballot_sync(0xffffffffu, bad != 0);
+      if (lane == 0 && g0 + u < n_groups) bitmap[g0 + u] = ballot;
+    }
   }
 }
 
@@ -73,8 +87,8 @@ int launch_pack2bit(const uint8_t* bytes, uint64_t n, uint32_t* words, uint32_t*
 {
   if (n == 0) return 0;
   const uint64_t n_words = (n + 15) >> 4;
-  uint64_t blocks = (n_words + 255) / 256;
-  if (blocks > 148 * 32) blocks = 148 * 32;          // grid-stride: a multiple of the SM count
+  uint64_t blocks = (n_words + 256 * kPackUnroll - 1) / (256 * kPackUnroll);
+  if (blocks > 148 * 16) blocks = 148 * 16;          // grid-stride: a multiple of the SM count
   pack2bit_kernel<<<(unsigned)blocks, 256, 0, st>>>(bytes, n, words, bitmap);
   return 1;
 }
