@@ -1077,7 +1077,15 @@ int long_ctas_per_sm() { return 4; }
 // max_read_len <= 192: every job is a single band, 32 x 6 rows waste fewer lanes than 32 x 10 on 150 bp reads
 int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st)
 {
-  return max_read_len <= 192 ? launch_long_t<6, 4, false>(b, ctas, st) : launch_long_t<10, 4, false>(b, ctas, st);
+  if (max_read_len <= 192) return launch_long_t<6, 4, false>(b, ctas, st);
+  static int k_env = -1;                                 // SWB_LONG_K: rows per lane (tuning experiments)
+  if (k_env < 0) { const char* v = getenv("SWB_LONG_K"); k_env = v ? atoi(v) : 0; }
+  switch (k_env) {                                       // measured on 10 kb pairs: K=10 4019, 12 4113, 14 3959, 16 3658 GCUPS
+    case 10: return launch_long_t<10, 4, false>(b, ctas, st);
+    case 14: return launch_long_t<14, 4, false>(b, ctas, st);
+    case 16: return launch_long_t<16, 3, false>(b, ctas * 3 / 4, st);
+    default: return launch_long_t<12, 4, false>(b, ctas, st);
+  }
 }
 int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st)
 {

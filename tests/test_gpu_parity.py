@@ -140,13 +140,18 @@ def test_mixed_batch_routing_and_empties(engine):
 
 
 def test_long_kernel_band_and_stride_edges(engine):
-    """sw_long_kernel: bands of 320 rows streamed through one warp.  Row counts around the band height, windows
+    """sw_long_kernel: bands of 32*K rows streamed through one warp (K = 12 for ACGT pairs -> 384 rows, K = 10 for raw
+    bytes -> 320, K = 6 -> 192 when every read of the batch is <= 192 bp).  Row counts around the band heights, windows
     shorter / longer than the minimum column stride (3 wavefronts), tall-and-narrow and short-and-wide pairs, many
     pairs per warp (work stealing), ties."""
     rng = np.random.default_rng(750)
     _assert_parity(engine, *_pairs(rng, 40, (161, 170), (1, 400)))                  # one band, window < stride
     assert engine.last_routing()["long"] == 40
     _assert_parity(engine, *_pairs(rng, 60, (318, 323), (900, 1100)))               # band boundary 320, stride boundary 970
+    _assert_parity(engine, *_pairs(rng, 60, (382, 387), (1100, 1200)))              # band boundary 384, stride boundary 1164
+    _assert_parity(engine, *_pairs(rng, 30, (766, 771), (1150, 1180)))              # two / three bands of 384
+    _assert_parity(engine, *_pairs(rng, 60, (318, 323), (900, 1100), alphabet=b"ACGTN"))   # the same edges on the byte kernel
+    _assert_parity(engine, *_pairs(rng, 40, (161, 192), (1, 700), alphabet=b"ACGTN"))      # K = 6 byte kernel
     _assert_parity(engine, *_pairs(rng, 30, (639, 642), (950, 990)))                # two / three bands
     _assert_parity(engine, *_pairs(rng, 12, (1500, 2500), (1, 50), related=False))  # tall and narrow
     _assert_parity(engine, *_pairs(rng, 12, (161, 200), (6000, 9000)))              # short and wide
