@@ -443,8 +443,9 @@ def main():
                                           "uploaded once)"},
         "roofline": {"bound": "int_issue", "kernel": "sw_stream_kernel" if args.variant < 0 or args.variant >= 4 else "sw_short_kernel", "achieved": round(k_gcups, 1), "peak": round(peak_gcups, 1),
                      "unit": "GCUPS", "frac": round(k_gcups / peak_gcups, 4),
-                     "traffic": None if traffic is None else {"dram_bytes_per_launch": int(traffic), "source": f"profiles/{traffic_src}",
-                                                              "algorithmic_bytes_per_launch": int(n * (rl / 4 + wl / 4 + 32 + 12))},
+                     "traffic": None if traffic is None else int(traffic),       # dram read+write bytes of one launch (ncu --set full)
+                     "traffic_source": None if traffic is None else f"profiles/{traffic_src}",
+                     "algorithmic_bytes_per_launch": int(n * (rl / 4 + wl / 4 + 32 + 12)),
                      "kernel_ms": round(k_ms, 4), "kernel_share_of_step": round(k_ms / (ms_total / args.steps), 4),
                      "peak_is": f"{sms} SMs x {peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} MEASURED_PEAKS.json) x {rate:.2f} DPX s16x2 "
                                 f"thread-instr/clk/SM (measured, {rate_src}) / {INT_ISSUE_PER_CELL} instr per cell"},
