@@ -60,6 +60,24 @@ int  swb_set_reference(swb_ctx*, const uint8_t* ref_bytes, uint64_t n);
 int  swb_score_batch_vs_reference(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off, uint64_t n_pairs,
                                   const uint64_t* win_start, const uint32_t* win_len, swb_result* out);
 
+/* FASTQ.gz ingest on the GPU for blocked gzip (BGZF: bgzip, BCL Convert): replaces the `zcat` child and the per-line
+ * String loop of process_fastq_file_in_chunks (aligner.rs:107-178) for the --full-wgs path.  The host only walks the
+ * block headers; a segment of whole blocks is copied to the device, inflated one warp per block, indexed (every 4th
+ * line + 2 is a read, aligner.rs:138) and scored against windows of the resident reference (window of read g of file f:
+ * start = splitmix64(((f << 40) + g) ^ 0xB202) mod (ref_len - window_len + 1), the pairing rule of the WGS driver).
+ *   blocks[k]      deflate payload of block k inside comp[] and its inflated size (the member's ISIZE)
+ *   carry          text left over from the previous segment of the file: the bytes after its last complete record
+ *   final_segment  no more data follows: an unterminated last line still counts (BufRead::lines)
+ * Outputs: sum of the scores, reads and bases scored, and the new carry (at most carry_cap bytes).
+ * *status = 0 ok; 1 = the data needs the host path (an inflate error, a non-ASCII byte, a carry larger than carry_cap):
+ * nothing was scored, the caller falls back to zlib + rsm_process_fastq_file_in_chunks semantics. */
+typedef struct { uint64_t in_off; uint32_t in_len; uint32_t out_len; } swb_bgzf_block;
+int  swb_fastq_bgzf_score(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
+                          const uint8_t* carry, uint64_t carry_len, int final_segment,
+                          uint64_t file_index, uint64_t first_read, uint32_t window_len,
+                          int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases,
+                          uint8_t* carry_out, uint64_t carry_cap, uint64_t* carry_out_len, int* status);
+
 /* Same, DEVICE-resident inputs and outputs (pointers from cudaMalloc / a torch tensor's data_ptr);
  * runs on the context's stream, returns after the work is enqueued; swb_sync() waits. */
 int  swb_score_batch_device(swb_ctx*, const uint8_t* d_q_bytes, const uint64_t* d_q_off, uint64_t q_total_bytes,

@@ -55,6 +55,7 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   Lane extra[kLanes - 1];
   Lane* lane(int i) { return i == 0 ? static_cast<Lane*>(this) : &extra[i - 1]; }
   DevBuf ref_bytes, ref_pk, ref_bad;       // device-resident reference (swb_set_reference)
+  DevBuf fq_comp, fq_blocks, fq_out_off, fq_text, fq_tile_count, fq_tile_prefix, fq_seq_beg, fq_seq_end, fq_scal;   // swb_fastq_bgzf_score
   uint64_t ref_len = 0;
   std::vector<ChunkEvents> chunk_ev;       // host path: one event set per chunk of the last call
   swb::Counters* h_counters = nullptr;     // pinned, one slot per chunk
@@ -131,7 +132,8 @@ void swb_destroy(swb_ctx* c)
     for (auto& e : l->ev) cudaEventDestroy(e);
     cudaStreamDestroy(l->st);
   }
-  for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad}) b->release();
+  for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->fq_comp, &c->fq_blocks, &c->fq_out_off, &c->fq_text, &c->fq_tile_count,
+                    &c->fq_tile_prefix, &c->fq_seq_beg, &c->fq_seq_end, &c->fq_scal}) b->release();
   for (auto& ce : c->chunk_ev) for (auto& e : ce.ev) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
@@ -161,7 +163,9 @@ int swb_sync(swb_ctx* c)
 // (d_rend == d_rbeg + 1, packed here) or ranges of the resident, already packed reference (ref_windows).
 static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
                                const uint8_t* d_r, const uint64_t* d_rbeg, const uint64_t* d_rend, uint64_t r_total,
-                               bool ref_windows, uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out, int* kernels)
+                               bool ref_windows, uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out, int* kernels,
+                               const uint64_t* d_qend = nullptr /* reads as [beg,end) ranges instead of CSR */,
+                               bool q_prepacked = false /* lane's q_pk / q_bad already hold the packed d_q */)
 {
   if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
   const uint64_t qw = (q_total + 15) / 16, rw = ref_windows ? 0 : (r_total + 15) / 16;
@@ -178,7 +182,7 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
       l->bytes_scratch.reserve((uint64_t)ctas * 4 * stride * 4)) return 1;
 
   swb::BatchView b;
-  b.q_bytes = d_q; b.q_beg = d_qo; b.q_end = d_qo + 1; b.r_bytes = d_r; b.r_beg = d_rbeg; b.r_end = d_rend;
+  b.q_bytes = d_q; b.q_beg = d_qo; b.q_end = d_qend ? d_qend : d_qo + 1; b.r_bytes = d_r; b.r_beg = d_rbeg; b.r_end = d_rend;
   b.q_pk = l->q_pk.as<uint32_t>(); b.q_bad = l->q_bad.as<uint32_t>();
   b.r_pk = ref_windows ? c->ref_pk.as<uint32_t>() : l->r_pk.as<uint32_t>();
   b.r_bad = ref_windows ? c->ref_bad.as<uint32_t>() : l->r_bad.as<uint32_t>();
@@ -193,7 +197,7 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   cudaStream_t st = l->st;
   CUDA_TRY(cudaMemsetAsync(l->counters.p, 0, sizeof(swb::Counters), st));
   CUDA_TRY(cudaEventRecord(ev[0], st));
-  k += swb::launch_pack2bit(d_q, q_total, l->q_pk.as<uint32_t>(), l->q_bad.as<uint32_t>(), st);
+  if (!q_prepacked) k += swb::launch_pack2bit(d_q, q_total, l->q_pk.as<uint32_t>(), l->q_bad.as<uint32_t>(), st);
   if (!ref_windows) k += swb::launch_pack2bit(d_r, r_total, l->r_pk.as<uint32_t>(), l->r_bad.as<uint32_t>(), st);
   k += swb::launch_classify(b, st);
   CUDA_TRY(cudaEventRecord(ev[1], st));
@@ -378,6 +382,117 @@ int swb_score_batch_vs_reference(swb_ctx* c, const uint8_t* q, const uint64_t* q
   CUDA_TRY(cudaSetDevice(c->device));
   static const uint8_t empty = 0;
   return score_host_batch(c, "swb_score_batch_vs_reference", q ? q : &empty, qo, nullptr, nullptr, win_start, win_len, n_pairs, out);
+}
+
+// ---- FASTQ.gz (BGZF) -> scores entirely on the device ----
+int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
+                         const uint8_t* carry, uint64_t carry_len, int final_segment,
+                         uint64_t file_index, uint64_t first_read, uint32_t window_len,
+                         int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases,
+                         uint8_t* carry_out, uint64_t carry_cap, uint64_t* carry_out_len, int* status)
+{
+  if (!c || !score_sum || !n_reads || !n_bases || !carry_out_len || !status) return fail("swb_fastq_bgzf_score: null pointer");
+  if ((n_blocks && (!comp || !blocks)) || (carry_len && !carry)) return fail("swb_fastq_bgzf_score: null input");
+  if (c->ref_len == 0) return fail("swb_fastq_bgzf_score: no resident reference (swb_set_reference)");
+  if (window_len == 0 || window_len > c->ref_len) return fail("swb_fastq_bgzf_score: window outside the reference");
+  CUDA_TRY(cudaSetDevice(c->device));
+  *score_sum = 0; *n_reads = 0; *n_bases = 0; *carry_out_len = 0; *status = 0;
+  cudaStream_t st = c->st;
+
+  // text layout: [room for the carry, right-aligned][inflated blocks]; tiles are 16-byte aligned, 64 bytes of slack
+  const uint64_t base_off = (carry_len + 255) & ~255ull;
+  std::vector<uint64_t> out_off(n_blocks);
+  uint64_t text_end = base_off;
+  for (uint64_t k = 0; k < n_blocks; ++k) {
+    if (blocks[k].in_off + blocks[k].in_len > comp_bytes) return fail("swb_fastq_bgzf_score: block outside the compressed buffer");
+    out_off[k] = text_end; text_end += blocks[k].out_len;
+  }
+  const uint64_t begin = base_off - carry_len, end = text_end;
+  if (end == begin) return 0;
+  const uint64_t n_tiles = swb::fq_tiles(begin, end);
+  if (c->fq_comp.reserve(comp_bytes + 64) || c->fq_blocks.reserve(n_blocks * sizeof(swb_bgzf_block) + 64) ||
+      c->fq_out_off.reserve(n_blocks * 8 + 64) || c->fq_text.reserve(end + 4096 + 64) || c->fq_tile_count.reserve(n_tiles * 4 + 64) ||
+      c->fq_tile_prefix.reserve(n_tiles * 8 + 64) || c->fq_scal.reserve(64)) return 1;
+  uint8_t* d_text = c->fq_text.as<uint8_t>();
+  uint64_t* d_scal = c->fq_scal.as<uint64_t>();          // [0] newlines [1] tail_start [2] score sum [3] bases [4] (u32) failed blocks, flags
+  uint32_t* d_fail = reinterpret_cast<uint32_t*>(d_scal + 4);
+  CUDA_TRY(cudaMemsetAsync(d_scal, 0, 64, st));
+  if (comp_bytes) CUDA_TRY(cudaMemcpyAsync(c->fq_comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
+  if (n_blocks) {
+    CUDA_TRY(cudaMemcpyAsync(c->fq_blocks.p, blocks, n_blocks * sizeof(swb_bgzf_block), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->fq_out_off.p, out_off.data(), n_blocks * 8, cudaMemcpyHostToDevice, st));
+  }
+  if (carry_len) CUDA_TRY(cudaMemcpyAsync(d_text + begin, carry, carry_len, cudaMemcpyHostToDevice, st));
+  int k = 0;
+  k += swb::launch_inflate_bgzf(c->fq_comp.as<uint8_t>(), c->fq_blocks.as<swb_bgzf_block>(), n_blocks, c->fq_out_off.as<uint64_t>(), d_text,
+                                d_fail, st);
+  k += swb::launch_fq_index(d_text, begin, end, c->fq_tile_count.as<uint32_t>(), c->fq_tile_prefix.as<uint64_t>(), d_scal, d_fail + 1, st);
+  uint64_t h_scal[8] = {};
+  uint8_t last = 0;
+  CUDA_TRY(cudaMemcpyAsync(h_scal, d_scal, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&last, d_text + end - 1, 1, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));                    // out_off lives on this stack frame; the counts size what follows
+  CUDA_TRY(cudaGetLastError());
+  const uint32_t failed = (uint32_t)(h_scal[4] & 0xffffffffu), flags = (uint32_t)(h_scal[4] >> 32);
+  if (std::getenv("SWB_DEBUG")) std::fprintf(stderr, "[fastq] blocks %llu text [%llu,%llu) newlines %llu failed %u (first status %u after %u bytes) flags %u last %d\n", (unsigned long long)n_blocks,
+                                            (unsigned long long)begin, (unsigned long long)end, (unsigned long long)h_scal[0], failed,
+                                            (uint32_t)(h_scal[5] & 0xffffffffu), (uint32_t)(h_scal[5] >> 32), flags, (int)last);
+  if (failed || flags) { *status = 1; return 0; }
+  const uint64_t newlines = h_scal[0];
+  const uint64_t lines = newlines + ((final_segment && last != '\n') ? 1 : 0);
+  const uint64_t R = final_segment ? (lines + 2) / 4 : newlines / 4;
+  if (c->fq_seq_beg.reserve((R + 1) * 8 + 64) || c->fq_seq_end.reserve((R + 1) * 8 + 64)) return 1;
+  uint64_t* d_beg = c->fq_seq_beg.as<uint64_t>(); uint64_t* d_end = c->fq_seq_end.as<uint64_t>();
+  CUDA_TRY(cudaMemsetAsync(d_beg, 0, (R + 1) * 8, st));
+  CUDA_TRY(cudaMemsetAsync(d_end, 0, (R + 1) * 8, st));
+  const unsigned long long tail0 = begin;
+  CUDA_TRY(cudaMemcpyAsync(d_scal + 1, &tail0, 8, cudaMemcpyHostToDevice, st));
+  k += swb::launch_fq_extract_mask(d_text, begin, end, c->fq_tile_prefix.as<uint64_t>(), d_beg, d_end, R,
+                                   reinterpret_cast<unsigned long long*>(d_scal + 1), final_segment, st);
+  if (const char* dump = std::getenv("SWB_FASTQ_DUMP")) {        // debug: text after masking and the read ranges
+    std::vector<uint8_t> ht(end - begin); std::vector<uint64_t> hb(R), he(R);
+    CUDA_TRY(cudaMemcpyAsync(ht.data(), d_text + begin, end - begin, cudaMemcpyDeviceToHost, st));
+    if (R) { CUDA_TRY(cudaMemcpyAsync(hb.data(), d_beg, R * 8, cudaMemcpyDeviceToHost, st)); CUDA_TRY(cudaMemcpyAsync(he.data(), d_end, R * 8, cudaMemcpyDeviceToHost, st)); }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (FILE* f = std::fopen(dump, "wb")) {
+      const uint64_t hdr[4] = {begin, end, R, newlines};
+      std::fwrite(hdr, 8, 4, f); std::fwrite(ht.data(), 1, ht.size(), f); std::fwrite(hb.data(), 8, R, f); std::fwrite(he.data(), 8, R, f);
+      std::fclose(f);
+    }
+  }
+  // pack the whole (masked) text once; the batches below score ranges of it in place
+  const uint64_t qw = (end + 15) / 16;
+  if (c->q_pk.reserve(qw * 4 + 64) || c->q_bad.reserve((qw + 31) / 32 * 4 + 64)) return 1;
+  k += swb::launch_pack2bit(d_text, end, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
+  const uint64_t batch = 4ull << 20;
+  if (R) {
+    const uint64_t nb = std::min(R, batch);
+    if (c->win_beg.reserve(nb * 8) || c->win_end.reserve(nb * 8) || c->out.reserve(nb * sizeof(swb_result))) return 1;
+  }
+  for (uint64_t a = 0; a < R; a += batch) {
+    const uint64_t n = std::min(batch, R - a);
+    k += swb::launch_fq_windows(file_index, first_read + a, n, c->ref_len, window_len, d_beg + a, d_end + a, c->win_beg.as<uint64_t>(),
+                                c->win_end.as<uint64_t>(), st);
+    if (run_device_pipeline(c, c, c->ev, d_text, d_beg + a, end, c->ref_bytes.as<uint8_t>(), c->win_beg.as<uint64_t>(),
+                            c->win_end.as<uint64_t>(), 0, true, n, 0xffffffffu, window_len, c->out.as<swb_result>(), &k, d_end + a, true)) return 1;
+    k += swb::launch_fq_reduce(c->out.as<swb_result>(), d_beg + a, d_end + a, n, reinterpret_cast<unsigned long long*>(d_scal + 2), st);
+  }
+  CUDA_TRY(cudaMemcpyAsync(h_scal, d_scal, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  if (!final_segment) {
+    const uint64_t tail_start = h_scal[1];
+    const uint64_t tl = end - tail_start;
+    if (tl > carry_cap || (tl && !carry_out)) { *status = 1; return 0; }          // a single record larger than the carry buffer
+    if (tl) {
+      CUDA_TRY(cudaMemcpyAsync(carry_out, d_text + tail_start, tl, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    *carry_out_len = tl;
+  }
+  *score_sum = (int64_t)h_scal[2]; *n_reads = R; *n_bases = h_scal[3];
+  c->last_kernels = k; c->host_path = false; c->timings_pending = false;
+  return 0;
 }
 
 int swb_score_pair(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, swb_result* out)

@@ -1,0 +1,238 @@
+// swb_inflate.cuh -- raw DEFLATE (RFC 1951) decoder for one small member, written once for two targets:
+//   * device: one WARP per BGZF block (<= 64 KiB of text).  All 32 lanes run the same decode loop on the same
+//     bits (uniform control flow, broadcast loads); Huffman table fills and LZ77 copies are split across the lanes.
+//   * host  : the same code with one "lane", compiled by g++ for the CPU unit test that compares it with zlib
+//     (tests/test_inflate_core.py).  No GPU is needed to check the bit-level logic.
+// The FASTQ.gz files of a WGS run are the reference's input (aligner.rs:107-120, inflated there by a `zcat` child);
+// blocked gzip (BGZF: bgzip / BCL Convert) makes every 64 KiB block an independent member, so a B200 can inflate
+// thousands of blocks at once instead of 16 host threads doing it.
+//
+// Every loop is bounded by the input or the output size; a malformed stream ends with a non-zero status, never a hang.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SWI_HD __device__ __forceinline__               /* nvcc build: device only; the host build is g++ (CPU unit test) */
+#define SWI_OUTLINED __device__ __noinline__
+#else
+#define SWI_HD inline
+#define SWI_OUTLINED inline
+#endif
+
+namespace swi {
+
+constexpr int LIT_BITS = 10, DIST_BITS = 8;
+constexpr int LIT_FAST = 1 << LIT_BITS, DIST_FAST = 1 << DIST_BITS;
+
+enum Status : int { OK = 0, ERR_INPUT_OVERRUN = 1, ERR_OUTPUT_OVERRUN = 2, ERR_BAD_BLOCK_TYPE = 3, ERR_BAD_STORED = 4,
+                    ERR_BAD_LENGTHS = 5, ERR_BAD_SYMBOL = 6, ERR_BAD_DISTANCE = 7, ERR_LENGTH_MISMATCH = 8 };
+
+// Decode tables of one member (shared memory on the device, stack on the host): ~3.9 KiB.
+struct Tables {
+  uint16_t lit_fast[LIT_FAST];     // (symbol << 4) | code length, 0 = code longer than LIT_BITS (slow path)
+  uint16_t dist_fast[DIST_FAST];
+  uint16_t lit_count[16], dist_count[16];
+  uint16_t lit_sym[288], dist_sym[32];
+  uint8_t  lengths[320];
+};
+
+struct Lanes { int lane, n; };     // this thread's index among the n threads that cooperate (host: 0 of 1)
+
+#if defined(__CUDA_ARCH__)
+#define SWI_SYNC() __syncwarp()
+#else
+#define SWI_SYNC() ((void)0)
+#endif
+
+struct Bits {
+  const uint8_t* p; uint64_t n;    // payload
+  uint64_t pos;                    // next byte to load
+  uint64_t buf; int cnt;           // bit buffer (LSB first)
+};
+
+SWI_HD uint32_t load_byte(const uint8_t* p, uint64_t n, uint64_t pos) { return pos < n ? p[pos] : 0u; }
+
+SWI_HD void refill(Bits& b)
+{
+  while (b.cnt <= 56) { b.buf |= (uint64_t)load_byte(b.p, b.n, b.pos) << b.cnt; ++b.pos; b.cnt += 8; }
+}
+SWI_HD uint32_t peek(const Bits& b, int k) { return (uint32_t)(b.buf & ((1ull << k) - 1)); }
+SWI_HD void consume(Bits& b, int k) { b.buf >>= k; b.cnt -= k; }
+SWI_HD uint32_t take(Bits& b, int k) { const uint32_t v = peek(b, k); consume(b, k); return v; }
+// bits consumed so far must not exceed the payload
+SWI_HD bool overrun(const Bits& b) { return b.pos * 8 - (uint64_t)b.cnt > b.n * 8; }
+
+SWI_HD uint32_t bitrev(uint32_t c, int len)
+{
+  uint32_t r = 0;
+  for (int i = 0; i < len; ++i) { r = (r << 1) | (c & 1u); c >>= 1; }
+  return r;
+}
+
+// Canonical Huffman tables from code lengths.  Returns false on an over-subscribed set.
+// (An incomplete set is accepted, as zlib accepts the single-code distance tree; unused codes decode as errors.)
+// Kept out of line on the device: inlined three times into inflate_member, nvcc 12.9 -O3 produced a build() that
+// reported a valid fixed-code length set as over-subscribed (tools/inflate_gpu_probe.cu reproduces it; -G, a printf in
+// the loop or __noinline__ all make it correct).  It runs two or three times per deflate block, the call costs nothing.
+SWI_OUTLINED bool build(const uint8_t* lengths, int n, uint16_t* fast, int fast_bits, uint16_t* count, uint16_t* sym, const Lanes& L)
+{
+  const int fast_size = 1 << fast_bits;
+  for (int k = L.lane; k < fast_size; k += L.n) fast[k] = 0;
+  uint32_t cnt[16];
+  for (int l = 0; l < 16; ++l) cnt[l] = 0;
+  for (int s = 0; s < n; ++s) ++cnt[lengths[s]];
+  int left = 1;
+  for (int l = 1; l < 16; ++l) { left <<= 1; left -= (int)cnt[l]; if (left < 0) return false; }
+  uint32_t offs[16], next_code[16];
+  offs[1] = 0;
+  for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + cnt[l];
+  uint32_t code = 0;
+  for (int l = 1; l < 16; ++l) { next_code[l] = code; code = (code + cnt[l]) << 1; }
+  SWI_SYNC();                                       // the cleared table before the fills, the old tables before the new
+  if (L.lane == 0) for (int l = 0; l < 16; ++l) count[l] = (uint16_t)(l ? cnt[l] : 0);
+  for (int s = 0; s < n; ++s) {
+    const int l = lengths[s];
+    if (!l) continue;
+    if (L.lane == 0) sym[offs[l]] = (uint16_t)s;
+    ++offs[l];
+    const uint32_t c = next_code[l]++;
+    if (l <= fast_bits) {
+      const uint32_t rev = bitrev(c, l);
+      for (uint32_t k = rev + ((uint32_t)L.lane << l); k < (uint32_t)fast_size; k += (uint32_t)L.n << l) fast[k] = (uint16_t)((s << 4) | l);
+    }
+  }
+  SWI_SYNC();
+  return true;
+}
+
+// One symbol: fast table, else the canonical bit-by-bit walk.  Returns -1 on an unused code.
+SWI_HD int decode(Bits& b, const uint16_t* fast, int fast_bits, const uint16_t* count, const uint16_t* sym)
+{
+  const uint32_t e = fast[peek(b, fast_bits)];
+  if (e) { consume(b, (int)(e & 15u)); return (int)(e >> 4); }
+  int code = 0, first = 0, index = 0;
+  uint64_t bits = b.buf;
+  for (int len = 1; len <= 15; ++len) {
+    code |= (int)(bits & 1u); bits >>= 1;
+    const int c = count[len];
+    if (code - c < first) { consume(b, len); return sym[index + (code - first)]; }
+    index += c; first += c; first <<= 1; code <<= 1;
+  }
+  return -1;
+}
+
+#if defined(__CUDACC__)
+#define SWI_CONST static __device__ __constant__        /* nvcc build: only the device side runs this code */
+#else
+#define SWI_CONST static const                          /* g++ build of the CPU unit test */
+#endif
+SWI_CONST uint16_t kLenBase[29]  = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+SWI_CONST uint8_t  kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+SWI_CONST uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193,
+                                    12289, 16385, 24577};
+SWI_CONST uint8_t  kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+SWI_CONST uint8_t  kClOrder[19]  = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// Inflate one raw-deflate member of in_len bytes into out[0, out_cap).  *produced = bytes written.
+SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint32_t out_cap, uint32_t* produced, Tables& T, const Lanes& L)
+{
+  Bits b; b.p = in; b.n = in_len; b.pos = 0; b.buf = 0; b.cnt = 0;
+  uint32_t opos = 0;
+  int status = OK;
+  for (int blocks = 0; blocks < 1 << 20; ++blocks) {          // a member of <= 64 KiB never has this many deflate blocks
+    refill(b);
+    const uint32_t bfinal = take(b, 1), btype = take(b, 2);
+    if (btype == 0) {                                          // stored
+      consume(b, b.cnt & 7);
+      refill(b);
+      const uint32_t len = take(b, 16), nlen = take(b, 16);
+      if ((len ^ nlen) != 0xFFFFu) { status = ERR_BAD_STORED; break; }
+      if (opos + len > out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
+      // the bit buffer holds whole bytes here: rewind to the first unread byte
+      const uint64_t src = b.pos - (uint64_t)(b.cnt >> 3);
+      if (src + len > in_len) { status = ERR_INPUT_OVERRUN; break; }
+      for (uint32_t i = L.lane; i < len; i += L.n) out[opos + i] = in[src + i];
+      opos += len;
+      b.pos = src + len; b.buf = 0; b.cnt = 0;
+    } else if (btype == 1 || btype == 2) {
+      int nlit, ndist;
+      if (btype == 1) {                                        // fixed code
+        for (int s = L.lane; s < 288; s += L.n) T.lengths[s] = (uint8_t)(s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8);
+        for (int s = L.lane; s < 30; s += L.n) T.lengths[288 + s] = 5;
+        SWI_SYNC();
+        nlit = 288; ndist = 30;
+      } else {                                                 // dynamic code
+        nlit = (int)take(b, 5) + 257; ndist = (int)take(b, 5) + 1;
+        const int ncl = (int)take(b, 4) + 4;
+        if (nlit > 286 || ndist > 30) { status = ERR_BAD_LENGTHS; break; }
+        uint8_t cl[19];
+        for (int i = 0; i < 19; ++i) cl[i] = 0;
+        for (int i = 0; i < ncl; ++i) { refill(b); cl[kClOrder[i]] = (uint8_t)take(b, 3); }
+        // the code-length code is tiny: decode it with the canonical walk only (fast table of 1 entry-bit is not worth it)
+        if (!build(cl, 19, T.dist_fast, 7, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
+        int i = 0;
+        uint8_t prev = 0;
+        bool bad = false;
+        while (i < nlit + ndist) {
+          refill(b);
+          const int s = decode(b, T.dist_fast, 7, T.dist_count, T.dist_sym);
+          if (s < 0) { bad = true; break; }
+          if (s < 16) { if (L.lane == 0) T.lengths[i] = (uint8_t)s; prev = (uint8_t)s; ++i; continue; }
+          int rep; uint8_t v = 0;
+          if (s == 16) { if (i == 0) { bad = true; break; } v = prev; rep = 3 + (int)take(b, 2); }
+          else if (s == 17) rep = 3 + (int)take(b, 3);
+          else rep = 11 + (int)take(b, 7);
+          if (i + rep > nlit + ndist) { bad = true; break; }
+          if (L.lane == 0) for (int k = 0; k < rep; ++k) T.lengths[i + k] = v;
+          i += rep; prev = v;
+        }
+        if (bad || overrun(b)) { status = bad ? ERR_BAD_LENGTHS : ERR_INPUT_OVERRUN; break; }
+        SWI_SYNC();
+        if (T.lengths[256] == 0) { status = ERR_BAD_LENGTHS; break; }
+        // distance lengths follow the literal/length lengths in the same array: move them to a fixed place
+        uint8_t dl[30];
+        for (int s = 0; s < 30; ++s) dl[s] = s < ndist ? T.lengths[nlit + s] : 0;
+        SWI_SYNC();
+        for (int s = L.lane; s < 30; s += L.n) T.lengths[288 + s] = dl[s];
+        for (int s = nlit + L.lane; s < 288; s += L.n) T.lengths[s] = 0;
+        SWI_SYNC();
+        nlit = 288; ndist = 30;
+      }
+      if (!build(T.lengths, nlit, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym, L) ||
+          !build(T.lengths + 288, ndist, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
+      // ---- symbols ----
+      for (uint32_t guard = 0; guard <= out_cap + 1u; ++guard) {      // every symbol but the last one emits >= 1 byte
+        refill(b);
+        const int s = decode(b, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym);
+        if (s < 0) { status = ERR_BAD_SYMBOL; break; }
+        if (s < 256) {
+          if (opos >= out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
+          if (L.lane == 0) out[opos] = (uint8_t)s;
+          ++opos;
+          continue;
+        }
+        if (s == 256) break;
+        if (s > 285) { status = ERR_BAD_SYMBOL; break; }
+        const uint32_t len = kLenBase[s - 257] + take(b, kLenExtra[s - 257]);
+        refill(b);
+        const int ds = decode(b, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym);
+        if (ds < 0 || ds > 29) { status = ERR_BAD_DISTANCE; break; }
+        const uint32_t dist = kDistBase[ds] + take(b, kDistExtra[ds]);
+        if (dist > opos) { status = ERR_BAD_DISTANCE; break; }
+        if (opos + len > out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
+        SWI_SYNC();                                            // earlier literals / copies are visible to every lane
+        const uint8_t* src = out + opos - dist;
+        for (uint32_t i = L.lane; i < len; i += L.n) out[opos + i] = src[i < dist ? i : i % dist];
+        opos += len;
+        if (overrun(b)) { status = ERR_INPUT_OVERRUN; break; }
+      }
+      if (status != OK) break;
+      if (overrun(b)) { status = ERR_INPUT_OVERRUN; break; }
+    } else { status = ERR_BAD_BLOCK_TYPE; break; }
+    if (bfinal) break;
+  }
+  *produced = opos;
+  return status;
+}
+
+}  // namespace swi

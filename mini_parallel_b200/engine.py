@@ -109,6 +109,24 @@ class Engine:
                                                                win_start.ctypes.data, win_len.ctypes.data, out.ctypes.data))
         return out
 
+    def fastq_bgzf_score(self, comp, blocks, carry=b"", final=True, file_index=0, first_read=0, window_len=500, carry_cap=1 << 16):
+        """swb_fastq_bgzf_score: one segment of whole BGZF blocks -> (score sum, reads, bases, new carry, status).
+        `blocks` is a sequence of (payload offset in comp, payload length, inflated length)."""
+        comp = np.ascontiguousarray(comp, dtype=np.uint8)
+        blk = np.zeros(len(blocks), dtype=np.dtype([("in_off", "<u8"), ("in_len", "<u4"), ("out_len", "<u4")]))
+        for k, (o, n, m) in enumerate(blocks):
+            blk[k] = (o, n, m)
+        car = np.frombuffer(bytes(carry), dtype=np.uint8)
+        cout = np.zeros(carry_cap, dtype=np.uint8)
+        ssum, nr, nb, cl, st = ctypes.c_int64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+        self._check(self._lib.swb_fastq_bgzf_score(self._h, comp.ctypes.data if comp.size else None, comp.size,
+                                                   blk.ctypes.data if len(blk) else None, len(blk),
+                                                   car.ctypes.data if car.size else None, car.size, int(bool(final)),
+                                                   int(file_index), int(first_read), int(window_len), ctypes.byref(ssum), ctypes.byref(nr),
+                                                   ctypes.byref(nb), cout.ctypes.data, carry_cap, ctypes.byref(cl), ctypes.byref(st)))
+        return {"score_sum": int(ssum.value), "reads": int(nr.value), "bases": int(nb.value), "carry": cout[: cl.value].tobytes(),
+                "status": int(st.value)}
+
     def score_batch_device(self, d_q, d_qo, q_total, d_r, d_ro, r_total, n_pairs, max_q_len, max_r_len, d_out):
         """All pointers are device addresses (ints).  Asynchronous on the engine's stream."""
         self._check(self._lib.swb_score_batch_device(self._h, d_q, d_qo, q_total, d_r, d_ro, r_total,

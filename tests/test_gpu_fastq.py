@@ -1,0 +1,116 @@
+"""FASTQ.gz ingest on the GPU (swb_fastq_bgzf_score): BGZF blocks inflated one warp per block, indexed and scored in
+place, against zlib + the oracle.  Segments, carries, ragged and N-containing reads, CRLF, unterminated last lines."""
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from mini_parallel_b200 import bgzf
+from mini_parallel_b200.engine import to_csr
+
+pytestmark = pytest.mark.gpu
+ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def splitmix64(x):
+    m = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & m
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & m
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & m
+    return x ^ (x >> 31)
+
+
+def _expected(reads, ref, file_index, first_read, w):
+    starts = [splitmix64((((file_index << 40) + first_read + k)) ^ 0xB202) % (len(ref) - w + 1) for k in range(len(reads))]
+    q, qo = to_csr(reads)
+    r, ro = to_csr([ref[s:s + w] for s in starts])
+    res = ol.batch(q, qo, r, ro, threads=8, simd=True)
+    return int(res["score"].astype(np.int64).sum()), sum(len(x) for x in reads)
+
+
+def _make(rng, ref, n, eol=b"\n", with_n=True, file_index=0, w=500):
+    reads, recs = [], []
+    for k in range(n):
+        s = splitmix64(((file_index << 40) + k) ^ 0xB202) % (len(ref) - w + 1)
+        ln = int(rng.integers(1, 161))
+        o = int(rng.integers(0, w - ln + 1))
+        r = ref[s + o:s + o + ln].copy()
+        m = rng.random(ln) < 0.02
+        r[m] = ACGT[rng.integers(0, 4, int(m.sum()))]
+        if with_n and k % 37 == 0:
+            r[int(rng.integers(0, ln))] = ord("N")
+        reads.append(r.tobytes())
+        recs.append(b"@read%d some description" % k + eol + reads[-1] + eol + b"+" + eol + b"I" * ln + eol)
+    return reads, b"".join(recs)
+
+
+def _run_segments(engine, gz, seg_blocks, file_index=0, w=500, carry_cap=1 << 16):
+    blocks, used = bgzf.walk(gz)
+    assert used == len(gz)
+    comp = np.frombuffer(gz, dtype=np.uint8)
+    tot = {"score_sum": 0, "reads": 0, "bases": 0}
+    carry = b""
+    for a in range(0, len(blocks), seg_blocks):
+        seg = blocks[a:a + seg_blocks]
+        lo, hi = seg[0][0], seg[-1][0] + seg[-1][1]
+        rel = [(o - lo, n, m) for o, n, m in seg]
+        final = a + seg_blocks >= len(blocks)
+        out = engine.fastq_bgzf_score(comp[lo:hi], rel, carry, final, file_index, tot["reads"], w, carry_cap)
+        assert out["status"] == 0
+        carry = out["carry"]
+        for k in tot:
+            tot[k] += out[k]
+    assert carry == b""
+    return tot
+
+
+@pytest.mark.parametrize("eol,with_n", [(b"\n", True), (b"\r\n", False)])
+def test_bgzf_segments_match_the_oracle(engine, eol, with_n):
+    rng = np.random.default_rng(77)
+    ref = ACGT[rng.integers(0, 4, 120_000)]
+    engine.set_reference(ref)
+    reads, text = _make(rng, ref, 9000, eol, with_n, file_index=3)
+    exp_score, exp_bases = _expected(reads, ref, 3, 0, 500)
+    for level, block_size, seg_blocks in ((1, 65280, 1000), (6, 20000, 7), (9, 3001, 1), (0, 65280, 3)):
+        gz = bgzf.compress(text, level, block_size)
+        assert zlib.decompress(gz, 31) == text[: len(zlib.decompress(gz, 31))]          # zcat-compatible (first member at least)
+        tot = _run_segments(engine, gz, seg_blocks, file_index=3)
+        assert tot == {"score_sum": exp_score, "reads": len(reads), "bases": exp_bases}, (level, block_size, seg_blocks)
+
+
+def test_unterminated_last_line_and_truncated_record(engine):
+    rng = np.random.default_rng(78)
+    ref = ACGT[rng.integers(0, 4, 50_000)]
+    engine.set_reference(ref)
+    reads, text = _make(rng, ref, 200, with_n=False)
+    # (a) no newline after the last quality line; (b) the file ends inside the last sequence line: the reference's reader
+    # still yields that line as a read (BufRead::lines, aligner.rs:133-141)
+    for cut, n_reads in ((len(text) - 1, 200), (text.rfind(b"\n+\n") - 5, 200)):
+        t = text[:cut]
+        rd = list(reads)
+        if n_reads == 200 and cut != len(text) - 1:
+            rd[-1] = rd[-1][:-5]
+        exp_score, exp_bases = _expected(rd, ref, 0, 0, 500)
+        tot = _run_segments(engine, bgzf.compress(t, 1, 4000), 5)
+        assert tot == {"score_sum": exp_score, "reads": n_reads, "bases": exp_bases}
+
+
+def test_bad_data_asks_for_the_host_path(engine):
+    rng = np.random.default_rng(79)
+    ref = ACGT[rng.integers(0, 4, 50_000)]
+    engine.set_reference(ref)
+    _, text = _make(rng, ref, 300, with_n=False)
+    gz = bytearray(bgzf.compress(text, 6, 8000))
+    blocks, _ = bgzf.walk(bytes(gz))
+    o, n, m = blocks[2]
+    for k in range(o + 10, o + 40):
+        gz[k] ^= 0x5A                                                                   # corrupt one block's payload
+    out = engine.fastq_bgzf_score(np.frombuffer(bytes(gz), dtype=np.uint8), blocks, b"", True, 0, 0, 500)
+    assert out["status"] == 1 and out["reads"] == 0
+    latin = text.replace(b"some description", "déscription!!!!".encode("latin1"), 1)   # a non-ASCII byte: lines() semantics -> host
+    out = engine.fastq_bgzf_score(np.frombuffer(bgzf.compress(latin, 1), dtype=np.uint8), bgzf.walk(bgzf.compress(latin, 1))[0], b"", True, 0, 0, 500)
+    assert out["status"] == 1
+    reads, text = _make(rng, ref, 50, with_n=False)                                     # and the context still works
+    tot = _run_segments(engine, bgzf.compress(text, 1), 100)
+    assert tot["reads"] == 50
