@@ -68,14 +68,14 @@ int  swb_score_batch_vs_reference(swb_ctx*, const uint8_t* q_bytes, const uint64
  *   blocks[k]      deflate payload of block k inside comp[] and its inflated size (the member's ISIZE)
  *   carry          text left over from the previous segment of the file: the bytes after its last complete record
  *   final_segment  no more data follows: an unterminated last line still counts (BufRead::lines)
- * Outputs: sum of the scores, reads and bases scored, and the new carry (at most carry_cap bytes).
+ * Outputs: sum of the scores, reads, bases and lines consumed, and the new carry (at most carry_cap bytes).
  * *status = 0 ok; 1 = the data needs the host path (an inflate error, a non-ASCII byte, a carry larger than carry_cap):
  * nothing was scored, the caller falls back to zlib + rsm_process_fastq_file_in_chunks semantics. */
 typedef struct { uint64_t in_off; uint32_t in_len; uint32_t out_len; } swb_bgzf_block;
 int  swb_fastq_bgzf_score(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
                           const uint8_t* carry, uint64_t carry_len, int final_segment,
                           uint64_t file_index, uint64_t first_read, uint32_t window_len,
-                          int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases,
+                          int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases, uint64_t* n_lines,
                           uint8_t* carry_out, uint64_t carry_cap, uint64_t* carry_out_len, int* status);
 
 /* Same, DEVICE-resident inputs and outputs (pointers from cudaMalloc / a torch tensor's data_ptr);

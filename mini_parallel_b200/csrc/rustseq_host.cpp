@@ -321,13 +321,92 @@ struct WgsChunk {
   pinned_vector<uint8_t> bases; pinned_vector<uint64_t> offs, wstart; pinned_vector<uint32_t> wlen;
   pinned_vector<swb_result> res;
   bool ends_chunk = true;                      // last piece of a GPU_CHUNK_SIZE_READS/BASES chunk (progress accounting)
+  // BGZF files: a segment of whole compressed blocks for swb_fastq_bgzf_score (the GPU inflates and parses)
+  bool bgzf = false, final_segment = false;
+  pinned_vector<uint8_t>* comp = nullptr; uint64_t comp_len = 0;     // a buffer of the consumer's CompPool while the segment is in flight
+  std::vector<swb_bgzf_block> blocks;
 };
+
+// Compressed bytes per BGZF segment.  The inflate kernel decodes one block per warp, and a warp takes the same ~6 ms for
+// its block whether 500 or 9000 blocks are in flight (64 warps/SM x 148 SMs = 9472), so a segment should carry close to a
+// full wave: 112 MiB of compressed FASTQ is ~9000 blocks, ~600 MB of text, ~1.9 M reads of 150 bp.  Smaller files use
+// segments of their own size (pinned memory is slow to allocate).
+constexpr uint64_t kBgzfSegmentMax = 112ull << 20;
+
+// Is this a blocked-gzip file (first member carries a 'BC' extra field)?  SWB_GPU_INFLATE=0 keeps every file on the host.
+bool file_is_bgzf(const std::string& path)
+{
+  if (const char* v = std::getenv("SWB_GPU_INFLATE")) if (std::string(v) == "0") return false;
+  if (path.size() < 3 || path.compare(path.size() - 3, 3, ".gz") != 0) return false;
+  FILE* fp = std::fopen(path.c_str(), "rb");
+  if (!fp) return false;
+  uint8_t h[18];
+  const size_t n = std::fread(h, 1, sizeof h, fp);
+  std::fclose(fp);
+  return n == 18 && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[10] == 6 && h[11] == 0 && h[12] == 'B' && h[13] == 'C' &&
+         h[14] == 2 && h[15] == 0;
+}
+
+// Whole BGZF blocks in buf[0, n): payload ranges + inflated sizes; returns the bytes consumed, or (uint64_t)-1 on a
+// member that is not BGZF (the caller falls back to the host path).
+uint64_t walk_bgzf(const uint8_t* buf, uint64_t n, std::vector<swb_bgzf_block>& blocks)
+{
+  uint64_t pos = 0;
+  while (pos + 18 <= n) {
+    const uint8_t* h = buf + pos;
+    if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return ~0ull;
+    const uint64_t xlen = h[10] | ((uint64_t)h[11] << 8);
+    if (pos + 12 + xlen > n) break;
+    uint64_t bsize = ~0ull;
+    for (uint64_t q = 12; q + 4 <= 12 + xlen;) {
+      const uint64_t slen = h[q + 2] | ((uint64_t)h[q + 3] << 8);
+      if (h[q] == 'B' && h[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) bsize = h[q + 4] | ((uint64_t)h[q + 5] << 8);
+      q += 4 + slen;
+    }
+    if (bsize == ~0ull || bsize + 1 < 12 + xlen + 8) return ~0ull;
+    const uint64_t total = bsize + 1;
+    if (pos + total > n) break;
+    swb_bgzf_block b;
+    b.in_off = pos + 12 + xlen; b.in_len = (uint32_t)(total - 12 - xlen - 8);
+    b.out_len = (uint32_t)h[total - 4] | ((uint32_t)h[total - 3] << 8) | ((uint32_t)h[total - 2] << 16) | ((uint32_t)h[total - 1] << 24);
+    if (b.out_len > 65536) return ~0ull;
+    blocks.push_back(b);
+    pos += total;
+  }
+  return pos;
+}
 
 // A reference-sized chunk (GPU_CHUNK_SIZE_READS can be millions of reads) moves through the pipeline in pieces of at most
 // this many reads: pinned memory stays small (page-locking is slow) and inflate, PCIe and the SMs overlap inside a chunk.
 constexpr uint64_t kWgsPieceReads = 16384;
 
 struct DeviceGate { std::mutex mu; std::condition_variable cv; };   // wakes the consumer of one GPU
+
+// Pinned staging buffers for compressed BGZF segments, shared by all files of one consumer: the consumer works on one
+// segment at a time, so three buffers keep it fed however many files it serves (page-locking 112 MiB per file and per
+// pipeline slot would cost seconds).
+struct CompPool {
+  std::mutex mu; std::condition_variable cv;
+  std::vector<std::unique_ptr<pinned_vector<uint8_t>>> all;
+  std::vector<pinned_vector<uint8_t>*> free;
+  size_t max_buffers = 3; uint64_t bytes = 0;
+  pinned_vector<uint8_t>* acquire()
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      if (!free.empty()) { auto* b = free.back(); free.pop_back(); return b; }
+      if (all.size() < max_buffers) {
+        all.push_back(std::make_unique<pinned_vector<uint8_t>>());
+        auto* b = all.back().get();
+        lk.unlock();
+        b->resize(bytes);                           // the slow part, outside the lock
+        return b;
+      }
+      cv.wait(lk);
+    }
+  }
+  void release(pinned_vector<uint8_t>* b) { { std::lock_guard<std::mutex> lk(mu); free.push_back(b); } cv.notify_one(); }
+};
 
 struct WgsFile {
   size_t index = 0; std::string path;
@@ -339,7 +418,56 @@ struct WgsFile {
   std::chrono::steady_clock::time_point t0;
   // consumer side
   int64_t score = 0; uint64_t chunks = 0, bases = 0, reads = 0, chunk_reads_seen = 0;
+  bool bgzf = false, gpu_path_failed = false;  // BGZF: inflated and parsed on the GPU; failed -> the file is redone on the host
+  std::vector<uint8_t> carry; uint64_t lines = 0;
+  uint64_t seg_bytes = 0; CompPool* comp_pool = nullptr;
 };
+
+// BGZF files: the reader only moves compressed bytes and walks block headers; inflate + parse happen on the GPU.
+void wgs_bgzf_reader_thread(WgsFile* f)
+{
+  FILE* fp = std::fopen(f->path.c_str(), "rb");
+  int rc = 0; std::string err;
+  if (!fp) { rc = 1; err = "Failed to open file " + f->path + ": " + std::strerror(errno); }
+  std::vector<uint8_t> left;                                  // a partial block at the end of the previous segment
+  const uint64_t seg_bytes = f->seg_bytes;
+  bool eof = false;
+  while (rc == 0 && !eof) {
+    WgsChunk* c = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(f->gate->mu);
+      f->gate->cv.wait(lk, [&] { return !f->spare.empty() || f->gpu_path_failed; });
+      if (f->gpu_path_failed) break;
+      c = f->spare.front(); f->spare.pop_front();
+    }
+    bool push = false;
+    try {
+      c->bgzf = true; c->blocks.clear();
+      c->comp = f->comp_pool->acquire();
+      uint8_t* buf = c->comp->data();
+      std::memcpy(buf, left.data(), left.size());
+      const size_t got = std::fread(buf + left.size(), 1, seg_bytes, fp);
+      eof = got < seg_bytes;
+      const uint64_t have = left.size() + got;
+      const uint64_t used = walk_bgzf(buf, have, c->blocks);
+      if (used == ~0ull || (eof && used != have)) { rc = 2; err = "not a BGZF stream"; }      // -> host path
+      else {
+        left.assign(buf + used, buf + have);
+        c->comp_len = used; c->final_segment = eof;
+        push = true;
+      }
+    } catch (const std::bad_alloc&) { rc = 1; err = "out of pinned host memory"; }
+    if (!push && c->comp) { f->comp_pool->release(c->comp); c->comp = nullptr; }
+    std::lock_guard<std::mutex> lk(f->gate->mu);
+    if (push) f->ready.push_back(c); else f->spare.push_back(c);
+    if (rc == 2) f->gpu_path_failed = true;
+    f->gate->cv.notify_all();
+  }
+  if (fp) std::fclose(fp);
+  std::lock_guard<std::mutex> lk(f->gate->mu);
+  f->rc = rc == 2 ? 0 : rc; f->err = err; f->closed = true;
+  f->gate->cv.notify_all();
+}
 
 void wgs_reader_thread(WgsFile* f, uint64_t chunk_reads, uint64_t chunk_bases, uint64_t ref_len, uint32_t window_len)
 {
@@ -388,6 +516,7 @@ void wgs_finish_file(WgsFile* f, size_t total, uint64_t chunk_reads, const rsm_g
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - f->t0).count();
   if (f->rc == 0) {
     const uint64_t cr = chunk_reads ? chunk_reads : 1;
+    if (f->bgzf) { f->total_reads = f->reads; f->line_count = f->lines; }
     std::printf("    Processed %llu total reads in %llu chunks\n", (unsigned long long)f->total_reads, (unsigned long long)((f->total_reads + cr - 1) / cr));
     std::printf("    Total lines read: %llu\n", (unsigned long long)f->line_count);
     std::printf("  File %zu complete: Score=%lld, Bases=%llu, Time: %.2f s \n", f->index + 1, (long long)f->score, (unsigned long long)f->bases, secs);
@@ -408,28 +537,50 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
                          std::vector<FileOutcome>* outcomes)
 {
   DeviceGate gate;
+  CompPool pool;
   std::vector<std::unique_ptr<WgsFile>> fs;
   const size_t depth = 3;
   for (size_t i : mine) {
     auto f = std::make_unique<WgsFile>();
     f->index = i; f->path = files[i]; f->gate = &gate; f->t0 = std::chrono::steady_clock::now();
-    for (size_t d = 0; d < depth; ++d) {
+    f->bgzf = file_is_bgzf(files[i]);
+    if (f->bgzf) {
+      f->comp_pool = &pool;
+      f->seg_bytes = kBgzfSegmentMax;
+      if (FILE* fp = std::fopen(files[i].c_str(), "rb")) {
+        if (std::fseek(fp, 0, SEEK_END) == 0) {
+          const long sz = std::ftell(fp);
+          if (sz > 0) f->seg_bytes = std::min<uint64_t>(kBgzfSegmentMax, (((uint64_t)sz + 1) / 2 + (1u << 16) + 4095) & ~4095ull);   // at least two segments
+        }
+        std::fclose(fp);
+      }
+      if (const char* v = std::getenv("SWB_BGZF_SEGMENT_MB")) { const long mb = std::atol(v); if (mb > 0) f->seg_bytes = (uint64_t)mb << 20; }
+      pool.bytes = std::max<uint64_t>(pool.bytes, f->seg_bytes + (1u << 17));
+    }
+    for (size_t d = 0; d < (f->bgzf ? 2 : depth); ++d) {
       f->pool.push_back(std::make_unique<WgsChunk>());
       WgsChunk* c = f->pool.back().get();
-      // one pinned allocation per buffer instead of a doubling series (page-locking is slow and serialised in the driver)
-      const uint64_t nr = std::min<uint64_t>(chunk_reads ? chunk_reads : 1, kWgsPieceReads);
-      const uint64_t nb = chunk_bases ? std::min<uint64_t>(chunk_bases + 1024, nr * 152) : nr * 152;
-      try {
-        c->bases.reserve(std::min<uint64_t>(nb, 600ull << 20)); c->offs.reserve(nr + 1); c->wstart.reserve(nr); c->wlen.reserve(nr); c->res.reserve(nr);
-      } catch (const std::bad_alloc&) {}
+      if (!f->bgzf) {
+        // one pinned allocation per buffer instead of a doubling series (page-locking is slow and serialised in the driver)
+        const uint64_t nr = std::min<uint64_t>(chunk_reads ? chunk_reads : 1, kWgsPieceReads);
+        const uint64_t nb = chunk_bases ? std::min<uint64_t>(chunk_bases + 1024, nr * 152) : nr * 152;
+        try {
+          c->bases.reserve(std::min<uint64_t>(nb, 600ull << 20)); c->offs.reserve(nr + 1); c->wstart.reserve(nr); c->wlen.reserve(nr); c->res.reserve(nr);
+        } catch (const std::bad_alloc&) {}
+      }
       f->spare.push_back(c);
     }
     std::printf("Processing file %zu/%zu: %s\n", i + 1, total, base_name(files[i]).c_str());
     std::printf("    Using chunk size: %llu reads \n", (unsigned long long)chunk_reads);
+    if (f->bgzf) std::printf("    Blocked gzip (BGZF): inflate + FASTQ parsing on the GPU\n");
     fs.push_back(std::move(f));
   }
   std::vector<std::thread> readers;
-  for (auto& f : fs) readers.emplace_back(wgs_reader_thread, f.get(), chunk_reads, chunk_bases, ref_len, window_len);
+  for (auto& f : fs) {
+    if (f->bgzf) readers.emplace_back(wgs_bgzf_reader_thread, f.get());
+    else readers.emplace_back(wgs_reader_thread, f.get(), chunk_reads, chunk_bases, ref_len, window_len);
+  }
+  std::vector<uint8_t> carry_out(1 << 20);
   std::vector<WgsFile*> active;
   for (auto& f : fs) active.push_back(f.get());
   bool abort_run = false;
@@ -449,10 +600,61 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
       }
       ++rr;
     }
+    if (finished && f->bgzf && f->gpu_path_failed && f->rc == 0 && !abort_run) {
+      // the GPU path declined the file (not really BGZF, a corrupt block, non-ASCII text, a giant record): redo it with
+      // zlib and the line reader, in this thread
+      std::printf("    GPU FASTQ path not applicable to %s: falling back to the host reader\n", base_name(f->path).c_str());
+      f->score = 0; f->reads = f->bases = f->chunks = f->lines = 0; f->bgzf = false;
+      FastqReader rd;
+      int rc = rd.open(f->path);
+      std::vector<uint8_t> hb; std::vector<uint64_t> ho, hs; std::vector<uint32_t> hl; std::vector<swb_result> hr;
+      bool eof = false;
+      while (rc == 0 && !eof) {
+        rc = rd.next_chunk(std::min<uint64_t>(chunk_reads ? chunk_reads : 1, 1u << 20), chunk_bases, hb, ho, &eof);
+        const uint64_t n = ho.size() - 1;
+        if (rc || n == 0) break;
+        hs.resize(n); hl.resize(n); hr.resize(n);
+        const uint32_t w = (uint32_t)std::min<uint64_t>(window_len, ref_len);
+        for (uint64_t k = 0; k < n; ++k) { hs[k] = splitmix64((((uint64_t)f->index << 40) + f->reads + k) ^ 0xB202ull) % (ref_len - w + 1); hl[k] = w; }
+        if (swb_score_batch_vs_reference(ctx, hb.data(), ho.data(), n, hs.data(), hl.data(), hr.data())) { rc = 1; g_err = swb_last_error(); break; }
+        for (uint64_t k = 0; k < n; ++k) f->score += hr[k].score;
+        f->reads += n; f->bases += hb.size(); ++f->chunks;
+      }
+      f->total_reads = rd.total_reads; f->line_count = rd.line_count;
+      if (rc) { f->rc = 1; f->err = g_err; }
+    }
     if (finished) {
       wgs_finish_file(f, total, chunk_reads, dev, &(*outcomes)[f->index]);
       if (f->rc) abort_run = true;                                   // aligner.rs:336: a failed file aborts the run
       active.erase(std::find(active.begin(), active.end(), f));
+      continue;
+    }
+    if (c->bgzf) {                                                   // one segment of compressed blocks: everything on the GPU
+      if (!f->gpu_path_failed && !abort_run) {
+        int64_t ssum = 0; uint64_t nr = 0, nb = 0, nl = 0, ncarry = 0; int status = 0;
+        const uint32_t w = (uint32_t)std::min<uint64_t>(window_len, ref_len);
+        const int crc = swb_fastq_bgzf_score(ctx, c->comp->data(), c->comp_len, c->blocks.data(), c->blocks.size(), f->carry.data(), f->carry.size(),
+                                             c->final_segment ? 1 : 0, f->index, f->reads, w, &ssum, &nr, &nb, &nl, carry_out.data(),
+                                             carry_out.size(), &ncarry, &status);
+        if (crc != 0 || status != 0) {
+          if (crc) std::printf("    Warning: GPU FASTQ path failed on %s: %s\n", base_name(f->path).c_str(), swb_last_error());
+          std::lock_guard<std::mutex> lk(gate.mu);
+          f->gpu_path_failed = true;
+        } else {
+          const uint64_t cr = chunk_reads ? chunk_reads : 1;
+          const uint64_t before = f->reads / cr;
+          f->score += ssum; f->reads += nr; f->bases += nb; f->lines += nl;
+          f->carry.assign(carry_out.begin(), carry_out.begin() + ncarry);
+          f->chunks = f->reads / cr;
+          if (f->chunks / 10 > before / 10)                            // aligner.rs:278-282, in units of GPU_CHUNK_SIZE_READS
+            std::printf("    Processed %llu chunks (%llu reads), current score: %lld\n", (unsigned long long)(f->chunks / 10 * 10),
+                        (unsigned long long)cr, (long long)f->score);
+        }
+      }
+      if (c->comp) { pool.release(c->comp); c->comp = nullptr; }
+      std::lock_guard<std::mutex> lk(gate.mu);
+      f->spare.push_back(c);
+      gate.cv.notify_all();
       continue;
     }
     const uint64_t n = c->offs.size() - 1;
@@ -708,28 +910,40 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   }
   std::vector<FileOutcome> outcomes(total);
   std::vector<std::thread> workers;
-  std::vector<std::string> werr(order.size());
-  for (size_t w = 0; w < order.size(); ++w) {
+  // Smith-Waterman mode: SWB_CONSUMERS_PER_GPU scoring threads per device, each with its own context (streams, arenas, a
+  // copy of the packed reference).  Default 1: on one B200 a second consumer did not pay for its context and arenas
+  // (128 M reads from BGZF: 43.1 M reads/s with one, 39.8 M with two).
+  uint64_t per_gpu = 1;
+  if (const char* v = std::getenv("SWB_CONSUMERS_PER_GPU")) if (parse_usize(v, &per_gpu, &why) || per_gpu < 1 || per_gpu > 8) per_gpu = 1;
+  if (compat) per_gpu = 1;
+  const size_t n_workers = std::min<size_t>(order.size() * per_gpu, std::max<size_t>(total, 1));
+  std::vector<std::string> werr(n_workers);
+  std::vector<swb_ctx*> own_ctx(n_workers, nullptr);
+  for (size_t w = 0; w < n_workers; ++w) {
     workers.emplace_back([&, w]() {
-      const int ord = order[w];
+      const int ord = order[w % order.size()];
       if (compat) {
-        for (size_t i = w; i < total; i += order.size()) {
+        for (size_t i = w; i < total; i += n_workers) {
           process_one_file_compat(i, total, files[i], chunk, chunk_bases, &devs[ord], &outcomes[i]);
           if (outcomes[i].rc) return;                             // aligner.rs:336: a failed file aborts the run
         }
         return;
       }
-      swb_ctx* ctx = context_for(ord);
+      swb_ctx* ctx = nullptr;
+      if (w < order.size()) ctx = context_for(ord);               // the first consumer of a device uses the process-wide context
+      else if (swb_create(&ctx, ord, nullptr) == 0) own_ctx[w] = ctx;
+      else { g_err = std::string("Failed to get GPU context: ") + swb_last_error(); ctx = nullptr; }
       if (!ctx) { werr[w] = g_err; return; }
       if (swb_set_reference(ctx, ref.data(), ref.size())) { werr[w] = swb_last_error(); return; }
       stamp("context + reference on device");
       std::vector<size_t> mine;
-      for (size_t i = w; i < total; i += order.size()) mine.push_back(i);
+      for (size_t i = w; i < total; i += n_workers) mine.push_back(i);
       wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes);
     });
   }
   stamp("reference + workers started");
   for (auto& t : workers) t.join();
+  for (swb_ctx* x : own_ctx) if (x) swb_destroy(x);
   stamp("all files done");
   for (const auto& e : werr) if (!e.empty()) return fail(e);
   int n = 0;

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <cstdio>
+#include <chrono>
 
 namespace swb {
 int launch_generic_single(const BatchView& b, int32_t* last_row_out, cudaStream_t st);
@@ -388,16 +389,17 @@ int swb_score_batch_vs_reference(swb_ctx* c, const uint8_t* q, const uint64_t* q
 int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
                          const uint8_t* carry, uint64_t carry_len, int final_segment,
                          uint64_t file_index, uint64_t first_read, uint32_t window_len,
-                         int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases,
+                         int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases, uint64_t* n_lines,
                          uint8_t* carry_out, uint64_t carry_cap, uint64_t* carry_out_len, int* status)
 {
-  if (!c || !score_sum || !n_reads || !n_bases || !carry_out_len || !status) return fail("swb_fastq_bgzf_score: null pointer");
+  if (!c || !score_sum || !n_reads || !n_bases || !n_lines || !carry_out_len || !status) return fail("swb_fastq_bgzf_score: null pointer");
   if ((n_blocks && (!comp || !blocks)) || (carry_len && !carry)) return fail("swb_fastq_bgzf_score: null input");
   if (c->ref_len == 0) return fail("swb_fastq_bgzf_score: no resident reference (swb_set_reference)");
   if (window_len == 0 || window_len > c->ref_len) return fail("swb_fastq_bgzf_score: window outside the reference");
   CUDA_TRY(cudaSetDevice(c->device));
-  *score_sum = 0; *n_reads = 0; *n_bases = 0; *carry_out_len = 0; *status = 0;
+  *score_sum = 0; *n_reads = 0; *n_bases = 0; *n_lines = 0; *carry_out_len = 0; *status = 0;
   cudaStream_t st = c->st;
+  const auto wall0 = std::chrono::steady_clock::now();
 
   // text layout: [room for the carry, right-aligned][inflated blocks]; tiles are 16-byte aligned, 64 bytes of slack
   const uint64_t base_off = (carry_len + 255) & ~255ull;
@@ -423,10 +425,16 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
     CUDA_TRY(cudaMemcpyAsync(c->fq_out_off.p, out_off.data(), n_blocks * 8, cudaMemcpyHostToDevice, st));
   }
   if (carry_len) CUDA_TRY(cudaMemcpyAsync(d_text + begin, carry, carry_len, cudaMemcpyHostToDevice, st));
+  const bool dbg = std::getenv("SWB_DEBUG") != nullptr;
+  cudaEvent_t te[6] = {};
+  if (dbg) for (auto& e : te) cudaEventCreate(&e);
+  if (dbg) cudaEventRecord(te[0], st);
   int k = 0;
   k += swb::launch_inflate_bgzf(c->fq_comp.as<uint8_t>(), c->fq_blocks.as<swb_bgzf_block>(), n_blocks, c->fq_out_off.as<uint64_t>(), d_text,
                                 d_fail, st);
+  if (dbg) cudaEventRecord(te[1], st);
   k += swb::launch_fq_index(d_text, begin, end, c->fq_tile_count.as<uint32_t>(), c->fq_tile_prefix.as<uint64_t>(), d_scal, d_fail + 1, st);
+  if (dbg) cudaEventRecord(te[2], st);
   uint64_t h_scal[8] = {};
   uint8_t last = 0;
   CUDA_TRY(cudaMemcpyAsync(h_scal, d_scal, 64, cudaMemcpyDeviceToHost, st));
@@ -464,6 +472,7 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   const uint64_t qw = (end + 15) / 16;
   if (c->q_pk.reserve(qw * 4 + 64) || c->q_bad.reserve((qw + 31) / 32 * 4 + 64)) return 1;
   k += swb::launch_pack2bit(d_text, end, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
+  if (dbg) cudaEventRecord(te[3], st);
   const uint64_t batch = 4ull << 20;
   if (R) {
     const uint64_t nb = std::min(R, batch);
@@ -477,9 +486,18 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
                             c->win_end.as<uint64_t>(), 0, true, n, 0xffffffffu, window_len, c->out.as<swb_result>(), &k, d_end + a, true)) return 1;
     k += swb::launch_fq_reduce(c->out.as<swb_result>(), d_beg + a, d_end + a, n, reinterpret_cast<unsigned long long*>(d_scal + 2), st);
   }
+  if (dbg) cudaEventRecord(te[4], st);
   CUDA_TRY(cudaMemcpyAsync(h_scal, d_scal, 64, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
+  if (dbg) {
+    float a, b2, c2, d2;
+    cudaEventElapsedTime(&a, te[0], te[1]); cudaEventElapsedTime(&b2, te[1], te[2]); cudaEventElapsedTime(&c2, te[2], te[3]); cudaEventElapsedTime(&d2, te[3], te[4]);
+    std::fprintf(stderr, "[fastq] %llu blocks, %.1f MB text, %llu reads: inflate %.2f ms (%.1f GB/s), index %.2f, extract+mask+pack %.2f, score %.2f ms; call wall %.2f ms\n",
+                 (unsigned long long)n_blocks, (end - begin) / 1e6, (unsigned long long)R, a, (end - begin) / 1e6 / a, b2, c2, d2,
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+    for (auto& e : te) cudaEventDestroy(e);
+  }
   if (!final_segment) {
     const uint64_t tail_start = h_scal[1];
     const uint64_t tl = end - tail_start;
@@ -491,6 +509,7 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
     *carry_out_len = tl;
   }
   *score_sum = (int64_t)h_scal[2]; *n_reads = R; *n_bases = h_scal[3];
+  *n_lines = final_segment ? lines : 4 * R;               // lines of the records scored here (the carried ones count next time)
   c->last_kernels = k; c->host_path = false; c->timings_pending = false;
   return 0;
 }

@@ -52,9 +52,26 @@ struct Bits {
 
 SWI_HD uint32_t load_byte(const uint8_t* p, uint64_t n, uint64_t pos) { return pos < n ? p[pos] : 0u; }
 
+// 32 payload bits starting at byte `pos`, whatever its alignment.  The caller guarantees 8 readable bytes after the
+// payload (the compressed arena has slack); bits past the payload are never trusted: consuming them trips overrun().
+SWI_HD uint32_t load_u32(const uint8_t* p, uint64_t pos)
+{
+#if defined(__CUDA_ARCH__)
+  const uintptr_t a = (uintptr_t)(p + pos);
+  const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+#else
+  return (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+#endif
+}
+
+// At least 32 valid bits in the buffer afterwards (a symbol with its extra bits needs at most 28).
 SWI_HD void refill(Bits& b)
 {
-  while (b.cnt <= 56) { b.buf |= (uint64_t)load_byte(b.p, b.n, b.pos) << b.cnt; ++b.pos; b.cnt += 8; }
+  if (b.cnt <= 32) {
+    if (b.pos + 4 <= b.n) { b.buf |= (uint64_t)load_u32(b.p, b.pos) << b.cnt; b.pos += 4; b.cnt += 32; }
+    else while (b.cnt <= 56) { b.buf |= (uint64_t)load_byte(b.p, b.n, b.pos) << b.cnt; ++b.pos; b.cnt += 8; }   // last bytes of the payload
+  }
 }
 SWI_HD uint32_t peek(const Bits& b, int k) { return (uint32_t)(b.buf & ((1ull << k) - 1)); }
 SWI_HD void consume(Bits& b, int k) { b.buf >>= k; b.cnt -= k; }

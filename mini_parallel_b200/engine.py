@@ -118,13 +118,13 @@ class Engine:
             blk[k] = (o, n, m)
         car = np.frombuffer(bytes(carry), dtype=np.uint8)
         cout = np.zeros(carry_cap, dtype=np.uint8)
-        ssum, nr, nb, cl, st = ctypes.c_int64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+        ssum, nr, nb, nl, cl, st = ctypes.c_int64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
         self._check(self._lib.swb_fastq_bgzf_score(self._h, comp.ctypes.data if comp.size else None, comp.size,
                                                    blk.ctypes.data if len(blk) else None, len(blk),
                                                    car.ctypes.data if car.size else None, car.size, int(bool(final)),
                                                    int(file_index), int(first_read), int(window_len), ctypes.byref(ssum), ctypes.byref(nr),
-                                                   ctypes.byref(nb), cout.ctypes.data, carry_cap, ctypes.byref(cl), ctypes.byref(st)))
-        return {"score_sum": int(ssum.value), "reads": int(nr.value), "bases": int(nb.value), "carry": cout[: cl.value].tobytes(),
+                                                   ctypes.byref(nb), ctypes.byref(nl), cout.ctypes.data, carry_cap, ctypes.byref(cl), ctypes.byref(st)))
+        return {"score_sum": int(ssum.value), "reads": int(nr.value), "bases": int(nb.value), "lines": int(nl.value), "carry": cout[: cl.value].tobytes(),
                 "status": int(st.value)}
 
     def score_batch_device(self, d_q, d_qo, q_total, d_r, d_ro, r_total, n_pairs, max_q_len, max_r_len, d_out):

@@ -61,7 +61,9 @@ def _run_segments(engine, gz, seg_blocks, file_index=0, w=500, carry_cap=1 << 16
         carry = out["carry"]
         for k in tot:
             tot[k] += out[k]
+        lines = lines + out["lines"] if a else out["lines"]
     assert carry == b""
+    tot["lines"] = lines
     return tot
 
 
@@ -76,7 +78,7 @@ def test_bgzf_segments_match_the_oracle(engine, eol, with_n):
         gz = bgzf.compress(text, level, block_size)
         assert zlib.decompress(gz, 31) == text[: len(zlib.decompress(gz, 31))]          # zcat-compatible (first member at least)
         tot = _run_segments(engine, gz, seg_blocks, file_index=3)
-        assert tot == {"score_sum": exp_score, "reads": len(reads), "bases": exp_bases}, (level, block_size, seg_blocks)
+        assert tot == {"score_sum": exp_score, "reads": len(reads), "bases": exp_bases, "lines": 4 * len(reads)}, (level, block_size, seg_blocks)
 
 
 def test_unterminated_last_line_and_truncated_record(engine):
@@ -93,7 +95,8 @@ def test_unterminated_last_line_and_truncated_record(engine):
             rd[-1] = rd[-1][:-5]
         exp_score, exp_bases = _expected(rd, ref, 0, 0, 500)
         tot = _run_segments(engine, bgzf.compress(t, 1, 4000), 5)
-        assert tot == {"score_sum": exp_score, "reads": n_reads, "bases": exp_bases}
+        assert {k: tot[k] for k in ("score_sum", "reads", "bases")} == {"score_sum": exp_score, "reads": n_reads, "bases": exp_bases}
+        assert tot["lines"] == t.count(b"\n") + 1
 
 
 def test_bad_data_asks_for_the_host_path(engine):

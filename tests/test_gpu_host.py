@@ -174,6 +174,56 @@ def test_full_wgs_pipeline_pieces_and_caps(tmp_path, device, monkeypatch):
             assert res[fi].total_reads == n_reads and res[fi].total_bases == sum(len(x) for x in files[name][0])
 
 
+def test_full_wgs_bgzf_files_take_the_gpu_ingest_path(tmp_path, device, monkeypatch, capfd):
+    """The same reads as plain gzip (host zlib + line reader) and as BGZF (inflate + parse on the GPU) give the same
+    per-file totals; a corrupt BGZF file falls back to the host reader (which then reports the zlib error)."""
+    from mini_parallel_b200 import bgzf
+    rng = np.random.default_rng(44)
+    n_reads = 30_000
+    texts = {}
+    for lane, rd in ((1, 1), (1, 2)):
+        reads = [bytes(ACGT[rng.integers(0, 4, int(rng.integers(20, 161)))]) for _ in range(n_reads)]
+        reads[7] = reads[7][:5] + b"N" + reads[7][6:]
+        texts[(lane, rd)] = b"".join(b"@r%d\n%s\n+\n%s\n" % (j, r, b"I" * len(r)) for j, r in enumerate(reads))
+    for kk, v in dict(WGS_SAMPLE_ID="SYN", WGS_LANES="1", WGS_READS_PER_LANE="2", WGS_SYNTH_REFERENCE_BASES="300000",
+                      WGS_WINDOW_LEN="500", GPU_CHUNK_SIZE_READS="7000").items():
+        monkeypatch.setenv(kk, v)
+    monkeypatch.delenv("SWB_GPU_ALIGN_MODE", raising=False)
+    monkeypatch.delenv("GPU_CHUNK_SIZE_BASES", raising=False)
+    results = {}
+    for fmt in ("gzip", "bgzf"):
+        d = tmp_path / fmt
+        d.mkdir()
+        for (lane, rd), text in texts.items():
+            path = d / f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"
+            if fmt == "gzip":
+                with gzip.open(path, "wb", compresslevel=1) as f:
+                    f.write(text)
+            else:
+                path.write_bytes(bgzf.compress(text, 1, 40_000))
+        monkeypatch.setenv("WGS_DATA_DIR", str(d))
+        res = aligner.process_full_wgs_dataset(device)
+        results[fmt] = [(r.score64, r.total_reads, r.total_bases) for r in res]
+        out = capfd.readouterr().out
+        assert ("inflate + FASTQ parsing on the GPU" in out) == (fmt == "bgzf")
+        assert "Total lines read: %d" % (4 * n_reads) in out
+    assert results["gzip"] == results["bgzf"] and results["gzip"][0][1] == n_reads
+    # a block with a damaged payload: the GPU path declines, the host reader takes over and fails like zlib does
+    d = tmp_path / "bad"
+    d.mkdir()
+    for (lane, rd), text in texts.items():
+        gz = bytearray(bgzf.compress(text, 1, 40_000))
+        if rd == 2:
+            blocks, _ = bgzf.walk(bytes(gz))
+            for k in range(blocks[3][0] + 5, blocks[3][0] + 60):
+                gz[k] ^= 0xA5
+        (d / f"SYN_L{lane:03d}_R{rd}_001.fastq.gz").write_bytes(bytes(gz))
+    monkeypatch.setenv("WGS_DATA_DIR", str(d))
+    with pytest.raises(aligner.AlignerError):
+        aligner.process_full_wgs_dataset(device)
+    assert "falling back to the host reader" in capfd.readouterr().out
+
+
 def test_cli_on_gpu(tmp_path):
     env = {k: v for k, v in os.environ.items() if k != "SWB_GPU_ALIGN_MODE"}
     r = subprocess.run([CLI, "-1", "TGTTACGG", "-2", "GGTTGACTA", "--gpu"], env=env, capture_output=True, text=True)

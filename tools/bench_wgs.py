@@ -36,9 +36,12 @@ def synth_reference(n):
 
 
 def make_file(args):
-    path, fi, n_reads, ref_len, rl, wl, level = args
+    path, fi, n_reads, ref_len, rl, wl, level, blocked = args
     ref = synth_reference(ref_len)
-    co = zlib.compressobj(level, zlib.DEFLATED, 31)
+    if blocked:                                    # BGZF: independent <= 64 KiB members with a 'BC' size field (bgzip / BCL Convert)
+        sys.path.insert(0, ROOT)
+        from mini_parallel_b200 import bgzf
+    co = None if blocked else zlib.compressobj(level, zlib.DEFLATED, 31)
     step = 100_000
     with open(path, "wb") as f:
         for a in range(0, n_reads, step):
@@ -62,8 +65,11 @@ def make_file(args):
             rec[:, 12 + rl:12 + rl + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8)
             rec[:, 12 + rl + 3:12 + 2 * rl + 3] = ord("I")
             rec[:, -1] = 10
-            f.write(co.compress(rec.tobytes()))
-        f.write(co.flush())
+            if blocked:
+                f.write(bgzf.compress(rec.tobytes(), level, 65280, eof=False))     # blocks may end anywhere inside a record
+            else:
+                f.write(co.compress(rec.tobytes()))
+        f.write(bgzf.EOF_BLOCK if blocked else co.flush())
     return os.path.getsize(path), n_reads * rec.shape[1]
 
 
@@ -76,17 +82,23 @@ def main():
     ap.add_argument("--ref-bases", type=int, default=16_000_000)
     ap.add_argument("--dir", default="/tmp/synwgs")
     ap.add_argument("--level", type=int, default=1)
+    ap.add_argument("--reuse", action="store_true", help="keep the files already in --dir (same parameters) instead of regenerating them")
+    ap.add_argument("--bgzf", action="store_true", help="write blocked gzip (BGZF): the driver inflates and parses it on the GPU")
     args = ap.parse_args()
     os.makedirs(args.dir, exist_ok=True)
     jobs = []
     fi = 0
     for lane in range(1, args.lanes + 1):
         for rd in (1, 2):
-            jobs.append((os.path.join(args.dir, f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"), fi, args.reads_per_file, args.ref_bases, 150, 500, args.level))
+            jobs.append((os.path.join(args.dir, f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"), fi, args.reads_per_file, args.ref_bases, 150, 500, args.level, args.bgzf))
             fi += 1
     t0 = time.time()
-    with ProcessPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
-        sizes = list(ex.map(make_file, jobs))
+    if args.reuse and all(os.path.exists(j[0]) for j in jobs):     # files of an earlier run with the same parameters
+        rec_len = 12 + 150 + 3 + 150 + 1
+        sizes = [(os.path.getsize(j[0]), args.reads_per_file * rec_len) for j in jobs]
+    else:
+        with ProcessPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            sizes = list(ex.map(make_file, jobs))
     gen_s = time.time() - t0
     gz_bytes = sum(s[0] for s in sizes); text_bytes = sum(s[1] for s in sizes)
     env = dict(os.environ, GPU_CHUNK_SIZE_READS=str(args.chunk_reads), WGS_DATA_DIR=args.dir, WGS_SAMPLE_ID="SYN", WGS_LANES=str(args.lanes),
@@ -106,7 +118,7 @@ def main():
     file_s = [float(l.split("Time:")[1].split("s")[0]) for l in r.stdout.splitlines() if "complete: Score=" in l]
     n_reads = args.reads_per_file * len(jobs)
     print(json.dumps({
-        "workload": f"BASELINE.json configs[4] scaled: {len(jobs)} files x {args.reads_per_file} reads of 150 bp (gzip -{args.level}), each read vs a 500 bp window "
+        "workload": f"BASELINE.json configs[4] scaled: {len(jobs)} files x {args.reads_per_file} reads of 150 bp ({'BGZF blocked gzip' if args.bgzf else 'gzip'} -{args.level}), each read vs a 500 bp window "
                     f"of a {args.ref_bases} bp device-resident reference, GPU_CHUNK_SIZE_READS={args.chunk_reads}, {args.devices} GPU(s)",
         "wall_s": round(wall, 3), "reads_per_s": round(n_reads / wall, 1), "gcups_end_to_end": round(n_reads * 150 * 500 / wall / 1e9, 1),
         "gz_mb_per_s": round(gz_bytes / wall / 1e6, 1), "fastq_text_mb_per_s": round(text_bytes / wall / 1e6, 1),
