@@ -72,6 +72,9 @@ int  swb_score_batch_vs_reference(swb_ctx*, const uint8_t* q_bytes, const uint64
  * *status = 0 ok; 1 = the data needs the host path (an inflate error, a non-ASCII byte, a carry larger than carry_cap):
  * nothing was scored, the caller falls back to zlib + rsm_process_fastq_file_in_chunks semantics. */
 typedef struct { uint64_t in_off; uint32_t in_len; uint32_t out_len; } swb_bgzf_block;
+/* Optional: start copying and inflating the NEXT segment on a second stream while the current one is being scored.  The
+ * buffers must stay untouched until swb_fastq_bgzf_score is called with the same comp pointer and returns. */
+int  swb_fastq_bgzf_prefetch(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks);
 int  swb_fastq_bgzf_score(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
                           const uint8_t* carry, uint64_t carry_len, int final_segment,
                           uint64_t file_index, uint64_t first_read, uint32_t window_len,

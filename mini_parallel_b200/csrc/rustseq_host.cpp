@@ -585,11 +585,14 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
   for (auto& f : fs) active.push_back(f.get());
   bool abort_run = false;
   size_t rr = 0;
+  WgsFile* pre_f = nullptr; WgsChunk* pre_c = nullptr;             // the BGZF segment already being inflated (prefetch)
   while (!active.empty()) {
     WgsFile* f = nullptr; WgsChunk* c = nullptr; bool finished = false;
+    WgsFile* nf = nullptr; WgsChunk* nc = nullptr;
     {
       std::unique_lock<std::mutex> lk(gate.mu);
-      for (;;) {
+      if (pre_c) { f = pre_f; c = pre_c; f->ready.pop_front(); pre_f = nullptr; pre_c = nullptr; }      // it is the front of its file's queue
+      for (; !f;) {
         for (size_t k = 0; k < active.size() && !f; ++k) {
           WgsFile* g = active[(rr + k) % active.size()];
           if (!g->ready.empty()) { f = g; c = g->ready.front(); g->ready.pop_front(); }
@@ -599,6 +602,14 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
         gate.cv.wait(lk);
       }
       ++rr;
+      if (!finished && c->bgzf && !f->gpu_path_failed)            // the next BGZF segment, whichever file has one ready
+        for (size_t k = 0; k < active.size() && !nc; ++k) {
+          WgsFile* g = active[(rr + k) % active.size()];
+          if (g->bgzf && !g->gpu_path_failed && !g->ready.empty() && g->ready.front()->bgzf) { nf = g; nc = g->ready.front(); }
+        }
+    }
+    if (nc && !abort_run && swb_fastq_bgzf_prefetch(ctx, nc->comp->data(), nc->comp_len, nc->blocks.data(), nc->blocks.size()) == 0) {
+      pre_f = nf; pre_c = nc;                                      // copied in and inflated on a second stream while `c` is scored
     }
     if (finished && f->bgzf && f->gpu_path_failed && f->rc == 0 && !abort_run) {
       // the GPU path declined the file (not really BGZF, a corrupt block, non-ASCII text, a giant record): redo it with

@@ -56,7 +56,15 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   Lane extra[kLanes - 1];
   Lane* lane(int i) { return i == 0 ? static_cast<Lane*>(this) : &extra[i - 1]; }
   DevBuf ref_bytes, ref_pk, ref_bad;       // device-resident reference (swb_set_reference)
-  DevBuf fq_comp, fq_blocks, fq_out_off, fq_text, fq_tile_count, fq_tile_prefix, fq_seq_beg, fq_seq_end, fq_scal;   // swb_fastq_bgzf_score
+  // swb_fastq_bgzf_score / _prefetch: two segment slots (compressed bytes, block table, text) so that the next segment can be
+  // copied in and inflated on lane 1's stream while this one is indexed and scored on lane 0's
+  struct FqSlot {
+    DevBuf comp, blocks, out_off, text, fail;
+    std::vector<uint64_t> out_off_host;
+    const uint8_t* key = nullptr; uint64_t key_bytes = 0, n_blocks = 0, text_end = 0;
+    cudaEvent_t done = nullptr; bool pending = false;
+  } fq_slot[2];
+  DevBuf fq_tile_count, fq_tile_prefix, fq_seq_beg, fq_seq_end, fq_scal;
   uint64_t ref_len = 0;
   std::vector<ChunkEvents> chunk_ev;       // host path: one event set per chunk of the last call
   swb::Counters* h_counters = nullptr;     // pinned, one slot per chunk
@@ -133,8 +141,11 @@ void swb_destroy(swb_ctx* c)
     for (auto& e : l->ev) cudaEventDestroy(e);
     cudaStreamDestroy(l->st);
   }
-  for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->fq_comp, &c->fq_blocks, &c->fq_out_off, &c->fq_text, &c->fq_tile_count,
-                    &c->fq_tile_prefix, &c->fq_seq_beg, &c->fq_seq_end, &c->fq_scal}) b->release();
+  for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->fq_tile_count, &c->fq_tile_prefix, &c->fq_seq_beg, &c->fq_seq_end, &c->fq_scal}) b->release();
+  for (auto& sl : c->fq_slot) {
+    for (DevBuf* b : {&sl.comp, &sl.blocks, &sl.out_off, &sl.text, &sl.fail}) b->release();
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
   for (auto& ce : c->chunk_ev) for (auto& e : ce.ev) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
@@ -386,6 +397,50 @@ int swb_score_batch_vs_reference(swb_ctx* c, const uint8_t* q, const uint64_t* q
 }
 
 // ---- FASTQ.gz (BGZF) -> scores entirely on the device ----
+constexpr uint64_t kFqCarryRoom = 1ull << 20;            // text layout: [carry, right-aligned in 1 MiB][inflated blocks]
+
+// copy one segment to the device and inflate it on `st` into slot `s` (asynchronous; s.done fires when the text is there)
+static int fq_enqueue_inflate(swb_ctx* c, swb_ctx::FqSlot& s, cudaStream_t st, const uint8_t* comp, uint64_t comp_bytes,
+                              const swb_bgzf_block* blocks, uint64_t n_blocks, int* kernels)
+{
+  s.out_off_host.resize(n_blocks);
+  uint64_t text_end = kFqCarryRoom;
+  for (uint64_t k = 0; k < n_blocks; ++k) {
+    if (blocks[k].in_off + blocks[k].in_len > comp_bytes) return fail("swb_fastq_bgzf: block outside the compressed buffer");
+    s.out_off_host[k] = text_end; text_end += blocks[k].out_len;
+  }
+  if (s.comp.reserve(comp_bytes + 64) || s.blocks.reserve(n_blocks * sizeof(swb_bgzf_block) + 64) || s.out_off.reserve(n_blocks * 8 + 64) ||
+      s.text.reserve(text_end + 4096 + 64) || s.fail.reserve(64)) return 1;
+  if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  CUDA_TRY(cudaMemsetAsync(s.fail.p, 0, 64, st));
+  if (comp_bytes) CUDA_TRY(cudaMemcpyAsync(s.comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
+  if (n_blocks) {
+    CUDA_TRY(cudaMemcpyAsync(s.blocks.p, blocks, n_blocks * sizeof(swb_bgzf_block), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.out_off.p, s.out_off_host.data(), n_blocks * 8, cudaMemcpyHostToDevice, st));
+  }
+  *kernels += swb::launch_inflate_bgzf(s.comp.as<uint8_t>(), s.blocks.as<swb_bgzf_block>(), n_blocks, s.out_off.as<uint64_t>(), s.text.as<uint8_t>(),
+                                       s.fail.as<uint32_t>(), st);
+  CUDA_TRY(cudaEventRecord(s.done, st));
+  s.key = comp; s.key_bytes = comp_bytes; s.n_blocks = n_blocks; s.text_end = text_end;
+  return 0;
+}
+
+int swb_fastq_bgzf_prefetch(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks)
+{
+  if (!c) return fail("null ctx");
+  if (n_blocks && (!comp || !blocks)) return fail("swb_fastq_bgzf_prefetch: null input");
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (auto& s : c->fq_slot) if (s.pending && s.key == comp && s.key_bytes == comp_bytes) return 0;      // already on its way
+  for (auto& s : c->fq_slot) {
+    if (s.pending) continue;
+    int k = 0;
+    if (fq_enqueue_inflate(c, s, c->lane(1)->st, comp, comp_bytes, blocks, n_blocks, &k)) return 1;
+    s.pending = true;
+    return 0;
+  }
+  return 0;                                               // both slots busy: the segment is inflated when it is scored
+}
+
 int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
                          const uint8_t* carry, uint64_t carry_len, int final_segment,
                          uint64_t file_index, uint64_t first_read, uint32_t window_len,
@@ -396,52 +451,53 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   if ((n_blocks && (!comp || !blocks)) || (carry_len && !carry)) return fail("swb_fastq_bgzf_score: null input");
   if (c->ref_len == 0) return fail("swb_fastq_bgzf_score: no resident reference (swb_set_reference)");
   if (window_len == 0 || window_len > c->ref_len) return fail("swb_fastq_bgzf_score: window outside the reference");
+  if (carry_len > kFqCarryRoom) return fail("swb_fastq_bgzf_score: carry larger than 1 MiB");
   CUDA_TRY(cudaSetDevice(c->device));
   *score_sum = 0; *n_reads = 0; *n_bases = 0; *n_lines = 0; *carry_out_len = 0; *status = 0;
   cudaStream_t st = c->st;
   const auto wall0 = std::chrono::steady_clock::now();
+  int k = 0;
 
-  // text layout: [room for the carry, right-aligned][inflated blocks]; tiles are 16-byte aligned, 64 bytes of slack
-  const uint64_t base_off = (carry_len + 255) & ~255ull;
-  std::vector<uint64_t> out_off(n_blocks);
-  uint64_t text_end = base_off;
-  for (uint64_t k = 0; k < n_blocks; ++k) {
-    if (blocks[k].in_off + blocks[k].in_len > comp_bytes) return fail("swb_fastq_bgzf_score: block outside the compressed buffer");
-    out_off[k] = text_end; text_end += blocks[k].out_len;
+  // the segment is either already being inflated (swb_fastq_bgzf_prefetch) or goes into a free slot now
+  swb_ctx::FqSlot* slot = nullptr;
+  for (auto& s : c->fq_slot) if (s.pending && s.key == comp && s.key_bytes == comp_bytes && s.n_blocks == n_blocks) slot = &s;
+  if (!slot) {
+    for (auto& s : c->fq_slot) if (!s.pending) { slot = &s; break; }
+    if (!slot) {                                          // two stale prefetches: wait for them and reuse the first slot
+      CUDA_TRY(cudaStreamSynchronize(c->lane(1)->st));
+      for (auto& s : c->fq_slot) s.pending = false;
+      slot = &c->fq_slot[0];
+    }
+    if (fq_enqueue_inflate(c, *slot, st, comp, comp_bytes, blocks, n_blocks, &k)) return 1;
   }
-  const uint64_t begin = base_off - carry_len, end = text_end;
-  if (end == begin) return 0;
+  struct Release { swb_ctx::FqSlot* s; ~Release() { s->pending = false; s->key = nullptr; } } release{slot};
+  CUDA_TRY(cudaStreamWaitEvent(st, slot->done, 0));
+  const uint64_t begin = kFqCarryRoom - carry_len, end = slot->text_end;
+  if (end == begin) { CUDA_TRY(cudaStreamSynchronize(st)); return 0; }
   const uint64_t n_tiles = swb::fq_tiles(begin, end);
-  if (c->fq_comp.reserve(comp_bytes + 64) || c->fq_blocks.reserve(n_blocks * sizeof(swb_bgzf_block) + 64) ||
-      c->fq_out_off.reserve(n_blocks * 8 + 64) || c->fq_text.reserve(end + 4096 + 64) || c->fq_tile_count.reserve(n_tiles * 4 + 64) ||
-      c->fq_tile_prefix.reserve(n_tiles * 8 + 64) || c->fq_scal.reserve(64)) return 1;
-  uint8_t* d_text = c->fq_text.as<uint8_t>();
-  uint64_t* d_scal = c->fq_scal.as<uint64_t>();          // [0] newlines [1] tail_start [2] score sum [3] bases [4] (u32) failed blocks, flags
+  if (c->fq_tile_count.reserve(n_tiles * 4 + 64) || c->fq_tile_prefix.reserve(n_tiles * 8 + 64) || c->fq_scal.reserve(64)) return 1;
+  uint8_t* d_text = slot->text.as<uint8_t>();
+  uint64_t* d_scal = c->fq_scal.as<uint64_t>();          // [0] newlines [1] tail_start [2] score sum [3] bases [4] (u32) -, flags
   uint32_t* d_fail = reinterpret_cast<uint32_t*>(d_scal + 4);
   CUDA_TRY(cudaMemsetAsync(d_scal, 0, 64, st));
-  if (comp_bytes) CUDA_TRY(cudaMemcpyAsync(c->fq_comp.p, comp, comp_bytes, cudaMemcpyHostToDevice, st));
-  if (n_blocks) {
-    CUDA_TRY(cudaMemcpyAsync(c->fq_blocks.p, blocks, n_blocks * sizeof(swb_bgzf_block), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(c->fq_out_off.p, out_off.data(), n_blocks * 8, cudaMemcpyHostToDevice, st));
-  }
   if (carry_len) CUDA_TRY(cudaMemcpyAsync(d_text + begin, carry, carry_len, cudaMemcpyHostToDevice, st));
   const bool dbg = std::getenv("SWB_DEBUG") != nullptr;
   cudaEvent_t te[6] = {};
   if (dbg) for (auto& e : te) cudaEventCreate(&e);
   if (dbg) cudaEventRecord(te[0], st);
-  int k = 0;
-  k += swb::launch_inflate_bgzf(c->fq_comp.as<uint8_t>(), c->fq_blocks.as<swb_bgzf_block>(), n_blocks, c->fq_out_off.as<uint64_t>(), d_text,
-                                d_fail, st);
   if (dbg) cudaEventRecord(te[1], st);
   k += swb::launch_fq_index(d_text, begin, end, c->fq_tile_count.as<uint32_t>(), c->fq_tile_prefix.as<uint64_t>(), d_scal, d_fail + 1, st);
   if (dbg) cudaEventRecord(te[2], st);
   uint64_t h_scal[8] = {};
+  uint32_t h_fail[4] = {};
   uint8_t last = 0;
   CUDA_TRY(cudaMemcpyAsync(h_scal, d_scal, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_fail, slot->fail.p, 16, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(&last, d_text + end - 1, 1, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));                    // out_off lives on this stack frame; the counts size what follows
+  CUDA_TRY(cudaStreamSynchronize(st));                    // the counts size what follows
   CUDA_TRY(cudaGetLastError());
-  const uint32_t failed = (uint32_t)(h_scal[4] & 0xffffffffu), flags = (uint32_t)(h_scal[4] >> 32);
+  const uint32_t failed = h_fail[0], flags = (uint32_t)(h_scal[4] >> 32);
+  h_scal[5] = (uint64_t)h_fail[2] | ((uint64_t)h_fail[3] << 32);
   if (std::getenv("SWB_DEBUG")) std::fprintf(stderr, "[fastq] blocks %llu text [%llu,%llu) newlines %llu failed %u (first status %u after %u bytes) flags %u last %d\n", (unsigned long long)n_blocks,
                                             (unsigned long long)begin, (unsigned long long)end, (unsigned long long)h_scal[0], failed,
                                             (uint32_t)(h_scal[5] & 0xffffffffu), (uint32_t)(h_scal[5] >> 32), flags, (int)last);
@@ -493,8 +549,8 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   if (dbg) {
     float a, b2, c2, d2;
     cudaEventElapsedTime(&a, te[0], te[1]); cudaEventElapsedTime(&b2, te[1], te[2]); cudaEventElapsedTime(&c2, te[2], te[3]); cudaEventElapsedTime(&d2, te[3], te[4]);
-    std::fprintf(stderr, "[fastq] %llu blocks, %.1f MB text, %llu reads: inflate %.2f ms (%.1f GB/s), index %.2f, extract+mask+pack %.2f, score %.2f ms; call wall %.2f ms\n",
-                 (unsigned long long)n_blocks, (end - begin) / 1e6, (unsigned long long)R, a, (end - begin) / 1e6 / a, b2, c2, d2,
+    std::fprintf(stderr, "[fastq] %llu blocks, %.1f MB text, %llu reads: (inflate %s) index %.2f, extract+mask+pack %.2f, score %.2f ms; call wall %.2f ms\n",
+                 (unsigned long long)n_blocks, (end - begin) / 1e6, (unsigned long long)R, a > 1e9 ? "?" : "on its own stream", b2, c2, d2,
                  std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
     for (auto& e : te) cudaEventDestroy(e);
   }
