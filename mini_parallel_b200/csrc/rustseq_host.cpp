@@ -538,6 +538,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
 {
   DeviceGate gate;
   CompPool pool;
+  if (const char* v = std::getenv("SWB_BGZF_POOL")) { const long n = std::atol(v); if (n >= 2 && n <= 16) pool.max_buffers = (size_t)n; }
   std::vector<std::unique_ptr<WgsFile>> fs;
   const size_t depth = 3;
   for (size_t i : mine) {
