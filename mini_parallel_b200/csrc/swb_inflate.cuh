@@ -224,7 +224,7 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
         if (s < 0) { status = ERR_BAD_SYMBOL; break; }
         if (s < 256) {
           if (opos >= out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
-          if (L.lane == 0) out[opos] = (uint8_t)s;
+          out[opos] = (uint8_t)s;                                // every lane stores the same byte to the same address: no branch
           ++opos;
           continue;
         }
@@ -239,11 +239,20 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
         if (opos + len > out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
         SWI_SYNC();                                            // earlier literals / copies are visible to every lane
         const uint8_t* src = out + opos - dist;
-        for (uint32_t i = L.lane; i < len; i += L.n) out[opos + i] = src[i < dist ? i : i % dist];
+        uint8_t* dst = out + opos;
+        if (dist >= len) {                                     // no overlap (the usual case): a plain strided copy
+          for (uint32_t i = L.lane; i < len; i += L.n) dst[i] = src[i];
+        } else if (dist == 1) {                                // a run of one byte (quality strings)
+          const uint8_t v = src[0];
+          for (uint32_t i = L.lane; i < len; i += L.n) dst[i] = v;
+        } else {                                               // the pattern of `dist` bytes repeats: read only what existed before
+          for (uint32_t i = L.lane; i < len; i += L.n) dst[i] = src[i % dist];
+        }
         opos += len;
-        if (overrun(b)) { status = ERR_INPUT_OVERRUN; break; }
       }
       if (status != OK) break;
+      // one input check per deflate block: past the payload the bit buffer feeds zeros, the symbol loop above still ends
+      // (it is bounded by out_cap), and the block is rejected here
       if (overrun(b)) { status = ERR_INPUT_OVERRUN; break; }
     } else { status = ERR_BAD_BLOCK_TYPE; break; }
     if (bfinal) break;
