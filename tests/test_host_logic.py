@@ -1,6 +1,8 @@
 """CPU tests of the host mirror (csrc/rustseq_host.cpp): the FASTQ chunk reader, the chunk-size configuration,
 the lane/read file naming, --test-wgs (which needs no GPU, main.rs:127-153) and the CLI's exit codes."""
 import gzip
+
+import numpy as np
 import os
 import subprocess
 
@@ -165,3 +167,22 @@ def test_dotenv_is_loaded_and_does_not_override(tmp_path):
     env.update(WGS_SAMPLE_ID="S", CUDA_VISIBLE_DEVICES="")                               # the process environment wins over .env
     r = subprocess.run([CLI, "-t"], env=env, cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 0 and "Successfully counted 12 bases in S_L001_R1_001.fastq.gz" in r.stdout
+
+
+def test_bgzf_files_are_ordinary_gzip_for_the_host_reader(tmp_path, clean_env):
+    """Blocked gzip is multi-member gzip: the host reader (zlib) and the Python walker agree on it without a GPU."""
+    import zlib
+    from mini_parallel_b200 import bgzf
+    rng = np.random.default_rng(9)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), int(rng.integers(1, 200)))) for _ in range(3000)]
+    text = b"".join(b"@r%d\n%s\n+\n%s\n" % (k, r, b"I" * len(r)) for k, r in enumerate(reads))
+    gz = bgzf.compress(text, 6, 5000)
+    blocks, used = bgzf.walk(gz)
+    assert used == len(gz) and blocks[-1][2] == 0 and sum(b[2] for b in blocks) == len(text)      # ends with the empty EOF block
+    assert b"".join(zlib.decompress(gz[o:o + n], -15) for o, n, m in blocks) == text
+    path = tmp_path / "SYN_L001_R1_001.fastq.gz"
+    path.write_bytes(gz)
+    os.environ["GPU_CHUNK_SIZE_READS"] = "700"
+    assert aligner.count_bases_in_fastq(path) == sum(len(r) for r in reads)
+    with pytest.raises(ValueError):
+        bgzf.walk(gzip.compress(text))                                                            # plain gzip has no BC field
