@@ -400,15 +400,6 @@ static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t 
   return 1;
 }
 
-size_t short_smem_bytes(uint32_t window_cap, int variant)
-{
-  const int G = (variant & 1) ? 16 : 8, K = (variant & 1) ? 10 : 20;
-  const uint32_t NPAD = G * K;
-  const uint32_t w_pad = (window_cap + K - 1) / K * K;
-  const uint32_t n_iters = (NPAD + w_pad + K - 1) / K;
-  return (size_t)((NPAD + n_iters * K + 15) & ~15u) * 4 * (32 / G);
-}
-
 template <int G, int K, int MINB> static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st);
 
 // variant 4..6: streaming kernel; else bit0: 0 = G8/K20, 1 = G16/K10 ; bit1: split tracking (VIADD + VIMNMX) instead of VIADDMNMX
@@ -1070,8 +1061,6 @@ static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
   return 1;
 }
 
-int long_ctas_per_sm() { return 4; }
-
 // persistent grids (ctas = a multiple of the SM count unless the scratch clamp reduced it), work-stealing over the long /
 // the bytes list; the two launches use disjoint scratch halves
 // max_read_len <= 192: every job is a single band, 32 x 6 rows waste fewer lanes than 32 x 10 on 150 bp reads
@@ -1188,8 +1177,6 @@ sw_generic_kernel(BatchView b, const uint32_t* __restrict__ list, const uint32_t
   }
 }
 
-int generic_warps_per_sm() { return 16; }
-
 int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cudaStream_t st)
 {
   // persistent grid: 4 CTAs x 4 warps per SM, work-stealing over the generic list
@@ -1200,11 +1187,6 @@ int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cud
 __global__ void single_pair_setup_kernel(Counters* c, uint32_t* list)
 {
   c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; list[0] = 0;
-}
-
-int launch_last_row_max(const uint8_t*, uint64_t, const uint8_t*, uint64_t, int32_t*, int32_t*, cudaStream_t)
-{
-  return 0;   // served by sw_generic_kernel's last_row_out (see swb_capi.cu)
 }
 
 // exposed for the C API: run the generic kernel on a prepared single-pair view

@@ -65,8 +65,6 @@ int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_
 int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st);
 int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32_t wgs, uint64_t groups,
                       int32_t* result, cudaStream_t st);
-int launch_last_row_max(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,
-                        int32_t* rows /* 2*(n2+1) */, int32_t* result, cudaStream_t st);
 int launch_synth(uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len, int distribution,
                  uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, cudaStream_t st);
 // FASTQ.gz ingest on the GPU (swb_fastq_kernels.cu)
@@ -80,7 +78,5 @@ int launch_fq_extract_mask(uint8_t* text, uint64_t begin, uint64_t end, const ui
 int launch_fq_windows(uint64_t file_index, uint64_t first_read, uint64_t n, uint64_t ref_len, uint32_t w, uint64_t* seq_beg, uint64_t* seq_end,
                       uint64_t* win_beg, uint64_t* win_end, cudaStream_t st);
 int launch_fq_reduce(const swb_result* res, const uint64_t* seq_beg, const uint64_t* seq_end, uint64_t n, unsigned long long* sums, cudaStream_t st);
-int generic_warps_per_sm();
-size_t short_smem_bytes(uint32_t window_cap, int variant);
 
 }  // namespace swb
