@@ -6,14 +6,20 @@
 // Output per pair: max H and the first cell (row-major) that reaches it.
 //
 // Kernels
-//   pack2bit_kernel   ASCII -> 2 bits/base, 128-bit loads, HBM-bound (1.25 B/base algorithmic)
-//   classify_kernel   routes each pair: empty / short (int16x2 DPX kernel) / generic (32-bit)
-//   sw_short_kernel   inter-task kernel for reads <= 160 bp: a group of G lanes owns TWO pairs,
-//                     packed hi/lo in int16x2 words, updated with DPX VIADDMNMX / VIMNMX3
-//   sw_generic_kernel one warp per pair, 32-bit, any length / any bytes (anti-diagonal wavefront,
-//                     boundary column through warp shuffles, row bands through a scratch row)
-//   ref_compat_kernel the reference's LIVE kernel semantics (smith_waterman.cl:11-71)
-//   synth_*           counter-RNG synthetic reads/windows
+//   pack2bit_kernel       ASCII -> 2 bits/base, 128-bit streaming loads, HBM-bound (1.25 B/base algorithmic)
+//   classify_kernel       routes each pair: empty / short / long / bytes / generic, device-side work lists
+//   chunk_prepare_kernel  offset rebase and window ends of one chunk of a host batch
+//   sw_stream_kernel      DEFAULT short-read path (reads <= 160 bp): int16x2 DPX, two pairs per word, runs of pair
+//                         couples stream through a lane group (no per-pair fill/drain), window ring in shared memory,
+//                         conflict-free ADD-indexed substitution table
+//   sw_short_kernel       the earlier one-couple-per-group int16x2 kernel (variants 0-3), kept as a cross-check
+//   sw_long_kernel        32-bit banded wavefront, one warp per pair, bands stream through the warp; table variant for
+//                         ACGT-only pairs, raw-byte variant (arithmetic substitution term) for everything else
+//   sw_generic_kernel     one warp per pair, 32-bit, explicit tracking: pairs beyond 2^20 rows/columns, last-row maximum
+//   ref_compat_kernel     the reference's LIVE kernel semantics (smith_waterman.cl:11-71)
+//   synth_*               counter-RNG synthetic reads/windows
+// (FASTQ.gz ingest kernels: swb_fastq_kernels.cu.)  -DSWB_ABLATE=n builds timing experiments of the stream kernel whose
+// results are wrong on purpose; the product is always built with SWB_ABLATE=0.
 #include "swb_kernels.cuh"
 #ifndef SWB_ABLATE
 #define SWB_ABLATE 0
