@@ -55,6 +55,16 @@ int  rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_re
 /* the file list of aligner.rs:197-204: {WGS_DATA_DIR}/{WGS_SAMPLE_ID}_L{lane:03}_R{read}_001.fastq.gz */
 int  rsm_wgs_file_list(char* buf, size_t cap, int* n_files);       /* newline-separated paths */
 
+/* aligner.rs:23-104  FileCheckpoint / CheckpointState, serialised like serde_json::to_string_pretty does.  The reference
+ * never finds its own checkpoints (load opens checkpoint_{run_id}.json with a fresh run id, save writes
+ * checkpoint_run_{N}.json); here both sides use checkpoint_{run_id}.json in the working directory and the run id
+ * is WGS_RUN_ID when set (resume), else wgs_{unix time} like aligner.rs:219.  score64 is an extra field (the i32 wraps). */
+typedef struct { char file_path[1024]; uint64_t file_index; int32_t score; int64_t score64; double processing_time_ms;
+                 uint64_t total_bases; uint64_t total_reads; int32_t completed; } rsm_file_checkpoint;
+int  rsm_checkpoint_save(const char* path, const char* run_id, const rsm_file_checkpoint* files, int n_files, uint64_t total_files);
+int  rsm_checkpoint_load(const char* path, char* run_id, size_t run_id_cap, rsm_file_checkpoint* files, int cap, int* n_files,
+                         uint64_t* total_files);       /* returns 0 and *n_files = -1 when the file does not exist */
+
 /* main.rs:48-192  the CLI (rustseq_mini).  Returns the process exit code. */
 int  rsm_main(int argc, char** argv);
 

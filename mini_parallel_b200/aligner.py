@@ -33,6 +33,12 @@ class GpuDevice(ctypes.Structure):            # gpu.rs:17-23
                 ("max_work_group_size", ctypes.c_uint64), ("ordinal", ctypes.c_int32)]
 
 
+class FileCheckpoint(ctypes.Structure):       # aligner.rs:23-32 (+ score64)
+    _fields_ = [("file_path", ctypes.c_char * 1024), ("file_index", ctypes.c_uint64), ("score", ctypes.c_int32),
+                ("score64", ctypes.c_int64), ("processing_time_ms", ctypes.c_double), ("total_bases", ctypes.c_uint64),
+                ("total_reads", ctypes.c_uint64), ("completed", ctypes.c_int32)]
+
+
 class GpuAlignmentResult(ctypes.Structure):   # gpu.rs:26-30
     _fields_ = [("score", ctypes.c_int32), ("score64", ctypes.c_int64), ("processing_time_ms", ctypes.c_double),
                 ("gpu_device", ctypes.c_char * 256), ("total_reads", ctypes.c_uint64), ("total_bases", ctypes.c_uint64)]
@@ -65,6 +71,9 @@ def _lib():
                                                      ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
         lib.rsm_wgs_file_list.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int)]
         lib.rsm_main.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p)]
+        lib.rsm_checkpoint_save.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(FileCheckpoint), ctypes.c_int, ctypes.c_uint64]
+        lib.rsm_checkpoint_load.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(FileCheckpoint), ctypes.c_int,
+                                            ctypes.POINTER(ctypes.c_int), u64p]
         _sig_done = True
     return lib
 
@@ -168,6 +177,23 @@ def process_full_wgs_dataset(device):
     n = ctypes.c_int()
     _check(_lib().rsm_process_full_wgs_dataset(ctypes.byref(device), arr, 4096, ctypes.byref(n)))
     return [arr[i] for i in range(n.value)]
+
+
+def checkpoint_save(path, run_id, files, total_files):
+    """CheckpointState::save (aligner.rs:52-72): `files` is a list of FileCheckpoint."""
+    arr = (FileCheckpoint * max(len(files), 1))(*files)
+    _check(_lib().rsm_checkpoint_save(str(path).encode(), run_id.encode(), arr, len(files), total_files))
+
+
+def checkpoint_load(path):
+    """CheckpointState::load (aligner.rs:74-83): None when the file does not exist, else (run_id, files, total_files)."""
+    arr = (FileCheckpoint * 4096)()
+    rid = ctypes.create_string_buffer(256)
+    n, tot = ctypes.c_int(), ctypes.c_uint64()
+    _check(_lib().rsm_checkpoint_load(str(path).encode(), rid, 256, arr, 4096, ctypes.byref(n), ctypes.byref(tot)))
+    if n.value < 0:
+        return None
+    return rid.value.decode(), [arr[i] for i in range(n.value)], int(tot.value)
 
 
 def main(argv):

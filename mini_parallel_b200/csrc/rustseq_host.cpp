@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <condition_variable>
 #include <deque>
 #include <memory>
@@ -267,6 +268,36 @@ int load_reference(std::vector<uint8_t>& ref)
 
 struct FileOutcome { int rc = 0; std::string err; rsm_alignment_result res{}; };
 
+// The run's checkpoint (aligner.rs:23-104): one entry per finished file, rewritten after every file.
+struct CheckpointBook {
+  std::mutex mu; std::string path, run_id; uint64_t total_files = 0;
+  std::vector<rsm_file_checkpoint> files;
+  void add(const rsm_file_checkpoint& fc)        // CheckpointState::add_file_result (aligner.rs:86-99)
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    files.erase(std::remove_if(files.begin(), files.end(), [&](const rsm_file_checkpoint& f) { return f.file_index == fc.file_index; }), files.end());
+    files.push_back(fc);
+    if (rsm_checkpoint_save(path.c_str(), run_id.c_str(), files.data(), (int)files.size(), total_files))
+      std::printf("Warning: Failed to save checkpoint: %s\n", g_err.c_str());                    // aligner.rs:309
+  }
+  const rsm_file_checkpoint* completed(size_t index)                                               // is_file_completed (aligner.rs:101-103)
+  {
+    for (const auto& f : files) if (f.file_index == index && f.completed) return &f;
+    return nullptr;
+  }
+};
+CheckpointBook* g_book = nullptr;
+
+void record_checkpoint(size_t index, const std::string& path, const FileOutcome& o)
+{
+  if (!g_book) return;
+  rsm_file_checkpoint fc; std::memset(&fc, 0, sizeof fc);
+  std::snprintf(fc.file_path, sizeof fc.file_path, "%s", path.c_str());
+  fc.file_index = index; fc.score = o.res.score; fc.score64 = o.res.score64; fc.processing_time_ms = o.res.processing_time_ms;
+  fc.total_bases = o.res.total_bases; fc.total_reads = o.res.total_reads; fc.completed = o.rc == 0;
+  g_book->add(fc);
+}
+
 // One file of the --full-wgs loop (aligner.rs:261-339) in ref_compat mode: sequential, concat + self-align.
 void process_one_file_compat(size_t index, size_t total, const std::string& file, uint64_t chunk_reads, uint64_t chunk_bases,
                              const rsm_gpu_device* dev, FileOutcome* out)
@@ -309,6 +340,7 @@ void process_one_file_compat(size_t index, size_t total, const std::string& file
   out->res.processing_time_ms = std::floor(secs * 1000.0);
   std::snprintf(out->res.gpu_device, sizeof out->res.gpu_device, "%s", dev->name);
   out->res.total_reads = total_reads; out->res.total_bases = total_bases;
+  record_checkpoint(index, file, *out);                                                           // aligner.rs:298-310, :322-334
 }
 
 // ---- the --full-wgs pipeline in Smith-Waterman mode ----
@@ -529,6 +561,7 @@ void wgs_finish_file(WgsFile* f, size_t total, uint64_t chunk_reads, const rsm_g
   out->res.processing_time_ms = std::floor(secs * 1000.0);            // as_millis() as f64
   std::snprintf(out->res.gpu_device, sizeof out->res.gpu_device, "%s", dev->name);
   out->res.total_reads = f->reads; out->res.total_bases = f->bases;
+  record_checkpoint(f->index, f->path, *out);                                                     // aligner.rs:298-310, :322-334
 }
 
 // All files of one GPU: readers in parallel, one consumer (this thread) scoring whatever is ready.
@@ -873,6 +906,137 @@ int rsm_gpu_align_pair(const char* file1, const char* file2, const rsm_gpu_devic
   return 0;
 }
 
+// ---- checkpoint / resume (aligner.rs:23-104) ----
+static std::string json_escape(const std::string& s)
+{
+  std::string o;
+  for (unsigned char ch : s) {
+    if (ch == '"' || ch == '\\') { o += '\\'; o += (char)ch; }
+    else if (ch == '\n') o += "\\n";
+    else if (ch == '\t') o += "\\t";
+    else if (ch < 0x20) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", ch); o += b; }
+    else o += (char)ch;
+  }
+  return o;
+}
+
+int rsm_checkpoint_save(const char* path, const char* run_id, const rsm_file_checkpoint* files, int n_files, uint64_t total_files)
+{
+  // serde_json::to_string_pretty layout (aligner.rs:58-59): two-space indent, fields in declaration order
+  std::string j = "{\n  \"run_id\": \"" + json_escape(run_id ? run_id : "") + "\",\n  \"files\": [";
+  uint64_t completed = 0;
+  for (int k = 0; k < n_files; ++k) {
+    const rsm_file_checkpoint& f = files[k];
+    char num[64];
+    j += k ? ",\n    {\n" : "\n    {\n";
+    j += "      \"file_path\": \"" + json_escape(f.file_path) + "\",\n";
+    j += "      \"file_index\": " + std::to_string(f.file_index) + ",\n";
+    j += "      \"score\": " + std::to_string(f.score) + ",\n";
+    std::snprintf(num, sizeof num, "%.1f", f.processing_time_ms);
+    j += std::string("      \"processing_time_ms\": ") + num + ",\n";
+    j += "      \"total_bases\": " + std::to_string(f.total_bases) + ",\n";
+    j += "      \"total_reads\": " + std::to_string(f.total_reads) + ",\n";
+    j += std::string("      \"completed\": ") + (f.completed ? "true" : "false") + ",\n";
+    j += "      \"score64\": " + std::to_string(f.score64) + "\n    }";
+    completed += f.completed ? 1 : 0;
+  }
+  j += n_files ? "\n  ],\n" : "],\n";
+  j += "  \"total_files\": " + std::to_string(total_files) + ",\n  \"completed_files\": " + std::to_string(completed) + "\n}";
+  const std::string tmp = std::string(path) + ".tmp";
+  FILE* fp = std::fopen(tmp.c_str(), "wb");
+  if (!fp) return fail(std::string("Failed to create checkpoint file: ") + std::strerror(errno));      // aligner.rs:66
+  const bool ok = std::fwrite(j.data(), 1, j.size(), fp) == j.size();
+  if (std::fclose(fp) != 0 || !ok) return fail("Failed to write checkpoint: short write");             // aligner.rs:69
+  if (std::rename(tmp.c_str(), path) != 0) return fail(std::string("Failed to write checkpoint: ") + std::strerror(errno));
+  return 0;
+}
+
+// A reader for exactly the JSON the function above (and serde) writes: objects with string / number / bool members.
+namespace {
+struct JsonCursor {
+  const std::string& s; size_t p = 0;
+  void ws() { while (p < s.size() && (s[p] == ' ' || s[p] == '\n' || s[p] == '\r' || s[p] == '\t')) ++p; }
+  bool eat(char c) { ws(); if (p < s.size() && s[p] == c) { ++p; return true; } return false; }
+  bool str(std::string* out)
+  {
+    ws();
+    if (p >= s.size() || s[p] != '"') return false;
+    ++p; out->clear();
+    while (p < s.size() && s[p] != '"') {
+      if (s[p] == '\\' && p + 1 < s.size()) {
+        const char e = s[p + 1];
+        if (e == 'n') *out += '\n'; else if (e == 't') *out += '\t';
+        else if (e == 'u' && p + 5 < s.size()) { *out += (char)std::strtol(s.substr(p + 2, 4).c_str(), nullptr, 16); p += 4; }
+        else *out += e;
+        p += 2;
+      } else *out += s[p++];
+    }
+    if (p >= s.size()) return false;
+    ++p;
+    return true;
+  }
+  bool scalar(std::string* out)       // number / true / false / null as text
+  {
+    ws(); out->clear();
+    while (p < s.size() && s[p] != ',' && s[p] != '}' && s[p] != ']' && s[p] != ' ' && s[p] != '\n') *out += s[p++];
+    return !out->empty();
+  }
+};
+}  // namespace
+
+int rsm_checkpoint_load(const char* path, char* run_id, size_t run_id_cap, rsm_file_checkpoint* files, int cap, int* n_files, uint64_t* total_files)
+{
+  if (n_files) *n_files = -1;
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) return 0;                                            // aligner.rs:81: no checkpoint file exists
+  std::string text; char buf[65536]; size_t got;
+  while ((got = std::fread(buf, 1, sizeof buf, fp)) > 0) text.append(buf, got);
+  std::fclose(fp);
+  JsonCursor c{text};
+  auto bad = [&]() { return fail("Failed to parse checkpoint: malformed JSON in " + std::string(path)); };   // aligner.rs:77
+  if (!c.eat('{')) return bad();
+  int n = 0; uint64_t tot = 0; std::string rid;
+  for (bool first = true;; first = false) {
+    if (c.eat('}')) break;
+    if (!first && !c.eat(',')) return bad();
+    std::string key, val;
+    if (!c.str(&key) || !c.eat(':')) return bad();
+    if (key == "files") {
+      if (!c.eat('[')) return bad();
+      for (bool f0 = true;; f0 = false) {
+        if (c.eat(']')) break;
+        if (!f0 && !c.eat(',')) return bad();
+        if (!c.eat('{')) return bad();
+        rsm_file_checkpoint fc; std::memset(&fc, 0, sizeof fc);
+        bool has64 = false;
+        for (bool m0 = true;; m0 = false) {
+          if (c.eat('}')) break;
+          if (!m0 && !c.eat(',')) return bad();
+          std::string k2, v2;
+          if (!c.str(&k2) || !c.eat(':')) return bad();
+          if (k2 == "file_path") { if (!c.str(&v2)) return bad(); std::snprintf(fc.file_path, sizeof fc.file_path, "%s", v2.c_str()); continue; }
+          if (!c.scalar(&v2)) return bad();
+          if (k2 == "file_index") fc.file_index = std::strtoull(v2.c_str(), nullptr, 10);
+          else if (k2 == "score") fc.score = (int32_t)std::strtoll(v2.c_str(), nullptr, 10);
+          else if (k2 == "score64") { fc.score64 = std::strtoll(v2.c_str(), nullptr, 10); has64 = true; }
+          else if (k2 == "processing_time_ms") fc.processing_time_ms = std::strtod(v2.c_str(), nullptr);
+          else if (k2 == "total_bases") fc.total_bases = std::strtoull(v2.c_str(), nullptr, 10);
+          else if (k2 == "total_reads") fc.total_reads = std::strtoull(v2.c_str(), nullptr, 10);
+          else if (k2 == "completed") fc.completed = v2 == "true";
+        }
+        if (!has64) fc.score64 = fc.score;
+        if (files && n < cap) files[n] = fc;
+        ++n;
+      }
+    } else if (key == "run_id") { if (!c.str(&rid)) return bad(); }
+    else { if (!c.scalar(&val)) return bad(); if (key == "total_files") tot = std::strtoull(val.c_str(), nullptr, 10); }
+  }
+  if (run_id && run_id_cap) std::snprintf(run_id, run_id_cap, "%s", rid.c_str());
+  if (n_files) *n_files = n;
+  if (total_files) *total_files = tot;
+  return 0;
+}
+
 int rsm_wgs_file_list(char* buf, size_t cap, int* n_files)
 {
   const auto files = wgs_files();
@@ -921,6 +1085,39 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
     std::printf("Reference: %zu bases, window %u bp, %zu GPU(s)\n", ref.size(), window_len, order.size());
   }
   std::vector<FileOutcome> outcomes(total);
+  // ---- checkpoint / resume (aligner.rs:218-259) ----
+  CheckpointBook book;
+  const char* rid = std::getenv("WGS_RUN_ID");
+  book.run_id = (rid && *rid) ? rid : "wgs_" + std::to_string((long long)std::time(nullptr));      // aligner.rs:219
+  book.path = "checkpoint_" + book.run_id + ".json";                                                // aligner.rs:74 (and, unlike :55, also where it is saved)
+  if (const char* d = std::getenv("WGS_CHECKPOINT_DIR")) if (*d) book.path = std::string(d) + "/" + book.path;   // default: the working directory, like the reference
+  book.total_files = total;
+  {
+    std::vector<rsm_file_checkpoint> prior(total + 16);
+    char rbuf[256]; int np = -1; uint64_t ptotal = 0;
+    // a run without WGS_RUN_ID is a fresh run by definition (its id is a new time stamp, aligner.rs:219): nothing to find
+    if (rid && *rid && rsm_checkpoint_load(book.path.c_str(), rbuf, sizeof rbuf, prior.data(), (int)prior.size(), &np, &ptotal)) return 1;
+    if (np >= 0) {
+      for (int k = 0; k < np && k < (int)prior.size(); ++k) if (prior[k].file_index < total) book.files.push_back(prior[k]);
+      size_t done = 0;
+      for (const auto& f : book.files) done += f.completed ? 1 : 0;
+      std::printf("Found existing checkpoint: %zu files completed\n", done);                       // aligner.rs:224
+    } else {
+      std::printf("No existing checkpoint found, starting fresh run \n");                          // aligner.rs:228
+    }
+  }
+  std::printf("Checkpoint file: %s \n", book.path.c_str());                                        // aligner.rs:240
+  std::vector<size_t> todo;
+  for (size_t i = 0; i < total; ++i) {
+    if (const rsm_file_checkpoint* fc = book.completed(i)) {                                        // aligner.rs:248-259
+      std::printf("Skipping file %zu/%zu (already completed): %s\n", i + 1, total, base_name(files[i]).c_str());
+      outcomes[i].res.score = fc->score; outcomes[i].res.score64 = fc->score64; outcomes[i].res.processing_time_ms = fc->processing_time_ms;
+      outcomes[i].res.total_reads = fc->total_reads; outcomes[i].res.total_bases = fc->total_bases;
+      std::snprintf(outcomes[i].res.gpu_device, sizeof outcomes[i].res.gpu_device, "%s", devs[first].name);
+    } else todo.push_back(i);
+  }
+  g_book = &book;
+  struct BookGuard { ~BookGuard() { g_book = nullptr; } } book_guard;
   std::vector<std::thread> workers;
   // Smith-Waterman mode: SWB_CONSUMERS_PER_GPU scoring threads per device, each with its own context (streams, arenas, a
   // copy of the packed reference).  Default 1: on one B200 a second consumer did not pay for its context and arenas
@@ -928,14 +1125,15 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   uint64_t per_gpu = 1;
   if (const char* v = std::getenv("SWB_CONSUMERS_PER_GPU")) if (parse_usize(v, &per_gpu, &why) || per_gpu < 1 || per_gpu > 8) per_gpu = 1;
   if (compat) per_gpu = 1;
-  const size_t n_workers = std::min<size_t>(order.size() * per_gpu, std::max<size_t>(total, 1));
+  const size_t n_workers = std::min<size_t>(order.size() * per_gpu, todo.size());      // nothing left to do: no worker, no context
   std::vector<std::string> werr(n_workers);
   std::vector<swb_ctx*> own_ctx(n_workers, nullptr);
   for (size_t w = 0; w < n_workers; ++w) {
     workers.emplace_back([&, w]() {
       const int ord = order[w % order.size()];
       if (compat) {
-        for (size_t i = w; i < total; i += n_workers) {
+        for (size_t t = w; t < todo.size(); t += n_workers) {
+          const size_t i = todo[t];
           process_one_file_compat(i, total, files[i], chunk, chunk_bases, &devs[ord], &outcomes[i]);
           if (outcomes[i].rc) return;                             // aligner.rs:336: a failed file aborts the run
         }
@@ -949,7 +1147,8 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
       if (swb_set_reference(ctx, ref.data(), ref.size())) { werr[w] = swb_last_error(); return; }
       stamp("context + reference on device");
       std::vector<size_t> mine;
-      for (size_t i = w; i < total; i += n_workers) mine.push_back(i);
+      for (size_t t = w; t < todo.size(); t += n_workers) mine.push_back(todo[t]);
+      if (mine.empty()) return;
       wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes);
     });
   }

@@ -86,6 +86,7 @@ def _make_lanes(tmp_path, lanes, reads_per_file, rng):
 
 
 def test_full_wgs_driver_both_modes(tmp_path, device, monkeypatch):
+    monkeypatch.setenv("WGS_CHECKPOINT_DIR", str(tmp_path))
     rng = np.random.default_rng(3)
     files = _make_lanes(tmp_path, 2, 45, rng)
     for k, v in dict(WGS_DATA_DIR=str(tmp_path), WGS_SAMPLE_ID="SYN", WGS_LANES="2", WGS_READS_PER_LANE="2",
@@ -131,6 +132,7 @@ def test_full_wgs_pipeline_pieces_and_caps(tmp_path, device, monkeypatch):
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_wgs
+    monkeypatch.setenv("WGS_CHECKPOINT_DIR", str(tmp_path))
     rng = np.random.default_rng(33)
     n_ref, n_reads = 300_000, 40_000
     ref = bench_wgs.synth_reference(n_ref)
@@ -178,6 +180,7 @@ def test_full_wgs_bgzf_files_take_the_gpu_ingest_path(tmp_path, device, monkeypa
     """The same reads as plain gzip (host zlib + line reader) and as BGZF (inflate + parse on the GPU) give the same
     per-file totals; a corrupt BGZF file falls back to the host reader (which then reports the zlib error)."""
     from mini_parallel_b200 import bgzf
+    monkeypatch.setenv("WGS_CHECKPOINT_DIR", str(tmp_path))
     rng = np.random.default_rng(44)
     n_reads = 30_000
     texts = {}
@@ -222,6 +225,36 @@ def test_full_wgs_bgzf_files_take_the_gpu_ingest_path(tmp_path, device, monkeypa
     with pytest.raises(aligner.AlignerError):
         aligner.process_full_wgs_dataset(device)
     assert "falling back to the host reader" in capfd.readouterr().out
+
+
+def test_full_wgs_checkpoint_resume(tmp_path, device, monkeypatch, capfd):
+    """A run with WGS_RUN_ID set leaves checkpoint_{run_id}.json; a second run skips the completed files and returns the
+    same results; removing one entry makes exactly that file run again (aligner.rs:218-259, working here)."""
+    import json
+    rng = np.random.default_rng(55)
+    _make_lanes(tmp_path, 2, 300, rng)
+    for kk, v in dict(WGS_DATA_DIR=str(tmp_path), WGS_SAMPLE_ID="SYN", WGS_LANES="2", WGS_READS_PER_LANE="2", GPU_CHUNK_SIZE_READS="100",
+                      WGS_SYNTH_REFERENCE_BASES="200000", WGS_RUN_ID="resume_test", WGS_CHECKPOINT_DIR=str(tmp_path)).items():
+        monkeypatch.setenv(kk, v)
+    monkeypatch.delenv("SWB_GPU_ALIGN_MODE", raising=False)
+    first = [(r.score64, r.total_reads, r.total_bases) for r in aligner.process_full_wgs_dataset(device)]
+    out = capfd.readouterr().out
+    assert "No existing checkpoint found, starting fresh run" in out and "checkpoint_resume_test.json" in out
+    ck = tmp_path / "checkpoint_resume_test.json"
+    doc = json.loads(ck.read_text())
+    assert doc["completed_files"] == 4 and sorted(f["file_index"] for f in doc["files"]) == [0, 1, 2, 3]
+    assert [f["score64"] for f in sorted(doc["files"], key=lambda f: f["file_index"])] == [r[0] for r in first]
+    second = [(r.score64, r.total_reads, r.total_bases) for r in aligner.process_full_wgs_dataset(device)]
+    out = capfd.readouterr().out
+    assert second == first and "Found existing checkpoint: 4 files completed" in out
+    assert out.count("Skipping file") == 4 and "Processing file" not in out
+    doc["files"] = [f for f in doc["files"] if f["file_index"] != 2]
+    doc["completed_files"] = 3
+    ck.write_text(json.dumps(doc, indent=2))
+    third = [(r.score64, r.total_reads, r.total_bases) for r in aligner.process_full_wgs_dataset(device)]
+    out = capfd.readouterr().out
+    assert third == first and out.count("Skipping file") == 3 and "Processing file 3/4" in out
+    assert json.loads(ck.read_text())["completed_files"] == 4
 
 
 def test_cli_on_gpu(tmp_path):

@@ -186,3 +186,38 @@ def test_bgzf_files_are_ordinary_gzip_for_the_host_reader(tmp_path, clean_env):
     assert aligner.count_bases_in_fastq(path) == sum(len(r) for r in reads)
     with pytest.raises(ValueError):
         bgzf.walk(gzip.compress(text))                                                            # plain gzip has no BC field
+
+
+def test_checkpoint_round_trip_and_serde_layout(tmp_path, clean_env):
+    """CheckpointState (aligner.rs:23-104): what save writes is what serde_json::to_string_pretty would write for the
+    reference's structs (plus score64), and load reads it back -- also when it was written by the reference's serde."""
+    import json
+    files = []
+    for k, (name, score, done) in enumerate((("/data/S_L001_R1_001.fastq.gz", 12345, True), ('/data/we"ird\\name.gz', -7, False))):
+        fc = aligner.FileCheckpoint()
+        fc.file_path = name.encode(); fc.file_index = k; fc.score = score; fc.score64 = score + (1 << 40) * k
+        fc.processing_time_ms = 1234.0 + k; fc.total_bases = 150 * (k + 1); fc.total_reads = k + 1; fc.completed = int(done)
+        files.append(fc)
+    path = tmp_path / "checkpoint_wgs_1.json"
+    assert aligner.checkpoint_load(path) is None                                   # aligner.rs:81
+    aligner.checkpoint_save(path, "wgs_1", files, 16)
+    text = path.read_text()
+    doc = json.loads(text)
+    assert list(doc) == ["run_id", "files", "total_files", "completed_files"]      # declaration order, aligner.rs:35-40
+    assert doc["run_id"] == "wgs_1" and doc["total_files"] == 16 and doc["completed_files"] == 1
+    assert list(doc["files"][0])[:7] == ["file_path", "file_index", "score", "processing_time_ms", "total_bases", "total_reads", "completed"]
+    assert doc["files"][1]["file_path"] == '/data/we"ird\\name.gz' and doc["files"][1]["completed"] is False
+    assert text.startswith('{\n  "run_id": "wgs_1",\n  "files": [\n    {\n      "file_path"')      # to_string_pretty indentation
+    rid, back, tot = aligner.checkpoint_load(path)
+    assert rid == "wgs_1" and tot == 16 and len(back) == 2
+    for a, b in zip(files, back):
+        for f, _ in aligner.FileCheckpoint._fields_:
+            assert getattr(a, f) == getattr(b, f), f
+    # a file in the reference's own format (no score64)
+    path.write_text(json.dumps({"run_id": "x", "files": [{"file_path": "a", "file_index": 3, "score": 9, "processing_time_ms": 1.5,
+                                                          "total_bases": 7, "total_reads": 2, "completed": True}], "total_files": 4, "completed_files": 1}, indent=2))
+    rid, back, tot = aligner.checkpoint_load(path)
+    assert (rid, tot, back[0].file_index, back[0].score, back[0].score64, back[0].completed) == ("x", 4, 3, 9, 9, 1)
+    path.write_text("{ not json")
+    with pytest.raises(aligner.AlignerError, match="Failed to parse checkpoint"):
+        aligner.checkpoint_load(path)

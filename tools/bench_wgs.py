@@ -102,7 +102,7 @@ def main():
     gen_s = time.time() - t0
     gz_bytes = sum(s[0] for s in sizes); text_bytes = sum(s[1] for s in sizes)
     env = dict(os.environ, GPU_CHUNK_SIZE_READS=str(args.chunk_reads), WGS_DATA_DIR=args.dir, WGS_SAMPLE_ID="SYN", WGS_LANES=str(args.lanes),
-               WGS_READS_PER_LANE="2", WGS_SYNTH_REFERENCE_BASES=str(args.ref_bases), SWB_NUM_DEVICES=str(args.devices))
+               WGS_READS_PER_LANE="2", WGS_SYNTH_REFERENCE_BASES=str(args.ref_bases), SWB_NUM_DEVICES=str(args.devices), WGS_CHECKPOINT_DIR=args.dir)
     env.pop("SWB_GPU_ALIGN_MODE", None)
     cli = os.path.join(ROOT, "build", "rustseq_mini")
     subprocess.run([cli, "-1", "ACGT", "-2", "ACGT", "--gpu"], env=env, capture_output=True)      # warm the driver / context creation
