@@ -37,6 +37,9 @@ int  swb_device_count(void);
 /* name / memory / max work-group size of a device: the GpuDevice struct, gpu.rs:17-23. */
 int  swb_device_info(int device_id, char* name, size_t name_cap, double* memory_gb, int* max_work_group_size);
 
+/* Free / total device memory in bytes (system_info.rs:236-243 budgets 80 % of VRAM; the WGS report states what is in use). */
+int  swb_memory_info(int device_id, uint64_t* free_bytes, uint64_t* total_bytes);
+
 /* Context: replaces get_opencl_context/init_opencl (gpu.rs:97-132).  One device per context. */
 int  swb_create(swb_ctx** out, int device_id, const swb_params* params /* NULL = reference constants */);
 void swb_destroy(swb_ctx*);

@@ -23,6 +23,7 @@ _int = ctypes.c_int
 SIGNATURES = {
     "swb_device_count": (_int, []),
     "swb_device_info": (_int, [_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_int)]),
+    "swb_memory_info": (_int, [_int, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
     "swb_create": (_int, [ctypes.POINTER(_vp), _int, _vp]),
     "swb_destroy": (None, [_vp]),
     "swb_score_pair": (_int, [_vp, _u8p, _u64, _u8p, _u64, ctypes.POINTER(SwbResult)]),

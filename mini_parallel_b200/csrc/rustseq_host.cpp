@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <memory>
@@ -287,6 +288,7 @@ struct CheckpointBook {
   }
 };
 CheckpointBook* g_book = nullptr;
+std::atomic<uint64_t> g_gpu_call_us{0};              // wall time the scoring threads spent inside GPU calls (benchmark report)
 
 void record_checkpoint(size_t index, const std::string& path, const FileOutcome& o)
 {
@@ -678,9 +680,11 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
       if (!f->gpu_path_failed && !abort_run) {
         int64_t ssum = 0; uint64_t nr = 0, nb = 0, nl = 0, ncarry = 0; int status = 0;
         const uint32_t w = (uint32_t)std::min<uint64_t>(window_len, ref_len);
+        const auto tc0 = std::chrono::steady_clock::now();
         const int crc = swb_fastq_bgzf_score(ctx, c->comp->data(), c->comp_len, c->blocks.data(), c->blocks.size(), f->carry.data(), f->carry.size(),
                                              c->final_segment ? 1 : 0, f->index, f->reads, w, &ssum, &nr, &nb, &nl, carry_out.data(),
                                              carry_out.size(), &ncarry, &status);
+        g_gpu_call_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tc0).count();
         if (crc != 0 || status != 0) {
           if (crc) std::printf("    Warning: GPU FASTQ path failed on %s: %s\n", base_name(f->path).c_str(), swb_last_error());
           std::lock_guard<std::mutex> lk(gate.mu);
@@ -703,7 +707,9 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
       continue;
     }
     const uint64_t n = c->offs.size() - 1;
+    const auto th0 = std::chrono::steady_clock::now();
     int crc = abort_run ? 0 : swb_score_batch_vs_reference(ctx, c->bases.data(), c->offs.data(), n, c->wstart.data(), c->wlen.data(), c->res.data());
+    g_gpu_call_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - th0).count();
     if (crc == 0 && !abort_run) {
       int64_t cs = 0;
       for (uint64_t k = 0; k < n; ++k) cs += c->res[k].score;
@@ -1117,6 +1123,7 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
     } else todo.push_back(i);
   }
   g_book = &book;
+  g_gpu_call_us = 0;
   struct BookGuard { ~BookGuard() { g_book = nullptr; } } book_guard;
   std::vector<std::thread> workers;
   // Smith-Waterman mode: SWB_CONSUMERS_PER_GPU scoring threads per device, each with its own context (streams, arenas, a
@@ -1154,6 +1161,8 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   }
   stamp("reference + workers started");
   for (auto& t : workers) t.join();
+  double mem_used_mb = 0;
+  { uint64_t fr = 0, to = 0; if (swb_memory_info(first, &fr, &to) == 0) mem_used_mb = (double)(to - fr) / 1048576.0; }
   for (swb_ctx* x : own_ctx) if (x) swb_destroy(x);
   stamp("all files done");
   for (const auto& e : werr) if (!e.empty()) return fail(e);
@@ -1164,6 +1173,39 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
     ++n;
   }
   if (n_out) *n_out = n;
+
+  // ---- benchmark report (tools/benchmark.rs:17-42, :165-208), with measured numbers instead of the constants of :159-163 ----
+  {
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    uint64_t reads = 0, bases = 0; int64_t score = 0;
+    for (size_t i = 0; i < total; ++i) { reads += outcomes[i].res.total_reads; bases += outcomes[i].res.total_bases; score += outcomes[i].res.score64; }
+    const time_t now = std::time(nullptr);
+    char stamp_s[64]; std::strftime(stamp_s, sizeof stamp_s, "%Y-%m-%dT%H:%M:%SZ", std::gmtime(&now));
+    double ram_gb = 0;
+    if (FILE* mi = std::fopen("/proc/meminfo", "r")) { unsigned long long kb = 0; if (std::fscanf(mi, "MemTotal: %llu kB", &kb) == 1) ram_gb = kb / 1048576.0; std::fclose(mi); }
+    const double busy = n_workers ? std::min(1.0, (double)g_gpu_call_us.load() / 1e6 / secs / (double)n_workers) : 0.0;
+    const uint64_t w = compat ? 0 : window_len;
+    std::string dir = "benchmark_results";
+    if (const char* d = std::getenv("WGS_CHECKPOINT_DIR")) if (*d) dir = std::string(d) + "/benchmark_results";
+    const std::string mk = "mkdir -p '" + dir + "'";
+    if (std::system(mk.c_str()) == 0) {
+      const std::string path = dir + "/run_" + book.run_id + "_benchmark_results.json";
+      if (FILE* fp = std::fopen(path.c_str(), "w")) {
+        std::fprintf(fp, "{\n  \"timestamp\": \"%s\",\n  \"run_id\": \"%s\",\n  \"mode\": \"full_wgs\",\n  \"files_processed\": %zu,\n"
+                         "  \"total_reads\": %llu,\n  \"total_bases\": %llu,\n  \"total_score\": %d,\n  \"total_time_seconds\": %.6f,\n"
+                         "  \"throughput_reads_per_second\": %.3f,\n  \"throughput_bases_per_second\": %.3f,\n  \"chunk_size\": %llu,\n"
+                         "  \"gpu_utilization_avg\": %.2f,\n  \"gpu_memory_used_mb\": %.1f,\n  \"cpu_cores_used\": %u,\n  \"parallel_files\": true,\n"
+                         "  \"system_info\": {\n    \"gpu_name\": \"%s\",\n    \"gpu_memory_gb\": %.1f,\n    \"cpu_cores\": %u,\n    \"total_ram_gb\": %.1f\n  },\n"
+                         "  \"total_score64\": %lld,\n  \"n_gpus\": %zu,\n  \"window_len\": %llu,\n  \"gcups_end_to_end\": %.3f\n}\n",
+                     stamp_s, book.run_id.c_str(), total, (unsigned long long)reads, (unsigned long long)bases, (int)score, secs,
+                     reads / secs, bases / secs, (unsigned long long)chunk, 100.0 * busy, mem_used_mb, std::thread::hardware_concurrency(),
+                     devs[first].name, (double)devs[first].memory_gb, std::thread::hardware_concurrency(), ram_gb,
+                     (long long)score, order.size(), (unsigned long long)w, (double)bases * (double)w / secs / 1e9);
+        std::fclose(fp);
+        std::printf("Benchmark results saved to: %s\n", path.c_str());                            // benchmark.rs:187
+      }
+    }
+  }
   return 0;
 }
 

@@ -103,6 +103,16 @@ int swb_device_info(int device_id, char* name, size_t name_cap, double* memory_g
   return 0;
 }
 
+int swb_memory_info(int device_id, uint64_t* free_bytes, uint64_t* total_bytes)
+{
+  CUDA_TRY(cudaSetDevice(device_id));
+  size_t f = 0, t = 0;
+  CUDA_TRY(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return 0;
+}
+
 int swb_create(swb_ctx** out, int device_id, const swb_params* params)
 {
   if (!out) return fail("swb_create: null out pointer");

@@ -255,6 +255,11 @@ def test_full_wgs_checkpoint_resume(tmp_path, device, monkeypatch, capfd):
     out = capfd.readouterr().out
     assert third == first and out.count("Skipping file") == 3 and "Processing file 3/4" in out
     assert json.loads(ck.read_text())["completed_files"] == 4
+    # the run report (tools/benchmark.rs:17-42) with measured numbers
+    rep = json.loads((tmp_path / "benchmark_results" / "run_resume_test_benchmark_results.json").read_text())
+    assert rep["mode"] == "full_wgs" and rep["files_processed"] == 4 and rep["total_reads"] == 1200 and rep["total_bases"] == 1200 * 150
+    assert rep["total_score64"] == sum(r[0] for r in first) and rep["throughput_reads_per_second"] > 0
+    assert rep["system_info"]["gpu_name"].startswith("NVIDIA") and rep["gpu_memory_used_mb"] > 100 and rep["n_gpus"] >= 1
 
 
 def test_cli_on_gpu(tmp_path):
