@@ -27,10 +27,13 @@ constexpr int LIT_FAST = 1 << LIT_BITS, DIST_FAST = 1 << DIST_BITS;
 enum Status : int { OK = 0, ERR_INPUT_OVERRUN = 1, ERR_OUTPUT_OVERRUN = 2, ERR_BAD_BLOCK_TYPE = 3, ERR_BAD_STORED = 4,
                     ERR_BAD_LENGTHS = 5, ERR_BAD_SYMBOL = 6, ERR_BAD_DISTANCE = 7, ERR_LENGTH_MISMATCH = 8 };
 
-// Decode tables of one member (shared memory on the device, stack on the host): ~3.9 KiB.
+// Decode tables of one member (shared memory on the device, stack on the host): 4 KiB.
+// A fast-table entry says everything the symbol loop needs, so it never touches the base / extra-bits tables:
+//   [3:0] code length (0 = longer than the table's index: canonical walk)   [7:4] kind   [15:8] extra bits   [31:16] value
+//   kind 0 literal (value = byte) | 1 length or distance (value = base) | 2 end of block | 3 not a legal symbol
 struct Tables {
-  uint16_t lit_fast[LIT_FAST];     // (symbol << 4) | code length, 0 = code longer than LIT_BITS (slow path)
-  uint16_t dist_fast[DIST_FAST];
+  uint32_t lit_fast[LIT_FAST];
+  uint32_t dist_fast[DIST_FAST];
   uint16_t lit_count[16], dist_count[16];
   uint16_t lit_sym[288], dist_sym[32];
   uint8_t  lengths[320];
@@ -86,12 +89,42 @@ SWI_HD uint32_t bitrev(uint32_t c, int len)
   return r;
 }
 
+#if defined(__CUDACC__)
+#define SWI_CONST static __device__ __constant__        /* nvcc build: only the device side runs this code */
+#else
+#define SWI_CONST static const                          /* g++ build of the CPU unit test */
+#endif
+SWI_CONST uint16_t kLenBase[29]  = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+SWI_CONST uint8_t  kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+SWI_CONST uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193,
+                                    12289, 16385, 24577};
+SWI_CONST uint8_t  kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+SWI_CONST uint8_t  kClOrder[19]  = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+enum Alphabet : int { ALPHA_PLAIN = 0, ALPHA_LITLEN = 1, ALPHA_DIST = 2 };
+
+// what the symbol loop needs to know about symbol s of the given alphabet (see Tables)
+SWI_HD uint32_t make_entry(int alphabet, int s, int len)
+{
+  if (alphabet == ALPHA_LITLEN) {
+    if (s < 256) return ((uint32_t)s << 16) | (uint32_t)len;
+    if (s == 256) return (2u << 4) | (uint32_t)len;
+    if (s <= 285) return ((uint32_t)kLenBase[s - 257] << 16) | ((uint32_t)kLenExtra[s - 257] << 8) | (1u << 4) | (uint32_t)len;
+    return (3u << 4) | (uint32_t)len;
+  }
+  if (alphabet == ALPHA_DIST) {
+    if (s <= 29) return ((uint32_t)kDistBase[s] << 16) | ((uint32_t)kDistExtra[s] << 8) | (1u << 4) | (uint32_t)len;
+    return (3u << 4) | (uint32_t)len;
+  }
+  return ((uint32_t)s << 16) | (uint32_t)len;
+}
+
 // Canonical Huffman tables from code lengths.  Returns false on an over-subscribed set.
 // (An incomplete set is accepted, as zlib accepts the single-code distance tree; unused codes decode as errors.)
 // Kept out of line on the device: inlined three times into inflate_member, nvcc 12.9 -O3 produced a build() that
 // reported a valid fixed-code length set as over-subscribed (tools/inflate_gpu_probe.cu reproduces it; -G, a printf in
 // the loop or __noinline__ all make it correct).  It runs two or three times per deflate block, the call costs nothing.
-SWI_OUTLINED bool build(const uint8_t* lengths, int n, uint16_t* fast, int fast_bits, uint16_t* count, uint16_t* sym, const Lanes& L)
+SWI_OUTLINED bool build(const uint8_t* lengths, int n, int alphabet, uint32_t* fast, int fast_bits, uint16_t* count, uint16_t* sym, const Lanes& L)
 {
   const int fast_size = 1 << fast_bits;
   for (int k = L.lane; k < fast_size; k += L.n) fast[k] = 0;
@@ -114,41 +147,30 @@ SWI_OUTLINED bool build(const uint8_t* lengths, int n, uint16_t* fast, int fast_
     ++offs[l];
     const uint32_t c = next_code[l]++;
     if (l <= fast_bits) {
-      const uint32_t rev = bitrev(c, l);
-      for (uint32_t k = rev + ((uint32_t)L.lane << l); k < (uint32_t)fast_size; k += (uint32_t)L.n << l) fast[k] = (uint16_t)((s << 4) | l);
+      const uint32_t rev = bitrev(c, l), e = make_entry(alphabet, s, l);
+      for (uint32_t k = rev + ((uint32_t)L.lane << l); k < (uint32_t)fast_size; k += (uint32_t)L.n << l) fast[k] = e;
     }
   }
   SWI_SYNC();
   return true;
 }
 
-// One symbol: fast table, else the canonical bit-by-bit walk.  Returns -1 on an unused code.
-SWI_HD int decode(Bits& b, const uint16_t* fast, int fast_bits, const uint16_t* count, const uint16_t* sym)
+// One symbol: its table entry (code bits consumed).  Fast table, else the canonical bit-by-bit walk; an unused code
+// comes back as kind 3.
+SWI_HD uint32_t decode(Bits& b, int alphabet, const uint32_t* fast, int fast_bits, const uint16_t* count, const uint16_t* sym)
 {
   const uint32_t e = fast[peek(b, fast_bits)];
-  if (e) { consume(b, (int)(e & 15u)); return (int)(e >> 4); }
+  if (e) { consume(b, (int)(e & 15u)); return e; }
   int code = 0, first = 0, index = 0;
   uint64_t bits = b.buf;
   for (int len = 1; len <= 15; ++len) {
     code |= (int)(bits & 1u); bits >>= 1;
     const int c = count[len];
-    if (code - c < first) { consume(b, len); return sym[index + (code - first)]; }
+    if (code - c < first) { consume(b, len); return make_entry(alphabet, sym[index + (code - first)], len); }
     index += c; first += c; first <<= 1; code <<= 1;
   }
-  return -1;
+  return 3u << 4;
 }
-
-#if defined(__CUDACC__)
-#define SWI_CONST static __device__ __constant__        /* nvcc build: only the device side runs this code */
-#else
-#define SWI_CONST static const                          /* g++ build of the CPU unit test */
-#endif
-SWI_CONST uint16_t kLenBase[29]  = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-SWI_CONST uint8_t  kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-SWI_CONST uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193,
-                                    12289, 16385, 24577};
-SWI_CONST uint8_t  kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-SWI_CONST uint8_t  kClOrder[19]  = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 // Inflate one raw-deflate member of in_len bytes into out[0, out_cap).  *produced = bytes written.
 SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint32_t out_cap, uint32_t* produced, Tables& T, const Lanes& L)
@@ -186,14 +208,15 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
         for (int i = 0; i < 19; ++i) cl[i] = 0;
         for (int i = 0; i < ncl; ++i) { refill(b); cl[kClOrder[i]] = (uint8_t)take(b, 3); }
         // the code-length code is tiny: decode it with the canonical walk only (fast table of 1 entry-bit is not worth it)
-        if (!build(cl, 19, T.dist_fast, 7, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
+        if (!build(cl, 19, ALPHA_PLAIN, T.dist_fast, 7, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
         int i = 0;
         uint8_t prev = 0;
         bool bad = false;
         while (i < nlit + ndist) {
           refill(b);
-          const int s = decode(b, T.dist_fast, 7, T.dist_count, T.dist_sym);
-          if (s < 0) { bad = true; break; }
+          const uint32_t ce = decode(b, ALPHA_PLAIN, T.dist_fast, 7, T.dist_count, T.dist_sym);
+          if ((ce >> 4) & 15u) { bad = true; break; }
+          const int s = (int)(ce >> 16);
           if (s < 16) { if (L.lane == 0) T.lengths[i] = (uint8_t)s; prev = (uint8_t)s; ++i; continue; }
           int rep; uint8_t v = 0;
           if (s == 16) { if (i == 0) { bad = true; break; } v = prev; rep = 3 + (int)take(b, 2); }
@@ -215,26 +238,25 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
         SWI_SYNC();
         nlit = 288; ndist = 30;
       }
-      if (!build(T.lengths, nlit, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym, L) ||
-          !build(T.lengths + 288, ndist, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
+      if (!build(T.lengths, nlit, ALPHA_LITLEN, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym, L) ||
+          !build(T.lengths + 288, ndist, ALPHA_DIST, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
       // ---- symbols ----
-      for (uint32_t guard = 0; guard <= out_cap + 1u; ++guard) {      // every symbol but the last one emits >= 1 byte
+      for (;;) {                                               // every pass emits >= 1 byte (bounded by out_cap), ends the block or fails
         refill(b);
-        const int s = decode(b, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym);
-        if (s < 0) { status = ERR_BAD_SYMBOL; break; }
-        if (s < 256) {
+        const uint32_t e = decode(b, ALPHA_LITLEN, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym);
+        const uint32_t kind = (e >> 4) & 15u;
+        if (kind == 0) {
           if (opos >= out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
-          out[opos] = (uint8_t)s;                                // every lane stores the same byte to the same address: no branch
+          out[opos] = (uint8_t)(e >> 16);                        // every lane stores the same byte to the same address: no branch
           ++opos;
           continue;
         }
-        if (s == 256) break;
-        if (s > 285) { status = ERR_BAD_SYMBOL; break; }
-        const uint32_t len = kLenBase[s - 257] + take(b, kLenExtra[s - 257]);
+        if (kind != 1) { if (kind != 2) status = ERR_BAD_SYMBOL; break; }
+        const uint32_t len = (e >> 16) + take(b, (int)((e >> 8) & 255u));
         refill(b);
-        const int ds = decode(b, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym);
-        if (ds < 0 || ds > 29) { status = ERR_BAD_DISTANCE; break; }
-        const uint32_t dist = kDistBase[ds] + take(b, kDistExtra[ds]);
+        const uint32_t de = decode(b, ALPHA_DIST, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym);
+        if (((de >> 4) & 15u) != 1) { status = ERR_BAD_DISTANCE; break; }
+        const uint32_t dist = (de >> 16) + take(b, (int)((de >> 8) & 255u));
         if (dist > opos) { status = ERR_BAD_DISTANCE; break; }
         if (opos + len > out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
         SWI_SYNC();                                            // earlier literals / copies are visible to every lane
