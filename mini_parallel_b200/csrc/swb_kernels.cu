@@ -615,7 +615,11 @@ sw_stream_kernel(StreamArgs a)
       const int32_t P0 = Pconst - blockStart + pairBase;
 #pragma unroll
       for (int m = 0; m < K; ++m) {
+#if SWB_ABLATE != 3
         fold_word(cur[m], P0 - 8191 * m, recA, recB);
+#else
+        recA |= cur[m];
+#endif
         cur[m] = 0;
         A[m] = __vsub2(A[m], REBASE); B[m] = __vsub2(B[m], REBASE);
       }
@@ -673,12 +677,20 @@ sw_stream_kernel(StreamArgs a)
     const uint16_t* wp = ring + ((it + G - L) & (RSLOTS - 1)) * K;
 #pragma unroll
     for (int u = 0; u < K; ++u) {
+#if SWB_ABLATE == 5
+      W[u] = WPADV + u;                                 /* no ring read */
+#else
       W[u] = wp[u];
+#endif
+#if SWB_ABLATE == 4
+      uint32_t up = fm1 + ((u & 1) ? A[K - 1] : B[K - 1]);   /* no shuffle, no select */
+#else
       uint32_t up = __shfl_up_sync(0xffffffffu, (u & 1) ? A[K - 1] : B[K - 1], 1, G);
       if (L == 0) up = fm1;
+#endif
 #pragma unroll
       for (int m = K - 1; m >= 0; --m) {
-#if SWB_ABLATE >= 1                                  /* timing experiments only: results are wrong */
+#if SWB_ABLATE == 1                                  /* timing experiments only: results are wrong */
         const uint32_t sub = Q[m] ^ W[(u - m + K) % K];
 #else
         const uint32_t x = Q[m] + W[(u - m + K) % K];
@@ -698,9 +710,11 @@ sw_stream_kernel(StreamArgs a)
 #endif
       }
       upPrev = up;
+#if SWB_ABLATE != 6
       fm1 = floor_;
       floor_ += 0x00800080u;
       e = __vsub2(e, 0x00810081u);
+#endif
     }
   }
 }
