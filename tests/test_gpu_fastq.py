@@ -117,3 +117,31 @@ def test_bad_data_asks_for_the_host_path(engine):
     reads, text = _make(rng, ref, 50, with_n=False)                                     # and the context still works
     tot = _run_segments(engine, bgzf.compress(text, 1), 100)
     assert tot["reads"] == 50
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_fastq_shapes_agree_with_the_host_path(engine, seed):
+    """Random record shapes (reads from 0 to 3000 bases, N and lower-case bases, long headers, CRLF or LF), random block
+    sizes, levels and segmentations: the GPU ingest totals equal scoring the same reads through the host API."""
+    rng = np.random.default_rng(1000 + seed)
+    ref = ACGT[rng.integers(0, 4, 80_000)]
+    engine.set_reference(ref)
+    eol = b"\r\n" if seed % 2 else b"\n"
+    alphabet = np.frombuffer(b"ACGT" * 8 + b"Nacgt", dtype=np.uint8)
+    reads, recs = [], []
+    for k in range(int(rng.integers(300, 2500))):
+        ln = int(rng.choice([0, 1, 36, 100, 150, 151, 160, 161, 250, 3000], p=[.02, .03, .1, .2, .4, .05, .05, .05, .08, .02]))
+        r = bytes(alphabet[rng.integers(0, alphabet.size, ln)])
+        reads.append(r)
+        recs.append(b"@" + bytes(rng.integers(48, 123, int(rng.integers(1, 120)), dtype=np.uint8)) + eol + r + eol + b"+" + eol + b"#" * ln + eol)
+    text = b"".join(recs)
+    w = 400
+    starts = np.array([splitmix64(((7 << 40) + k) ^ 0xB202) % (len(ref) - w + 1) for k in range(len(reads))], dtype=np.uint64)
+    q, qo = to_csr(reads)
+    host = engine.score_batch_vs_reference(q, qo, starts, np.full(len(reads), w, dtype=np.uint32))
+    exp = {"score_sum": int(host["score"].astype(np.int64).sum()), "reads": len(reads), "bases": sum(len(r) for r in reads)}
+    for _ in range(3):
+        gz = bgzf.compress(text, int(rng.integers(0, 10)), int(rng.integers(200, 65281)))
+        tot = _run_segments(engine, gz, int(rng.integers(1, 40)), file_index=7, w=w)
+        assert {k: tot[k] for k in exp} == exp
+        assert tot["lines"] == 4 * len(reads)
