@@ -41,6 +41,7 @@ SIGNATURES = {
     "swb_last_routing": (_int, [_vp, ctypes.POINTER(_u64)]),
     "swb_set_short_variant": (_int, [_vp, _int]),
     "swb_set_chunking": (_int, [_vp, _u64, _u64]),
+    "swb_set_chunk_ramp": (_int, [_vp, _int]),
     "swb_fastq_bgzf_prefetch": (_int, [_vp, _u8p, _u64, _vp, _u64]),
     "swb_fastq_bgzf_score": (_int, [_vp, _u8p, _u64, _vp, _u64, _u8p, _u64, _int, _u64, _u64, _u32,
                                     ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64),

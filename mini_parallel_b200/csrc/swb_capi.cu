@@ -47,7 +47,8 @@ struct Lane {
   }
 };
 
-constexpr int kLanes = 3;                  // chunks of a host batch in flight: H2D / kernels / D2H overlap
+constexpr int kLanes = 6;                  // pipeline lanes a context owns; a host batch uses the first n_lanes of them
+                                           // (chunks in flight: H2D / kernels / D2H overlap)
 
 struct ChunkEvents { cudaEvent_t ev[8]; };
 
@@ -73,6 +74,9 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   uint64_t chunk_bytes = 32ull << 20;      // ASCII bytes per chunk of a host batch (SWB_CHUNK_MB, swb_set_chunking); half of it
                                            // when only reads travel (windows of the resident reference): measured optima on B200
   uint64_t min_chunk_pairs = 16384;
+  int n_lanes = 3;                         // SWB_LANES
+  int chunk_ramp = 1;                      // SWB_CHUNK_RAMP=0: equal chunks
+  std::vector<uint64_t> chunk_bounds;      // pair index where every chunk of the last host batch starts (+ n_pairs)
   float last_ms[6] = {0, 0, 0, 0, 0, 0};
   int last_kernels = 0;
   uint64_t last_routing[3] = {0, 0, 0};
@@ -135,6 +139,8 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   }
   if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 7;
   if (const char* v = std::getenv("SWB_FORCE_BYTES")) c->force_bytes = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SWB_LANES")) c->n_lanes = std::min(kLanes, std::max(1, std::atoi(v)));
+  if (const char* v = std::getenv("SWB_CHUNK_RAMP")) c->chunk_ramp = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_CHUNK_MB")) { const long mb = std::atol(v); if (mb > 0) c->chunk_bytes = (uint64_t)mb << 20; }
   *out = c;
   return 0;
@@ -169,6 +175,13 @@ int swb_set_chunking(swb_ctx* c, uint64_t chunk_bytes, uint64_t min_chunk_pairs)
   if (!c) return fail("null ctx");
   if (chunk_bytes == 0 || min_chunk_pairs == 0) return fail("swb_set_chunking: sizes must be positive");
   c->chunk_bytes = chunk_bytes; c->min_chunk_pairs = min_chunk_pairs;
+  return 0;
+}
+
+int swb_set_chunk_ramp(swb_ctx* c, int ramp)
+{
+  if (!c) return fail("null ctx");
+  c->chunk_ramp = ramp != 0;
   return 0;
 }
 
@@ -256,7 +269,7 @@ int swb_score_batch_device(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo,
 }
 
 // ---- host batches: chunks of pairs pipelined over kLanes streams ----
-// Chunk k runs on lane k % kLanes: H2D of its bytes and offsets, offset rebase, the device pipeline, D2H of its
+// Chunk k runs on lane k % n_lanes: H2D of its bytes and offsets, offset rebase, the device pipeline, D2H of its
 // results.  While one lane computes, the next lane's H2D and the previous lane's D2H are in flight (one copy
 // engine per direction), so a large batch costs max(PCIe, kernels) instead of their sum.
 static int ensure_chunk_slots(swb_ctx* c, size_t n_chunks)
@@ -284,16 +297,40 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
   if (qo[0] != 0 || (!ref_windows && ro[0] != 0)) return fail(std::string(who) + ": offsets must start at 0");
   const uint64_t bytes_total = qo[n_pairs] + (ref_windows ? 0 : ro[n_pairs]);
   const uint64_t cb = ref_windows ? std::max<uint64_t>(c->chunk_bytes / 2, 1) : c->chunk_bytes;
-  uint64_t n_chunks = std::max<uint64_t>(1, (bytes_total + cb - 1) / cb);
-  uint64_t per = (n_pairs + n_chunks - 1) / n_chunks;
+  uint64_t n_uniform = std::max<uint64_t>(1, (bytes_total + cb - 1) / cb);
+  uint64_t per = (n_pairs + n_uniform - 1) / n_uniform;
   per = std::max<uint64_t>(per, std::min<uint64_t>(n_pairs, c->min_chunk_pairs));
-  n_chunks = (n_pairs + per - 1) / per;
+  n_uniform = (n_pairs + per - 1) / per;
+  // Chunk schedule (pairs per chunk).  A long batch ramps up from per/8 and down again to per/4: the first H2D and the
+  // last chunk's kernels + D2H are the only parts of the pipeline nothing overlaps with, so they are kept short, while the
+  // steady chunks stay large enough for the persistent kernels (few launches, little tail per launch).
+  std::vector<uint64_t>& bounds = c->chunk_bounds;
+  bounds.clear(); bounds.push_back(0);
+  if (c->chunk_ramp && n_uniform >= 4) {
+    const uint64_t lo = std::max<uint64_t>(1, std::min<uint64_t>(per, c->min_chunk_pairs));
+    const uint64_t head[3] = {std::max(per / 8, lo), std::max(per / 4, lo), std::max(per / 2, lo)};
+    const uint64_t tail[2] = {std::max(per / 2, lo), std::max(per / 4, lo)};
+    const uint64_t tail_sum = tail[0] + tail[1];
+    uint64_t p = 0;
+    for (int k = 0; k < 3 && p + head[k] + tail_sum < n_pairs; ++k) { p += head[k]; bounds.push_back(p); }
+    while (p + per + tail_sum < n_pairs) { p += per; bounds.push_back(p); }
+    const uint64_t rest = n_pairs - p;                     // 0 < rest <= per + tail_sum: three pieces 4 : 2 : 1
+    const uint64_t a = rest * 4 / 7, b = rest * 2 / 7;
+    if (a) { p += a; bounds.push_back(p); }
+    if (b) { p += b; bounds.push_back(p); }
+    if (p == n_pairs) bounds.pop_back();
+    bounds.push_back(n_pairs);
+  } else {
+    for (uint64_t p = per; p < n_pairs; p += per) bounds.push_back(p);
+    bounds.push_back(n_pairs);
+  }
+  const uint64_t n_chunks = bounds.size() - 1;
   if (ensure_chunk_slots(c, n_chunks)) return 1;
   c->last_kernels = 0;
 
   for (uint64_t ch = 0; ch < n_chunks; ++ch) {
-    const uint64_t p0 = ch * per, p1 = std::min(n_pairs, p0 + per), n = p1 - p0;
-    Lane* l = c->lane((int)(ch % kLanes));
+    const uint64_t p0 = bounds[ch], p1 = bounds[ch + 1], n = p1 - p0;
+    Lane* l = c->lane((int)(ch % (uint64_t)c->n_lanes));
     cudaEvent_t* ev = c->chunk_ev[ch].ev;
     cudaStream_t st = l->st;
     uint32_t max_r = 0, max_q = 0;
@@ -615,6 +652,14 @@ int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
         cudaEventElapsedTime(&t, ev[6], ev[7]); c->last_ms[5] += t;
         c->last_routing[0] += c->h_counters[ch].n_short; c->last_routing[1] += c->h_counters[ch].n_generic + c->h_counters[ch].n_bytes;
         c->last_routing[2] += c->h_counters[ch].n_long;
+      }
+      if (std::getenv("SWB_DEBUG_TIMELINE")) {                 // per chunk, ms since the first event of the call
+        for (size_t ch = 0; ch < c->last_chunks; ++ch) {
+          float t[6]; const int idx[6] = {4, 5, 1, 2, 3, 7};
+          for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], c->chunk_ev[0].ev[4], c->chunk_ev[ch].ev[idx[k]]);
+          std::fprintf(stderr, "[timeline] chunk %2zu lane %zu pairs %8llu: h2d %7.3f -> %7.3f | pack+classify -> %7.3f | short -> %7.3f | other -> %7.3f | d2h -> %7.3f\n",
+                       ch, ch % (size_t)c->n_lanes, (unsigned long long)(c->chunk_bounds[ch + 1] - c->chunk_bounds[ch]), t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
       }
       if (c->last_chunks) {
         float span = 0;

@@ -173,6 +173,10 @@ class Engine:
         """Chunk size of the pipelined host path (swb_set_chunking)."""
         self._check(self._lib.swb_set_chunking(self._h, int(chunk_bytes), int(min_chunk_pairs)))
 
+    def set_chunk_ramp(self, ramp):
+        """Ramped (default) or equal chunk sizes of the pipelined host path (swb_set_chunk_ramp)."""
+        self._check(self._lib.swb_set_chunk_ramp(self._h, int(bool(ramp))))
+
     def last_timings(self):
         ms = (ctypes.c_float * 6)()
         k = ctypes.c_int()
