@@ -604,7 +604,8 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   if (!final_segment) {
     const uint64_t tail_start = h_scal[1];
     const uint64_t tl = end - tail_start;
-    if (tl > carry_cap || (tl && !carry_out)) { *status = 1; return 0; }          // a single record larger than the carry buffer
+    if (tl > carry_cap || tl > kFqCarryRoom || (tl && !carry_out)) { *status = 1; return 0; }   // a single record larger than the carry buffer (or than
+                                                                                              // the next call would take; fq_extract_kernel only looks that far back)
     if (tl) {
       CUDA_TRY(cudaMemcpyAsync(carry_out, d_text + tail_start, tl, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));

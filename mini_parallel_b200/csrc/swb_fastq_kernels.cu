@@ -13,7 +13,7 @@ namespace swb {
 // inflate: one warp per BGZF block, 8 warps per CTA, decode tables in shared memory
 // ------------------------------------------------------------------------------------------------
 template <bool SOLO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)            // 4 CTAs = 32 warps = 32 blocks in flight per SM (shared memory allows no more)
 inflate_bgzf_kernel(const uint8_t* __restrict__ comp, const swb_bgzf_block* __restrict__ blocks, uint64_t n_blocks,
                     const uint64_t* __restrict__ out_off, uint8_t* __restrict__ text, uint32_t* __restrict__ n_failed)   // n_failed[0] count, [2] first status, [3] its produced
 {
@@ -116,6 +116,11 @@ __device__ __forceinline__ uint64_t thread_line_base(const uint8_t (&b)[16], uin
   return tile_prefix + before + (inc - n);
 }
 
+// Only record ends in the last kTailSearch bytes compete for tail_start: the tail a caller can carry is at most 1 MiB
+// (swb_fastq_bgzf_score), so an older record end can only belong to a segment that is declined anyway -- and one atomic per
+// record on a single address (2 M per segment) was most of this kernel's time.
+constexpr uint64_t kTailSearch = 4ull << 20;
+
 // sequence-line ranges (read-only pass).  seq_beg[r] / seq_end[r] are positions in the buffer; tail_start = first byte
 // after the last complete record (atomicMax); with `final` an unterminated last sequence line still counts as a read.
 __global__ void __launch_bounds__(256)
@@ -139,7 +144,7 @@ fq_extract_kernel(const uint8_t* __restrict__ text, uint64_t begin, uint64_t end
           seq_end[rec] = p - (cr ? 1 : 0);
         }
       }
-      if (ph == 3) atomicMax(tail_start, (unsigned long long)(p + 1));
+      if (ph == 3 && p + kTailSearch >= end) atomicMax(tail_start, (unsigned long long)(p + 1));
       ++line;
     } else if (final_segment && p + 1 == end && (line & 3) == 1 && (line >> 2) < n_records_cap) {
       seq_end[line >> 2] = end;                                                 // last line without a newline (BufRead::lines yields it)

@@ -47,40 +47,61 @@ struct Lanes { int lane, n; };     // this thread's index among the n threads th
 #define SWI_SYNC() ((void)0)
 #endif
 
+// Bit reader: a 64-bit WINDOW of the stream (bits [pos, pos+64) relative to the word-aligned base) is loaded with three
+// aligned word loads; `used` counts the bits of it already consumed.  Taking bits is a shift of the window and an add to
+// `used` -- no 64-bit buffer to shift and refill per symbol.  The caller guarantees 16 readable bytes after the payload
+// (device: the compressed arena has slack; host: bounds-checked loads); bits past the payload are never trusted:
+// consuming them trips overrun().
 struct Bits {
   const uint8_t* p; uint64_t n;    // payload
-  uint64_t pos;                    // next byte to load
-  uint64_t buf; int cnt;           // bit buffer (LSB first)
+  const uint32_t* w;               // p rounded down to a word boundary
+  uint32_t pos, end;               // window start / first bit after the payload, in bits from w
+  uint32_t lo, hi, used;
 };
 
-SWI_HD uint32_t load_byte(const uint8_t* p, uint64_t n, uint64_t pos) { return pos < n ? p[pos] : 0u; }
-
-// 32 payload bits starting at byte `pos`, whatever its alignment.  The caller guarantees 8 readable bytes after the
-// payload (the compressed arena has slack); bits past the payload are never trusted: consuming them trips overrun().
-SWI_HD uint32_t load_u32(const uint8_t* p, uint64_t pos)
+SWI_HD uint32_t load_word(const Bits& b, uint32_t idx)
 {
 #if defined(__CUDA_ARCH__)
-  const uintptr_t a = (uintptr_t)(p + pos);
-  const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
-  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+  return b.w[idx];
 #else
-  return (uint32_t)p[pos] | ((uint32_t)p[pos + 1] << 8) | ((uint32_t)p[pos + 2] << 16) | ((uint32_t)p[pos + 3] << 24);
+  const uint8_t* q = reinterpret_cast<const uint8_t*>(b.w) + 4ull * idx;
+  uint32_t v = 0;
+  for (int k = 0; k < 4; ++k) if (q + k >= b.p && q + k < b.p + b.n) v |= (uint32_t)q[k] << (8 * k);
+  return v;
 #endif
 }
 
-// At least 32 valid bits in the buffer afterwards (a symbol with its extra bits needs at most 28).
+// new window at the first unconsumed bit
 SWI_HD void refill(Bits& b)
 {
-  if (b.cnt <= 32) {
-    if (b.pos + 4 <= b.n) { b.buf |= (uint64_t)load_u32(b.p, b.pos) << b.cnt; b.pos += 4; b.cnt += 32; }
-    else while (b.cnt <= 56) { b.buf |= (uint64_t)load_byte(b.p, b.n, b.pos) << b.cnt; ++b.pos; b.cnt += 8; }   // last bytes of the payload
-  }
+  b.pos += b.used; b.used = 0;
+  const uint32_t idx = b.pos >> 5, s = b.pos & 31u;
+  const uint32_t w0 = load_word(b, idx), w1 = load_word(b, idx + 1), w2 = load_word(b, idx + 2);
+  b.lo = (uint32_t)((((uint64_t)w1 << 32) | w0) >> s);
+  b.hi = (uint32_t)((((uint64_t)w2 << 32) | w1) >> s);
 }
-SWI_HD uint32_t peek(const Bits& b, int k) { return (uint32_t)(b.buf & ((1ull << k) - 1)); }
-SWI_HD void consume(Bits& b, int k) { b.buf >>= k; b.cnt -= k; }
-SWI_HD uint32_t take(Bits& b, int k) { const uint32_t v = peek(b, k); consume(b, k); return v; }
+SWI_HD void init_bits(Bits& b, const uint8_t* in, uint64_t in_len)
+{
+  const uintptr_t a = (uintptr_t)in;
+  b.p = in; b.n = in_len;
+  b.w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  b.pos = (uint32_t)(a & 3) * 8u; b.end = b.pos + (uint32_t)in_len * 8u; b.used = 0;
+  refill(b);
+}
+// the 32 stream bits that start `off` bits into the window (off < 64; the top off-32 of them are zero beyond the window)
+SWI_HD uint32_t window(const Bits& b, uint32_t off) { return (uint32_t)((((uint64_t)b.hi << 32) | b.lo) >> off); }
+SWI_HD uint32_t low_bits(uint32_t v, uint32_t k) { return v & ((1u << k) - 1u); }   // k <= 31
+// k <= 16 bits.  The window is renewed whenever fewer than 32 unconsumed bits would remain, so a caller may take up to
+// 32 bits between two calls of its own refill().
+SWI_HD uint32_t take(Bits& b, int k)
+{
+  if (b.used > 32) refill(b);
+  const uint32_t v = low_bits(window(b, b.used), (uint32_t)k);
+  b.used += (uint32_t)k;
+  return v;
+}
 // bits consumed so far must not exceed the payload
-SWI_HD bool overrun(const Bits& b) { return b.pos * 8 - (uint64_t)b.cnt > b.n * 8; }
+SWI_HD bool overrun(const Bits& b) { return b.pos + b.used > b.end; }
 
 SWI_HD uint32_t bitrev(uint32_t c, int len)
 {
@@ -155,44 +176,85 @@ SWI_OUTLINED bool build(const uint8_t* lengths, int n, int alphabet, uint32_t* f
   return true;
 }
 
-// One symbol: its table entry (code bits consumed).  Fast table, else the canonical bit-by-bit walk; an unused code
-// comes back as kind 3.
-SWI_HD uint32_t decode(Bits& b, int alphabet, const uint32_t* fast, int fast_bits, const uint16_t* count, const uint16_t* sym)
+// An LZ77 copy that has been decoded but not carried out yet (see the symbol loop): len bytes from out[from..] to out[at..].
+struct Pending { uint32_t len, from, at; };
+
+// The bytes of a short pending copy between its loads and its stores.  Device: lane i holds byte i; host: all of them.
+constexpr uint32_t kShortCopy = 32;
+#if defined(__CUDA_ARCH__)
+struct CopyRegs { uint8_t v; };
+SWI_HD void short_load(CopyRegs& r, const uint8_t* out, const Pending& p, const Lanes& L) { if ((uint32_t)L.lane < p.len) r.v = out[p.from + L.lane]; }
+SWI_HD void short_store(const CopyRegs& r, uint8_t* out, const Pending& p, const Lanes& L) { if ((uint32_t)L.lane < p.len) out[p.at + L.lane] = r.v; }
+#else
+struct CopyRegs { uint8_t v[kShortCopy]; };
+SWI_HD void short_load(CopyRegs& r, const uint8_t* out, const Pending& p, const Lanes&) { for (uint32_t i = 0; i < p.len; ++i) r.v[i] = out[p.from + i]; }
+SWI_HD void short_store(const CopyRegs& r, uint8_t* out, const Pending& p, const Lanes&) { for (uint32_t i = 0; i < p.len; ++i) out[p.at + i] = r.v[i]; }
+#endif
+
+// out[at, at+len) = the len bytes that follow out[from], which repeat with period at-from when the ranges overlap
+SWI_HD void copy_match(uint8_t* out, const Pending& p, const Lanes& L)
 {
-  const uint32_t e = fast[peek(b, fast_bits)];
-  if (e) { consume(b, (int)(e & 15u)); return e; }
+  const uint8_t* src = out + p.from;
+  uint8_t* dst = out + p.at;
+  const uint32_t dist = p.at - p.from;
+  if (dist >= p.len) {                                     // no overlap (the usual case): a plain strided copy
+    for (uint32_t i = L.lane; i < p.len; i += L.n) dst[i] = src[i];
+  } else if (dist == 1) {                                  // a run of one byte (quality strings)
+    const uint8_t v1 = src[0];
+    for (uint32_t i = L.lane; i < p.len; i += L.n) dst[i] = v1;
+  } else {                                                 // the pattern of `dist` bytes repeats: read only what existed before
+    for (uint32_t i = L.lane; i < p.len; i += L.n) dst[i] = src[i % dist];
+  }
+}
+
+// Canonical bit-by-bit walk for a code longer than the fast table's index; v = the stream bits that start at the code.
+// An unused code comes back as kind 3 with code length 0.
+SWI_HD uint32_t decode_slow(uint32_t v, int alphabet, const uint16_t* count, const uint16_t* sym)
+{
   int code = 0, first = 0, index = 0;
-  uint64_t bits = b.buf;
   for (int len = 1; len <= 15; ++len) {
-    code |= (int)(bits & 1u); bits >>= 1;
+    code |= (int)(v & 1u); v >>= 1;
     const int c = count[len];
-    if (code - c < first) { consume(b, len); return make_entry(alphabet, sym[index + (code - first)], len); }
+    if (code - c < first) return make_entry(alphabet, sym[index + (code - first)], len);
     index += c; first += c; first <<= 1; code <<= 1;
   }
   return 3u << 4;
 }
 
+// One symbol: its table entry (code bits consumed).
+SWI_HD uint32_t decode(Bits& b, int alphabet, const uint32_t* fast, int fast_bits, const uint16_t* count, const uint16_t* sym)
+{
+  if (b.used > 32) refill(b);
+  const uint32_t v = window(b, b.used);
+  uint32_t e = fast[low_bits(v, (uint32_t)fast_bits)];
+  if (!e) e = decode_slow(v, alphabet, count, sym);
+  b.used += e & 15u;
+  return e;
+}
+
 // Inflate one raw-deflate member of in_len bytes into out[0, out_cap).  *produced = bytes written.
 SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint32_t out_cap, uint32_t* produced, Tables& T, const Lanes& L)
 {
-  Bits b; b.p = in; b.n = in_len; b.pos = 0; b.buf = 0; b.cnt = 0;
+  *produced = 0;
+  if (in_len >= (1ull << 28)) return ERR_INPUT_OVERRUN;       // bit positions are 32-bit; a BGZF member is < 64 KiB
+  Bits b;
+  init_bits(b, in, in_len);
   uint32_t opos = 0;
   int status = OK;
   for (int blocks = 0; blocks < 1 << 20; ++blocks) {          // a member of <= 64 KiB never has this many deflate blocks
-    refill(b);
     const uint32_t bfinal = take(b, 1), btype = take(b, 2);
     if (btype == 0) {                                          // stored
-      consume(b, b.cnt & 7);
+      b.pos = (b.pos + b.used + 7u) & ~7u; b.used = 0;         // to the next byte boundary (w is word aligned, so this is one of p too)
       refill(b);
       const uint32_t len = take(b, 16), nlen = take(b, 16);
       if ((len ^ nlen) != 0xFFFFu) { status = ERR_BAD_STORED; break; }
       if (opos + len > out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
-      // the bit buffer holds whole bytes here: rewind to the first unread byte
-      const uint64_t src = b.pos - (uint64_t)(b.cnt >> 3);
+      const uint64_t src = (uint64_t)((b.pos + b.used) >> 3) - (uint64_t)(in - reinterpret_cast<const uint8_t*>(b.w));
       if (src + len > in_len) { status = ERR_INPUT_OVERRUN; break; }
       for (uint32_t i = L.lane; i < len; i += L.n) out[opos + i] = in[src + i];
       opos += len;
-      b.pos = src + len; b.buf = 0; b.cnt = 0;
+      b.pos += b.used + 8u * len; b.used = 0;
+      refill(b);
     } else if (btype == 1 || btype == 2) {
       int nlit, ndist;
       if (btype == 1) {                                        // fixed code
@@ -206,14 +268,13 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
         if (nlit > 286 || ndist > 30) { status = ERR_BAD_LENGTHS; break; }
         uint8_t cl[19];
         for (int i = 0; i < 19; ++i) cl[i] = 0;
-        for (int i = 0; i < ncl; ++i) { refill(b); cl[kClOrder[i]] = (uint8_t)take(b, 3); }
-        // the code-length code is tiny: decode it with the canonical walk only (fast table of 1 entry-bit is not worth it)
+        for (int i = 0; i < ncl; ++i) cl[kClOrder[i]] = (uint8_t)take(b, 3);
+        // the code-length code is tiny: a 7-bit fast table in the distance table's place
         if (!build(cl, 19, ALPHA_PLAIN, T.dist_fast, 7, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
         int i = 0;
         uint8_t prev = 0;
         bool bad = false;
         while (i < nlit + ndist) {
-          refill(b);
           const uint32_t ce = decode(b, ALPHA_PLAIN, T.dist_fast, 7, T.dist_count, T.dist_sym);
           if ((ce >> 4) & 15u) { bad = true; break; }
           const int s = (int)(ce >> 16);
@@ -241,40 +302,63 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
       if (!build(T.lengths, nlit, ALPHA_LITLEN, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym, L) ||
           !build(T.lengths + 288, ndist, ALPHA_DIST, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym, L)) { status = ERR_BAD_LENGTHS; break; }
       // ---- symbols ----
+      // A literal/length code with its extra bits is at most 20 bits, a distance code with its extra bits at most 28: with
+      // no more than 16 bits of the 64-bit window consumed, a whole match decodes from one window.
+      // The copy of a match is software-pipelined round the symbol loop: a match decoded in one pass is LOADED at the top
+      // of the next pass and STORED at its bottom, with the decoding of the next symbol in between.  In FASTQ text a match
+      // is 3-8 bases found up to 32 KiB back -- an L2 round trip the warp would otherwise sit out once per match.  Loads
+      // and stores of one copy stay inside one pass (no load is in flight across the back edge, where the compiler would
+      // wait for it), copies run in stream order, each after a __syncwarp that makes everything written so far visible.
+#if defined(__CUDA_ARCH__)
+      const bool pipelined = L.n == (int)kShortCopy;           // one byte per lane (the one-lane debug kernel copies in place)
+#else
+      const bool pipelined = true;
+#endif
+      Pending P; P.len = 0; P.from = 0; P.at = 0;
+      CopyRegs R = {};
       for (;;) {                                               // every pass emits >= 1 byte (bounded by out_cap), ends the block or fails
-        refill(b);
-        const uint32_t e = decode(b, ALPHA_LITLEN, T.lit_fast, LIT_BITS, T.lit_count, T.lit_sym);
-        const uint32_t kind = (e >> 4) & 15u;
+        if (P.len) {
+          SWI_SYNC();
+          if (P.len <= kShortCopy && P.at - P.from >= P.len && pipelined) short_load(R, out, P, L);
+          else { copy_match(out, P, L); P.len = 0; }
+        }
+        if (b.used > 16) refill(b);
+        const uint32_t v = window(b, b.used);
+        uint32_t e = T.lit_fast[v & (LIT_FAST - 1)];
+        if (!e) e = decode_slow(v, ALPHA_LITLEN, T.lit_count, T.lit_sym);
+        const uint32_t cl = e & 15u, kind = (e >> 4) & 15u;
         if (kind == 0) {
           if (opos >= out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
           out[opos] = (uint8_t)(e >> 16);                        // every lane stores the same byte to the same address: no branch
           ++opos;
+          b.used += cl;
+          if (P.len) { short_store(R, out, P, L); P.len = 0; }
           continue;
         }
-        if (kind != 1) { if (kind != 2) status = ERR_BAD_SYMBOL; break; }
-        const uint32_t len = (e >> 16) + take(b, (int)((e >> 8) & 255u));
-        refill(b);
-        const uint32_t de = decode(b, ALPHA_DIST, T.dist_fast, DIST_BITS, T.dist_count, T.dist_sym);
-        if (((de >> 4) & 15u) != 1) { status = ERR_BAD_DISTANCE; break; }
-        const uint32_t dist = (de >> 16) + take(b, (int)((de >> 8) & 255u));
-        if (dist > opos) { status = ERR_BAD_DISTANCE; break; }
-        if (opos + len > out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
-        SWI_SYNC();                                            // earlier literals / copies are visible to every lane
-        const uint8_t* src = out + opos - dist;
-        uint8_t* dst = out + opos;
-        if (dist >= len) {                                     // no overlap (the usual case): a plain strided copy
-          for (uint32_t i = L.lane; i < len; i += L.n) dst[i] = src[i];
-        } else if (dist == 1) {                                // a run of one byte (quality strings)
-          const uint8_t v = src[0];
-          for (uint32_t i = L.lane; i < len; i += L.n) dst[i] = v;
-        } else {                                               // the pattern of `dist` bytes repeats: read only what existed before
-          for (uint32_t i = L.lane; i < len; i += L.n) dst[i] = src[i % dist];
+        if (kind != 1) { b.used += cl; if (kind != 2) status = ERR_BAD_SYMBOL; break; }
+        const uint32_t xb = (e >> 8) & 255u;
+        const uint32_t len = (e >> 16) + low_bits(v >> cl, xb);
+        const uint32_t at = b.used + cl + xb;                    // <= 36
+        const uint32_t d = window(b, at);
+        uint32_t de = T.dist_fast[d & (DIST_FAST - 1)];
+        if (!de) de = decode_slow(d, ALPHA_DIST, T.dist_count, T.dist_sym);
+        const uint32_t dcl = de & 15u, dxb = (de >> 8) & 255u;
+        const uint32_t dist = (de >> 16) + low_bits(d >> dcl, dxb);
+        b.used = at + dcl + dxb;
+        if ((((de >> 4) & 15u) != 1) | (dist > opos) | (opos + len > out_cap)) {      // one branch for the three ways a match can be wrong
+          status = ((de >> 4) & 15u) != 1 || dist > opos ? ERR_BAD_DISTANCE : ERR_OUTPUT_OVERRUN;
+          break;
         }
+        if (P.len) short_store(R, out, P, L);
+        P.len = len; P.from = opos - dist; P.at = opos;
         opos += len;
       }
+      // every way out of the loop is a break below its top, so a copy still pending here has been loaded, not stored
+      if (P.len) short_store(R, out, P, L);                    // (also on the error paths: `produced` bytes are really there)
+      SWI_SYNC();
       if (status != OK) break;
-      // one input check per deflate block: past the payload the bit buffer feeds zeros, the symbol loop above still ends
-      // (it is bounded by out_cap), and the block is rejected here
+      // one input check per deflate block: the bits past the payload are not the stream's, the symbol loop above still
+      // ends (it is bounded by out_cap), and the block is rejected here
       if (overrun(b)) { status = ERR_INPUT_OVERRUN; break; }
     } else { status = ERR_BAD_BLOCK_TYPE; break; }
     if (bfinal) break;
