@@ -558,8 +558,11 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   CUDA_TRY(cudaMemsetAsync(d_end, 0, (R + 1) * 8, st));
   const unsigned long long tail0 = begin;
   CUDA_TRY(cudaMemcpyAsync(d_scal + 1, &tail0, 8, cudaMemcpyHostToDevice, st));
-  k += swb::launch_fq_extract_mask(d_text, begin, end, c->fq_tile_prefix.as<uint64_t>(), d_beg, d_end, R,
-                                   reinterpret_cast<unsigned long long*>(d_scal + 1), final_segment, st);
+  // one pass: read ranges, tail, masked text, and the 2-bit packed text + non-ACGT bitmap the batches below score in place
+  const uint64_t pk_bytes = (swb::fq_tiles(0, end) + 1) * 4096;        // the kernel's tiles cover [begin & ~511, end)
+  if (c->q_pk.reserve(pk_bytes / 4 + 64) || c->q_bad.reserve(pk_bytes / 128 + 64)) return 1;
+  k += swb::launch_fq_extract(d_text, begin, end, c->fq_tile_count.as<uint32_t>(), c->fq_tile_prefix.as<uint64_t>(), d_scal, d_beg, d_end, R,
+                              reinterpret_cast<unsigned long long*>(d_scal + 1), final_segment, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
   if (const char* dump = std::getenv("SWB_FASTQ_DUMP")) {        // debug: text after masking and the read ranges
     std::vector<uint8_t> ht(end - begin); std::vector<uint64_t> hb(R), he(R);
     CUDA_TRY(cudaMemcpyAsync(ht.data(), d_text + begin, end - begin, cudaMemcpyDeviceToHost, st));
@@ -571,10 +574,6 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
       std::fclose(f);
     }
   }
-  // pack the whole (masked) text once; the batches below score ranges of it in place
-  const uint64_t qw = (end + 15) / 16;
-  if (c->q_pk.reserve(qw * 4 + 64) || c->q_bad.reserve((qw + 31) / 32 * 4 + 64)) return 1;
-  k += swb::launch_pack2bit(d_text, end, c->q_pk.as<uint32_t>(), c->q_bad.as<uint32_t>(), st);
   if (dbg) cudaEventRecord(te[3], st);
   const uint64_t batch = 4ull << 20;
   if (R) {

@@ -40,41 +40,61 @@ int launch_inflate_bgzf(const uint8_t* comp, const swb_bgzf_block* blocks, uint6
 
 // ------------------------------------------------------------------------------------------------
 // FASTQ index.  The text of a segment is text[begin, end); it starts at the first byte of a record.  Tiles of 4096 bytes
-// are aligned to 16 bytes of the buffer (128-bit loads); bytes outside [begin, end) count as filler.
+// start at a multiple of 512 bytes of the buffer (128-bit loads; one warp = 32 chunks of 16 bytes = one word of the
+// non-ACGT bitmap); bytes outside [begin, end) count as filler.
 // Line index of a byte = number of '\n' before it; the sequence line of record r is line 4r+1 (aligner.rs:138:
 // line_count % 4 == 2 with a 1-based count).
+// Everything works on 32-bit words (4 bytes per instruction), not bytes: newlines are rare (4 per record), so a thread
+// walks the 0-2 newlines of its 16 bytes instead of its 16 bytes.
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kTile = 4096;
+constexpr uint32_t kFillWord = 0x41414141u;                 // "AAAA"
 
-__device__ __forceinline__ void load16(const uint8_t* __restrict__ text, uint64_t pos, uint64_t begin, uint64_t end, uint8_t (&b)[16])
+__host__ __device__ __forceinline__ uint64_t fq_tile0(uint64_t begin) { return begin & ~511ull; }
+
+// 0x80 in every byte of x that equals the byte replicated in pat (exact: no borrow between bytes)
+__device__ __forceinline__ uint32_t eq_flags(uint32_t x, uint32_t pat)
 {
-  const uint4 v = (pos + 16 <= begin || pos >= end) ? make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u)
-                                                    : *reinterpret_cast<const uint4*>(text + pos);
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const uint32_t y = x ^ pat;
+  return ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y | 0x7F7F7F7Fu);
+}
+// the four 0x80 flags of a word as bits 0..3
+__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return ((f >> 7) * 0x01020408u) >> 24; }
+// bits 0..3 as four byte masks (0xFF / 0x00)
+__device__ __forceinline__ uint32_t nibble_to_bytes(uint32_t n) { return (((n & 15u) * 0x00204081u) & 0x01010101u) * 0xFFu; }
+
+struct FqChunk { uint32_t w[4]; uint32_t nl; };             // 16 bytes of text; nl: bit k = byte k is '\n'
+
+__device__ __forceinline__ FqChunk fq_load(const uint8_t* __restrict__ text, uint64_t pos, uint64_t begin, uint64_t end)
+{
+  FqChunk c;
+  if (pos + 16 <= begin || pos >= end) { c.w[0] = c.w[1] = c.w[2] = c.w[3] = kFillWord; c.nl = 0; return c; }
+  const uint4 v = *reinterpret_cast<const uint4*>(text + pos);
+  c.w[0] = v.x; c.w[1] = v.y; c.w[2] = v.z; c.w[3] = v.w;
+  if (pos < begin || pos + 16 > end) {                       // the first / last chunk of the text: filler outside the range
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const uint8_t c = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
-    b[k] = (pos + k >= begin && pos + k < end) ? c : (uint8_t)'A';
+    for (int k = 0; k < 16; ++k)
+      if (pos + k < begin || pos + k >= end) c.w[k >> 2] = (c.w[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (0x41u << (8 * (k & 3)));
   }
+  c.nl = flags_to_nibble(eq_flags(c.w[0], 0x0A0A0A0Au)) | (flags_to_nibble(eq_flags(c.w[1], 0x0A0A0A0Au)) << 4) |
+         (flags_to_nibble(eq_flags(c.w[2], 0x0A0A0A0Au)) << 8) | (flags_to_nibble(eq_flags(c.w[3], 0x0A0A0A0Au)) << 12);
+  return c;
 }
 
 __global__ void __launch_bounds__(256)
 fq_count_kernel(const uint8_t* __restrict__ text, uint64_t begin, uint64_t end, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ flags)
 {
-  const uint64_t base = (begin & ~15ull) + (uint64_t)blockIdx.x * kTile + threadIdx.x * 16;
-  uint8_t b[16];
-  load16(text, base, begin, end, b);
-  uint32_t n = 0, hi = 0;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) { n += b[k] == '\n'; hi |= b[k]; }
+  const uint64_t pos = fq_tile0(begin) + (uint64_t)blockIdx.x * kTile + threadIdx.x * 16;
+  const FqChunk c = fq_load(text, pos, begin, end);
+  uint32_t n = __popc(c.nl), hi = (c.w[0] | c.w[1] | c.w[2] | c.w[3]) & 0x80808080u;
   __shared__ uint32_t wsum[8];
-  for (int o = 16; o; o >>= 1) { n += __shfl_xor_sync(0xffffffffu, n, o); hi |= __shfl_xor_sync(0xffffffffu, hi, o); }
-  if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = n; if (hi & 0x80u) atomicOr(flags, 1u); }   // not ASCII: host path
+  n = __reduce_add_sync(0xffffffffu, n); hi = __reduce_or_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = n; if (hi) atomicOr(flags, 1u); }   // not ASCII: host path
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t t = 0;
-    for (int w = 0; w < 8; ++w) t += wsum[w];
-    tile_count[blockIdx.x] = t;
+  if (threadIdx.x == 255) {                                   // newlines of the tile (<= 4096) | its last byte << 24: the next tile's
+    uint32_t t = 0;                                           // first thread needs it to strip "\r\n" without reading text that
+    for (int w = 0; w < 8; ++w) t += wsum[w];                 // fq_extract_kernel is rewriting
+    tile_count[blockIdx.x] = t | (c.w[3] & 0xFF000000u);
   }
 }
 
@@ -86,7 +106,7 @@ fq_scan_kernel(const uint32_t* __restrict__ tile_count, uint64_t n_tiles, uint64
   const uint64_t per = (n_tiles + 1023) / 1024;
   const uint64_t lo = min(n_tiles, (uint64_t)threadIdx.x * per), hi = min(n_tiles, lo + per);
   uint64_t s = 0;
-  for (uint64_t t = lo; t < hi; ++t) s += tile_count[t];
+  for (uint64_t t = lo; t < hi; ++t) s += tile_count[t] & 0xFFFFFFu;
   part[threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -96,84 +116,82 @@ fq_scan_kernel(const uint32_t* __restrict__ tile_count, uint64_t n_tiles, uint64
   }
   __syncthreads();
   uint64_t run = part[threadIdx.x];
-  for (uint64_t t = lo; t < hi; ++t) { tile_prefix[t] = run; run += tile_count[t]; }
+  for (uint64_t t = lo; t < hi; ++t) { tile_prefix[t] = run; run += tile_count[t] & 0xFFFFFFu; }
 }
 
-// line index at the first byte of this thread's 16 bytes
-__device__ __forceinline__ uint64_t thread_line_base(const uint8_t (&b)[16], uint64_t tile_prefix)
+// One pass over the text that does everything the scoring pipeline needs from it:
+//  * sequence-line ranges: seq_beg[r] / seq_end[r] are positions in the buffer ("\r\n" stripped like BufRead::lines);
+//    with `final_segment` an unterminated last sequence line still counts as a read;
+//  * tail_start = first byte after the last complete record of a non-final segment (the line index says which newline
+//    that is: newline 4*floor(N/4), N = all newlines of the text -- no atomics); the bytes from there on stay as they
+//    are, the host carries them into the next segment;
+//  * everything else that is not a base of a sequence line becomes 'A' in the text (the byte-compare kernels read it in
+//    place), so that only real non-ACGT bases are flagged;
+//  * the 2-bit packed text and its non-ACGT bitmap (what pack2bit_kernel would make of the masked text).
+__global__ void __launch_bounds__(256)
+fq_extract_kernel(uint8_t* __restrict__ text, uint64_t begin, uint64_t end, const uint32_t* __restrict__ tile_count, const uint64_t* __restrict__ tile_prefix,
+                  const uint64_t* __restrict__ n_newlines, uint64_t* __restrict__ seq_beg, uint64_t* __restrict__ seq_end, uint64_t n_records_cap,
+                  unsigned long long* __restrict__ tail_start, int final_segment, uint32_t* __restrict__ pk_words, uint32_t* __restrict__ pk_bitmap)
 {
-  uint32_t n = 0;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) n += b[k] == '\n';
+  const uint64_t pos = fq_tile0(begin) + (uint64_t)blockIdx.x * kTile + threadIdx.x * 16;
+  const FqChunk c = fq_load(text, pos, begin, end);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // line index at the first byte of this thread's chunk
+  const uint32_t n = __popc(c.nl);
   uint32_t inc = n;
+#pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += v; }
-  __shared__ uint32_t wtot[8];
-  if (lane == 31) wtot[warp] = inc;
+  __shared__ uint32_t wtot[8], wlast[8];
+  if (lane == 31) { wtot[warp] = inc; wlast[warp] = c.w[3] >> 24; }
   __syncthreads();
   uint32_t before = 0;
-  for (uint32_t w = 0; w < warp; ++w) before += wtot[w];
-  return tile_prefix + before + (inc - n);
-}
-
-// Only record ends in the last kTailSearch bytes compete for tail_start: the tail a caller can carry is at most 1 MiB
-// (swb_fastq_bgzf_score), so an older record end can only belong to a segment that is declined anyway -- and one atomic per
-// record on a single address (2 M per segment) was most of this kernel's time.
-constexpr uint64_t kTailSearch = 4ull << 20;
-
-// sequence-line ranges (read-only pass).  seq_beg[r] / seq_end[r] are positions in the buffer; tail_start = first byte
-// after the last complete record (atomicMax); with `final` an unterminated last sequence line still counts as a read.
-__global__ void __launch_bounds__(256)
-fq_extract_kernel(const uint8_t* __restrict__ text, uint64_t begin, uint64_t end, const uint64_t* __restrict__ tile_prefix,
-                  uint64_t* __restrict__ seq_beg, uint64_t* __restrict__ seq_end, uint64_t n_records_cap,
-                  unsigned long long* __restrict__ tail_start, int final_segment)
-{
-  const uint64_t base = (begin & ~15ull) + (uint64_t)blockIdx.x * kTile + threadIdx.x * 16;
-  uint8_t b[16];
-  load16(text, base, begin, end, b);
-  uint64_t line = thread_line_base(b, tile_prefix[blockIdx.x]);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const uint64_t p = base + k;
-    if (b[k] == '\n') {
-      const uint64_t rec = line >> 2; const uint32_t ph = (uint32_t)(line & 3);
-      if (rec < n_records_cap) {
-        if (ph == 0) seq_beg[rec] = p + 1;
-        if (ph == 1) {
-          const bool cr = p > begin && (k ? b[k - 1] : text[p - 1]) == '\r';      // lines() strips "\r\n"
-          seq_end[rec] = p - (cr ? 1 : 0);
-        }
+  for (uint32_t w = 0; w < 8; ++w) before += w < warp ? wtot[w] : 0u;
+  // the byte before this chunk, as it was before anybody masked it (for "\r\n" at a chunk boundary)
+  uint32_t prev_byte = __shfl_up_sync(0xffffffffu, c.w[3] >> 24, 1);
+  if (lane == 0) prev_byte = warp ? wlast[warp - 1] : (blockIdx.x ? tile_count[blockIdx.x - 1] >> 24 : 0u);
+  uint64_t line = tile_prefix[blockIdx.x] + before + (inc - n);
+  const uint64_t keep_line = final_segment ? ~0ull : (*n_newlines & ~3ull);     // lines from here on are the carried tail
+
+  // walk the newlines of the chunk: seq (bit k: byte k is a base of a sequence line), tail (bit k: byte k is carried)
+  uint32_t seq = 0, tail = 0, rest = c.nl, a = 0;
+  for (;;) {
+    const uint32_t b = rest ? (uint32_t)__ffs((int)rest) - 1u : 16u;      // next newline, or the end of the chunk
+    const uint32_t span = ((1u << b) - 1u) & ~((1u << a) - 1u);            // bytes [a, b) lie on line `line`
+    if (line >= keep_line) tail |= span | (b < 16 ? 1u << b : 0u);
+    else if ((line & 3) == 1) seq |= span;
+    if (b == 16) break;
+    const uint64_t p = pos + b, rec = line >> 2;
+    const uint32_t ph = (uint32_t)line & 3u;
+    if (rec < n_records_cap) {
+      if (ph == 0) seq_beg[rec] = p + 1;
+      if (ph == 1) {
+        const uint32_t prev = b ? (c.w[(b - 1) >> 2] >> (8 * ((b - 1) & 3))) & 0xFFu : prev_byte;
+        seq_end[rec] = p - (prev == '\r' && p > begin ? 1 : 0);           // lines() strips "\r\n"
       }
-      if (ph == 3 && p + kTailSearch >= end) atomicMax(tail_start, (unsigned long long)(p + 1));
-      ++line;
-    } else if (final_segment && p + 1 == end && (line & 3) == 1 && (line >> 2) < n_records_cap) {
-      seq_end[line >> 2] = end;                                                 // last line without a newline (BufRead::lines yields it)
     }
+    if (line + 1 == keep_line) *tail_start = (unsigned long long)(p + 1);
+    rest &= rest - 1; a = b + 1; ++line;
   }
-}
-
-// everything that is not a base of a sequence line becomes 'A' (so the packing kernel flags real non-ACGT bases only)
-// Bytes from *keep_from on (the incomplete record at the end of a non-final segment) stay as they are: the host carries
-// them, unmasked, into the next segment.
-__global__ void __launch_bounds__(256)
-fq_mask_kernel(uint8_t* __restrict__ text, uint64_t begin, uint64_t end, const uint64_t* __restrict__ tile_prefix,
-               const unsigned long long* __restrict__ keep_from)
-{
-  const uint64_t base = (begin & ~15ull) + (uint64_t)blockIdx.x * kTile + threadIdx.x * 16;
-  const uint64_t keep = keep_from ? (uint64_t)*keep_from : ~0ull;
-  uint8_t b[16];
-  load16(text, base, begin, end, b);
-  uint64_t line = thread_line_base(b, tile_prefix[blockIdx.x]);
-  uint32_t w[4] = {0, 0, 0, 0};
+  if (final_segment && end > pos && end <= pos + 16) {       // the text's last byte: a last line without a newline (BufRead::lines yields it)
+    const uint32_t k = (uint32_t)(end - 1 - pos);
+    const uint64_t l = line - __popc(c.nl >> k);               // `line` is past the whole chunk: back to byte k's line ...
+    if (!((c.nl >> k) & 1u) && (l & 3) == 1 && (l >> 2) < n_records_cap) seq_end[l >> 2] = end;
+  }
+  // '\r' on a sequence line is not a base
+  const uint32_t crf[4] = {eq_flags(c.w[0], 0x0D0D0D0Du), eq_flags(c.w[1], 0x0D0D0D0Du), eq_flags(c.w[2], 0x0D0D0D0Du), eq_flags(c.w[3], 0x0D0D0D0Du)};
+  if (crf[0] | crf[1] | crf[2] | crf[3])
+    seq &= ~(flags_to_nibble(crf[0]) | (flags_to_nibble(crf[1]) << 4) | (flags_to_nibble(crf[2]) << 8) | (flags_to_nibble(crf[3]) << 12));
+  const uint32_t keep = seq | tail;
+  uint32_t m[4];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    uint8_t c = b[k];
-    const bool nl = c == '\n';
-    if ((nl || (line & 3) != 1 || c == '\r') && base + k < keep) c = 'A';
-    if (nl) ++line;
-    w[k >> 2] |= (uint32_t)c << (8 * (k & 3));
-  }
-  if (base + 16 > begin && base < end) *reinterpret_cast<uint4*>(text + base) = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int i = 0; i < 4; ++i) { const uint32_t km = nibble_to_bytes(keep >> (4 * i)); m[i] = (c.w[i] & km) | (kFillWord & ~km); }
+  if (pos + 16 > begin && pos < end) *reinterpret_cast<uint4*>(text + pos) = make_uint4(m[0], m[1], m[2], m[3]);
+  uint32_t bad = 0;
+  const uint32_t word = pack4(m[0], bad) | (pack4(m[1], bad) << 8) | (pack4(m[2], bad) << 16) | (pack4(m[3], bad) << 24);
+  pk_words[pos >> 4] = word;
+  const uint32_t ballot = __ballot_sync(0xffffffffu, bad != 0);
+  if (lane == 0) pk_bitmap[pos >> 9] = ballot;
 }
 
 int launch_fq_index(const uint8_t* text, uint64_t begin, uint64_t end, uint32_t* tile_count, uint64_t* tile_prefix, uint64_t* total,
@@ -186,17 +204,19 @@ int launch_fq_index(const uint8_t* text, uint64_t begin, uint64_t end, uint32_t*
   return 2;
 }
 
-int launch_fq_extract_mask(uint8_t* text, uint64_t begin, uint64_t end, const uint64_t* tile_prefix, uint64_t* seq_beg, uint64_t* seq_end,
-                           uint64_t n_records_cap, unsigned long long* tail_start, int final_segment, cudaStream_t st)
+// pk_words / pk_bitmap: room for every 16-byte word / 512-byte group of text[0, end rounded up to a tile)
+int launch_fq_extract(uint8_t* text, uint64_t begin, uint64_t end, const uint32_t* tile_count, const uint64_t* tile_prefix, const uint64_t* n_newlines, uint64_t* seq_beg,
+                      uint64_t* seq_end, uint64_t n_records_cap, unsigned long long* tail_start, int final_segment, uint32_t* pk_words,
+                      uint32_t* pk_bitmap, cudaStream_t st)
 {
   if (end <= begin) return 0;
   const uint64_t n_tiles = fq_tiles(begin, end);
-  fq_extract_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(text, begin, end, tile_prefix, seq_beg, seq_end, n_records_cap, tail_start, final_segment);
-  fq_mask_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(text, begin, end, tile_prefix, final_segment ? nullptr : tail_start);
-  return 2;
+  fq_extract_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(text, begin, end, tile_count, tile_prefix, n_newlines, seq_beg, seq_end, n_records_cap, tail_start,
+                                                       final_segment, pk_words, pk_bitmap);
+  return 1;
 }
 
-uint64_t fq_tiles(uint64_t begin, uint64_t end) { return end > begin ? (end - (begin & ~15ull) + kTile - 1) / kTile : 0; }
+uint64_t fq_tiles(uint64_t begin, uint64_t end) { return end > begin ? (end - fq_tile0(begin) + kTile - 1) / kTile : 0; }
 
 // ------------------------------------------------------------------------------------------------
 // per-batch helpers: the window every read is paired with (this engine's --full-wgs pairing rule, rustseq_host.cpp)

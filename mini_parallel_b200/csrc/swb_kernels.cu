@@ -30,21 +30,8 @@
 namespace swb {
 
 // =====================================================================================
-// 2-bit packing.  code = (byte >> 1) & 3 : A->0 C->1 T->2 G->3 (any bijection works, only
-// equality matters).  A word is flagged when any of its bytes is not exactly A/C/G/T,
-// because the reference compares raw bytes (cl:114): 'a' != 'A', 'N' == 'N'.
+// 2-bit packing (pack4 in swb_kernels.cuh).  A word is flagged when any of its bytes is not exactly A/C/G/T.
 // =====================================================================================
-__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t& bad)
-{
-  const uint32_t c0 = (x >> 1) & 0x01010101u, c1 = (x >> 2) & 0x01010101u;
-  const uint32_t is2 = c1 & ~c0;
-  const uint32_t canon = 0x41414141u + 2u * c0 + 4u * c1 + 15u * is2;   // A,C,G,T rebuilt from the code
-  bad |= x ^ canon;
-  uint32_t t = (x >> 1) & 0x03030303u;
-  t |= t >> 6;
-  return (t & 0xFu) | ((t >> 12) & 0xF0u);
-}
-
 // One warp packs UNROLL groups of 32 words (512 bases each) per iteration: every lane issues UNROLL independent
 // 128-bit loads before it touches the first result, which is what keeps enough bytes in flight for HBM3e.
 constexpr int kPackUnroll = 4;

@@ -54,6 +54,22 @@ struct BatchView {            // everything the kernels need about one batch (de
   uint64_t        scratch_stride;
 };
 
+#if defined(__CUDACC__)
+// 2-bit packing of four bytes.  code = (byte >> 1) & 3 : A->0 C->1 T->2 G->3 (any bijection works, only equality
+// matters).  `bad` collects the bits of every byte that is not exactly A/C/G/T, because the reference compares raw bytes
+// (cl:114): 'a' != 'A', 'N' == 'N'.
+__device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t& bad)
+{
+  const uint32_t c0 = (x >> 1) & 0x01010101u, c1 = (x >> 2) & 0x01010101u;
+  const uint32_t is2 = c1 & ~c0;
+  const uint32_t canon = 0x41414141u + 2u * c0 + 4u * c1 + 15u * is2;   // A,C,G,T rebuilt from the code
+  bad |= x ^ canon;
+  uint32_t t = (x >> 1) & 0x03030303u;
+  t |= t >> 6;
+  return (t & 0xFu) | ((t >> 12) & 0xF0u);
+}
+#endif
+
 // launchers (all asynchronous on `st`); each returns the number of kernels it launched
 int launch_pack2bit(const uint8_t* bytes, uint64_t n, uint32_t* words, uint32_t* bitmap, cudaStream_t st);
 int launch_classify(const BatchView& b, cudaStream_t st);
@@ -73,8 +89,9 @@ int launch_inflate_bgzf(const uint8_t* comp, const swb_bgzf_block* blocks, uint6
                         uint32_t* n_failed, cudaStream_t st);
 int launch_fq_index(const uint8_t* text, uint64_t begin, uint64_t end, uint32_t* tile_count, uint64_t* tile_prefix, uint64_t* total,
                     uint32_t* flags, cudaStream_t st);
-int launch_fq_extract_mask(uint8_t* text, uint64_t begin, uint64_t end, const uint64_t* tile_prefix, uint64_t* seq_beg, uint64_t* seq_end,
-                           uint64_t n_records_cap, unsigned long long* tail_start, int final_segment, cudaStream_t st);
+int launch_fq_extract(uint8_t* text, uint64_t begin, uint64_t end, const uint32_t* tile_count, const uint64_t* tile_prefix, const uint64_t* n_newlines, uint64_t* seq_beg,
+                      uint64_t* seq_end, uint64_t n_records_cap, unsigned long long* tail_start, int final_segment, uint32_t* pk_words,
+                      uint32_t* pk_bitmap, cudaStream_t st);
 int launch_fq_windows(uint64_t file_index, uint64_t first_read, uint64_t n, uint64_t ref_len, uint32_t w, uint64_t* seq_beg, uint64_t* seq_end,
                       uint64_t* win_beg, uint64_t* win_end, cudaStream_t st);
 int launch_fq_reduce(const swb_result* res, const uint64_t* seq_beg, const uint64_t* seq_end, uint64_t n, unsigned long long* sums, cudaStream_t st);

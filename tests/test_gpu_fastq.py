@@ -119,6 +119,27 @@ def test_bad_data_asks_for_the_host_path(engine):
     assert tot["reads"] == 50
 
 
+def test_crlf_at_chunk_and_tile_boundaries(engine):
+    """Many short CRLF records of varying length: the "\\r\\n" that ends a sequence line falls on every offset of the index
+    kernel's 16-byte chunks, 512-byte warps and 4096-byte tiles (where the '\\r' belongs to another thread, warp or CTA).
+    One missed '\\r' would show up as an extra base and a different score."""
+    rng = np.random.default_rng(77)
+    ref = ACGT[rng.integers(0, 4, 60_000)]
+    engine.set_reference(ref)
+    reads, recs = [], []
+    for k in range(30_000):
+        ln = int(rng.integers(1, 41))
+        s = splitmix64(((3 << 40) + k) ^ 0xB202) % (len(ref) - 500 + 1)
+        r = ref[s + 7:s + 7 + ln].tobytes()
+        reads.append(r)
+        recs.append(b"@" + b"h" * int(rng.integers(1, 30)) + b"\r\n" + r + b"\r\n+\r\n" + b"I" * ln + b"\r\n")
+    text = b"".join(recs)
+    exp_score, exp_bases = _expected(reads, ref, 3, 0, 500)
+    tot = _run_segments(engine, bgzf.compress(text, 1, 60000), 7, file_index=3)
+    assert tot["reads"] == len(reads) and tot["bases"] == exp_bases and tot["score_sum"] == exp_score
+    assert tot["lines"] == 4 * len(reads)
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
 def test_random_fastq_shapes_agree_with_the_host_path(engine, seed):
     """Random record shapes (reads from 0 to 3000 bases, N and lower-case bases, long headers, CRLF or LF), random block
