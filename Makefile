@@ -5,7 +5,7 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 CSRC      := mini_parallel_b200/csrc
 LIB       := mini_parallel_b200/libswb200.so
 
-all: $(LIB) build/rustseq_mini build/issue_rate_bench build/cell_loop_bench oracle
+all: $(LIB) build/rustseq_mini build/issue_rate_bench build/cell_loop_bench build/inflate_bench oracle
 
 $(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh include/swb200.h include/rustseq_host.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
@@ -22,6 +22,11 @@ build/issue_rate_bench: $(CSRC)/issue_rate_bench.cu
 build/cell_loop_bench: $(CSRC)/cell_loop_bench.cu
 	mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+
+# the BGZF inflate kernel and the FASTQ index kernels alone (self-contained: compiles the kernels in)
+build/inflate_bench: tools/inflate_bench.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh include/swb200.h
+	mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ tools/inflate_bench.cu $(CSRC)/swb_fastq_kernels.cu -lz
 
 oracle:
 	$(MAKE) -C oracle

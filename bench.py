@@ -407,7 +407,7 @@ def main():
     k_gcups = cells_step / (k_ms * 1e-3) / 1e9
     p_ms = statistics.mean(pack_ms)
     pack_bytes = 1.25 * n * (rl + wl)                      # 1 B read + 0.25 B written per base
-    cpu_val, cpu_pairs, cpu_s = cpu_simd_gcups(0, min(n, 1_000_000), args.dist, os.cpu_count() or 1, args.cpu_budget_s)
+    cpu_val, cpu_pairs, cpu_s = cpu_simd_gcups(0, 2_000_000, args.dist, os.cpu_count() or 1, args.cpu_budget_s)
     import oracle_lib as ol
     from mini_parallel_b200 import synth as _synth
     sq, sqo, sr, sro = _synth.make_pairs(0, 2000, rl, wl, args.dist)
@@ -460,7 +460,8 @@ def main():
         "aux": aux,
         "cpu_baseline": {"value": round(cpu_val, 3), "unit": "GCUPS", "cores": os.cpu_count() or 1, "kind": "port", "isa": ol.simd_isa(),
                          "scalar_oracle_gcups_1_core": round(scalar_gcups, 3),
-                         "sample": f"first {cpu_pairs} pairs of the same workload, {cpu_s:.1f} s of CPU time (oracle/sw_simd.c)"},
+                         "sample": f"first {cpu_pairs} pairs of the same counter-RNG stream, {cpu_s:.1f} s wall on {os.cpu_count() or 1} threads = "
+                                   f"{cpu_s * (os.cpu_count() or 1):.0f} core-seconds (oracle/sw_simd.c)"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -174,8 +174,8 @@ class Engine:
         self._check(self._lib.swb_set_chunking(self._h, int(chunk_bytes), int(min_chunk_pairs)))
 
     def set_chunk_ramp(self, ramp):
-        """Ramped (default) or equal chunk sizes of the pipelined host path (swb_set_chunk_ramp)."""
-        self._check(self._lib.swb_set_chunk_ramp(self._h, int(bool(ramp))))
+        """Chunk size schedule of the pipelined host path (swb_set_chunk_ramp): 0 equal, 1 auto (default), 2 always ramped."""
+        self._check(self._lib.swb_set_chunk_ramp(self._h, int(ramp)))
 
     def last_timings(self):
         ms = (ctypes.c_float * 6)()

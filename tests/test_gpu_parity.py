@@ -275,15 +275,18 @@ def test_host_path_is_chunked_over_streams_and_stays_exact(engine):
     r, ro = to_csr(wins)
     exp = ol.batch(q, qo, r, ro, threads=8, simd=False)
     try:
-        for chunk_bytes, min_pairs in ((1 << 14, 1), (1 << 16, 1024), (1 << 20, 999), (64 << 20, 16384)):
-            engine.set_chunking(chunk_bytes, min_pairs)
-            got = engine.score_batch_csr(q, qo, r, ro)
-            assert np.array_equal(got, exp), (chunk_bytes, min_pairs)
-            rt = engine.last_routing()
-            assert rt["short"] + rt["generic"] + rt["long"] == 4998, rt      # the two empty pairs are routed nowhere
-            assert rt["generic"] >= 1
+        for ramp in (0, 2):                                       # equal chunks / sizes ramping up and down again
+            engine.set_chunk_ramp(ramp)
+            for chunk_bytes, min_pairs in ((1 << 14, 1), (1 << 16, 1024), (1 << 20, 999), (64 << 20, 16384)):
+                engine.set_chunking(chunk_bytes, min_pairs)
+                got = engine.score_batch_csr(q, qo, r, ro)
+                assert np.array_equal(got, exp), (ramp, chunk_bytes, min_pairs)
+                rt = engine.last_routing()
+                assert rt["short"] + rt["generic"] + rt["long"] == 4998, rt      # the two empty pairs are routed nowhere
+                assert rt["generic"] >= 1
     finally:
         engine.set_chunking(32 << 20, 16384)
+        engine.set_chunk_ramp(1)
 
 
 def test_reference_windows_chunked(engine):
@@ -303,12 +306,15 @@ def test_reference_windows_chunked(engine):
     exp = ol.batch(q, qo, r, ro, threads=8, simd=False)
     engine.set_reference(ref)
     try:
-        for chunk_bytes, min_pairs in ((1 << 15, 1), (64 << 20, 16384)):
-            engine.set_chunking(chunk_bytes, min_pairs)
-            got = engine.score_batch_vs_reference(q, qo, start, wlen)
-            assert np.array_equal(got, exp), (chunk_bytes, min_pairs)
+        for ramp in (0, 1):                                       # 1 (the default) ramps batches against the resident reference
+            engine.set_chunk_ramp(ramp)
+            for chunk_bytes, min_pairs in ((1 << 15, 1), (1 << 17, 300), (64 << 20, 16384)):
+                engine.set_chunking(chunk_bytes, min_pairs)
+                got = engine.score_batch_vs_reference(q, qo, start, wlen)
+                assert np.array_equal(got, exp), (ramp, chunk_bytes, min_pairs)
     finally:
         engine.set_chunking(32 << 20, 16384)
+        engine.set_chunk_ramp(1)
 
 
 def test_config4_full_size_long_pairs(engine):

@@ -65,7 +65,7 @@ def main():
       if lib.swb_set_reference(eng._h, h_r.data_ptr(), n * wl) != 0:
           raise RuntimeError(lib.swb_last_error().decode())
       for mb in [int(x) for x in args.chunk_mb.split(",")]:
-        for ramp in (0, 1):
+        for ramp in (0, 2):
             eng.set_chunking(mb << 20, 16384); eng.set_chunk_ramp(ramp)
             row = {"lanes": lanes, "chunk_mb": mb, "ramp": ramp}
             for tag, fn in (("host", host), ("vs_reference", vs_ref)):

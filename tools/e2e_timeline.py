@@ -14,7 +14,7 @@ d_qo = torch.empty(n + 1, dtype=torch.int64, device=dev); d_ro = torch.empty(n +
 eng.synth_device(0, n, rl, wl, 0, d_q.data_ptr(), d_qo.data_ptr(), d_r.data_ptr(), d_ro.data_ptr()); eng.sync()
 h_q = d_q.cpu().pin_memory(); h_r = d_r.cpu().pin_memory(); h_qo = d_qo.cpu().pin_memory(); h_ro = d_ro.cpu().pin_memory()
 h_out = torch.empty(n * 3, dtype=torch.int32).pin_memory()
-for mb, ramp in ((32, 0), (32, 1), (64, 1)):
+for mb, ramp in ((32, 0), (32, 2), (64, 2)):
     eng.set_chunking(mb << 20, 16384); eng.set_chunk_ramp(ramp)
     for k in range(3):
         lib.swb_score_batch(eng._h, h_q.data_ptr(), h_qo.data_ptr(), h_r.data_ptr(), h_ro.data_ptr(), n, h_out.data_ptr())
