@@ -7,8 +7,8 @@ LIB       := mini_parallel_b200/libswb200.so
 
 all: $(LIB) build/rustseq_mini build/issue_rate_bench build/cell_loop_bench build/inflate_bench oracle
 
-$(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh include/swb200.h include/rustseq_host.h
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
+$(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh include/swb200.h include/rustseq_host.h
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
 
 # the reference's CLI (main.rs) over the library; finds libswb200.so next to the package via rpath
 build/rustseq_mini: $(CSRC)/rustseq_mini_main.cpp $(LIB)

@@ -123,6 +123,20 @@ int  swb_last_routing(swb_ctx*, uint64_t* counts /* 3 */);
 /* The packing stage alone on device-resident bytes (bench: HBM roofline of the packing kernel). */
 int  swb_pack2bit_device(swb_ctx*, const uint8_t* d_bytes, uint64_t n, uint32_t* d_words, uint32_t* d_bitmap);
 
+/* The alignment behind a result.  Like the end cell, it does not exist upstream (gpu_align returns
+ * one i32, aligner.rs:410, 531); the rule is this repository's (the checker restates it on the CPU): walk back from the end
+ * cell while H > 0 (recurrence smith_waterman.cl:114-125), at every cell the first predecessor that explains its value
+ * in the order diagonal, up, left.  Operations are BAM-style words (length << 4 | op) in alignment order:
+ * '=' 7 equal bytes, 'X' 8 different bytes, 'I' 1 a base of s1 (read) against a gap, 'D' 2 a base of s2 (window) against
+ * a gap.  results[] are what swb_score_* returned for the same pairs.  cigar[] receives all operations, alignment k's
+ * are cigar[out[k].cigar_off .. + cigar_len) (slices in no particular order); *cigar_used = operations of the whole
+ * batch.  If that exceeds cigar_cap the call fails and *cigar_used says how much room a retry needs.
+ * out[k].status: 0 ok (start = (-1,-1) and no operations when the score is 0), 1 results[k] is not an end cell of pair k. */
+typedef struct { int32_t start_i, start_j; uint32_t cigar_len; uint32_t status; uint64_t cigar_off; } swb_alignment;
+int  swb_traceback_batch(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
+                         uint64_t n_pairs, const swb_result* results, swb_alignment* out,
+                         uint32_t* cigar, uint64_t cigar_cap, uint64_t* cigar_used);
+
 /* Tuning knob: which instantiation of the short-read kernel runs.  4 (default), 5, 6: the streaming kernel
  * (16 lanes x 10 rows at 4 or 5 CTAs/SM, 8 lanes x 20 rows); 0..3: the one-couple-per-group kernel (bit0: 0 = 8 lanes
  * x 20 rows, 1 = 16 lanes x 10 rows; bit1: split end-cell tracking).  All variants return identical results. */

@@ -15,6 +15,17 @@ pub struct SwbResult {
     pub end_j: i32,
 }
 
+/// swb_alignment: start cell and CIGAR slice behind a result (operations are BAM-style words, length << 4 | op).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct SwbAlignment {
+    pub start_i: i32,
+    pub start_j: i32,
+    pub cigar_len: u32,
+    pub status: u32,
+    pub cigar_off: u64,
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
 pub struct SwbBgzfBlock {
@@ -31,6 +42,10 @@ extern "C" {
     pub fn swb_score_pair(ctx: *mut SwbCtx, s1: *const u8, n1: u64, s2: *const u8, n2: u64, out: *mut SwbResult) -> c_int;
     pub fn swb_score_batch(ctx: *mut SwbCtx, q: *const u8, q_off: *const u64, r: *const u8, r_off: *const u64, n_pairs: u64,
                            out: *mut SwbResult) -> c_int;
+    pub fn swb_traceback_batch(ctx: *mut SwbCtx, q: *const u8, q_off: *const u64, r: *const u8, r_off: *const u64, n_pairs: u64,
+                               results: *const SwbResult, out: *mut SwbAlignment, cigar: *mut u32, cigar_cap: u64,
+                               cigar_used: *mut u64) -> c_int;
+    pub fn swb_set_chunk_ramp(ctx: *mut SwbCtx, ramp: c_int) -> c_int;
     pub fn swb_set_reference(ctx: *mut SwbCtx, reference: *const u8, n: u64) -> c_int;
     pub fn swb_score_batch_vs_reference(ctx: *mut SwbCtx, q: *const u8, q_off: *const u64, n_pairs: u64, win_start: *const u64,
                                         win_len: *const u32, out: *mut SwbResult) -> c_int;
@@ -84,6 +99,29 @@ impl Engine {
             swb_score_batch(self.ctx, reads.as_ptr(), read_off.as_ptr(), windows.as_ptr(), window_off.as_ptr(), n as u64, out.as_mut_ptr())
         };
         if rc != 0 { Err(last_error()) } else { Ok(out) }
+    }
+
+    /// Start cell and CIGAR behind the results of `score_batch` on the same pairs; grows the operation buffer once if the
+    /// first guess was too small (the library reports how much the batch needs).
+    pub fn traceback_batch(&mut self, reads: &[u8], read_off: &[u64], windows: &[u8], window_off: &[u64], results: &[SwbResult])
+                           -> Result<(Vec<SwbAlignment>, Vec<u32>), String> {
+        let n = results.len();
+        let mut out = vec![SwbAlignment::default(); n];
+        let mut cigar = vec![0u32; 8 * n + 1024];
+        let mut used = 0u64;
+        for _ in 0..2 {
+            let rc = unsafe {
+                swb_traceback_batch(self.ctx, reads.as_ptr(), read_off.as_ptr(), windows.as_ptr(), window_off.as_ptr(), n as u64,
+                                    results.as_ptr(), out.as_mut_ptr(), cigar.as_mut_ptr(), cigar.len() as u64, &mut used)
+            };
+            if rc == 0 {
+                cigar.truncate(used as usize);
+                return Ok((out, cigar));
+            }
+            if used as usize <= cigar.len() { break; }
+            cigar.resize(used as usize, 0);
+        }
+        Err(last_error())
     }
 
     /// What the reference's gpu_align returns today (its live kernel): 2 if any aligned position matches, else 0.

@@ -12,6 +12,7 @@ class SwbResult(ctypes.Structure):
 
 
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("end_i", "<i4"), ("end_j", "<i4")])
+ALIGNMENT_DTYPE = np.dtype([("start_i", "<i4"), ("start_j", "<i4"), ("cigar_len", "<u4"), ("status", "<u4"), ("cigar_off", "<u8")])   # swb_alignment
 
 _u8p = ctypes.c_void_p
 _u64 = ctypes.c_uint64
@@ -40,6 +41,7 @@ SIGNATURES = {
     "swb_last_timings": (_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_int)]),
     "swb_last_routing": (_int, [_vp, ctypes.POINTER(_u64)]),
     "swb_set_short_variant": (_int, [_vp, _int]),
+    "swb_traceback_batch": (_int, [_vp, _u8p, _vp, _u8p, _vp, _u64, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64)]),
     "swb_set_chunking": (_int, [_vp, _u64, _u64]),
     "swb_set_chunk_ramp": (_int, [_vp, _int]),
     "swb_fastq_bgzf_prefetch": (_int, [_vp, _u8p, _u64, _vp, _u64]),

@@ -66,6 +66,7 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
     cudaEvent_t done = nullptr; bool pending = false;
   } fq_slot[2];
   DevBuf fq_tile_count, fq_tile_prefix, fq_seq_beg, fq_seq_end, fq_scal;
+  DevBuf tb_scratch, tb_res, tb_out, tb_cigar, tb_cursor;   // swb_traceback_batch
   uint64_t ref_len = 0;
   std::vector<ChunkEvents> chunk_ev;       // host path: one event set per chunk of the last call
   swb::Counters* h_counters = nullptr;     // pinned, one slot per chunk
@@ -157,7 +158,8 @@ void swb_destroy(swb_ctx* c)
     for (auto& e : l->ev) cudaEventDestroy(e);
     cudaStreamDestroy(l->st);
   }
-  for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->fq_tile_count, &c->fq_tile_prefix, &c->fq_seq_beg, &c->fq_seq_end, &c->fq_scal}) b->release();
+  for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->fq_tile_count, &c->fq_tile_prefix, &c->fq_seq_beg, &c->fq_seq_end, &c->fq_scal,
+                    &c->tb_scratch, &c->tb_res, &c->tb_out, &c->tb_cigar, &c->tb_cursor}) b->release();
   for (auto& sl : c->fq_slot) {
     for (DevBuf* b : {&sl.comp, &sl.blocks, &sl.out_off, &sl.text, &sl.fail}) b->release();
     if (sl.done) cudaEventDestroy(sl.done);
@@ -617,6 +619,66 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   *score_sum = (int64_t)h_scal[2]; *n_reads = R; *n_bases = h_scal[3];
   *n_lines = final_segment ? lines : 4 * R;               // lines of the records scored here (the carried ones count next time)
   c->last_kernels = k; c->host_path = false; c->timings_pending = false;
+  return 0;
+}
+
+// ---- alignments behind the scores ----
+int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro, uint64_t n_pairs,
+                        const swb_result* results, swb_alignment* out, uint32_t* cigar, uint64_t cigar_cap, uint64_t* cigar_used)
+{
+  if (!c) return fail("null ctx");
+  if (cigar_used) *cigar_used = 0;
+  if (n_pairs == 0) return 0;
+  if (!qo || !ro || !results || !out || !cigar_used || (cigar_cap && !cigar)) return fail("swb_traceback_batch: null pointer");
+  if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
+  if (qo[0] != 0 || ro[0] != 0) return fail("swb_traceback_batch: offsets must start at 0");
+  CUDA_TRY(cudaSetDevice(c->device));
+  // per-warp scratch: the largest rectangle of the batch (rows 0..end_i, at most twice as many columns)
+  uint64_t need = 0;
+  for (uint64_t k = 0; k < n_pairs; ++k) {
+    if (qo[k + 1] < qo[k] || ro[k + 1] < ro[k]) return fail("swb_traceback_batch: offsets must be non-decreasing");
+    const swb_result& e = results[k];
+    if (e.score <= 0 || e.end_i < 0 || e.end_j < 0 || (uint64_t)e.end_i >= qo[k + 1] - qo[k] || (uint64_t)e.end_j >= ro[k + 1] - ro[k]) continue;
+    const uint64_t rows = (uint64_t)e.end_i + 1, width = std::min<uint64_t>((uint64_t)e.end_j + 1, 2 * rows);
+    need = std::max(need, swb::tb_scratch_bytes(rows, width));
+  }
+  need = (need + 255) & ~255ull;
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t budget = std::max<uint64_t>(c->tb_scratch.cap, std::min<uint64_t>(4ull << 30, free_b / 2));
+  if (need > budget) return fail("swb_traceback_batch: a pair needs " + std::to_string(need >> 20) + " MiB of direction bits, more than the device has room for");
+  int warps = c->sm_count * 16;
+  if (need) warps = (int)std::min<uint64_t>((uint64_t)warps, std::max<uint64_t>(1, budget / need));
+  warps = (int)std::min<uint64_t>((uint64_t)warps, n_pairs);
+  warps = (warps + 3) / 4 * 4;                               // whole CTAs of four warps
+  if (need && (uint64_t)warps * need > budget) warps = std::max(4, warps - 4);
+  const uint64_t qb = qo[n_pairs], rb = ro[n_pairs];
+  if (c->q_bytes.reserve(qb + 64) || c->r_bytes.reserve(rb + 64) || c->q_off.reserve((n_pairs + 1) * 8) || c->r_off.reserve((n_pairs + 1) * 8) ||
+      c->tb_res.reserve(n_pairs * sizeof(swb_result)) || c->tb_out.reserve(n_pairs * sizeof(swb_alignment)) ||
+      c->tb_cigar.reserve(cigar_cap * 4 + 64) || c->tb_cursor.reserve(64) || c->tb_scratch.reserve((uint64_t)warps * std::max<uint64_t>(need, 256))) return 1;
+  cudaStream_t st = c->st;
+  if (qb) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, qb, cudaMemcpyHostToDevice, st));
+  if (rb) CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, r, rb, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->q_off.p, qo, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->r_off.p, ro, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(c->tb_res.p, results, n_pairs * sizeof(swb_result), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(c->tb_cursor.p, 0, 64, st));
+  swb::TracebackArgs a;
+  a.q = c->q_bytes.as<uint8_t>(); a.qo = c->q_off.as<uint64_t>(); a.r = c->r_bytes.as<uint8_t>(); a.ro = c->r_off.as<uint64_t>();
+  a.res = c->tb_res.as<swb_result>(); a.out = c->tb_out.as<swb_alignment>(); a.cigar = c->tb_cigar.as<uint32_t>(); a.cigar_cap = cigar_cap;
+  a.cursor = c->tb_cursor.as<unsigned long long>(); a.n_pairs = n_pairs;
+  a.scratch = c->tb_scratch.as<uint8_t>(); a.scratch_per_warp = std::max<uint64_t>(need, 256);
+  c->last_kernels = swb::launch_traceback(a, warps, st);
+  unsigned long long h_cursor[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h_cursor, c->tb_cursor.p, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out, c->tb_out.p, n_pairs * sizeof(swb_alignment), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  *cigar_used = h_cursor[1];
+  if (h_cursor[1] > cigar_cap)
+    return fail("swb_traceback_batch: the batch has " + std::to_string(h_cursor[1]) + " operations, cigar_cap is " + std::to_string(cigar_cap));
+  if (h_cursor[1]) CUDA_TRY(cudaMemcpy(cigar, c->tb_cigar.p, h_cursor[1] * 4, cudaMemcpyDeviceToHost));
+  c->host_path = false; c->timings_pending = false;
   return 0;
 }
 

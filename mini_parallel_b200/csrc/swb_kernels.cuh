@@ -8,6 +8,7 @@ namespace swb {
 
 // Scoring constants: smith_waterman.cl:5-7.
 constexpr int kMatch = 2, kMismatch = -1, kGap = -2;
+constexpr int kGapAbs = -kGap;
 
 // ---- routing classes written by classify_pairs ----
 enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2, CLASS_LONG = 3, CLASS_BYTES = 4 };
@@ -83,6 +84,18 @@ int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32
                       int32_t* result, cudaStream_t st);
 int launch_synth(uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len, int distribution,
                  uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, cudaStream_t st);
+// alignments behind the scores (swb_traceback.cu)
+struct TracebackArgs {
+  const uint8_t* q; const uint64_t* qo; const uint8_t* r; const uint64_t* ro;     // CSR pairs (device)
+  const swb_result* res;                     // their scores and end cells
+  swb_alignment* out;
+  uint32_t* cigar; uint64_t cigar_cap;       // operation words; alignments reserve their slices with an atomic add
+  unsigned long long* cursor;                // [0] next pair, [1] operation words reserved (may exceed cigar_cap)
+  uint64_t n_pairs;
+  uint8_t* scratch; uint64_t scratch_per_warp;
+};
+uint64_t tb_scratch_bytes(uint64_t rows, uint64_t width);
+int launch_traceback(const TracebackArgs& a, int warps, cudaStream_t st);
 // FASTQ.gz ingest on the GPU (swb_fastq_kernels.cu)
 uint64_t fq_tiles(uint64_t begin, uint64_t end);
 int launch_inflate_bgzf(const uint8_t* comp, const swb_bgzf_block* blocks, uint64_t n_blocks, const uint64_t* out_off, uint8_t* text,

@@ -3,7 +3,7 @@ import ctypes
 
 import numpy as np
 
-from ._lib import RESULT_DTYPE, SwbResult, load_library
+from ._lib import ALIGNMENT_DTYPE, RESULT_DTYPE, SwbResult, load_library
 
 
 class SwbError(RuntimeError):
@@ -92,6 +92,39 @@ class Engine:
         q, qo = to_csr(reads)
         r, ro = to_csr(windows)
         return self.score_batch_csr(q, qo, r, ro)
+
+    CIGAR_OPS = "MIDNSHP=X"
+
+    def traceback_batch(self, q_bytes, q_off, r_bytes, r_off, results, cigar_cap=None):
+        """Start cell and CIGAR behind the results of score_batch_csr on the same pairs (swb_traceback_batch).
+        Returns (alignments[ALIGNMENT_DTYPE], ops): alignment k's operations are ops[cigar_off : cigar_off + cigar_len],
+        words of length << 4 | op with op indexing CIGAR_OPS ('=' 7, 'X' 8, 'I' 1, 'D' 2)."""
+        q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8)
+        r_bytes = np.ascontiguousarray(r_bytes, dtype=np.uint8)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        r_off = np.ascontiguousarray(r_off, dtype=np.uint64)
+        results = np.ascontiguousarray(results, dtype=RESULT_DTYPE)
+        n = q_off.size - 1
+        if r_off.size - 1 != n or results.size != n:
+            raise ValueError("offsets and results must describe the same number of pairs")
+        out = np.zeros(max(n, 0), dtype=ALIGNMENT_DTYPE)
+        cap = int(cigar_cap) if cigar_cap is not None else 8 * max(n, 1) + 1024
+        used = ctypes.c_uint64()
+        while n > 0:
+            ops = np.zeros(cap, dtype=np.uint32)
+            rc = self._lib.swb_traceback_batch(self._h, q_bytes.ctypes.data, q_off.ctypes.data, r_bytes.ctypes.data, r_off.ctypes.data, n,
+                                               results.ctypes.data, out.ctypes.data, ops.ctypes.data, cap, ctypes.byref(used))
+            if rc != 0 and used.value > cap and cigar_cap is None:
+                cap = int(used.value)                              # the call says how much room the batch needs
+                continue
+            self._check(rc)
+            return out, ops[:used.value]
+        return out, np.zeros(0, dtype=np.uint32)
+
+    def cigar_of(self, alignment, ops):
+        """[(length, op), ...] of one alignment returned by traceback_batch."""
+        a, n = int(alignment["cigar_off"]), int(alignment["cigar_len"])
+        return [(int(v >> 4), self.CIGAR_OPS[int(v & 15)]) for v in ops[a:a + n]]
 
     def set_reference(self, ref):
         a = _as_bytes_array(ref)

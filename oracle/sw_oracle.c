@@ -71,6 +71,51 @@ int sw_linear(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, sw
     return 0;
 }
 
+/* Alignment behind sw_linear()'s result: start cell and CIGAR.  Like the end cell, this does not
+ * exist in the reference (gpu_align returns one i32, aligner.rs:410); the rule is this repository's definition:
+ * full H matrix of the recurrence above (cl:114-125), then walk back from (end_i, end_j) while H > 0, at every cell taking
+ * the FIRST predecessor that explains its value in the order
+ *     diagonal  H == H[i-1][j-1] + s     '=' (7) on equal bytes, 'X' (8) otherwise
+ *     up        H == H[i-1][j] + gap     'I' (1): a base of s1 (the read) against a gap
+ *     left      H == H[i][j-1] + gap     'D' (2): a base of s2 (the window) against a gap
+ * ops[] receives BAM-style run-length operations (len << 4 | op) in alignment order (start -> end).
+ * Returns the number of operations, -1 on allocation failure, -2 when cap is too small. */
+int sw_traceback(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, int32_t end_i, int32_t end_j,
+                 int32_t* start_i, int32_t* start_j, uint32_t* ops, uint32_t cap)
+{
+    *start_i = -1; *start_j = -1;
+    if (end_i < 0 || end_j < 0 || (uint64_t)end_i >= n1 || (uint64_t)end_j >= n2) return 0;
+    const uint64_t R = (uint64_t)end_i + 1, W = (uint64_t)end_j + 1, stride = W + 1;
+    int32_t* H = (int32_t*)calloc((R + 1) * stride, sizeof(int32_t));      /* H[(i+1)*stride + j+1], zero borders */
+    if (!H) return -1;
+    for (uint64_t i = 0; i < R; ++i)
+        for (uint64_t j = 0; j < W; ++j) {
+            const int32_t s = (s1[i] == s2[j]) ? SW_MATCH : SW_MISMATCH;
+            H[(i + 1) * stride + j + 1] = max2(max2(H[i * stride + j] + s, H[(i + 1) * stride + j] + SW_GAP),
+                                               max2(H[i * stride + j + 1] + SW_GAP, 0));
+        }
+    uint32_t* rev = (uint32_t*)malloc((R + W + 1) * sizeof(uint32_t));
+    if (!rev) { free(H); return -1; }
+    uint32_t n_ops = 0;
+    int64_t i = end_i, j = end_j;
+    while (i >= 0 && j >= 0 && H[(i + 1) * stride + j + 1] > 0) {
+        const int32_t h = H[(i + 1) * stride + j + 1];
+        const int32_t s = (s1[i] == s2[j]) ? SW_MATCH : SW_MISMATCH;
+        uint32_t op;
+        *start_i = (int32_t)i; *start_j = (int32_t)j;
+        if (h == H[i * stride + j] + s) { op = (s1[i] == s2[j]) ? 7u : 8u; --i; --j; }
+        else if (h == H[i * stride + j + 1] + SW_GAP) { op = 1u; --i; }
+        else { op = 2u; --j; }
+        if (n_ops && (rev[n_ops - 1] & 15u) == op) rev[n_ops - 1] += 16u;
+        else rev[n_ops++] = (1u << 4) | op;
+    }
+    free(H);
+    if (n_ops > cap) { free(rev); return -2; }
+    for (uint32_t k = 0; k < n_ops; ++k) ops[k] = rev[n_ops - 1 - k];
+    free(rev);
+    return (int)n_ops;
+}
+
 /* Same recurrence, reduced the way the dead kernel reduces it: max over the LAST
  * row only (smith_waterman.cl:130-134). */
 int32_t sw_last_row_max(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2)

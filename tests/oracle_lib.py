@@ -77,6 +77,22 @@ def sw_linear(a, b):
     return int(res.score), int(res.end_i), int(res.end_j)
 
 
+def traceback(a, b, end_i, end_j):
+    """(start_i, start_j, [(length, op), ...]) behind an end cell; op is one of '=', 'X', 'I', 'D'."""
+    a, b = _buf(a), _buf(b)
+    cap = a.size + b.size + 2
+    ops = np.zeros(cap, dtype=np.uint32)
+    si, sj = ctypes.c_int32(), ctypes.c_int32()
+    o = oracle()
+    o.sw_traceback.restype = ctypes.c_int
+    o.sw_traceback.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int32,
+                               ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), ctypes.c_void_p, ctypes.c_uint32]
+    n = o.sw_traceback(a.ctypes.data, a.size, b.ctypes.data, b.size, int(end_i), int(end_j), ctypes.byref(si), ctypes.byref(sj),
+                       ops.ctypes.data, cap)
+    assert n >= 0
+    return int(si.value), int(sj.value), [(int(v >> 4), "MIDNSHP=X"[int(v & 15)]) for v in ops[:n]]
+
+
 def last_row_max(a, b):
     a, b = _buf(a), _buf(b)
     return int(oracle().sw_last_row_max(a.ctypes.data, a.size, b.ctypes.data, b.size))
