@@ -272,6 +272,7 @@ def main():
     del pk_words, pk_bits
 
     # ---- timed region 2: end to end through the host API (pinned host buffers) ----
+    numa_node = mp.load_library().swb_numa_prefer_device(local_rank)   # pinned buffers on the GPU's own NUMA node (a preference)
     h_q = torch.empty(n * rl, dtype=torch.uint8).pin_memory()
     h_r = torch.empty(n * wl, dtype=torch.uint8).pin_memory()
     h_qo = torch.empty(n + 1, dtype=torch.int64).pin_memory()
@@ -280,6 +281,7 @@ def main():
     h_q.copy_(d_q); h_r.copy_(d_r); h_qo.copy_(d_qo); h_ro.copy_(d_ro)
     torch.cuda.synchronize()
     lib = mp.load_library()
+    lib.swb_numa_reset()
 
     def step_host():
         rc = lib.swb_score_batch(eng._h, h_q.data_ptr(), h_qo.data_ptr(), h_r.data_ptr(), h_ro.data_ptr(), n, h_out.data_ptr())
@@ -433,6 +435,7 @@ def main():
                 "h2d_bytes_per_step": int(h_q.numel() + h_r.numel() + 8 * (h_qo.numel() + h_ro.numel())),
                 "d2h_bytes_per_step": int(4 * h_out.numel()),
                 "api": "swb_score_batch (ASCII reads + windows from pinned host memory, chunks pipelined over 3 streams)",
+                "pinned_numa_node": numa_node,
                 "stage_ms_sum_over_chunks": {k: round(v, 3) for k, v in e2e_t.items() if k.endswith("_ms")}},
         "e2e_resident_reference": {"value": round(ref_gcups, 2), "unit": "GCUPS",
                                    "reads_per_s": round(world * n * e2e_steps / (ref_ms * 1e-3), 1), "steps": e2e_steps,

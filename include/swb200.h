@@ -165,6 +165,12 @@ int  swb_free_pinned(void* p);
 int  swb_memcpy_h2d(swb_ctx*, void* d_dst, const void* h_src, uint64_t bytes);
 int  swb_memcpy_d2h(swb_ctx*, void* h_dst, const void* d_src, uint64_t bytes);
 
+/* Host memory placement: make the calling thread PREFER the NUMA node the device hangs off for its next allocations
+ * (pinned buffers the GPU reads over PCIe), and back to the default policy.  A preference only: no CPU affinity, nothing
+ * fails when the node is not allowed.  Returns the node, or -1 when the platform does not say. */
+int  swb_numa_prefer_device(int device_id);
+void swb_numa_reset(void);
+
 void*       swb_stream(swb_ctx*);            /* the cudaStream_t the context launches on */
 const char* swb_last_error(void);
 const char* swb_version(void);

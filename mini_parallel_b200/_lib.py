@@ -48,6 +48,8 @@ SIGNATURES = {
     "swb_fastq_bgzf_score": (_int, [_vp, _u8p, _u64, _vp, _u64, _u8p, _u64, _int, _u64, _u64, _u32,
                                     ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64),
                                     _u8p, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_int)]),
+    "swb_numa_prefer_device": (_int, [_int]),
+    "swb_numa_reset": (None, []),
     "swb_stream": (_vp, [_vp]),
     "swb_last_error": (ctypes.c_char_p, []),
     "swb_version": (ctypes.c_char_p, []),

@@ -9,6 +9,10 @@
 #include <cstdlib>
 #include <cstdio>
 #include <chrono>
+#include <cctype>
+#include <fstream>
+#include <unistd.h>
+#include <sys/syscall.h>
 
 namespace swb {
 int launch_generic_single(const BatchView& b, int32_t* last_row_out, cudaStream_t st);
@@ -167,6 +171,37 @@ void swb_destroy(swb_ctx* c)
   for (auto& ce : c->chunk_ev) for (auto& e : ce.ev) cudaEventDestroy(e);
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
+}
+
+// ---- host memory placement ----
+// Pinned buffers a GPU reads over PCIe should live on the NUMA node the GPU hangs off: with eight ranks pulling ~50 GB/s
+// each, buffers that all sit on one socket make the other socket's GPUs cross the inter-socket link.  This only sets the
+// calling thread's allocation PREFERENCE (MPOL_PREFERRED; no CPU affinity, nothing fails if the node is not allowed):
+// call it before allocating (swb_malloc_pinned, cudaHostAlloc, a pinned torch tensor), and swb_numa_reset() afterwards.
+// Returns the node (>= 0), or -1 when the platform does not say (single node, container without the sysfs entry).
+int swb_numa_prefer_device(int device_id)
+{
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device_id) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* p = bus; *p; ++p) *p = (char)std::tolower((unsigned char)*p);
+  std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+  int node = -1;
+  if (!(f >> node) || node < 0 || node >= 1024) return -1;
+  unsigned long mask[16] = {0};
+  mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+#ifdef SYS_set_mempolicy
+  if (syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, 1024ul) != 0) return -1;
+  return node;
+#else
+  return -1;
+#endif
+}
+
+void swb_numa_reset(void)
+{
+#ifdef SYS_set_mempolicy
+  syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+#endif
 }
 
 void* swb_stream(swb_ctx* c) { return c ? (void*)c->st : nullptr; }
@@ -642,20 +677,27 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
     const uint64_t rows = (uint64_t)e.end_i + 1, width = std::min<uint64_t>((uint64_t)e.end_j + 1, 2 * rows);
     need = std::max(need, swb::tb_scratch_bytes(rows, width));
   }
-  need = (need + 255) & ~255ull;
-  size_t free_b = 0, total_b = 0;
-  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-  const uint64_t budget = std::max<uint64_t>(c->tb_scratch.cap, std::min<uint64_t>(4ull << 30, free_b / 2));
-  if (need > budget) return fail("swb_traceback_batch: a pair needs " + std::to_string(need >> 20) + " MiB of direction bits, more than the device has room for");
-  int warps = c->sm_count * 16;
-  if (need) warps = (int)std::min<uint64_t>((uint64_t)warps, std::max<uint64_t>(1, budget / need));
-  warps = (int)std::min<uint64_t>((uint64_t)warps, n_pairs);
-  warps = (warps + 3) / 4 * 4;                               // whole CTAs of four warps
-  if (need && (uint64_t)warps * need > budget) warps = std::max(4, warps - 4);
+  need = std::max<uint64_t>((need + 255) & ~255ull, 256);
+  // scratch in shared memory when four warps' worth fits one CTA (a 150 x 300 rectangle: 25 KB per warp), else global
+  const bool in_smem = need * 4 <= 224 * 1024;
+  int warps;
+  if (in_smem) {
+    const int ctas_per_sm = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (227 * 1024) / (need * 4 + 1024)));
+    warps = c->sm_count * ctas_per_sm * 4;
+  } else {
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget = std::max<uint64_t>(c->tb_scratch.cap, std::min<uint64_t>(4ull << 30, free_b / 2));
+    if (need > budget) return fail("swb_traceback_batch: a pair needs " + std::to_string(need >> 20) + " MiB of direction bits, more than the device has room for");
+    warps = (int)std::min<uint64_t>((uint64_t)c->sm_count * 16, std::max<uint64_t>(1, budget / need));
+    warps = std::max(4, warps / 4 * 4);                      // whole CTAs of four warps
+    if ((uint64_t)warps * need > budget && warps > 4) warps -= 4;
+  }
+  warps = (int)std::min<uint64_t>((uint64_t)warps, (n_pairs + 3) / 4 * 4);
   const uint64_t qb = qo[n_pairs], rb = ro[n_pairs];
   if (c->q_bytes.reserve(qb + 64) || c->r_bytes.reserve(rb + 64) || c->q_off.reserve((n_pairs + 1) * 8) || c->r_off.reserve((n_pairs + 1) * 8) ||
       c->tb_res.reserve(n_pairs * sizeof(swb_result)) || c->tb_out.reserve(n_pairs * sizeof(swb_alignment)) ||
-      c->tb_cigar.reserve(cigar_cap * 4 + 64) || c->tb_cursor.reserve(64) || c->tb_scratch.reserve((uint64_t)warps * std::max<uint64_t>(need, 256))) return 1;
+      c->tb_cigar.reserve(cigar_cap * 4 + 64) || c->tb_cursor.reserve(64) || (!in_smem && c->tb_scratch.reserve((uint64_t)warps * need))) return 1;
   cudaStream_t st = c->st;
   if (qb) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, qb, cudaMemcpyHostToDevice, st));
   if (rb) CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, r, rb, cudaMemcpyHostToDevice, st));
@@ -667,13 +709,18 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
   a.q = c->q_bytes.as<uint8_t>(); a.qo = c->q_off.as<uint64_t>(); a.r = c->r_bytes.as<uint8_t>(); a.ro = c->r_off.as<uint64_t>();
   a.res = c->tb_res.as<swb_result>(); a.out = c->tb_out.as<swb_alignment>(); a.cigar = c->tb_cigar.as<uint32_t>(); a.cigar_cap = cigar_cap;
   a.cursor = c->tb_cursor.as<unsigned long long>(); a.n_pairs = n_pairs;
-  a.scratch = c->tb_scratch.as<uint8_t>(); a.scratch_per_warp = std::max<uint64_t>(need, 256);
+  a.scratch = in_smem ? nullptr : c->tb_scratch.as<uint8_t>(); a.scratch_per_warp = need;
+  CUDA_TRY(cudaEventRecord(c->ev[0], st));
   c->last_kernels = swb::launch_traceback(a, warps, st);
+  CUDA_TRY(cudaEventRecord(c->ev[1], st));
   unsigned long long h_cursor[2] = {0, 0};
   CUDA_TRY(cudaMemcpyAsync(h_cursor, c->tb_cursor.p, 16, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(out, c->tb_out.p, n_pairs * sizeof(swb_alignment), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   CUDA_TRY(cudaGetLastError());
+  for (float& v : c->last_ms) v = 0;
+  cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[1]);          // swb_last_timings: device_ms = the traceback kernel
+  c->host_path = false; c->timings_pending = false;
   *cigar_used = h_cursor[1];
   if (h_cursor[1] > cigar_cap)
     return fail("swb_traceback_batch: the batch has " + std::to_string(h_cursor[1]) + " operations, cigar_cap is " + std::to_string(cigar_cap));

@@ -8,29 +8,38 @@
 // fewer gap steps than matches (2m - x - 2g >= 1), so it spans at most twice as many columns as rows.  Inside that
 // rectangle (zero borders) the values ON the path equal the full matrix's and every off-path neighbour is <= its true
 // value, so each "does this predecessor explain H" test comes out as in the full matrix.
-// Rows are computed 32 columns at a time: T = max(0, diag + s, up + gap) per lane, then the left dependency
-// H[j] = max(T[j], H[j-1] + gap) as a prefix maximum of T[j] - gap*j across the warp (five shuffles).  Two ballots per 32
-// cells store the 2-bit directions; the walk back reads them, run-length encodes the operations and writes them in
-// alignment order at a place reserved with one atomic add.
+// A row is computed in spans of 512 columns, 16 consecutive columns per lane: T = max(0, diag + s, up + gap) per cell,
+// then the left dependency H[j] = max(T[j], H[j-1] + gap) as a prefix maximum of T[j] - gap*j -- inside the lane's 16
+// cells, one five-shuffle scan across the warp per span, and a fix-up.  The 2-bit directions of a lane's 16 cells are
+// one word; the walk back reads them, run-length encodes the operations and writes them in alignment order at a place
+// reserved with one atomic add.  The two H rows, the directions and the runs live in shared memory when the largest
+// rectangle of the batch fits (a 150 x 300 one takes 24 KB), else in a per-warp slice of global scratch.
 #include "swb_kernels.cuh"
 #include <cstdint>
 
 namespace swb {
 
-__host__ __device__ __forceinline__ uint64_t tb_groups(uint64_t width) { return (width + 31) >> 5; }
+constexpr uint32_t kTbCols = 16;                     // consecutive columns per lane
+constexpr uint32_t kTbSpan = 32 * kTbCols;           // columns per span
+constexpr uint32_t kTbRow  = 32 * (kTbCols + 1) + 1; // H values of one span of a row: lane l's cells at l*17 + 1 .. + 16 (17: no
+                                                     // bank conflicts), the cell left of them at l*17
 
-// bytes of per-warp scratch a pair with `rows` rows and `width` columns needs
+__host__ __device__ __forceinline__ uint64_t tb_spans(uint64_t width) { return (width + kTbSpan - 1) / kTbSpan; }
+
+// bytes of scratch a pair with `rows` rows and `width` columns needs
 uint64_t tb_scratch_bytes(uint64_t rows, uint64_t width)
 {
-  return 2 * (width + 2) * 4 + rows * tb_groups(width) * 8 + (rows + width + 1) * 4 + 64;
+  const uint64_t sp = tb_spans(width);
+  return 2 * sp * kTbRow * 4 + rows * sp * 32 * 4 + (rows + width + 1) * 4 + 64;
 }
 
 __global__ void __launch_bounds__(128)
 traceback_kernel(TracebackArgs a)
 {
+  extern __shared__ __align__(16) uint8_t tb_smem[];
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  uint8_t* my = a.scratch + warp * a.scratch_per_warp;
+  uint8_t* my = a.scratch ? a.scratch + warp * a.scratch_per_warp : tb_smem + (threadIdx.x >> 5) * a.scratch_per_warp;
   for (;;) {
     unsigned long long pair = 0;
     if (lane == 0) pair = atomicAdd(&a.cursor[0], 1ull);
@@ -47,45 +56,73 @@ traceback_kernel(TracebackArgs a)
     const uint32_t R = (uint32_t)res.end_i + 1;
     const uint64_t w_all = (uint64_t)res.end_j + 1, w_cap = 2ull * R;
     const uint32_t Wd = (uint32_t)(w_all < w_cap ? w_all : w_cap);
-    const uint32_t c0 = (uint32_t)res.end_j + 1 - Wd, G = (uint32_t)tb_groups(Wd);
-    int32_t* Hp = reinterpret_cast<int32_t*>(my);                              // Hp[jj+1] = H[i-1][jj], Hp[0] = the border
-    int32_t* Hc = Hp + (Wd + 2);
-    uint32_t* dirs = reinterpret_cast<uint32_t*>(Hc + (Wd + 2));               // two ballots per 32 cells
-    uint32_t* runs = dirs + (uint64_t)R * G * 2;
-    for (uint32_t x = lane; x <= Wd; x += 32) Hp[x] = 0;
+    const uint32_t c0 = (uint32_t)res.end_j + 1 - Wd, SP = (uint32_t)tb_spans(Wd);
+    int32_t* Hp = reinterpret_cast<int32_t*>(my);                              // the row above, span by span (layout: kTbRow)
+    int32_t* Hc = Hp + (uint64_t)SP * kTbRow;
+    uint32_t* dirs = reinterpret_cast<uint32_t*>(Hc + (uint64_t)SP * kTbRow); // dirs[(i*SP + span)*32 + lane]: 16 cells x 2 bits
+    uint32_t* runs = dirs + (uint64_t)R * SP * 32;
+    for (uint32_t x = lane; x < SP * kTbRow; x += 32) Hp[x] = 0;
     __syncwarp();
     for (uint32_t i = 0; i < R; ++i) {
       const uint32_t qi = q[i];
-      int32_t carry = -kGapAbs;                                                // H[i][-1] - gap*(-1): the zero border, one column out
-      for (uint32_t g = 0; g < G; ++g) {
-        const uint32_t jj = g * 32 + lane;
-        const bool valid = jj < Wd;
-        const int32_t diag = valid ? Hp[jj] : 0, up = valid ? Hp[jj + 1] : 0;
-        const int32_t s = (valid && qi == (uint32_t)r[c0 + jj]) ? kMatch : kMismatch;
-        const int32_t t = max(max(diag + s, up + kGap), 0);
-        int32_t b = valid ? t + kGapAbs * (int32_t)jj : INT32_MIN / 2;
+      int32_t carry = -kGapAbs;                      // (H + gap*j) one column left of the row: the zero border at j = -1
+      int32_t left_h = 0;                            // H left of the span's first cell
+      for (uint32_t sp = 0; sp < SP; ++sp) {
+        const uint32_t j0 = sp * kTbSpan + lane * kTbCols;                     // this lane's first column (rectangle coordinates)
+        const int32_t* hp = Hp + (uint64_t)sp * kTbRow + lane * (kTbCols + 1);
+        int32_t* hc = Hc + (uint64_t)sp * kTbRow + lane * (kTbCols + 1);
+        int32_t up[kTbCols + 1];                                               // up[0] = the cell diagonal to the lane's first
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, b, o); if (lane >= (uint32_t)o) b = max(b, v); }
-        b = max(b, carry);
-        carry = __shfl_sync(0xffffffffu, b, 31);
-        const int32_t h = b - kGapAbs * (int32_t)jj;
-        const uint32_t d = !valid || h == 0 ? 0u : (h == diag + s ? 1u : (h == up + kGap ? 2u : 3u));
-        if (valid) Hc[jj + 1] = h;
-        const uint32_t b0 = __ballot_sync(0xffffffffu, d & 1u), b1 = __ballot_sync(0xffffffffu, d & 2u);
-        if (lane == 0) { dirs[((uint64_t)i * G + g) * 2] = b0; dirs[((uint64_t)i * G + g) * 2 + 1] = b1; }
+        for (uint32_t k = 0; k <= kTbCols; ++k) up[k] = hp[k];
+        int32_t b[kTbCols], ts[kTbCols];                                       // prefix maxima of T + gap*j; diag + s per cell
+        int32_t run = INT32_MIN / 2;
+#pragma unroll
+        for (uint32_t k = 0; k < kTbCols; ++k) {
+          const uint32_t jj = j0 + k;
+          const bool valid = jj < Wd;
+          const int32_t s = (valid && qi == (uint32_t)r[c0 + jj]) ? kMatch : kMismatch;
+          ts[k] = up[k] + s;
+          const int32_t t = max(max(ts[k], up[k + 1] + kGap), 0);
+          run = max(run, valid ? t + kGapAbs * (int32_t)jj : INT32_MIN / 2);
+          b[k] = run;
+        }
+        // exclusive prefix maximum of the lanes' totals, seeded with the carry of the previous span
+        int32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc = max(inc, v); }
+        int32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
+        before = lane ? max(before, carry) : carry;
+        carry = max(__shfl_sync(0xffffffffu, inc, 31), carry);
+        int32_t prev_h = __shfl_up_sync(0xffffffffu, max(b[kTbCols - 1], before) - kGapAbs * (int32_t)(j0 + kTbCols - 1), 1);
+        if (lane == 0) prev_h = left_h;                                        // H of the cell left of the lane's first
+        uint32_t word = 0;
+        int32_t h = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < kTbCols; ++k) {
+          const uint32_t jj = j0 + k;
+          h = max(b[k], before) - kGapAbs * (int32_t)jj;
+          const uint32_t d = jj >= Wd || h == 0 ? 0u : (h == ts[k] ? 1u : (h == up[k + 1] + kGap ? 2u : 3u));
+          word |= d << (2 * k);
+          hc[k + 1] = jj < Wd ? h : 0;
+        }
+        hc[0] = prev_h;
+        left_h = __shfl_sync(0xffffffffu, h, 31);
+        dirs[((uint64_t)i * SP + sp) * 32 + lane] = word;
       }
-      if (lane == 0) Hc[0] = 0;
       __syncwarp();
       int32_t* t2 = Hp; Hp = Hc; Hc = t2;
     }
-    if (Hp[Wd] != res.score) { al.status = 1; if (lane == 0) a.out[pair] = al; continue; }   // not this pair's end cell
+    {
+      const uint32_t je = Wd - 1;
+      const int32_t h_end = Hp[(uint64_t)(je / kTbSpan) * kTbRow + ((je % kTbSpan) / kTbCols) * (kTbCols + 1) + 1 + (je % kTbCols)];
+      if (h_end != res.score) { al.status = 1; if (lane == 0) a.out[pair] = al; __syncwarp(); continue; }   // not this pair's end cell
+    }
     // ---- walk back (every lane, same steps), operations run-length encoded end -> start ----
     int64_t i = res.end_i, jj = (int64_t)Wd - 1;
     uint32_t n_runs = 0, cur_op = 0, cur_len = 0;
     while (i >= 0 && jj >= 0) {
-      const uint64_t wi = ((uint64_t)i * G + ((uint64_t)jj >> 5)) * 2;
-      const uint32_t sh = (uint32_t)jj & 31u;
-      const uint32_t d = ((dirs[wi] >> sh) & 1u) | (((dirs[wi + 1] >> sh) & 1u) << 1);
+      const uint32_t word = dirs[((uint64_t)i * SP + (uint64_t)jj / kTbSpan) * 32 + ((uint64_t)jj % kTbSpan) / kTbCols];
+      const uint32_t d = (word >> (2 * ((uint32_t)jj % kTbCols))) & 3u;
       if (d == 0) break;
       al.start_i = (int32_t)i; al.start_j = (int32_t)(c0 + jj);
       uint32_t op;
@@ -109,11 +146,14 @@ traceback_kernel(TracebackArgs a)
   }
 }
 
+// a.scratch == nullptr: the per-warp scratch (a.scratch_per_warp bytes, <= kTbSmemPerWarp) lives in shared memory
 int launch_traceback(const TracebackArgs& a, int warps, cudaStream_t st)
 {
   if (a.n_pairs == 0) return 0;
   const int ctas = (warps + 3) / 4;
-  traceback_kernel<<<ctas, 128, 0, st>>>(a);
+  const size_t smem = a.scratch ? 0 : (size_t)a.scratch_per_warp * 4;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  traceback_kernel<<<ctas, 128, smem, st>>>(a);
   return 1;
 }
 
