@@ -668,36 +668,34 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
   if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
   if (qo[0] != 0 || ro[0] != 0) return fail("swb_traceback_batch: offsets must start at 0");
   CUDA_TRY(cudaSetDevice(c->device));
-  // per-warp scratch: the largest rectangle of the batch (rows 0..end_i, at most twice as many columns)
-  uint64_t need = 0;
+  // per-warp scratch: sized by the largest rectangle of the batch (rows 0..end_i, at most twice as many columns)
+  uint64_t max_rows = 0, max_width = 0;
   for (uint64_t k = 0; k < n_pairs; ++k) {
     if (qo[k + 1] < qo[k] || ro[k + 1] < ro[k]) return fail("swb_traceback_batch: offsets must be non-decreasing");
     const swb_result& e = results[k];
     if (e.score <= 0 || e.end_i < 0 || e.end_j < 0 || (uint64_t)e.end_i >= qo[k + 1] - qo[k] || (uint64_t)e.end_j >= ro[k + 1] - ro[k]) continue;
     const uint64_t rows = (uint64_t)e.end_i + 1, width = std::min<uint64_t>((uint64_t)e.end_j + 1, 2 * rows);
-    need = std::max(need, swb::tb_scratch_bytes(rows, width));
+    max_rows = std::max(max_rows, rows); max_width = std::max(max_width, width);
   }
-  need = std::max<uint64_t>((need + 255) & ~255ull, 256);
-  // scratch in shared memory when four warps' worth fits one CTA (a 150 x 300 rectangle: 25 KB per warp), else global
-  const bool in_smem = need * 4 <= 224 * 1024;
-  int warps;
-  if (in_smem) {
-    const int ctas_per_sm = (int)std::max<uint64_t>(1, std::min<uint64_t>(8, (227 * 1024) / (need * 4 + 1024)));
-    warps = c->sm_count * ctas_per_sm * 4;
-  } else {
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget = std::max<uint64_t>(c->tb_scratch.cap, std::min<uint64_t>(4ull << 30, free_b / 2));
-    if (need > budget) return fail("swb_traceback_batch: a pair needs " + std::to_string(need >> 20) + " MiB of direction bits, more than the device has room for");
-    warps = (int)std::min<uint64_t>((uint64_t)c->sm_count * 16, std::max<uint64_t>(1, budget / need));
-    warps = std::max(4, warps / 4 * 4);                      // whole CTAs of four warps
-    if ((uint64_t)warps * need > budget && warps > 4) warps -= 4;
-  }
+  const uint32_t cpl = swb::tb_pick_cpl(max_width);
+  const uint64_t rows_b = (swb::tb_rows_bytes(max_rows, max_width, cpl) + 255) & ~255ull;
+  const uint64_t dirs_b = (swb::tb_dirs_bytes(max_rows, max_width, cpl) + 255) & ~255ull;
+  const bool in_smem = rows_b * 4 <= 48 * 1024;                // the two H rows + the runs of four warps in one CTA's shared memory
+  const uint64_t need = dirs_b + (in_smem ? 0 : rows_b) + 256;
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t budget = std::max<uint64_t>(c->tb_scratch.cap, std::min<uint64_t>(4ull << 30, free_b / 2));
+  if (need > budget) return fail("swb_traceback_batch: a pair needs " + std::to_string(need >> 20) + " MiB of direction bits, more than the device has room for");
+  int warps = c->sm_count * 32;
+  if (in_smem) warps = std::min<int>(warps, c->sm_count * 4 * (int)std::max<uint64_t>(1, (200 * 1024) / (rows_b * 4)));
+  warps = (int)std::min<uint64_t>((uint64_t)warps, std::max<uint64_t>(1, budget / need));
+  warps = std::max(4, warps / 4 * 4);                          // whole CTAs of four warps
+  if ((uint64_t)warps * need > budget && warps > 4) warps -= 4;
   warps = (int)std::min<uint64_t>((uint64_t)warps, (n_pairs + 3) / 4 * 4);
   const uint64_t qb = qo[n_pairs], rb = ro[n_pairs];
   if (c->q_bytes.reserve(qb + 64) || c->r_bytes.reserve(rb + 64) || c->q_off.reserve((n_pairs + 1) * 8) || c->r_off.reserve((n_pairs + 1) * 8) ||
       c->tb_res.reserve(n_pairs * sizeof(swb_result)) || c->tb_out.reserve(n_pairs * sizeof(swb_alignment)) ||
-      c->tb_cigar.reserve(cigar_cap * 4 + 64) || c->tb_cursor.reserve(64) || (!in_smem && c->tb_scratch.reserve((uint64_t)warps * need))) return 1;
+      c->tb_cigar.reserve(cigar_cap * 4 + 64) || c->tb_cursor.reserve(64) || c->tb_scratch.reserve((uint64_t)warps * need)) return 1;
   cudaStream_t st = c->st;
   if (qb) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, qb, cudaMemcpyHostToDevice, st));
   if (rb) CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, r, rb, cudaMemcpyHostToDevice, st));
@@ -709,9 +707,9 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
   a.q = c->q_bytes.as<uint8_t>(); a.qo = c->q_off.as<uint64_t>(); a.r = c->r_bytes.as<uint8_t>(); a.ro = c->r_off.as<uint64_t>();
   a.res = c->tb_res.as<swb_result>(); a.out = c->tb_out.as<swb_alignment>(); a.cigar = c->tb_cigar.as<uint32_t>(); a.cigar_cap = cigar_cap;
   a.cursor = c->tb_cursor.as<unsigned long long>(); a.n_pairs = n_pairs;
-  a.scratch = in_smem ? nullptr : c->tb_scratch.as<uint8_t>(); a.scratch_per_warp = need;
+  a.scratch = c->tb_scratch.as<uint8_t>(); a.scratch_per_warp = need; a.dirs_per_warp = dirs_b; a.rows_per_warp = rows_b; a.rows_in_smem = in_smem;
   CUDA_TRY(cudaEventRecord(c->ev[0], st));
-  c->last_kernels = swb::launch_traceback(a, warps, st);
+  c->last_kernels = swb::launch_traceback(a, cpl, warps, st);
   CUDA_TRY(cudaEventRecord(c->ev[1], st));
   unsigned long long h_cursor[2] = {0, 0};
   CUDA_TRY(cudaMemcpyAsync(h_cursor, c->tb_cursor.p, 16, cudaMemcpyDeviceToHost, st));

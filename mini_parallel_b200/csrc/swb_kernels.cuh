@@ -92,10 +92,13 @@ struct TracebackArgs {
   uint32_t* cigar; uint64_t cigar_cap;       // operation words; alignments reserve their slices with an atomic add
   unsigned long long* cursor;                // [0] next pair, [1] operation words reserved (may exceed cigar_cap)
   uint64_t n_pairs;
-  uint8_t* scratch; uint64_t scratch_per_warp;
+  uint8_t* scratch; uint64_t scratch_per_warp;   // global: directions (dirs_per_warp bytes) [+ rows and runs when not in shared memory]
+  uint64_t dirs_per_warp, rows_per_warp; int rows_in_smem;
 };
-uint64_t tb_scratch_bytes(uint64_t rows, uint64_t width);
-int launch_traceback(const TracebackArgs& a, int warps, cudaStream_t st);
+uint32_t tb_pick_cpl(uint64_t max_width);
+uint64_t tb_rows_bytes(uint64_t rows, uint64_t width, uint32_t cpl);
+uint64_t tb_dirs_bytes(uint64_t rows, uint64_t width, uint32_t cpl);
+int launch_traceback(const TracebackArgs& a, uint32_t cpl, int warps, cudaStream_t st);
 // FASTQ.gz ingest on the GPU (swb_fastq_kernels.cu)
 uint64_t fq_tiles(uint64_t begin, uint64_t end);
 int launch_inflate_bgzf(const uint8_t* comp, const swb_bgzf_block* blocks, uint64_t n_blocks, const uint64_t* out_off, uint8_t* text,

@@ -8,38 +8,39 @@
 // fewer gap steps than matches (2m - x - 2g >= 1), so it spans at most twice as many columns as rows.  Inside that
 // rectangle (zero borders) the values ON the path equal the full matrix's and every off-path neighbour is <= its true
 // value, so each "does this predecessor explain H" test comes out as in the full matrix.
-// A row is computed in spans of 512 columns, 16 consecutive columns per lane: T = max(0, diag + s, up + gap) per cell,
-// then the left dependency H[j] = max(T[j], H[j-1] + gap) as a prefix maximum of T[j] - gap*j -- inside the lane's 16
-// cells, one five-shuffle scan across the warp per span, and a fix-up.  The 2-bit directions of a lane's 16 cells are
-// one word; the walk back reads them, run-length encodes the operations and writes them in alignment order at a place
-// reserved with one atomic add.  The two H rows, the directions and the runs live in shared memory when the largest
-// rectangle of the batch fits (a 150 x 300 one takes 24 KB), else in a per-warp slice of global scratch.
+// A row is computed in spans of 32*CPL columns, CPL consecutive columns per lane: T = max(0, diag + s, up + gap) per cell,
+// then the left dependency H[j] = max(T[j], H[j-1] + gap) as a prefix maximum of T[j] - gap*j -- inside the lane's
+// cells, one five-shuffle scan across the warp per span, and a fix-up.  The 2-bit directions of a lane's cells are one
+// word (global scratch, L2-resident: 19 KB per 150 x 300 rectangle); the walk back reads them, run-length encodes the
+// operations and writes them in alignment order at a place reserved with one atomic add.  The two H rows and the runs
+// live in shared memory when they fit (6 KB per warp at that shape, so 32 warps per SM hide the walk's load latency).
 #include "swb_kernels.cuh"
 #include <cstdint>
 
 namespace swb {
 
-constexpr uint32_t kTbCols = 16;                     // consecutive columns per lane
-constexpr uint32_t kTbSpan = 32 * kTbCols;           // columns per span
-constexpr uint32_t kTbRow  = 32 * (kTbCols + 1) + 1; // H values of one span of a row: lane l's cells at l*17 + 1 .. + 16 (17: no
-                                                     // bank conflicts), the cell left of them at l*17
+// CPL = consecutive columns per lane (4, 8, 12 or 16: the narrowest that covers the widest rectangle of the batch in one span
+// of 32*CPL columns, else 16 and several spans).  H values of one span of a row: lane l's cells at l*(CPL+1) + 1 .. + CPL
+// (an odd stride: no bank conflicts), the cell left of them at l*(CPL+1).
+__host__ __device__ __forceinline__ uint32_t tb_row_words(uint32_t cpl) { return 32 * (cpl + 1) + 1; }
+__host__ __device__ __forceinline__ uint64_t tb_spans(uint64_t width, uint32_t cpl) { return (width + 32 * cpl - 1) / (32 * cpl); }
 
-__host__ __device__ __forceinline__ uint64_t tb_spans(uint64_t width) { return (width + kTbSpan - 1) / kTbSpan; }
+uint32_t tb_pick_cpl(uint64_t max_width) { return max_width <= 128 ? 4 : max_width <= 256 ? 8 : max_width <= 384 ? 12 : 16; }
+// per-warp scratch of a pair with `rows` rows and `width` columns: the two H rows + the runs (small: shared memory when it
+// fits), and the directions (one word per lane, span and row: global, L2-resident)
+uint64_t tb_rows_bytes(uint64_t rows, uint64_t width, uint32_t cpl) { return 2 * tb_spans(width, cpl) * tb_row_words(cpl) * 4 + (rows + width + 1) * 4 + 64; }
+uint64_t tb_dirs_bytes(uint64_t rows, uint64_t width, uint32_t cpl) { return rows * tb_spans(width, cpl) * 32 * 4; }
 
-// bytes of scratch a pair with `rows` rows and `width` columns needs
-uint64_t tb_scratch_bytes(uint64_t rows, uint64_t width)
-{
-  const uint64_t sp = tb_spans(width);
-  return 2 * sp * kTbRow * 4 + rows * sp * 32 * 4 + (rows + width + 1) * 4 + 64;
-}
-
+template <uint32_t CPL>
 __global__ void __launch_bounds__(128)
 traceback_kernel(TracebackArgs a)
 {
   extern __shared__ __align__(16) uint8_t tb_smem[];
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  uint8_t* my = a.scratch ? a.scratch + warp * a.scratch_per_warp : tb_smem + (threadIdx.x >> 5) * a.scratch_per_warp;
+  constexpr uint32_t kTbCols = CPL, kTbSpan = 32 * CPL, kTbRow = 32 * (CPL + 1) + 1;
+  uint8_t* my_dirs = a.scratch + warp * a.scratch_per_warp;
+  uint8_t* my = a.rows_in_smem ? tb_smem + (threadIdx.x >> 5) * a.rows_per_warp : my_dirs + a.dirs_per_warp;
   for (;;) {
     unsigned long long pair = 0;
     if (lane == 0) pair = atomicAdd(&a.cursor[0], 1ull);
@@ -56,19 +57,34 @@ traceback_kernel(TracebackArgs a)
     const uint32_t R = (uint32_t)res.end_i + 1;
     const uint64_t w_all = (uint64_t)res.end_j + 1, w_cap = 2ull * R;
     const uint32_t Wd = (uint32_t)(w_all < w_cap ? w_all : w_cap);
-    const uint32_t c0 = (uint32_t)res.end_j + 1 - Wd, SP = (uint32_t)tb_spans(Wd);
+    const uint32_t c0 = (uint32_t)res.end_j + 1 - Wd, SP = (uint32_t)tb_spans(Wd, CPL);
     int32_t* Hp = reinterpret_cast<int32_t*>(my);                              // the row above, span by span (layout: kTbRow)
     int32_t* Hc = Hp + (uint64_t)SP * kTbRow;
-    uint32_t* dirs = reinterpret_cast<uint32_t*>(Hc + (uint64_t)SP * kTbRow); // dirs[(i*SP + span)*32 + lane]: 16 cells x 2 bits
-    uint32_t* runs = dirs + (uint64_t)R * SP * 32;
+    uint32_t* runs = reinterpret_cast<uint32_t*>(Hc + (uint64_t)SP * kTbRow);
+    uint32_t* dirs = reinterpret_cast<uint32_t*>(my_dirs);                     // dirs[(i*SP + span)*32 + lane]: CPL cells x 2 bits
     for (uint32_t x = lane; x < SP * kTbRow; x += 32) Hp[x] = 0;
     __syncwarp();
+    // the window bytes and the valid-cell mask of a lane's cells do not depend on the row: with one span (the usual case)
+    // they are loaded once per pair.  A cell past the rectangle's last column holds a byte that equals nothing: such cells
+    // lie right of every real cell of their row, so what they compute reaches nothing that is kept.
+    uint32_t wb[kTbCols], vmask = 0;
+    auto load_window = [&](uint32_t sp) {
+      vmask = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < kTbCols; ++k) {
+        const uint32_t jj = sp * kTbSpan + lane * kTbCols + k;
+        wb[k] = jj < Wd ? (uint32_t)r[c0 + jj] : 0x100u;
+        vmask |= (jj < Wd ? 3u : 0u) << (2 * k);
+      }
+    };
+    if (SP == 1) load_window(0);
     for (uint32_t i = 0; i < R; ++i) {
       const uint32_t qi = q[i];
       int32_t carry = -kGapAbs;                      // (H + gap*j) one column left of the row: the zero border at j = -1
       int32_t left_h = 0;                            // H left of the span's first cell
       for (uint32_t sp = 0; sp < SP; ++sp) {
-        const uint32_t j0 = sp * kTbSpan + lane * kTbCols;                     // this lane's first column (rectangle coordinates)
+        if (SP > 1) load_window(sp);
+        const int32_t g0 = kGapAbs * (int32_t)(sp * kTbSpan + lane * kTbCols);  // gap * (this lane's first column)
         const int32_t* hp = Hp + (uint64_t)sp * kTbRow + lane * (kTbCols + 1);
         int32_t* hc = Hc + (uint64_t)sp * kTbRow + lane * (kTbCols + 1);
         int32_t up[kTbCols + 1];                                               // up[0] = the cell diagonal to the lane's first
@@ -78,12 +94,9 @@ traceback_kernel(TracebackArgs a)
         int32_t run = INT32_MIN / 2;
 #pragma unroll
         for (uint32_t k = 0; k < kTbCols; ++k) {
-          const uint32_t jj = j0 + k;
-          const bool valid = jj < Wd;
-          const int32_t s = (valid && qi == (uint32_t)r[c0 + jj]) ? kMatch : kMismatch;
-          ts[k] = up[k] + s;
+          ts[k] = up[k] + (qi == wb[k] ? kMatch : kMismatch);
           const int32_t t = max(max(ts[k], up[k + 1] + kGap), 0);
-          run = max(run, valid ? t + kGapAbs * (int32_t)jj : INT32_MIN / 2);
+          run = max(run, t + g0 + kGapAbs * (int32_t)k);
           b[k] = run;
         }
         // exclusive prefix maximum of the lanes' totals, seeded with the carry of the previous span
@@ -93,21 +106,20 @@ traceback_kernel(TracebackArgs a)
         int32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
         before = lane ? max(before, carry) : carry;
         carry = max(__shfl_sync(0xffffffffu, inc, 31), carry);
-        int32_t prev_h = __shfl_up_sync(0xffffffffu, max(b[kTbCols - 1], before) - kGapAbs * (int32_t)(j0 + kTbCols - 1), 1);
+        int32_t prev_h = __shfl_up_sync(0xffffffffu, max(b[kTbCols - 1], before) - g0 - kGapAbs * (int32_t)(kTbCols - 1), 1);
         if (lane == 0) prev_h = left_h;                                        // H of the cell left of the lane's first
         uint32_t word = 0;
         int32_t h = 0;
 #pragma unroll
         for (uint32_t k = 0; k < kTbCols; ++k) {
-          const uint32_t jj = j0 + k;
-          h = max(b[k], before) - kGapAbs * (int32_t)jj;
-          const uint32_t d = jj >= Wd || h == 0 ? 0u : (h == ts[k] ? 1u : (h == up[k + 1] + kGap ? 2u : 3u));
+          h = max(b[k], before) - g0 - kGapAbs * (int32_t)k;
+          const uint32_t d = h == 0 ? 0u : (h == ts[k] ? 1u : (h == up[k + 1] + kGap ? 2u : 3u));
           word |= d << (2 * k);
-          hc[k + 1] = jj < Wd ? h : 0;
+          hc[k + 1] = h;
         }
         hc[0] = prev_h;
         left_h = __shfl_sync(0xffffffffu, h, 31);
-        dirs[((uint64_t)i * SP + sp) * 32 + lane] = word;
+        dirs[((uint64_t)i * SP + sp) * 32 + lane] = word & vmask;
       }
       __syncwarp();
       int32_t* t2 = Hp; Hp = Hc; Hc = t2;
@@ -146,14 +158,17 @@ traceback_kernel(TracebackArgs a)
   }
 }
 
-// a.scratch == nullptr: the per-warp scratch (a.scratch_per_warp bytes, <= kTbSmemPerWarp) lives in shared memory
-int launch_traceback(const TracebackArgs& a, int warps, cudaStream_t st)
+int launch_traceback(const TracebackArgs& a, uint32_t cpl, int warps, cudaStream_t st)
 {
   if (a.n_pairs == 0) return 0;
   const int ctas = (warps + 3) / 4;
-  const size_t smem = a.scratch ? 0 : (size_t)a.scratch_per_warp * 4;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  traceback_kernel<<<ctas, 128, smem, st>>>(a);
+  const size_t smem = a.rows_in_smem ? (size_t)a.rows_per_warp * 4 : 0;
+  switch (cpl) {
+    case 4:  traceback_kernel<4><<<ctas, 128, smem, st>>>(a); break;
+    case 8:  traceback_kernel<8><<<ctas, 128, smem, st>>>(a); break;
+    case 12: traceback_kernel<12><<<ctas, 128, smem, st>>>(a); break;
+    default: traceback_kernel<16><<<ctas, 128, smem, st>>>(a); break;
+  }
   return 1;
 }
 
