@@ -55,7 +55,7 @@ struct Lanes { int lane, n; };     // this thread's index among the n threads th
 struct Bits {
   const uint8_t* p; uint64_t n;    // payload
   const uint32_t* w;               // p rounded down to a word boundary
-  uint32_t pos, end;               // window start / first bit after the payload, in bits from w
+  uint32_t pos, end, last;         // window start / first bit after the payload, in bits from w; index of the payload's last word
   uint32_t lo, hi, used;
 };
 
@@ -75,7 +75,10 @@ SWI_HD uint32_t load_word(const Bits& b, uint32_t idx)
 SWI_HD void refill(Bits& b)
 {
   b.pos += b.used; b.used = 0;
-  const uint32_t idx = b.pos >> 5, s = b.pos & 31u;
+  // A malformed stream can run past its payload (the symbol loop is bounded by the output size, not by the input): the
+  // window then stops moving at the payload's last word -- its bits are wrong, which no longer matters: overrun() is
+  // already true -- so that no load ever lands more than 12 bytes behind the payload.
+  const uint32_t idx = b.pos >> 5 < b.last ? b.pos >> 5 : b.last, s = b.pos & 31u;
   const uint32_t w0 = load_word(b, idx), w1 = load_word(b, idx + 1), w2 = load_word(b, idx + 2);
   b.lo = (uint32_t)((((uint64_t)w1 << 32) | w0) >> s);
   b.hi = (uint32_t)((((uint64_t)w2 << 32) | w1) >> s);
@@ -85,7 +88,7 @@ SWI_HD void init_bits(Bits& b, const uint8_t* in, uint64_t in_len)
   const uintptr_t a = (uintptr_t)in;
   b.p = in; b.n = in_len;
   b.w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  b.pos = (uint32_t)(a & 3) * 8u; b.end = b.pos + (uint32_t)in_len * 8u; b.used = 0;
+  b.pos = (uint32_t)(a & 3) * 8u; b.end = b.pos + (uint32_t)in_len * 8u; b.last = b.end >> 5; b.used = 0;
   refill(b);
 }
 // the 32 stream bits that start `off` bits into the window (off < 64; the top off-32 of them are zero beyond the window)

@@ -18,7 +18,7 @@
 //   sw_generic_kernel     one warp per pair, 32-bit, explicit tracking: pairs beyond 2^20 rows/columns, last-row maximum
 //   ref_compat_kernel     the reference's LIVE kernel semantics (smith_waterman.cl:11-71)
 //   synth_*               counter-RNG synthetic reads/windows
-// (FASTQ.gz ingest kernels: swb_fastq_kernels.cu.)  -DSWB_ABLATE=n builds timing experiments of the stream kernel whose
+// (FASTQ.gz ingest kernels: swb_fastq_kernels.cu; start cell + CIGAR behind a score: swb_traceback.cu.)  -DSWB_ABLATE=n builds timing experiments of the stream kernel whose
 // results are wrong on purpose; the product is always built with SWB_ABLATE=0.
 #include "swb_kernels.cuh"
 #ifndef SWB_ABLATE
