@@ -361,10 +361,12 @@ struct WgsChunk {
   std::vector<swb_bgzf_block> blocks;
 };
 
-// Compressed bytes per BGZF segment.  The inflate kernel decodes one block per warp, and a warp takes the same ~6 ms for
-// its block whether 500 or 9000 blocks are in flight (64 warps/SM x 148 SMs = 9472), so a segment should carry close to a
-// full wave: 112 MiB of compressed FASTQ is ~9000 blocks, ~600 MB of text, ~1.9 M reads of 150 bp.  Smaller files use
-// segments of their own size (pinned memory is slow to allocate).
+// Compressed bytes per BGZF segment.  The inflate kernel decodes one block per warp (32 warps/SM x 148 SMs = 4736 blocks
+// at once), a segment should carry a few thousand blocks so the device is full: 112 MiB of the synthetic FASTQ is ~9470
+// blocks, ~600 MB of text, ~1.9 M reads of 150 bp.  (Cutting segments to whole multiples of 4736 blocks was tried for files
+// that compress differently and changes nothing measurable: the inflate of the next segment runs beside the scoring of
+// the current one, so a half-empty last wave leaves no SM idle.)  Smaller files use segments of their own size (pinned
+// memory is slow to allocate).
 constexpr uint64_t kBgzfSegmentMax = 112ull << 20;
 
 // Is this a blocked-gzip file (first member carries a 'BC' extra field)?  SWB_GPU_INFLATE=0 keeps every file on the host.

@@ -36,7 +36,7 @@ def synth_reference(n):
 
 
 def make_file(args):
-    path, fi, n_reads, ref_len, rl, wl, level, blocked = args
+    path, fi, n_reads, ref_len, rl, wl, level, blocked, noisy = args
     ref = synth_reference(ref_len)
     if blocked:                                    # BGZF: independent <= 64 KiB members with a 'BC' size field (bgzip / BCL Convert)
         sys.path.insert(0, ROOT)
@@ -63,7 +63,11 @@ def make_file(args):
             rec[:, 11] = 10
             rec[:, 12:12 + rl] = reads
             rec[:, 12 + rl:12 + rl + 3] = np.frombuffer(b"\n+\n", dtype=np.uint8)
-            rec[:, 12 + rl + 3:12 + 2 * rl + 3] = ord("I")
+            if noisy:                                  # four binned quality values (NovaSeq-like), 62 / 25 / 9 / 3 %
+                qn = (noise >> np.uint64(16)) & np.uint64(255)
+                rec[:, 12 + rl + 3:12 + 2 * rl + 3] = np.where(qn < 160, ord("F"), np.where(qn < 224, ord(":"), np.where(qn < 248, ord(","), ord("#"))))
+            else:
+                rec[:, 12 + rl + 3:12 + 2 * rl + 3] = ord("I")
             rec[:, -1] = 10
             if blocked:
                 f.write(bgzf.compress(rec.tobytes(), level, 65280, eof=False))     # blocks may end anywhere inside a record
@@ -84,13 +88,14 @@ def main():
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--reuse", action="store_true", help="keep the files already in --dir (same parameters) instead of regenerating them")
     ap.add_argument("--bgzf", action="store_true", help="write blocked gzip (BGZF): the driver inflates and parses it on the GPU")
+    ap.add_argument("--quals", default="constant", choices=["constant", "noisy"], help="quality strings: all 'I', or four binned values at random")
     args = ap.parse_args()
     os.makedirs(args.dir, exist_ok=True)
     jobs = []
     fi = 0
     for lane in range(1, args.lanes + 1):
         for rd in (1, 2):
-            jobs.append((os.path.join(args.dir, f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"), fi, args.reads_per_file, args.ref_bases, 150, 500, args.level, args.bgzf))
+            jobs.append((os.path.join(args.dir, f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"), fi, args.reads_per_file, args.ref_bases, 150, 500, args.level, args.bgzf, args.quals == "noisy"))
             fi += 1
     t0 = time.time()
     if args.reuse and all(os.path.exists(j[0]) for j in jobs):     # files of an earlier run with the same parameters
@@ -118,7 +123,7 @@ def main():
     file_s = [float(l.split("Time:")[1].split("s")[0]) for l in r.stdout.splitlines() if "complete: Score=" in l]
     n_reads = args.reads_per_file * len(jobs)
     print(json.dumps({
-        "workload": f"BASELINE.json configs[4] scaled: {len(jobs)} files x {args.reads_per_file} reads of 150 bp ({'BGZF blocked gzip' if args.bgzf else 'gzip'} -{args.level}), each read vs a 500 bp window "
+        "workload": f"BASELINE.json configs[4] scaled: {len(jobs)} files x {args.reads_per_file} reads of 150 bp ({'BGZF blocked gzip' if args.bgzf else 'gzip'} -{args.level}, {args.quals} qualities), each read vs a 500 bp window "
                     f"of a {args.ref_bases} bp device-resident reference, GPU_CHUNK_SIZE_READS={args.chunk_reads}, {args.devices} GPU(s)",
         "wall_s": round(wall, 3), "reads_per_s": round(n_reads / wall, 1), "gcups_end_to_end": round(n_reads * 150 * 500 / wall / 1e9, 1),
         "gz_mb_per_s": round(gz_bytes / wall / 1e6, 1), "fastq_text_mb_per_s": round(text_bytes / wall / 1e6, 1),
