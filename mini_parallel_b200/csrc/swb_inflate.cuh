@@ -31,6 +31,10 @@ enum Status : int { OK = 0, ERR_INPUT_OVERRUN = 1, ERR_OUTPUT_OVERRUN = 2, ERR_B
 // A fast-table entry says everything the symbol loop needs, so it never touches the base / extra-bits tables:
 //   [3:0] code length (0 = longer than the table's index: canonical walk)   [7:4] kind   [15:8] extra bits   [31:16] value
 //   kind 0 literal (value = byte) | 1 length or distance (value = base) | 2 end of block | 3 not a legal symbol
+//   kind 5 (code length 0) a code longer than the table's index: canonical walk.  Lengths / distances are kind 1 so that
+//   the symbol loop's usual case -- a match -- is ONE test per table lookup.
+constexpr uint32_t kLongCode = 5u << 4;
+
 struct Tables {
   uint32_t lit_fast[LIT_FAST];
   uint32_t dist_fast[DIST_FAST];
@@ -151,7 +155,7 @@ SWI_HD uint32_t make_entry(int alphabet, int s, int len)
 SWI_OUTLINED bool build(const uint8_t* lengths, int n, int alphabet, uint32_t* fast, int fast_bits, uint16_t* count, uint16_t* sym, const Lanes& L)
 {
   const int fast_size = 1 << fast_bits;
-  for (int k = L.lane; k < fast_size; k += L.n) fast[k] = 0;
+  for (int k = L.lane; k < fast_size; k += L.n) fast[k] = kLongCode;
   uint32_t cnt[16];
   for (int l = 0; l < 16; ++l) cnt[l] = 0;
   for (int s = 0; s < n; ++s) ++cnt[lengths[s]];
@@ -230,7 +234,7 @@ SWI_HD uint32_t decode(Bits& b, int alphabet, const uint32_t* fast, int fast_bit
   if (b.used > 32) refill(b);
   const uint32_t v = window(b, b.used);
   uint32_t e = fast[low_bits(v, (uint32_t)fast_bits)];
-  if (!e) e = decode_slow(v, alphabet, count, sym);
+  if (e == kLongCode) e = decode_slow(v, alphabet, count, sym);
   b.used += e & 15u;
   return e;
 }
@@ -318,33 +322,36 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
       const bool pipelined = true;
 #endif
       Pending P; P.len = 0; P.from = 0; P.at = 0;
+      bool p_short = false;                                    // the pending copy is short and does not overlap itself: pipelined
       CopyRegs R = {};
       for (;;) {                                               // every pass emits >= 1 byte (bounded by out_cap), ends the block or fails
         if (P.len) {
           SWI_SYNC();
-          if (P.len <= kShortCopy && P.at - P.from >= P.len && pipelined) short_load(R, out, P, L);
+          if (p_short) short_load(R, out, P, L);
           else { copy_match(out, P, L); P.len = 0; }
         }
         if (b.used > 16) refill(b);
         const uint32_t v = window(b, b.used);
         uint32_t e = T.lit_fast[v & (LIT_FAST - 1)];
-        if (!e) e = decode_slow(v, ALPHA_LITLEN, T.lit_count, T.lit_sym);
-        const uint32_t cl = e & 15u, kind = (e >> 4) & 15u;
-        if (kind == 0) {
-          if (opos >= out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
-          out[opos] = (uint8_t)(e >> 16);                        // every lane stores the same byte to the same address: no branch
-          ++opos;
-          b.used += cl;
-          if (P.len) { short_store(R, out, P, L); P.len = 0; }
-          continue;
+        if (((e >> 4) & 15u) != 1u) {                            // not a length: a literal, the end of the block, a long code
+          if (e == kLongCode) e = decode_slow(v, ALPHA_LITLEN, T.lit_count, T.lit_sym);
+          const uint32_t kind = (e >> 4) & 15u;
+          if (kind == 0) {
+            if (opos >= out_cap) { status = ERR_OUTPUT_OVERRUN; break; }
+            out[opos] = (uint8_t)(e >> 16);                      // every lane stores the same byte to the same address: no branch
+            ++opos;
+            b.used += e & 15u;
+            if (P.len) { short_store(R, out, P, L); P.len = 0; }
+            continue;
+          }
+          if (kind != 1) { b.used += e & 15u; if (kind != 2) status = ERR_BAD_SYMBOL; break; }
         }
-        if (kind != 1) { b.used += cl; if (kind != 2) status = ERR_BAD_SYMBOL; break; }
-        const uint32_t xb = (e >> 8) & 255u;
+        const uint32_t cl = e & 15u, xb = (e >> 8) & 255u;
         const uint32_t len = (e >> 16) + low_bits(v >> cl, xb);
         const uint32_t at = b.used + cl + xb;                    // <= 36
         const uint32_t d = window(b, at);
         uint32_t de = T.dist_fast[d & (DIST_FAST - 1)];
-        if (!de) de = decode_slow(d, ALPHA_DIST, T.dist_count, T.dist_sym);
+        if (de == kLongCode) de = decode_slow(d, ALPHA_DIST, T.dist_count, T.dist_sym);
         const uint32_t dcl = de & 15u, dxb = (de >> 8) & 255u;
         const uint32_t dist = (de >> 16) + low_bits(d >> dcl, dxb);
         b.used = at + dcl + dxb;
@@ -354,6 +361,7 @@ SWI_HD int inflate_member(const uint8_t* in, uint64_t in_len, uint8_t* out, uint
         }
         if (P.len) short_store(R, out, P, L);
         P.len = len; P.from = opos - dist; P.at = opos;
+        p_short = (len <= kShortCopy) & (dist >= len) & pipelined;
         opos += len;
       }
       // every way out of the loop is a break below its top, so a copy still pending here has been loaded, not stored
