@@ -394,6 +394,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
+    uniform_offsets = os.environ.get("SWB_UNIFORM_OFFSETS", "1") != "0"
     cells_step = float(n) * rl * wl
     gcups = world * cells_step * args.steps / (ms_total * 1e-3) / 1e9
     e2e_gcups = world * cells_step * e2e_steps / (e2e_ms * 1e-3) / 1e9
@@ -432,15 +433,18 @@ def main():
         "clocks": clocks,
         "e2e": {"value": round(e2e_gcups, 2), "unit": "GCUPS", "reads_per_s": round(world * n * e2e_steps / (e2e_ms * 1e-3), 1),
                 "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
-                "h2d_bytes_per_step": int(h_q.numel() + h_r.numel() + 8 * (h_qo.numel() + h_ro.numel())),
+                # reads and windows all have one length: the library sends no offsets for such chunks (it writes k * length
+                # on the device), unless SWB_UNIFORM_OFFSETS=0
+                "h2d_bytes_per_step": int(h_q.numel() + h_r.numel() + (8 * (h_qo.numel() + h_ro.numel()) if not uniform_offsets else 0)),
                 "d2h_bytes_per_step": int(4 * h_out.numel()),
-                "api": "swb_score_batch (ASCII reads + windows from pinned host memory, chunks pipelined over 3 streams)",
+                "api": "swb_score_batch (ASCII reads + windows from pinned host memory, chunks pipelined over 3 streams; offsets of "
+                       "uniform-length chunks are generated on the device)",
                 "pinned_numa_node": numa_node,
                 "stage_ms_sum_over_chunks": {k: round(v, 3) for k, v in e2e_t.items() if k.endswith("_ms")}},
         "e2e_resident_reference": {"value": round(ref_gcups, 2), "unit": "GCUPS",
                                    "reads_per_s": round(world * n * e2e_steps / (ref_ms * 1e-3), 1), "steps": e2e_steps,
                                    "ms_per_step": round(ref_ms / e2e_steps, 3),
-                                   "h2d_bytes_per_step": int(h_q.numel() + 8 * h_qo.numel() + 8 * h_ws.numel() + 4 * h_wl.numel()),
+                                   "h2d_bytes_per_step": int(h_q.numel() + (8 * h_qo.numel() if not uniform_offsets else 0) + 8 * h_ws.numel() + 4 * h_wl.numel()),
                                    "d2h_bytes_per_step": int(4 * h_out2.numel()), "equals_e2e_results": ref_same,
                                    "api": "swb_score_batch_vs_reference (reads from pinned host memory, windows of a reference "
                                           "uploaded once)"},

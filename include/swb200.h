@@ -148,6 +148,8 @@ int  swb_set_short_variant(swb_ctx*, int variant);
  * streams").  Defaults: 32 MiB (16 MiB when only reads travel), 16384 pairs; SWB_CHUNK_MB overrides the first.  Pass pinned host memory
  * (swb_malloc_pinned) for the copies to be asynchronous. */
 int  swb_set_chunking(swb_ctx*, uint64_t chunk_bytes, uint64_t min_chunk_pairs);
+/* A chunk whose reads (or whose windows) all have the same length uploads no offsets for that side: the device writes
+ * k * length itself (SWB_UNIFORM_OFFSETS=0 uploads them regardless). */
 /* A ramped batch (four or more chunks) starts with chunks of 1/8, 1/4, 1/2 of that size and ends with 1/2, 1/4 (never
  * below min_chunk_pairs): the first copy and the last chunk's kernels are the parts of the pipeline nothing overlaps
  * with.  ramp = 1 (default, or SWB_CHUNK_RAMP=1): only batches against the resident reference ramp (there the kernels

@@ -80,6 +80,7 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
                                            // when only reads travel (windows of the resident reference): measured optima on B200
   uint64_t min_chunk_pairs = 16384;
   int n_lanes = 3;                         // SWB_LANES
+  bool uniform_offsets = true;             // SWB_UNIFORM_OFFSETS=0: always upload the offsets
   int chunk_ramp = 1;                      // SWB_CHUNK_RAMP / swb_set_chunk_ramp: 0 equal chunks, 1 auto, 2 always ramp
   std::vector<uint64_t> chunk_bounds;      // pair index where every chunk of the last host batch starts (+ n_pairs)
   float last_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -144,6 +145,7 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   }
   if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 7;
   if (const char* v = std::getenv("SWB_FORCE_BYTES")) c->force_bytes = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SWB_UNIFORM_OFFSETS")) c->uniform_offsets = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_LANES")) c->n_lanes = std::min(kLanes, std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("SWB_CHUNK_RAMP")) c->chunk_ramp = std::min(2, std::max(0, std::atoi(v)));
   if (const char* v = std::getenv("SWB_CHUNK_MB")) { const long mb = std::atol(v); if (mb > 0) c->chunk_bytes = (uint64_t)mb << 20; }
@@ -374,10 +376,15 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
     cudaEvent_t* ev = c->chunk_ev[ch].ev;
     cudaStream_t st = l->st;
     uint32_t max_r = 0, max_q = 0;
+    // A side whose sequences all have the same length (150 bp reads, fixed windows: the usual FASTQ chunk) sends no
+    // offsets: the device writes k * length itself -- two of the chunk's four copies and 16 bytes per pair stay home.
+    const uint64_t q_len0 = qo[p0 + 1] - qo[p0], r_len0 = ref_windows ? 0 : ro[p0 + 1] - ro[p0];
+    bool q_uniform = q_len0 != 0 && c->uniform_offsets, r_uniform = !ref_windows && r_len0 != 0 && c->uniform_offsets;
     for (uint64_t k = p0; k < p1; ++k) {                      // validation + longest read / window of this chunk
       if (qo[k + 1] < qo[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
       if (qo[k + 1] - qo[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
       max_q = std::max<uint32_t>(max_q, (uint32_t)(qo[k + 1] - qo[k]));
+      q_uniform &= qo[k + 1] - qo[k] == q_len0;
       if (ref_windows) {
         if (win_start[k] + win_len[k] > c->ref_len) return fail(std::string(who) + ": window outside the reference");
         max_r = std::max<uint32_t>(max_r, win_len[k]);
@@ -385,6 +392,7 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
         if (ro[k + 1] < ro[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
         if (ro[k + 1] - ro[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
         max_r = std::max<uint32_t>(max_r, (uint32_t)(ro[k + 1] - ro[k]));
+        r_uniform &= ro[k + 1] - ro[k] == r_len0;
       }
     }
     const uint64_t qb = qo[p1] - qo[p0], rb = ref_windows ? 0 : ro[p1] - ro[p0];
@@ -394,18 +402,18 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
 
     CUDA_TRY(cudaEventRecord(ev[4], st));
     if (qb) CUDA_TRY(cudaMemcpyAsync(l->q_bytes.p, q + qo[p0], qb, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(l->q_off.p, qo + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (!q_uniform) CUDA_TRY(cudaMemcpyAsync(l->q_off.p, qo + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     int k = 0;
     if (ref_windows) {
       CUDA_TRY(cudaMemcpyAsync(l->win_beg.p, win_start + p0, n * 8, cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(l->win_len.p, win_len + p0, n * 4, cudaMemcpyHostToDevice, st));
-      k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], nullptr, 0, 0,
+      k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], q_uniform ? q_len0 : 0, nullptr, 0, 0, 0,
                                      l->win_beg.as<uint64_t>(), l->win_len.as<uint32_t>(), l->win_end.as<uint64_t>(), n, st);
     } else {
       if (rb) CUDA_TRY(cudaMemcpyAsync(l->r_bytes.p, r + ro[p0], rb, cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(l->r_off.p, ro + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-      k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], l->r_off.as<uint64_t>(), n + 1, ro[p0],
-                                     nullptr, nullptr, nullptr, 0, st);
+      if (!r_uniform) CUDA_TRY(cudaMemcpyAsync(l->r_off.p, ro + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+      k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], q_uniform ? q_len0 : 0, l->r_off.as<uint64_t>(), n + 1, ro[p0],
+                                     r_uniform ? r_len0 : 0, nullptr, nullptr, nullptr, 0, st);
     }
     CUDA_TRY(cudaEventRecord(ev[5], st));
     c->last_kernels += k;

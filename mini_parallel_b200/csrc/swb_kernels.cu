@@ -163,28 +163,29 @@ classify_kernel(BatchView b)
 
 // Chunk preparation of the host path: CSR offsets arrive as absolute positions in the caller's arrays and are
 // rebased to the chunk's own buffers; windows of the resident reference get their end positions.
+// len_a / len_b != 0: every sequence of that side has this length, its offsets were not uploaded: they are k * len.
 __global__ void __launch_bounds__(256)
-chunk_prepare_kernel(uint64_t* __restrict__ off_a, uint64_t n_a, uint64_t base_a,
-                     uint64_t* __restrict__ off_b, uint64_t n_b, uint64_t base_b,
+chunk_prepare_kernel(uint64_t* __restrict__ off_a, uint64_t n_a, uint64_t base_a, uint64_t len_a,
+                     uint64_t* __restrict__ off_b, uint64_t n_b, uint64_t base_b, uint64_t len_b,
                      const uint64_t* __restrict__ win_beg, const uint32_t* __restrict__ win_len,
                      uint64_t* __restrict__ win_end, uint64_t n_w)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_a || k < n_b || k < n_w; k += stride) {
-    if (k < n_a) off_a[k] -= base_a;
-    if (k < n_b) off_b[k] -= base_b;
+    if (k < n_a) off_a[k] = len_a ? k * len_a : off_a[k] - base_a;
+    if (k < n_b) off_b[k] = len_b ? k * len_b : off_b[k] - base_b;
     if (k < n_w) win_end[k] = win_beg[k] + win_len[k];
   }
 }
 
-int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_t* off_b, uint64_t n_b, uint64_t base_b,
-                         const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st)
+int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_t len_a, uint64_t* off_b, uint64_t n_b, uint64_t base_b,
+                         uint64_t len_b, const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st)
 {
   const uint64_t n = n_a > n_b ? (n_a > n_w ? n_a : n_w) : (n_b > n_w ? n_b : n_w);
   if (n == 0) return 0;
   uint64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  chunk_prepare_kernel<<<(unsigned)blocks, 256, 0, st>>>(off_a, n_a, base_a, off_b, n_b, base_b, win_beg, win_len, win_end, n_w);
+  chunk_prepare_kernel<<<(unsigned)blocks, 256, 0, st>>>(off_a, n_a, base_a, len_a, off_b, n_b, base_b, len_b, win_beg, win_len, win_end, n_w);
   return 1;
 }
 

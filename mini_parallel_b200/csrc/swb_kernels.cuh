@@ -74,8 +74,8 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t& bad)
 // launchers (all asynchronous on `st`); each returns the number of kernels it launched
 int launch_pack2bit(const uint8_t* bytes, uint64_t n, uint32_t* words, uint32_t* bitmap, cudaStream_t st);
 int launch_classify(const BatchView& b, cudaStream_t st);
-int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_t* off_b, uint64_t n_b, uint64_t base_b,
-                         const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st);
+int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_t len_a, uint64_t* off_b, uint64_t n_b, uint64_t base_b,
+                         uint64_t len_b, const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st);
 int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st);
 int launch_generic(const BatchView& b, int sm_count, int warps_resident, cudaStream_t st);
 int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st);

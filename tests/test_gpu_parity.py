@@ -289,6 +289,35 @@ def test_host_path_is_chunked_over_streams_and_stays_exact(engine):
         engine.set_chunk_ramp(1)
 
 
+def test_uniform_length_chunks_generate_their_offsets_on_the_device(engine):
+    """A chunk whose reads (or windows) all have one length uploads no offsets for that side; every mix of uniform and
+    ragged sides, and a single odd pair that makes a chunk ragged, must give the oracle's results."""
+    rng = np.random.default_rng(902)
+    n = 6000
+    cases = {
+        "both uniform": ([_rand(rng, 150) for _ in range(n)], [_rand(rng, 500) for _ in range(n)]),
+        "reads uniform": ([_rand(rng, 100) for _ in range(n)], [_rand(rng, int(rng.integers(1, 600))) for _ in range(n)]),
+        "windows uniform": ([_rand(rng, int(rng.integers(1, 160))) for _ in range(n)], [_rand(rng, 333) for _ in range(n)]),
+    }
+    odd_r, odd_w = [_rand(rng, 150) for _ in range(n)], [_rand(rng, 500) for _ in range(n)]
+    odd_r[4500] = _rand(rng, 149); odd_w[17] = _rand(rng, 501)         # one chunk of each side is ragged, the others are not
+    cases["one odd pair"] = (odd_r, odd_w)
+    try:
+        engine.set_chunking(1 << 18, 500)                              # several chunks per batch
+        for name, (reads, wins) in cases.items():
+            q, qo = to_csr(reads); r, ro = to_csr(wins)
+            exp = ol.batch(q, qo, r, ro, threads=8, simd=True)
+            assert np.array_equal(engine.score_batch_csr(q, qo, r, ro), exp), name
+        ref = _rand(rng, 100_000)
+        engine.set_reference(ref)
+        start = rng.integers(0, 100_000 - 500, n).astype(np.uint64); wlen = np.full(n, 500, dtype=np.uint32)
+        reads = [ref[int(s) + 100:int(s) + 250].copy() for s in start]
+        q, qo = to_csr(reads); r, ro = to_csr([ref[int(s):int(s) + 500] for s in start])
+        assert np.array_equal(engine.score_batch_vs_reference(q, qo, start, wlen), ol.batch(q, qo, r, ro, threads=8, simd=True))
+    finally:
+        engine.set_chunking(32 << 20, 16384)
+
+
 def test_reference_windows_chunked(engine):
     rng = np.random.default_rng(901)
     ref = _rand(rng, 200_000)
