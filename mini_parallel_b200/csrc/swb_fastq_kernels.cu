@@ -98,25 +98,39 @@ fq_count_kernel(const uint8_t* __restrict__ text, uint64_t begin, uint64_t end, 
   }
 }
 
-// exclusive scan of the tile counts by one CTA (a few hundred thousand tiles at most); total[0] = number of newlines
+// exclusive scan of the tile counts by one CTA (a few hundred thousand tiles at most), 1024 tiles per round: coalesced
+// loads, a shuffle scan per warp, the warp totals scanned by the first warp; total[0] = number of newlines
 __global__ void __launch_bounds__(1024)
 fq_scan_kernel(const uint32_t* __restrict__ tile_count, uint64_t n_tiles, uint64_t* __restrict__ tile_prefix, uint64_t* __restrict__ total)
 {
-  __shared__ uint64_t part[1024];
-  const uint64_t per = (n_tiles + 1023) / 1024;
-  const uint64_t lo = min(n_tiles, (uint64_t)threadIdx.x * per), hi = min(n_tiles, lo + per);
-  uint64_t s = 0;
-  for (uint64_t t = lo; t < hi; ++t) s += tile_count[t] & 0xFFFFFFu;
-  part[threadIdx.x] = s;
+  __shared__ uint32_t wsum[32], round_total;
+  __shared__ uint64_t base;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t run = 0;
-    for (int k = 0; k < 1024; ++k) { const uint64_t v = part[k]; part[k] = run; run += v; }
-    total[0] = run;
+  for (uint64_t t0 = 0; t0 < n_tiles; t0 += 1024) {
+    const uint64_t t = t0 + threadIdx.x;
+    const uint32_t v = t < n_tiles ? tile_count[t] & 0xFFFFFFu : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= (uint32_t)o) inc += x; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane], winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= (uint32_t)o) winc += x; }
+      wsum[lane] = winc - w;                                   // exclusive: newlines of the warps before this one
+      if (lane == 31) round_total = winc;
+    }
+    __syncthreads();
+    const uint64_t b0 = base;
+    if (t < n_tiles) tile_prefix[t] = b0 + wsum[warp] + (inc - v);
+    __syncthreads();
+    if (threadIdx.x == 0) base = b0 + round_total;
+    __syncthreads();
   }
-  __syncthreads();
-  uint64_t run = part[threadIdx.x];
-  for (uint64_t t = lo; t < hi; ++t) { tile_prefix[t] = run; run += tile_count[t] & 0xFFFFFFu; }
+  if (threadIdx.x == 0) total[0] = base;
 }
 
 // One pass over the text that does everything the scoring pipeline needs from it:
