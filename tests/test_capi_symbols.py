@@ -23,6 +23,16 @@ def test_library_exports_every_declared_symbol():
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in mini_parallel_b200/_lib.py"
 
 
+def test_struct_layouts_match_the_header():
+    """The numpy views of swb_result / swb_alignment have the C structs' layout (include/swb200.h)."""
+    src = open(os.path.join(ROOT, "include", "swb200.h")).read()
+    assert "typedef struct { int32_t score; int32_t end_i; int32_t end_j; } swb_result;" in re.sub(r"\s+", " ", src)
+    assert "typedef struct { int32_t start_i, start_j; uint32_t cigar_len; uint32_t status; uint64_t cigar_off; } swb_alignment;" in re.sub(r"\s+", " ", src)
+    assert _lib.RESULT_DTYPE.itemsize == 12 and _lib.RESULT_DTYPE.names == ("score", "end_i", "end_j")
+    a = _lib.ALIGNMENT_DTYPE
+    assert a.itemsize == 24 and [a.fields[n][1] for n in a.names] == [0, 4, 8, 12, 16]
+
+
 def test_no_device_is_an_error_not_a_fallback():
     """Like main.rs:76-79 / :160-163: without a GPU the engine refuses to run."""
     if mp.device_count() > 0:
