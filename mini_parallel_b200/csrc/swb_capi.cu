@@ -70,7 +70,7 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
     cudaEvent_t done = nullptr; bool pending = false;
   } fq_slot[2];
   DevBuf fq_tile_count, fq_tile_prefix, fq_seq_beg, fq_seq_end, fq_scal;
-  DevBuf tb_scratch, tb_res, tb_out, tb_cigar, tb_cursor;   // swb_traceback_batch
+  DevBuf tb_scratch, tb_res, tb_out, tb_cigar, tb_cursor, tb_handled;   // swb_traceback_batch
   uint64_t ref_len = 0;
   std::vector<ChunkEvents> chunk_ev;       // host path: one event set per chunk of the last call
   swb::Counters* h_counters = nullptr;     // pinned, one slot per chunk
@@ -165,7 +165,7 @@ void swb_destroy(swb_ctx* c)
     cudaStreamDestroy(l->st);
   }
   for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->fq_tile_count, &c->fq_tile_prefix, &c->fq_seq_beg, &c->fq_seq_end, &c->fq_scal,
-                    &c->tb_scratch, &c->tb_res, &c->tb_out, &c->tb_cigar, &c->tb_cursor}) b->release();
+                    &c->tb_scratch, &c->tb_res, &c->tb_out, &c->tb_cigar, &c->tb_cursor, &c->tb_handled}) b->release();
   for (auto& sl : c->fq_slot) {
     for (DevBuf* b : {&sl.comp, &sl.blocks, &sl.out_off, &sl.text, &sl.fail}) b->release();
     if (sl.done) cudaEventDestroy(sl.done);
@@ -703,7 +703,8 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
   const uint64_t qb = qo[n_pairs], rb = ro[n_pairs];
   if (c->q_bytes.reserve(qb + 64) || c->r_bytes.reserve(rb + 64) || c->q_off.reserve((n_pairs + 1) * 8) || c->r_off.reserve((n_pairs + 1) * 8) ||
       c->tb_res.reserve(n_pairs * sizeof(swb_result)) || c->tb_out.reserve(n_pairs * sizeof(swb_alignment)) ||
-      c->tb_cigar.reserve(cigar_cap * 4 + 64) || c->tb_cursor.reserve(64) || c->tb_scratch.reserve((uint64_t)warps * need)) return 1;
+      c->tb_cigar.reserve(cigar_cap * 4 + 64) || c->tb_cursor.reserve(64) || c->tb_handled.reserve(n_pairs + 64) ||
+      c->tb_scratch.reserve((uint64_t)warps * need)) return 1;
   cudaStream_t st = c->st;
   if (qb) CUDA_TRY(cudaMemcpyAsync(c->q_bytes.p, q, qb, cudaMemcpyHostToDevice, st));
   if (rb) CUDA_TRY(cudaMemcpyAsync(c->r_bytes.p, r, rb, cudaMemcpyHostToDevice, st));
@@ -716,6 +717,7 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
   a.res = c->tb_res.as<swb_result>(); a.out = c->tb_out.as<swb_alignment>(); a.cigar = c->tb_cigar.as<uint32_t>(); a.cigar_cap = cigar_cap;
   a.cursor = c->tb_cursor.as<unsigned long long>(); a.n_pairs = n_pairs;
   a.scratch = c->tb_scratch.as<uint8_t>(); a.scratch_per_warp = need; a.dirs_per_warp = dirs_b; a.rows_per_warp = rows_b; a.rows_in_smem = in_smem;
+  a.handled = c->tb_handled.as<uint8_t>();
   CUDA_TRY(cudaEventRecord(c->ev[0], st));
   c->last_kernels = swb::launch_traceback(a, cpl, warps, st);
   CUDA_TRY(cudaEventRecord(c->ev[1], st));

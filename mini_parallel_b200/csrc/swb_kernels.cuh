@@ -94,6 +94,7 @@ struct TracebackArgs {
   uint64_t n_pairs;
   uint8_t* scratch; uint64_t scratch_per_warp;   // global: directions (dirs_per_warp bytes) [+ rows and runs when not in shared memory]
   uint64_t dirs_per_warp, rows_per_warp; int rows_in_smem;
+  uint8_t* handled;                          // per pair: done by traceback_diag_kernel (gapless), the matrix kernel skips it
 };
 uint32_t tb_pick_cpl(uint64_t max_width);
 uint64_t tb_rows_bytes(uint64_t rows, uint64_t width, uint32_t cpl);

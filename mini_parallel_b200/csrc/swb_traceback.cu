@@ -46,6 +46,7 @@ traceback_kernel(TracebackArgs a)
     if (lane == 0) pair = atomicAdd(&a.cursor[0], 1ull);
     pair = __shfl_sync(0xffffffffu, pair, 0);
     if (pair >= a.n_pairs) break;
+    if (a.handled[pair]) continue;                                            // traceback_diag_kernel wrote this alignment
     const swb_result res = a.res[pair];
     const uint8_t* q = a.q + a.qo[pair]; const uint64_t n1 = a.qo[pair + 1] - a.qo[pair];
     const uint8_t* r = a.r + a.ro[pair]; const uint64_t n2 = a.ro[pair + 1] - a.ro[pair];
@@ -158,9 +159,55 @@ traceback_kernel(TracebackArgs a)
   }
 }
 
+// Gapless alignments without the matrix (one thread per pair).  Walking back along the diagonal from the end cell, let
+// sum(t) be the score of its last t cells.  If sum(k) == score for some k, the alignment IS those k cells: every H on the
+// diagonal is at least the score of the diagonal segment that ends there (H[t] >= score - sum(t)) and, by the recurrence,
+// at most its successor's value minus the successor's substitution score (H[t] <= H[t-1] - s), which from H[0] = score
+// pins H[t] = score - sum(t); so the diagonal predecessor explains every cell (it is asked first), and the walk ends at the
+// first k with sum(k) == score, where H reaches 0.  (sum(t) > score would mean H[end] > score: not this pair's result.)
+// Most reads of a real run align without a gap, and are done here in a few hundred byte compares.
+__global__ void __launch_bounds__(256)
+traceback_diag_kernel(TracebackArgs a)
+{
+  const uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= a.n_pairs) return;
+  a.handled[pair] = 0;
+  const swb_result res = a.res[pair];
+  const uint8_t* q = a.q + a.qo[pair]; const uint64_t n1 = a.qo[pair + 1] - a.qo[pair];
+  const uint8_t* r = a.r + a.ro[pair]; const uint64_t n2 = a.ro[pair + 1] - a.ro[pair];
+  if (res.score <= 0 || res.end_i < 0 || res.end_j < 0 || (uint64_t)res.end_i >= n1 || (uint64_t)res.end_j >= n2) return;
+  const uint32_t ei = (uint32_t)res.end_i, ej = (uint32_t)res.end_j, max_k = min(ei, ej) + 1;
+  int32_t sum = 0;
+  uint32_t k = 0, n_runs = 0, prev = 2;
+  for (uint32_t t = 0; t < max_k; ++t) {
+    const uint32_t eq = q[ei - t] == r[ej - t];
+    sum += eq ? kMatch : kMismatch;
+    n_runs += eq != prev; prev = eq;
+    if (sum == res.score) { k = t + 1; break; }
+    if (sum > res.score || sum + kMatch * (int32_t)(max_k - 1 - t) < res.score) break;
+  }
+  if (!k) return;                                              // a gap, or not a result of this pair: the matrix decides
+  swb_alignment al;
+  al.start_i = (int32_t)(ei + 1 - k); al.start_j = (int32_t)(ej + 1 - k); al.cigar_len = n_runs; al.status = 0;
+  al.cigar_off = atomicAdd(&a.cursor[1], (unsigned long long)n_runs);
+  if (al.cigar_off + n_runs <= a.cigar_cap) {
+    uint64_t at = al.cigar_off;
+    uint32_t cur = q[al.start_i] == r[al.start_j], len = 0;
+    for (uint32_t t = 0; t < k; ++t) {
+      const uint32_t eq = q[al.start_i + t] == r[al.start_j + t];
+      if (eq != cur) { a.cigar[at++] = (len << 4) | (cur ? 7u : 8u); cur = eq; len = 0; }
+      ++len;
+    }
+    a.cigar[at] = (len << 4) | (cur ? 7u : 8u);
+  } else al.status = 2;
+  a.out[pair] = al;
+  a.handled[pair] = 1;
+}
+
 int launch_traceback(const TracebackArgs& a, uint32_t cpl, int warps, cudaStream_t st)
 {
   if (a.n_pairs == 0) return 0;
+  traceback_diag_kernel<<<(unsigned)((a.n_pairs + 255) / 256), 256, 0, st>>>(a);
   const int ctas = (warps + 3) / 4;
   const size_t smem = a.rows_in_smem ? (size_t)a.rows_per_warp * 4 : 0;
   switch (cpl) {
@@ -169,7 +216,7 @@ int launch_traceback(const TracebackArgs& a, uint32_t cpl, int warps, cudaStream
     case 12: traceback_kernel<12><<<ctas, 128, smem, st>>>(a); break;
     default: traceback_kernel<16><<<ctas, 128, smem, st>>>(a); break;
   }
-  return 1;
+  return 2;
 }
 
 }  // namespace swb

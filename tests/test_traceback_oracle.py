@@ -86,3 +86,50 @@ def test_matches_the_python_twin_and_replays_to_the_score():
             rows = sum(l for l, o in cigar if o in "=XI"); cols = sum(l for l, o in cigar if o in "=XD")
             assert rows == ei - si + 1 and cols == ej - sj + 1 and cols <= 2 * rows
             assert cigar[0][1] == "=" and cigar[-1][1] == "="           # a local alignment starts and ends on a match
+
+
+def _diagonal_rule(a, b, score, ei, ej):
+    """What traceback_diag_kernel does on the GPU: walking back along the diagonal from the end cell, the first k cells whose
+    substitution scores add up to the score ARE the alignment (csrc/swb_traceback.cu has the argument); None when a partial
+    sum passes the score or the diagonal runs out (a gap: the matrix has to decide)."""
+    s, runs = 0, []
+    for t in range(min(ei, ej) + 1):
+        eq = a[ei - t] == b[ej - t]
+        s += 2 if eq else -1
+        if runs and runs[-1][1] == ("=" if eq else "X"):
+            runs[-1][0] += 1
+        else:
+            runs.append([1, "=" if eq else "X"])
+        if s == score:
+            return ei - t, ej - t, [(l, o) for l, o in reversed(runs)]
+        if s > score:
+            return None
+    return None
+
+
+def test_gapless_alignments_follow_the_diagonal_rule():
+    rng = np.random.default_rng(9)
+    alpha = np.frombuffer(b"ACGT", dtype=np.uint8)
+    handled = total = 0
+    for t in range(6000):
+        n, m, k = int(rng.integers(1, 40)), int(rng.integers(1, 60)), int(rng.integers(1, 5))
+        b = alpha[rng.integers(0, k, m)].tobytes()
+        if t % 3 == 0:
+            a = alpha[rng.integers(0, k, n)].tobytes()
+        else:
+            o = int(rng.integers(0, m)); piece = bytearray(b[o:o + n] or b[:1])
+            for _ in range(int(rng.integers(0, 3))):
+                p = int(rng.integers(0, len(piece))); c = int(rng.integers(0, 3))
+                if c == 0: piece[p] = int(alpha[rng.integers(0, 4)])
+                elif c == 1 and len(piece) > 1: del piece[p]
+                else: piece.insert(p, int(alpha[rng.integers(0, 4)]))
+            a = bytes(piece)
+        s, ei, ej = ol.sw_linear(a, b)
+        if s <= 0:
+            continue
+        total += 1
+        got = _diagonal_rule(a, b, s, ei, ej)
+        if got is not None:
+            handled += 1
+            assert got == ol.traceback(a, b, ei, ej), (a, b)
+    assert handled > total // 2                                       # most alignments of such pairs have no gap
