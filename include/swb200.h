@@ -131,7 +131,9 @@ int  swb_pack2bit_device(swb_ctx*, const uint8_t* d_bytes, uint64_t n, uint32_t*
  * a gap.  results[] are what swb_score_* returned for the same pairs.  cigar[] receives all operations, alignment k's
  * are cigar[out[k].cigar_off .. + cigar_len) (slices in no particular order); *cigar_used = operations of the whole
  * batch.  If that exceeds cigar_cap the call fails and *cigar_used says how much room a retry needs.
- * out[k].status: 0 ok (start = (-1,-1) and no operations when the score is 0), 1 results[k] is not an end cell of pair k,
+ * out[k].status: 0 ok (start = (-1,-1) and no operations when the score is 0), 1 results[k] is not an end cell of pair k
+ * (outside the pair, or the recomputed value differs from the score; a gapless diagonal that adds up to the score is taken
+ * at its word without recomputing the matrix),
  * 2 (only when the call fails for lack of room) this alignment's operations did not fit. */
 typedef struct { int32_t start_i, start_j; uint32_t cigar_len; uint32_t status; uint64_t cigar_off; } swb_alignment;
 int  swb_traceback_batch(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
