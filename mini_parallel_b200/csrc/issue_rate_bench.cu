@@ -27,14 +27,16 @@ constexpr int UNROLL = 8;
 
 enum Op { OP_VIADDMNMX_RELU = 0, OP_VIADDMNMX, OP_VIMNMX3, OP_VIMNMX, OP_VIADD16X2, OP_IADD3,
           OP_LOP3, OP_IMAD, OP_VIADDMNMX_S32, OP_VIMNMX3_S32, OP_PRMT, OP_SHFL, OP_LDS,
-          OP_MIX_CELL, OP_MIX_CELL_LDS, OP_MIX_ALU_FMA, OP_COUNT };
+          OP_MIX_CELL, OP_MIX_CELL_LDS, OP_MIX_ALU_FMA,
+          OP_HFMA2, OP_HFMA2_RELU, OP_HMNMX2, OP_HADD2, OP_MIX_ALU_HFMA2, OP_MIX_ALU_HMNMX2, OP_MIX_CELL_TRK0, OP_MIX_CELL_TRK1, OP_COUNT };
 
 static const char* op_name[OP_COUNT] = {
   "viaddmnmx_s16x2_relu", "viaddmnmx_s16x2", "vimnmx3_s16x2", "vimnmx_s16x2", "viadd_16x2", "iadd3",
   "lop3", "imad", "viaddmnmx_s32", "vimnmx3_s32", "prmt", "shfl", "lds",
-  "mix_cell4", "mix_cell4_lds", "mix_alu_fma" };
+  "mix_cell4", "mix_cell4_lds", "mix_alu_fma",
+  "hfma2", "hfma2_relu", "hmnmx2", "hadd2", "mix_alu_hfma2", "mix_alu_hmnmx2", "mix_cell_trk0", "mix_cell_trk1" };
 // thread-instructions issued per chain-iteration for each op kind
-static const int op_instr[OP_COUNT] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 4, 5, 2 };
+static const int op_instr[OP_COUNT] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 4, 5, 2, 1, 1, 1, 1, 2, 2, 5, 11 };
 
 template <int OP>
 __device__ __forceinline__ unsigned step(unsigned a, unsigned b, unsigned c, const unsigned* sm) {
@@ -68,6 +70,41 @@ __device__ __forceinline__ unsigned step(unsigned a, unsigned b, unsigned c, con
     unsigned t = __viaddmax_s16x2(a, b, c);
     unsigned r; asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(t), "r"(b), "r"(c));
     return r;
+  }
+  // round 2: do the fp16x2 instructions issue on the FMA pipe beside the ALU-pipe DPX instructions?
+  if (OP == OP_HFMA2)          { unsigned r; asm volatile("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  if (OP == OP_HFMA2_RELU)     { unsigned r; asm volatile("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  if (OP == OP_HMNMX2)         { unsigned r; asm volatile("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  if (OP == OP_HADD2)          { unsigned r; asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  if (OP == OP_MIX_ALU_HFMA2) {
+    unsigned t = __viaddmax_s16x2(a, b, c);
+    unsigned r; asm volatile("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(t), "r"(b), "r"(c));
+    return r;
+  }
+  if (OP == OP_MIX_ALU_HMNMX2) {
+    unsigned t = __viaddmax_s16x2(a, b, c);
+    unsigned r; asm volatile("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(t), "r"(b));
+    return r;
+  }
+  if (OP == OP_MIX_CELL_TRK0) { // the round-1 cell: ADD-indexed LUT fetch, two DPX for the cell, one DPX tracker
+    unsigned x; asm volatile("mad.lo.u32 %0, %1, 1, %2;" : "=r"(x) : "r"(a & 0xfcu), "r"(b & 0x3u));
+    unsigned s = sm[(x >> 2) & 63u];
+    unsigned t = __viaddmax_s16x2(a, s, c);
+    unsigned h = __vimax3_s16x2(t, b, c);
+    return __viaddmax_s16x2(h, c, a);
+  }
+  if (OP == OP_MIX_CELL_TRK1) { // two cells with the round-2 tracker: x = h + e as a plain add, one VIMNMX3 per two steps
+    unsigned x0; asm volatile("mad.lo.u32 %0, %1, 1, %2;" : "=r"(x0) : "r"(a & 0xfcu), "r"(b & 0x3u));
+    unsigned s0 = sm[(x0 >> 2) & 63u];
+    unsigned t0 = __viaddmax_s16x2(a, s0, c);
+    unsigned h0 = __vimax3_s16x2(t0, b, c);
+    unsigned y0; asm volatile("mad.lo.u32 %0, %1, 1, %2;" : "=r"(y0) : "r"(h0), "r"(c));
+    unsigned x1; asm volatile("mad.lo.u32 %0, %1, 1, %2;" : "=r"(x1) : "r"(h0 & 0xfcu), "r"(b & 0x3u));
+    unsigned s1 = sm[(x1 >> 2) & 63u];
+    unsigned t1 = __viaddmax_s16x2(h0, s1, c);
+    unsigned h1 = __vimax3_s16x2(t1, b, c);
+    unsigned y1; asm volatile("mad.lo.u32 %0, %1, 1, %2;" : "=r"(y1) : "r"(h1), "r"(b));
+    return __vimax3_s16x2(a, y0, y1);
   }
   return a;
 }
@@ -148,6 +185,10 @@ int main(int argc, char** argv) {
   r[10] = run<10>(p.multiProcessorCount, clock_hz);  r[11] = run<11>(p.multiProcessorCount, clock_hz);
   r[12] = run<12>(p.multiProcessorCount, clock_hz);  r[13] = run<13>(p.multiProcessorCount, clock_hz);
   r[14] = run<14>(p.multiProcessorCount, clock_hz);  r[15] = run<15>(p.multiProcessorCount, clock_hz);
+  r[16] = run<16>(p.multiProcessorCount, clock_hz);  r[17] = run<17>(p.multiProcessorCount, clock_hz);
+  r[18] = run<18>(p.multiProcessorCount, clock_hz);  r[19] = run<19>(p.multiProcessorCount, clock_hz);
+  r[20] = run<20>(p.multiProcessorCount, clock_hz);  r[21] = run<21>(p.multiProcessorCount, clock_hz);
+  r[22] = run<22>(p.multiProcessorCount, clock_hz);  r[23] = run<23>(p.multiProcessorCount, clock_hz);
   printf("{\"device\": \"%s\", \"sms\": %d, \"clock_rate_mhz\": %.1f, \"rates\": {", p.name, p.multiProcessorCount, clock_hz / 1e6);
   for (int i = 0; i < OP_COUNT; ++i)
     printf("%s\"%s\": {\"thread_instr_per_clk_per_sm\": %.2f, \"by_wall_at_max_clock\": %.2f, \"ms\": %.4f}",

@@ -143,7 +143,7 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
     if (cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
     for (auto& e : l->ev) cudaEventCreate(&e);
   }
-  if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 7;
+  if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 15;
   if (const char* v = std::getenv("SWB_FORCE_BYTES")) c->force_bytes = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_UNIFORM_OFFSETS")) c->uniform_offsets = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_LANES")) c->n_lanes = std::min(kLanes, std::max(1, std::atoi(v)));
@@ -207,7 +207,7 @@ void swb_numa_reset(void)
 }
 
 void* swb_stream(swb_ctx* c) { return c ? (void*)c->st : nullptr; }
-int   swb_set_short_variant(swb_ctx* c, int v) { if (!c) return fail("null ctx"); c->variant = v & 7; return 0; }
+int   swb_set_short_variant(swb_ctx* c, int v) { if (!c) return fail("null ctx"); c->variant = v & 15; return 0; }
 
 int swb_set_chunking(swb_ctx* c, uint64_t chunk_bytes, uint64_t min_chunk_pairs)
 {

@@ -394,15 +394,20 @@ static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t 
   return 1;
 }
 
-template <int G, int K, int MINB> static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st);
+template <int G, int K, int MINB, int FLAGS> static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st);
 
 // variant 4..6: streaming kernel; else bit0: 0 = G8/K20, 1 = G16/K10 ; bit1: split tracking (VIADD + VIMNMX) instead of VIADDMNMX
 int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st)
 {
   if (b.n_pairs == 0) return 0;
-  if ((variant & 7) == 4) return launch_stream_t<16, 10, 4>(b, sm_count, st);
-  if ((variant & 7) == 5) return launch_stream_t<16, 10, 5>(b, sm_count, st);
-  if ((variant & 7) == 6) return launch_stream_t<8, 20, 3>(b, sm_count, st);
+  if ((variant & 15) == 4) return launch_stream_t<16, 10, 4, 0>(b, sm_count, st);
+  if ((variant & 15) == 5) return launch_stream_t<16, 10, 5, 0>(b, sm_count, st);
+  if ((variant & 15) == 6) return launch_stream_t<8, 20, 3, 0>(b, sm_count, st);
+  if ((variant & 15) == 7) return launch_stream_t<16, 10, 4, 1>(b, sm_count, st);     // two-step tracker
+  if ((variant & 15) == 8) return launch_stream_t<16, 10, 4, 2>(b, sm_count, st);    // dynamic couple distribution
+  if ((variant & 15) == 9) return launch_stream_t<16, 10, 4, 3>(b, sm_count, st);    // both
+  if ((variant & 15) == 10) return launch_stream_t<16, 10, 5, 2>(b, sm_count, st);   // dynamic, five CTAs per SM
+  if ((variant & 15) == 11) return launch_stream_t<16, 10, 5, 3>(b, sm_count, st);
   switch (variant & 3) {
     case 0: return launch_short_t<8, 20, false>(b, window_cap, st);
     case 1: return launch_short_t<16, 10, false>(b, window_cap, st);
@@ -470,10 +475,13 @@ __device__ __forceinline__ ShortDesc load_desc(const ShortDesc* __restrict__ d)
 constexpr int kLutEntries = 81;
 constexpr int kLutBytes = kLutEntries * 128;
 
-template <int G, int K, int MINB>
+template <int G, int K, int MINB, int FLAGS>
 __global__ void __launch_bounds__(128, MINB)
 sw_stream_kernel(StreamArgs a)
 {
+  constexpr bool TRK = (FLAGS & 1) != 0;                 // two-step tracker (x = h + e as a plain add, one VIMNMX3 per two steps)
+  constexpr bool DYN = (FLAGS & 2) != 0;                 // couples beyond a group's first kStaticCouples come from a device-wide cursor
+  constexpr uint32_t NSTAT = 5;                          // couples per group assigned statically; the cursor is read NSTAT ahead
   static_assert(K % 2 == 0 && K <= 32, "K even, at most 32 codes per 64-bit code word");
   static_assert(32 % G == 0, "G must divide the warp");
   constexpr int NPAD  = G * K;
@@ -501,8 +509,7 @@ sw_stream_kernel(StreamArgs a)
   const uint32_t NG = gridDim.x * 4 * GPW;
   const uint32_t gidx0 = (blockIdx.x * 4 + warp) * GPW, gidx = gidx0 + g;
   if (gidx0 >= n_pp) return;                             // no pair couple for any group of this warp
-  const uint32_t myN   = gidx < n_pp ? (n_pp - 1 - gidx) / NG + 1 : 0;
-  const uint32_t warpN = (n_pp - 1 - gidx0) / NG + 1;    // the warp's first group has the longest run
+  const uint32_t warpN = (n_pp - 1 - gidx0) / NG + 1;    // static distribution: the warp's first group has the longest run
   uint32_t Wp = (a.counters->max_short_window + 2 * K - 2) / K * K;
   if (Wp < NPAD + K) Wp = NPAD + K;                      // at most two pairs in flight per group
   const uint32_t ipp = Wp / K;                           // iterations per pair
@@ -513,13 +520,23 @@ sw_stream_kernel(StreamArgs a)
   // lane's NEXT pair, and the row trackers a lane parks at its switch until the group folds them together
   uint32_t* qnext = reinterpret_cast<uint32_t*>(smem + kLutBytes + (size_t)4 * GPW * GSTRIDE) + threadIdx.x;
   uint32_t* csave = qnext + K * 128;
+  // Which couple is the group's n-th?  Static: gidx + n*NG.  DYN: the first NSTAT like that, the rest are taken from
+  // counters->stream_cursor one per couple period, NSTAT couples ahead of the one being finished (the ring refill and the
+  // query prefetch never look further), so that a warp the schedulers favour scores more couples instead of leaving early
+  // and every warp of the grid stays resident until the list is empty.  Ids only grow, a group's first id >= n_pp ends its run.
+  uint32_t* cidt = reinterpret_cast<uint32_t*>(smem + kLutBytes + (size_t)4 * GPW * GSTRIDE + (size_t)2 * K * 128 * 4) + (warp * GPW + g) * 8;
+  auto couple_of = [&](uint32_t n) -> uint32_t { return DYN ? cidt[n & 7] : gidx + n * NG; };
+  if (DYN) {
+    if (L < 8) cidt[L] = L < NSTAT ? gidx + L * NG : 0xFFFFFFFFu;
+    __syncwarp();
+  }
 
   // ---- producer side of the ring: columns [k*NPAD + L*K, +K) of the stream per call ----
   uint32_t stg_n = 0, stg_j = L * K;
   auto stage = [&](uint32_t slot) {
     uint64_t cA = 0, cB = 0; int32_t vA = 0, vB = 0;
-    if (stg_n < myN) {
-      const uint32_t pp = gidx + stg_n * NG;
+    const uint32_t pp = couple_of(stg_n);
+    if (pp < n_pp) {
       const ShortDesc dA = load_desc(a.desc + 2 * (uint64_t)pp);
       vA = (int32_t)dA.m - (int32_t)stg_j;
       if (vA > 0) cA = codes32(a.r_pk, dA.r0 + stg_j);
@@ -544,8 +561,8 @@ sw_stream_kernel(StreamArgs a)
   uint32_t Q[K];
   auto load_query = [&](uint32_t n, bool to_regs) {
     uint64_t cA = 0, cB = 0; int32_t vA = 0, vB = 0;
-    if (n < myN) {
-      const uint32_t pp = gidx + n * NG;
+    const uint32_t pp = couple_of(n);
+    if (pp < n_pp) {
       const ShortDesc dA = load_desc(a.desc + 2 * (uint64_t)pp);
       vA = (int32_t)dA.n - (int32_t)(K * L);
       if (vA > 0) cA = codes32(a.q_pk, dA.q0 + K * L);
@@ -575,12 +592,15 @@ sw_stream_kernel(StreamArgs a)
   load_query(1, false);
   __syncwarp();
 
-  uint32_t A[K], B[K], W[K], cur[K];
+  uint32_t A[K], B[K], W[K], cur[K], X[K];
 #pragma unroll
-  for (int m = 0; m < K; ++m) { A[m] = 0xFF00FF00u; B[m] = 0xFF80FF80u; W[m] = WPADV; cur[m] = 0; }
+  for (int m = 0; m < K; ++m) { A[m] = 0xFF00FF00u; B[m] = 0xFF80FF80u; W[m] = WPADV; cur[m] = 0; X[m] = 0; }
   uint32_t recA = 0, recB = 0, prevA = 0, prevB = 0;
   uint32_t floor_ = 0, fm1 = 0xFF80FF80u, upPrev = 0xFF00FF00u;
-  uint32_t e = (uint32_t)(BLOCK - 1) * 0x00010001u;
+  // e = tag - floor per half.  TRK == 1 adds it to h as ONE 32-bit integer: both halves of h are >= floor, so
+  // h_half + e_half >= tag >= 0 and the carry out of the low half cancels the borrow of a negative e_half
+  // exactly when e is held as e_half * 65537 (two's complement)
+  uint32_t e = TRK ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
   int32_t blockStart = 0;
   int32_t pairBase = 0;                                  // first stream column of the lane's current pair
   uint32_t fin_n = 0;
@@ -595,7 +615,7 @@ sw_stream_kernel(StreamArgs a)
   };
   const int32_t Pconst = (int32_t)(((255u - K * L) << 13) + K * L) + (8192 - NPAD - BLOCK);
 
-  const uint32_t n_iters = warpN * ipp + G;
+  const uint32_t n_iters = DYN ? 0xFFFFFFFFu : warpN * ipp + G;
   for (uint32_t it = 0; it < n_iters; ++it) {
     // ---- events at the iteration boundary ----
     if (bit == IPB) {                                    // block end (all lanes): fold, rebase
@@ -613,7 +633,7 @@ sw_stream_kernel(StreamArgs a)
       }
       upPrev = __vsub2(upPrev, REBASE);
       floor_ = 0; fm1 = 0xFF80FF80u;
-      e = (uint32_t)(BLOCK - 1) * 0x00010001u;
+      e = TRK ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
       blockStart += BLOCK;
     }
     if (it == stage_it) {                                // refill the ring one chunk ahead (all lanes)
@@ -647,8 +667,8 @@ sw_stream_kernel(StreamArgs a)
         ka = max(ka, __shfl_xor_sync(0xffffffffu, ka, o, G));
         kb = max(kb, __shfl_xor_sync(0xffffffffu, kb, o, G));
       }
-      if (L == 0 && fin_n < myN) {
-        const uint32_t pp = gidx + fin_n * NG;
+      const uint32_t pp = couple_of(fin_n);
+      if (L == 0 && pp < n_pp) {
         const uint32_t sA = ka >> 21, sB = kb >> 21;
         swb_result ra{0, -1, -1}, rb{0, -1, -1};
         if (sA) ra = swb_result{(int32_t)sA, 255 - (int32_t)((ka >> 13) & 255u), 8191 - NPAD - (int32_t)(ka & 8191u)};
@@ -657,6 +677,17 @@ sw_stream_kernel(StreamArgs a)
         if (2 * pp + 1 < n_list) a.out[a.desc[2 * (uint64_t)pp + 1].pair] = rb;
       }
       load_query(fin_n + 2, false);                      // every lane has consumed the codes of pair fin_n+1
+      if (DYN) {
+        // one cursor read per warp and couple period: the id of each group's couple fin_n + NSTAT
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(const_cast<uint32_t*>(&a.counters->stream_cursor), (uint32_t)GPW);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t next_valid = couple_of(fin_n + 1) < n_pp;
+        __syncwarp();
+        if (L == 0) cidt[(fin_n + NSTAT) & 7] = NSTAT * NG + base + g;
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, next_valid)) break;  // no group of this warp has another couple
+      }
       ++fin_n; fin_it += ipp;
     }
     ++bit;
@@ -692,7 +723,12 @@ sw_stream_kernel(StreamArgs a)
         const uint32_t h  = __vimax3_s16x2(t1, l, floor_);
         if (u & 1) B[m] = h; else A[m] = h;
 #if SWB_ABLATE != 2
-        cur[m] = __viaddmax_s16x2(h, e, cur[m]);
+        if (TRK) {                                       // two steps per tracker update: x = h + e is a plain add (FMA pipe)
+          if (u & 1) cur[m] = __vimax3_s16x2(cur[m], X[m], h + e);
+          else       X[m] = h + e;
+        } else {
+          cur[m] = __viaddmax_s16x2(h, e, cur[m]);
+        }
 #else
         cur[m] |= h;
 #endif
@@ -701,29 +737,29 @@ sw_stream_kernel(StreamArgs a)
 #if SWB_ABLATE != 6
       fm1 = floor_;
       floor_ += 0x00800080u;
-      e = __vsub2(e, 0x00810081u);
+      e = TRK ? e - 129u * 65537u : __vsub2(e, 0x00810081u);
 #endif
     }
   }
 }
 
-template <int G, int K, int MINB>
+template <int G, int K, int MINB, int FLAGS>
 static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
 {
   constexpr int GPW = 32 / G;
   constexpr int GSTRIDE = 4 * G * K * 2 + 128;
   StreamArgs a;
   a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.desc = b.short_desc; a.counters = b.counters; a.out = b.out;
-  const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4;
+  const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4 + (size_t)4 * GPW * 8 * 4;
   static int resident_by_device[64] = {};                // CTAs of this kernel one SM holds (asked once per device)
   int dev_id = 0; cudaGetDevice(&dev_id);
   int& resident = resident_by_device[dev_id & 63];
   if (!resident) {
-    cudaFuncSetAttribute(sw_stream_kernel<G, K, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sw_stream_kernel<G, K, MINB>, 128, smem) != cudaSuccess || resident < 1)
+    cudaFuncSetAttribute(sw_stream_kernel<G, K, MINB, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sw_stream_kernel<G, K, MINB, FLAGS>, 128, smem) != cudaSuccess || resident < 1)
       resident = 1;
     if (const char* v = getenv("SWB_STREAM_CTAS_PER_SM")) { const int w = atoi(v); if (w >= 1 && w <= resident) resident = w; }
-    if (getenv("SWB_DEBUG")) fprintf(stderr, "sw_stream_kernel<%d,%d,%d>: %d resident CTAs/SM, %zu B smem\n", G, K, MINB, resident, smem);
+    if (getenv("SWB_DEBUG")) fprintf(stderr, "sw_stream_kernel<%d,%d,%d,%d>: %d resident CTAs/SM, %zu B smem\n", G, K, MINB, FLAGS, resident, smem);
   }
   // persistent grid: every resident CTA slot of every SM; never more groups than pair couples in the worst case
   const uint64_t n_pp = (b.n_pairs + 1) / 2;
@@ -731,7 +767,7 @@ static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
   if (const char* v = getenv("SWB_STREAM_GRID")) { const long w = atol(v); if (w >= 1) blocks = (uint64_t)w; }
   const uint64_t need = (n_pp + 4 * GPW - 1) / (4 * GPW);
   if (blocks > need) blocks = need;
-  sw_stream_kernel<G, K, MINB><<<(unsigned)blocks, 128, smem, st>>>(a);
+  sw_stream_kernel<G, K, MINB, FLAGS><<<(unsigned)blocks, 128, smem, st>>>(a);
   return 1;
 }
 

@@ -27,6 +27,8 @@ struct Counters {             // device-resident, zeroed per batch
   uint32_t long_cursor;       // work-stealing cursor of the long kernel
   uint32_t n_bytes;           // pairs touching a non-ACGT byte (any length below kLongMaxLen): the same kernel on raw bytes
   uint32_t bytes_cursor;
+  uint32_t stream_cursor;     // sw_stream_kernel: couples handed out beyond every group's static ones
+  uint32_t pad_[3];
 };
 
 struct ShortDesc {            // one entry per short-listed pair, written by classify_kernel (32 B, 16-aligned)

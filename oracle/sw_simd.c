@@ -126,7 +126,8 @@ void sw_simd_force_isa(int isa) { detect_isa(); if (isa >= 0 && isa <= g_isa) g_
 
 typedef struct {
     const uint8_t* q; const uint64_t* qo; const uint8_t* r; const uint64_t* ro;
-    uint64_t lo, hi; sw_result* out; int rc;
+    uint64_t n_pairs, grain; uint64_t* next;     /* shared cursor: workers take `grain` pairs at a time (no static split: */
+    sw_result* out; int rc;                      /*  a thread the OS de-schedules does not hold the whole batch back)      */
 } simd_job;
 
 static void* simd_worker(void* p)
@@ -137,10 +138,15 @@ static void* simd_worker(void* p)
     uint64_t idx[32];
     size_t cap_q = 0, cap_r = 0;
     int16_t *qt = NULL, *rt = NULL; void* hrow = NULL;
-    uint64_t k = jb->lo;
-    while (k < jb->hi) {
+    uint64_t k = 0, hi = 0;
+    for (;;) {
+        if (k >= hi) {
+            k = __atomic_fetch_add(jb->next, jb->grain, __ATOMIC_RELAXED);
+            if (k >= jb->n_pairs) break;
+            hi = k + jb->grain < jb->n_pairs ? k + jb->grain : jb->n_pairs;
+        }
         int cnt = 0; uint32_t maxq = 0, maxr = 0;
-        while (k < jb->hi && cnt < L) {
+        while (k < hi && cnt < L) {
             const uint64_t n1 = jb->qo[k + 1] - jb->qo[k], n2 = jb->ro[k + 1] - jb->ro[k];
             const uint64_t mn = n1 < n2 ? n1 : n2;
             if (isa == 0 || n1 > 32000 || n2 > 32000 || 2 * mn > 32000) {   /* int16 lanes cannot hold it */
@@ -174,15 +180,17 @@ int sw_simd_batch(const uint8_t* q, const uint64_t* qo, const uint8_t* r, const 
                   uint64_t n_pairs, sw_result* out, int n_threads)
 {
     if (n_threads < 1) n_threads = 1;
-    uint64_t blocks = (n_pairs + 31) / 32;
+    const uint64_t blocks = (n_pairs + 31) / 32;
     if ((uint64_t)n_threads > blocks) n_threads = blocks ? (int)blocks : 1;
+    /* pieces of whole 32-pair vectors, about 16 per thread, at most 2048 pairs */
+    uint64_t grain = (blocks / ((uint64_t)n_threads * 16) + 1) * 32;
+    if (grain > 2048) grain = 2048;
+    uint64_t next = 0;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
     simd_job* jobs = (simd_job*)malloc(sizeof(simd_job) * n_threads);
     if (!th || !jobs) { free(th); free(jobs); return -1; }
     for (int t = 0; t < n_threads; ++t) {
-        uint64_t lo = blocks * t / n_threads * 32, hi = blocks * (t + 1) / n_threads * 32;
-        if (hi > n_pairs) hi = n_pairs;
-        jobs[t] = (simd_job){ q, qo, r, ro, lo, hi, out, 0 };
+        jobs[t] = (simd_job){ q, qo, r, ro, n_pairs, grain, &next, out, 0 };
         if (t) pthread_create(&th[t], NULL, simd_worker, &jobs[t]);
     }
     simd_worker(&jobs[0]);

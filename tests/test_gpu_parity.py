@@ -13,7 +13,7 @@ from mini_parallel_b200.engine import to_csr
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sw_vectors.json")))["vectors"]
-ALL_VARIANTS = (0, 1, 2, 3, 4, 5, 6)
+ALL_VARIANTS = (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11)
 
 
 def _rand(rng, n, alphabet=b"ACGT"):
@@ -229,8 +229,9 @@ def test_device_generator_matches_host_twin(engine, dist):
 
 
 def test_config2_full_size_device_resident(engine):
-    """BASELINE.json configs[1] at full size (1 M pairs, 150 x 500), inputs generated and kept in HBM.
-    Checked through size-independent properties plus a 30 k-pair sample against the SIMD oracle."""
+    """BASELINE.json configs[1] at full size (1 M pairs, 150 x 500), inputs generated and kept in HBM.  EVERY pair is
+    compared with the CPU SIMD oracle (bit-exact with sw_linear, tests/test_oracle.py); plus the size-independent
+    properties and the shard == whole check."""
     n, rl, wl = 1_000_000, 150, 500
     dq, dqo = engine.malloc_device(n * rl), engine.malloc_device((n + 1) * 8)
     dr, dro = engine.malloc_device(n * wl), engine.malloc_device((n + 1) * 8)
@@ -244,12 +245,22 @@ def test_config2_full_size_device_resident(engine):
         assert engine.last_routing() == {"short": n, "generic": 0, "long": 0}
         assert out["score"].min() > 200 and out["score"].max() <= 2 * rl            # related reads score high
         assert np.all(out["end_i"] < rl) and np.all(out["end_j"] < wl) and np.all(out["end_i"] >= 0)
-        m = 30_000
-        q = np.zeros(m * rl, dtype=np.uint8); r = np.zeros(m * wl, dtype=np.uint8)
+        q = np.zeros(n * rl, dtype=np.uint8); r = np.zeros(n * wl, dtype=np.uint8)
         engine.d2h(q, dq, q.nbytes); engine.d2h(r, dr, r.nbytes)
-        qo = np.arange(m + 1, dtype=np.uint64) * rl; ro = np.arange(m + 1, dtype=np.uint64) * wl
-        exp = ol.batch(q, qo, r, ro, threads=os.cpu_count() or 8, simd=True)
-        assert np.array_equal(out[:m], exp)
+        qo = np.arange(n + 1, dtype=np.uint64) * rl; ro = np.arange(n + 1, dtype=np.uint64) * wl
+        exp = ol.batch(q, qo, r, ro, threads=os.cpu_count() or 8, simd=True)         # all 1 M pairs, ~0.5 s of host cores
+        bad = np.nonzero(out != exp)[0]
+        assert bad.size == 0, f"{bad.size} of {n} pairs differ, first: pair {bad[0]} got {out[bad[0]]} expected {exp[bad[0]]}"
+        # the unrelated distribution too (scores ~20: the floor path), all pairs
+        engine.synth_device(0, n, rl, wl, 1, dq, dqo, dr, dro)
+        engine.score_batch_device(dq, dqo, n * rl, dr, dro, n * wl, n, rl, wl, dout)
+        engine.sync()
+        out1 = np.zeros(n, dtype=mp.RESULT_DTYPE)
+        engine.d2h(out1, dout, out1.nbytes)
+        engine.d2h(q, dq, q.nbytes); engine.d2h(r, dr, r.nbytes)
+        exp1 = ol.batch(q, qo, r, ro, threads=os.cpu_count() or 8, simd=True)
+        bad = np.nonzero(out1 != exp1)[0]
+        assert bad.size == 0, f"unrelated reads: {bad.size} of {n} pairs differ, first: pair {bad[0]} got {out1[bad[0]]} expected {exp1[bad[0]]}"
         # sharded == whole: score the second half alone (what a second rank would do) and compare
         h = n // 2
         engine.synth_device(h, n - h, rl, wl, 0, dq, dqo, dr, dro)
@@ -348,8 +359,9 @@ def test_reference_windows_chunked(engine):
 
 def test_config4_full_size_long_pairs(engine):
     """BASELINE.json configs[3] at full size: 10 000 pairs of 10 kb x 10 kb (1e12 cells) through sw_long_kernel,
-    inputs generated and kept in HBM.  Checked through size-independent properties -- an identical pair scores 2n and ends
-    in the last cell, the score is symmetric in its arguments, bounds -- plus three pairs against the oracle."""
+    inputs generated and kept in HBM.  EVERY pair is compared with the CPU SIMD oracle (1e12 cells, seconds on the box's
+    host cores); plus the size-independent properties: an identical pair scores 2n and ends in the last cell, the score
+    is symmetric in its arguments, bounds."""
     n, L = 10_000, 10_000
     dq, dqo = engine.malloc_device(n * L), engine.malloc_device((n + 1) * 8)
     dr, dro = engine.malloc_device(n * L), engine.malloc_device((n + 1) * 8)
@@ -363,9 +375,13 @@ def test_config4_full_size_long_pairs(engine):
         assert engine.last_routing() == {"short": 0, "generic": 0, "long": n}
         assert out["score"].min() > 18_000 and out["score"].max() <= 2 * L
         assert np.all(out["end_i"] < L) and np.all(out["end_j"] < L) and np.all(out["end_i"] > 9_000)
-        q = np.zeros(3 * L, dtype=np.uint8); r = np.zeros(3 * L, dtype=np.uint8)
+        q = np.zeros(n * L, dtype=np.uint8); r = np.zeros(n * L, dtype=np.uint8)
         engine.d2h(q, dq, q.nbytes); engine.d2h(r, dr, r.nbytes)
-        for k in range(3):
+        off = np.arange(n + 1, dtype=np.uint64) * L
+        exp = ol.batch(q, off, r, off, threads=os.cpu_count() or 8, simd=True)      # all 10 000 pairs
+        bad = np.nonzero(out != exp)[0]
+        assert bad.size == 0, f"{bad.size} of {n} pairs differ, first: pair {bad[0]} got {out[bad[0]]} expected {exp[bad[0]]}"
+        for k in range(2):                                                           # and the scalar oracle on two of them
             assert tuple(out[k]) == ol.sw_linear(q[k * L:(k + 1) * L].tobytes(), r[k * L:(k + 1) * L].tobytes())
         # symmetry: swapping reads and windows leaves every score unchanged (coordinates follow the tie-break, not checked)
         engine.score_batch_device(dr, dro, n * L, dq, dqo, n * L, n, L, L, dout)
