@@ -5,10 +5,18 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 CSRC      := mini_parallel_b200/csrc
 LIB       := mini_parallel_b200/libswb200.so
 
-all: $(LIB) build/rustseq_mini build/issue_rate_bench build/cell_loop_bench build/inflate_bench oracle
+all: $(LIB) variants build/rustseq_mini build/issue_rate_bench build/cell_loop_bench build/inflate_bench oracle
 
 $(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh include/swb200.h include/rustseq_host.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
+
+# TEST-ONLY build with every short-read / long-pair kernel variant (-DSWB_ALL_VARIANTS): the parity tests load it beside
+# the product library and cross-check the variants against the oracle.  Nothing in the product loads it.
+VARLIB := tests/native/libswb200_variants.so
+variants: $(VARLIB)
+$(VARLIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh include/swb200.h include/rustseq_host.h
+	mkdir -p tests/native
+	$(NVCC) $(NVCCFLAGS) -DSWB_ALL_VARIANTS -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
 
 # the reference's CLI (main.rs) over the library; finds libswb200.so next to the package via rpath
 build/rustseq_mini: $(CSRC)/rustseq_mini_main.cpp $(LIB)
@@ -32,7 +40,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(VARLIB)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean variants

@@ -63,6 +63,34 @@ int  swb_set_reference(swb_ctx*, const uint8_t* ref_bytes, uint64_t n);
 int  swb_score_batch_vs_reference(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off, uint64_t n_pairs,
                                   const uint64_t* win_start, const uint32_t* win_len, swb_result* out);
 
+/* Reads against windows that are RANGES of one HOST buffer: window k is w_bytes[win_start[k], win_start[k]+win_len[k]).
+ * Ranges may overlap, repeat and come in any order -- the candidate windows a read mapper cuts from a genome.  The part of
+ * the buffer the windows touch is uploaded and packed ONCE per call (not once per window), the reads are pipelined against
+ * it in chunks like in swb_score_batch_vs_reference; results are identical to swb_score_batch on the materialised windows.
+ * swb_last_ranges_info: bytes of the buffer the last such call uploaded, and the sum of its window lengths (what a CSR
+ * layout of the same windows would have uploaded).  gpu_align copies both whole strings per call (aligner.rs:478-492). */
+int  swb_score_batch_ranges(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off, uint64_t n_pairs,
+                            const uint8_t* w_bytes, uint64_t w_total_bytes, const uint64_t* win_start, const uint32_t* win_len,
+                            swb_result* out);
+int  swb_last_ranges_info(swb_ctx*, uint64_t* bytes_uploaded, uint64_t* window_bytes);
+
+/* Several devices behind one handle (north_star: each chunk is partitioned across the GPUs of one box with per-GPU
+ * streams; the reference uses devices[0] only, gpu.rs:117-131, main.rs:95).  device_ids == NULL or n_devices <= 0: every
+ * visible device.  One persistent host thread and one swb_ctx (three pipeline streams) per device, created concurrently.
+ * swb_multi_score_batch* cut the batch into contiguous slices of pairs of about equal bytes, one per device; every device
+ * writes its slice of out[]: no inter-GPU traffic, no collective.  Results are identical to the single-device calls.
+ * swb_multi_ctx gives the k-th device's context (tuning knobs, timings); do not score on it while a multi call runs. */
+typedef struct swb_multi swb_multi;
+int  swb_create_multi(swb_multi** out, const int* device_ids, int n_devices, const swb_params* params);
+void swb_destroy_multi(swb_multi*);
+int  swb_multi_device_count(swb_multi*);
+swb_ctx* swb_multi_ctx(swb_multi*, int k);
+int  swb_multi_score_batch(swb_multi*, const uint8_t* q_bytes, const uint64_t* q_off, const uint8_t* r_bytes, const uint64_t* r_off,
+                           uint64_t n_pairs, swb_result* out);
+int  swb_multi_set_reference(swb_multi*, const uint8_t* ref_bytes, uint64_t n);
+int  swb_multi_score_batch_vs_reference(swb_multi*, const uint8_t* q_bytes, const uint64_t* q_off, uint64_t n_pairs,
+                                        const uint64_t* win_start, const uint32_t* win_len, swb_result* out);
+
 /* FASTQ.gz ingest on the GPU for blocked gzip (BGZF: bgzip, BCL Convert): replaces the `zcat` child and the per-line
  * String loop of process_fastq_file_in_chunks (aligner.rs:107-178) for the --full-wgs path.  The host only walks the
  * block headers; a segment of whole blocks is copied to the device, inflated one warp per block, indexed (every 4th
@@ -85,7 +113,11 @@ int  swb_fastq_bgzf_score(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, co
                           uint8_t* carry_out, uint64_t carry_cap, uint64_t* carry_out_len, int* status);
 
 /* Same, DEVICE-resident inputs and outputs (pointers from cudaMalloc / a torch tensor's data_ptr);
- * runs on the context's stream, returns after the work is enqueued; swb_sync() waits. */
+ * runs on the context's stream, returns after the work is enqueued; swb_sync() waits.
+ * max_r_len is a HARD upper bound of the window lengths (the boundary-row scratch of the long-pair kernels is sized from
+ * it before the device has seen the offsets): a pair whose window is longer is not scored -- its result is
+ * (INT32_MIN, -1, -1) -- and swb_sync() / swb_last_routing() fail saying how many there were.  max_q_len is a hint only
+ * (0 = unknown): it picks the long-pair kernel's band height. */
 int  swb_score_batch_device(swb_ctx*, const uint8_t* d_q_bytes, const uint64_t* d_q_off, uint64_t q_total_bytes,
                             const uint8_t* d_r_bytes, const uint64_t* d_r_off, uint64_t r_total_bytes,
                             uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out);
@@ -111,6 +143,11 @@ int  swb_pack2bit(swb_ctx*, const uint8_t* bytes, uint64_t n, uint32_t* packed_w
  * [first_pair, first_pair + n_pairs) of shape read_len x window_len.  Device pointers. */
 int  swb_synth_device(swb_ctx*, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len,
                       int distribution, uint8_t* d_q_bytes, uint64_t* d_q_off, uint8_t* d_r_bytes, uint64_t* d_r_off);
+/* The same with windows CUT FROM A REFERENCE (device pointer, ref_len bases): window p starts at draw(0xB202, 0) mod
+ * (ref_len - window_len + 1), the read is made from it by the same rule.  Also writes the window starts. */
+int  swb_synth_device_ref(swb_ctx*, const uint8_t* d_ref, uint64_t ref_len, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len,
+                          uint32_t window_len, int distribution, uint8_t* d_q_bytes, uint64_t* d_q_off, uint8_t* d_r_bytes,
+                          uint64_t* d_r_off, uint64_t* d_win_start);
 
 /* Per-stage device times of the last swb_score_batch* call on this context, CUDA events on the
  * context's stream (ms): [0] pack, [1] short-read kernel, [2] generic kernel, [3] total device span,
@@ -140,9 +177,11 @@ int  swb_traceback_batch(swb_ctx*, const uint8_t* q_bytes, const uint64_t* q_off
                          uint64_t n_pairs, const swb_result* results, swb_alignment* out,
                          uint32_t* cigar, uint64_t cigar_cap, uint64_t* cigar_used);
 
-/* Tuning knob: which instantiation of the short-read kernel runs.  4 (default), 5, 6: the streaming kernel
- * (16 lanes x 10 rows at 4 or 5 CTAs/SM, 8 lanes x 20 rows); 0..3: the one-couple-per-group kernel (bit0: 0 = 8 lanes
- * x 20 rows, 1 = 16 lanes x 10 rows; bit1: split end-cell tracking).  All variants return identical results. */
+/* Which instantiation of the short-read kernel runs.  9 (default, the only one in the product library): the streaming
+ * kernel, 16 lanes x 10 rows, two-step end-cell tracker, couples handed out dynamically.  The test build (make variants,
+ * -DSWB_ALL_VARIANTS) also carries 4..8, 10, 11 (earlier stream kernels) and 0..3 (the one-couple-per-group kernel) as
+ * independent implementations the parity tests cross-check.  All variants return identical results; asking for one the
+ * build does not have fails. */
 int  swb_set_short_variant(swb_ctx*, int variant);
 
 /* Host batches (swb_score_batch, swb_score_batch_vs_reference) are cut into chunks of about chunk_bytes of ASCII

@@ -7,7 +7,7 @@ the tests, ``bench.py`` and ``__graft_entry__``.  There is no CPU fallback: load
 loudly when ``libswb200.so`` has not been built (``make`` / ``__graft_entry__.build()``).
 """
 from ._lib import load_library, LIB_PATH, SwbResult, RESULT_DTYPE  # noqa: F401
-from .engine import Engine, SwbError, device_count  # noqa: F401
+from .engine import Engine, MultiEngine, SwbError, device_count  # noqa: F401
 from . import aligner  # noqa: F401
 
-__all__ = ["Engine", "SwbError", "device_count", "load_library", "LIB_PATH", "SwbResult", "RESULT_DTYPE", "aligner"]
+__all__ = ["Engine", "MultiEngine", "SwbError", "device_count", "load_library", "LIB_PATH", "SwbResult", "RESULT_DTYPE", "aligner"]

@@ -33,6 +33,16 @@ SIGNATURES = {
     "swb_sync": (_int, [_vp]),
     "swb_set_reference": (_int, [_vp, _u8p, _u64]),
     "swb_score_batch_vs_reference": (_int, [_vp, _u8p, _vp, _u64, _vp, _vp, _vp]),
+    "swb_score_batch_ranges": (_int, [_vp, _u8p, _vp, _u64, _u8p, _u64, _vp, _vp, _vp]),
+    "swb_last_ranges_info": (_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
+    "swb_create_multi": (_int, [ctypes.POINTER(_vp), _vp, _int, _vp]),
+    "swb_destroy_multi": (None, [_vp]),
+    "swb_multi_device_count": (_int, [_vp]),
+    "swb_multi_ctx": (_vp, [_vp, _int]),
+    "swb_multi_score_batch": (_int, [_vp, _u8p, _vp, _u8p, _vp, _u64, _vp]),
+    "swb_multi_set_reference": (_int, [_vp, _u8p, _u64]),
+    "swb_multi_score_batch_vs_reference": (_int, [_vp, _u8p, _vp, _u64, _vp, _vp, _vp]),
+    "swb_synth_device_ref": (_int, [_vp, _vp, _u64, _u64, _u64, _u32, _u32, _int, _vp, _vp, _vp, _vp, _vp]),
     "swb_ref_compat_align": (_int, [_vp, _u8p, _u64, _u8p, _u64, _u32, ctypes.POINTER(ctypes.c_int32)]),
     "swb_last_row_max": (_int, [_vp, _u8p, _u64, _u8p, _u64, ctypes.POINTER(ctypes.c_int32)]),
     "swb_pack2bit": (_int, [_vp, _u8p, _u64, _vp, _vp]),
@@ -64,19 +74,23 @@ SIGNATURES = {
 _lib = None
 
 
-def load_library():
-    """Load libswb200.so.  Raises (never falls back) when the CUDA library is missing."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def bind(path):
+    """ctypes handle of one build of the library with every declared symbol typed."""
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build the CUDA library first (make, or __graft_entry__.build()). "
+            f"{path} is missing: build the CUDA library first (make, or __graft_entry__.build()). "
             "There is no CPU fallback in this package.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError = the library does not export what the header declares
         fn.restype = res
         fn.argtypes = args
-    _lib = lib
     return lib
+
+
+def load_library():
+    """Load libswb200.so.  Raises (never falls back) when the CUDA library is missing."""
+    global _lib
+    if _lib is None:
+        _lib = bind(LIB_PATH)
+    return _lib

@@ -13,6 +13,10 @@
 #include <fstream>
 #include <unistd.h>
 #include <sys/syscall.h>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <functional>
 
 namespace swb {
 int launch_generic_single(const BatchView& b, int32_t* last_row_out, cudaStream_t st);
@@ -56,11 +60,24 @@ constexpr int kLanes = 6;                  // pipeline lanes a context owns; a h
 
 struct ChunkEvents { cudaEvent_t ev[8]; };
 
+// The packed text the windows of a batch are cut from: the resident reference (swb_set_reference) or the window buffer of
+// one swb_score_batch_ranges call.  Window coordinates are relative to `base` (the first byte that was uploaded).
+struct RefSrc {
+  const uint8_t* bytes = nullptr; const uint32_t* pk = nullptr; const uint32_t* bad = nullptr;
+  uint64_t len = 0;            // bytes the caller's coordinates may address
+  uint64_t base = 0;           // caller coordinate of bytes[0]
+  cudaEvent_t ready = nullptr; // recorded after upload + pack (lanes other than the uploading one wait for it)
+};
+
 struct swb_ctx : Lane {                    // lane 0 is the context itself (device-resident API, single-pair calls)
   int device = 0, sm_count = 0;
   Lane extra[kLanes - 1];
   Lane* lane(int i) { return i == 0 ? static_cast<Lane*>(this) : &extra[i - 1]; }
   DevBuf ref_bytes, ref_pk, ref_bad;       // device-resident reference (swb_set_reference)
+  DevBuf call_ref_bytes, call_ref_pk, call_ref_bad;   // window buffer of one swb_score_batch_ranges call
+  cudaEvent_t call_ref_ready = nullptr;
+  swb::LaunchCfg lc;                       // launch state of this context's kernels (no process-wide statics)
+  uint64_t last_ranges_uploaded = 0, last_ranges_window_bytes = 0;   // swb_last_ranges_info
   // swb_fastq_bgzf_score / _prefetch: two segment slots (compressed bytes, block table, text) so that the next segment can be
   // copied in and inflated on lane 1's stream while this one is indexed and scored on lane 0's
   struct FqSlot {
@@ -87,7 +104,7 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   int last_kernels = 0;
   uint64_t last_routing[3] = {0, 0, 0};
   bool timings_pending = false, host_path = false;
-  int variant = 4;
+  int variant = 9;                         // sw_stream_kernel<16,10,4, two-step tracker + dynamic couple distribution>
   int force_bytes = 0;                     // SWB_FORCE_BYTES=1: every non-short pair through the byte-compare kernel (bench / tests)
 };
 
@@ -138,12 +155,13 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device_id) != cudaSuccess) { delete c; return fail("cudaGetDeviceProperties failed"); }
   c->sm_count = p.multiProcessorCount;
+  swb::launch_cfg_init(c->lc, c->sm_count);
   for (int i = 0; i < kLanes; ++i) {
     Lane* l = c->lane(i);
     if (cudaStreamCreateWithFlags(&l->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return fail("cudaStreamCreate failed"); }
     for (auto& e : l->ev) cudaEventCreate(&e);
   }
-  if (const char* v = std::getenv("SWB_SHORT_VARIANT")) c->variant = std::atoi(v) & 15;
+  if (const char* v = std::getenv("SWB_SHORT_VARIANT")) { const int w = std::atoi(v) & 15; if (swb::short_variant_available(w)) c->variant = w; }
   if (const char* v = std::getenv("SWB_FORCE_BYTES")) c->force_bytes = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_UNIFORM_OFFSETS")) c->uniform_offsets = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_LANES")) c->n_lanes = std::min(kLanes, std::max(1, std::atoi(v)));
@@ -164,6 +182,8 @@ void swb_destroy(swb_ctx* c)
     for (auto& e : l->ev) cudaEventDestroy(e);
     cudaStreamDestroy(l->st);
   }
+  if (c->call_ref_ready) cudaEventDestroy(c->call_ref_ready);
+  for (DevBuf* b : {&c->call_ref_bytes, &c->call_ref_pk, &c->call_ref_bad}) b->release();
   for (DevBuf* b : {&c->ref_bytes, &c->ref_pk, &c->ref_bad, &c->fq_tile_count, &c->fq_tile_prefix, &c->fq_seq_beg, &c->fq_seq_end, &c->fq_scal,
                     &c->tb_scratch, &c->tb_res, &c->tb_out, &c->tb_cigar, &c->tb_cursor, &c->tb_handled}) b->release();
   for (auto& sl : c->fq_slot) {
@@ -207,7 +227,13 @@ void swb_numa_reset(void)
 }
 
 void* swb_stream(swb_ctx* c) { return c ? (void*)c->st : nullptr; }
-int   swb_set_short_variant(swb_ctx* c, int v) { if (!c) return fail("null ctx"); c->variant = v & 15; return 0; }
+int   swb_set_short_variant(swb_ctx* c, int v)
+{
+  if (!c) return fail("null ctx");
+  if (!swb::short_variant_available(v)) return fail("swb_set_short_variant: variant " + std::to_string(v) + " is not in this build (the product library carries the default, 9; the others are in the test build, make variants)");
+  c->variant = v;
+  return 0;
+}
 
 int swb_set_chunking(swb_ctx* c, uint64_t chunk_bytes, uint64_t min_chunk_pairs)
 {
@@ -230,6 +256,11 @@ int swb_sync(swb_ctx* c)
   if (!c) return fail("null ctx");
   CUDA_TRY(cudaSetDevice(c->device));
   for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamSynchronize(c->lane(i)->st));
+  if (c->timings_pending && !c->host_path && c->counters.p) {         // a device batch: was the caller's window bound right?
+    uint32_t refused = 0;
+    CUDA_TRY(cudaMemcpy(&refused, &c->counters.as<swb::Counters>()->n_overflow, 4, cudaMemcpyDeviceToHost));
+    if (refused) return fail("swb_score_batch_device: " + std::to_string(refused) + " pairs have a window longer than max_r_len; they were not scored (score INT32_MIN)");
+  }
   return 0;
 }
 
@@ -238,11 +269,12 @@ int swb_sync(swb_ctx* c)
 // (d_rend == d_rbeg + 1, packed here) or ranges of the resident, already packed reference (ref_windows).
 static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8_t* d_q, const uint64_t* d_qo, uint64_t q_total,
                                const uint8_t* d_r, const uint64_t* d_rbeg, const uint64_t* d_rend, uint64_t r_total,
-                               bool ref_windows, uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out, int* kernels,
+                               const RefSrc* ref /* windows are ranges of this packed text; nullptr: CSR windows in d_r */, uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out, int* kernels,
                                const uint64_t* d_qend = nullptr /* reads as [beg,end) ranges instead of CSR */,
                                bool q_prepacked = false /* lane's q_pk / q_bad already hold the packed d_q */)
 {
   if (n_pairs >= (1ull << 32)) return fail("swb: at most 2^32-1 pairs per batch");
+  const bool ref_windows = ref != nullptr;
   const uint64_t qw = (q_total + 15) / 16, rw = ref_windows ? 0 : (r_total + 15) / 16;
   if (l->q_pk.reserve(qw * 4 + 64) || l->r_pk.reserve(rw * 4 + 64) ||
       l->q_bad.reserve((qw + 31) / 32 * 4 + 64) || l->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
@@ -259,14 +291,14 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   swb::BatchView b;
   b.q_bytes = d_q; b.q_beg = d_qo; b.q_end = d_qend ? d_qend : d_qo + 1; b.r_bytes = d_r; b.r_beg = d_rbeg; b.r_end = d_rend;
   b.q_pk = l->q_pk.as<uint32_t>(); b.q_bad = l->q_bad.as<uint32_t>();
-  b.r_pk = ref_windows ? c->ref_pk.as<uint32_t>() : l->r_pk.as<uint32_t>();
-  b.r_bad = ref_windows ? c->ref_bad.as<uint32_t>() : l->r_bad.as<uint32_t>();
+  b.r_pk = ref_windows ? ref->pk : l->r_pk.as<uint32_t>();
+  b.r_bad = ref_windows ? ref->bad : l->r_bad.as<uint32_t>();
   b.n_pairs = n_pairs;
   b.short_list = l->short_list.as<uint32_t>(); b.short_desc = l->short_desc.as<swb::ShortDesc>();
   b.generic_list = l->generic_list.as<uint32_t>(); b.long_list = l->long_list.as<uint32_t>(); b.bytes_list = l->bytes_list.as<uint32_t>();
   b.force_bytes = c->force_bytes;
   b.counters = l->counters.as<swb::Counters>(); b.out = d_out;
-  b.scratch = l->scratch.as<int32_t>(); b.scratch_stride = stride;
+  b.scratch = l->scratch.as<int32_t>(); b.scratch_stride = stride; b.max_window = max_r_len;
 
   int k = 0;
   cudaStream_t st = l->st;
@@ -274,18 +306,19 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   CUDA_TRY(cudaEventRecord(ev[0], st));
   if (!q_prepacked) k += swb::launch_pack2bit(d_q, q_total, l->q_pk.as<uint32_t>(), l->q_bad.as<uint32_t>(), st);
   if (!ref_windows) k += swb::launch_pack2bit(d_r, r_total, l->r_pk.as<uint32_t>(), l->r_bad.as<uint32_t>(), st);
+  if (ref_windows && ref->ready) CUDA_TRY(cudaStreamWaitEvent(st, ref->ready, 0));
   k += swb::launch_classify(b, st);
   CUDA_TRY(cudaEventRecord(ev[1], st));
   const uint32_t wcap = std::min<uint32_t>(std::max<uint32_t>(max_r_len, 1), swb::kShortMaxWindow);
-  k += swb::launch_short(b, wcap, c->variant, c->sm_count, st);
+  k += swb::launch_short(b, wcap, c->variant, c->lc, st);
   CUDA_TRY(cudaEventRecord(ev[2], st));
   k += swb::launch_generic(b, ctas / 4 > 0 ? ctas / 4 : 1, 0, st);
   {
     swb::BatchView bl = b;
     bl.scratch = l->long_scratch.as<int32_t>();
-    k += swb::launch_long(bl, ctas, max_q_len, st);
+    k += swb::launch_long(bl, ctas, max_q_len, c->lc, st);
     bl.scratch = l->bytes_scratch.as<int32_t>();
-    k += swb::launch_long_bytes(bl, ctas, max_q_len, st);
+    k += swb::launch_long_bytes(bl, ctas, max_q_len, c->lc, st);
   }
   CUDA_TRY(cudaEventRecord(ev[3], st));
   CUDA_TRY(cudaGetLastError());
@@ -302,7 +335,7 @@ int swb_score_batch_device(swb_ctx* c, const uint8_t* d_q, const uint64_t* d_qo,
   c->host_path = false;
   c->last_kernels = 0; c->last_chunks = 0;
   if (n_pairs == 0) { c->timings_pending = false; return 0; }
-  if (run_device_pipeline(c, c, c->ev, d_q, d_qo, q_total, d_r, d_ro, d_ro + 1, r_total, false, n_pairs,
+  if (run_device_pipeline(c, c, c->ev, d_q, d_qo, q_total, d_r, d_ro, d_ro + 1, r_total, nullptr, n_pairs,
                           max_q_len ? max_q_len : 0xffffffffu, max_r_len, d_out, &c->last_kernels)) return 1;
   c->timings_pending = true;
   return 0;
@@ -328,14 +361,22 @@ static int ensure_chunk_slots(swb_ctx* c, size_t n_chunks)
   return 0;
 }
 
+static RefSrc resident_ref(swb_ctx* c)
+{
+  RefSrc r;
+  r.bytes = c->ref_bytes.as<uint8_t>(); r.pk = c->ref_pk.as<uint32_t>(); r.bad = c->ref_bad.as<uint32_t>(); r.len = c->ref_len;
+  return r;
+}
+
+// q / r are the bases of the caller's byte arrays and qo / ro hold ABSOLUTE offsets into them, so a slice of a larger batch
+// (swb_multi_score_batch: pairs [lo, hi) of the whole) is scored by passing qo + lo, ro + lo, out + lo unchanged.
 static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* q, const uint64_t* qo,
                                    const uint8_t* r, const uint64_t* ro,                     /* CSR windows, or */
-                                   const uint64_t* win_start, const uint32_t* win_len,       /* windows of the resident reference */
-                                   uint64_t n_pairs, swb_result* out)
+                                   const uint64_t* win_start, const uint32_t* win_len,       /* windows of `ref` */
+                                   const RefSrc* ref, uint64_t n_pairs, swb_result* out)
 {
   const bool ref_windows = (r == nullptr && ro == nullptr);
-  if (qo[0] != 0 || (!ref_windows && ro[0] != 0)) return fail(std::string(who) + ": offsets must start at 0");
-  const uint64_t bytes_total = qo[n_pairs] + (ref_windows ? 0 : ro[n_pairs]);
+  const uint64_t bytes_total = (qo[n_pairs] - qo[0]) + (ref_windows ? 0 : ro[n_pairs] - ro[0]);
   const uint64_t cb = ref_windows ? std::max<uint64_t>(c->chunk_bytes / 2, 1) : c->chunk_bytes;
   uint64_t n_uniform = std::max<uint64_t>(1, (bytes_total + cb - 1) / cb);
   uint64_t per = (n_pairs + n_uniform - 1) / n_uniform;
@@ -380,14 +421,17 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
     // offsets: the device writes k * length itself -- two of the chunk's four copies and 16 bytes per pair stay home.
     const uint64_t q_len0 = qo[p0 + 1] - qo[p0], r_len0 = ref_windows ? 0 : ro[p0 + 1] - ro[p0];
     bool q_uniform = q_len0 != 0 && c->uniform_offsets, r_uniform = !ref_windows && r_len0 != 0 && c->uniform_offsets;
+    const uint32_t w_len0 = ref_windows ? win_len[p0] : 0;
+    bool w_uniform = ref_windows && w_len0 != 0 && c->uniform_offsets;
     for (uint64_t k = p0; k < p1; ++k) {                      // validation + longest read / window of this chunk
       if (qo[k + 1] < qo[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
       if (qo[k + 1] - qo[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
       max_q = std::max<uint32_t>(max_q, (uint32_t)(qo[k + 1] - qo[k]));
       q_uniform &= qo[k + 1] - qo[k] == q_len0;
       if (ref_windows) {
-        if (win_start[k] + win_len[k] > c->ref_len) return fail(std::string(who) + ": window outside the reference");
+        if (win_start[k] > ref->len || win_len[k] > ref->len - win_start[k]) return fail(std::string(who) + ": window outside the reference");
         max_r = std::max<uint32_t>(max_r, win_len[k]);
+        w_uniform &= win_len[k] == w_len0;
       } else {
         if (ro[k + 1] < ro[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
         if (ro[k + 1] - ro[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
@@ -406,24 +450,24 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
     int k = 0;
     if (ref_windows) {
       CUDA_TRY(cudaMemcpyAsync(l->win_beg.p, win_start + p0, n * 8, cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(l->win_len.p, win_len + p0, n * 4, cudaMemcpyHostToDevice, st));
+      if (!w_uniform) CUDA_TRY(cudaMemcpyAsync(l->win_len.p, win_len + p0, n * 4, cudaMemcpyHostToDevice, st));
       k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], q_uniform ? q_len0 : 0, nullptr, 0, 0, 0,
-                                     l->win_beg.as<uint64_t>(), l->win_len.as<uint32_t>(), l->win_end.as<uint64_t>(), n, st);
+                                     l->win_beg.as<uint64_t>(), l->win_len.as<uint32_t>(), w_uniform ? w_len0 : 0, l->win_end.as<uint64_t>(), n, ref->base, st);
     } else {
       if (rb) CUDA_TRY(cudaMemcpyAsync(l->r_bytes.p, r + ro[p0], rb, cudaMemcpyHostToDevice, st));
       if (!r_uniform) CUDA_TRY(cudaMemcpyAsync(l->r_off.p, ro + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
       k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], q_uniform ? q_len0 : 0, l->r_off.as<uint64_t>(), n + 1, ro[p0],
-                                     r_uniform ? r_len0 : 0, nullptr, nullptr, nullptr, 0, st);
+                                     r_uniform ? r_len0 : 0, nullptr, nullptr, 0, nullptr, 0, 0, st);
     }
     CUDA_TRY(cudaEventRecord(ev[5], st));
     c->last_kernels += k;
     if (ref_windows) {
-      if (run_device_pipeline(c, l, ev, l->q_bytes.as<uint8_t>(), l->q_off.as<uint64_t>(), qb, c->ref_bytes.as<uint8_t>(),
-                              l->win_beg.as<uint64_t>(), l->win_end.as<uint64_t>(), 0, true, n, max_q, max_r, l->out.as<swb_result>(),
+      if (run_device_pipeline(c, l, ev, l->q_bytes.as<uint8_t>(), l->q_off.as<uint64_t>(), qb, ref->bytes,
+                              l->win_beg.as<uint64_t>(), l->win_end.as<uint64_t>(), 0, ref, n, max_q, max_r, l->out.as<swb_result>(),
                               &c->last_kernels)) return 1;
     } else {
       if (run_device_pipeline(c, l, ev, l->q_bytes.as<uint8_t>(), l->q_off.as<uint64_t>(), qb, l->r_bytes.as<uint8_t>(),
-                              l->r_off.as<uint64_t>(), l->r_off.as<uint64_t>() + 1, rb, false, n, max_q, max_r, l->out.as<swb_result>(),
+                              l->r_off.as<uint64_t>(), l->r_off.as<uint64_t>() + 1, rb, nullptr, n, max_q, max_r, l->out.as<swb_result>(),
                               &c->last_kernels)) return 1;
     }
     CUDA_TRY(cudaEventRecord(ev[6], st));
@@ -438,9 +482,9 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
 }
 
 static int score_host_batch(swb_ctx* c, const char* who, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro,
-                            const uint64_t* win_start, const uint32_t* win_len, uint64_t n_pairs, swb_result* out)
+                            const uint64_t* win_start, const uint32_t* win_len, const RefSrc* ref, uint64_t n_pairs, swb_result* out)
 {
-  const int rc = score_host_batch_enqueue(c, who, q, qo, r, ro, win_start, win_len, n_pairs, out);
+  const int rc = score_host_batch_enqueue(c, who, q, qo, r, ro, win_start, win_len, ref, n_pairs, out);
   if (rc != 0) {
     // an error after some chunks were enqueued: the caller's buffers are borrowed for the call only, so nothing may
     // still be reading or writing them when we return
@@ -459,9 +503,10 @@ int swb_score_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint
   if (!c) return fail("null ctx");
   if (n_pairs == 0) return 0;
   if (!qo || !ro || !out) return fail("swb_score_batch: null pointer");
+  if (qo[0] != 0 || ro[0] != 0) return fail("swb_score_batch: offsets must start at 0");
   CUDA_TRY(cudaSetDevice(c->device));
   static const uint8_t empty = 0;
-  return score_host_batch(c, "swb_score_batch", q ? q : &empty, qo, r ? r : &empty, ro, nullptr, nullptr, n_pairs, out);
+  return score_host_batch(c, "swb_score_batch", q ? q : &empty, qo, r ? r : &empty, ro, nullptr, nullptr, nullptr, n_pairs, out);
 }
 
 // ---- reads against windows of a device-resident reference ----
@@ -486,9 +531,56 @@ int swb_score_batch_vs_reference(swb_ctx* c, const uint8_t* q, const uint64_t* q
   if (!c) return fail("null ctx");
   if (n_pairs == 0) return 0;
   if (!qo || !win_start || !win_len || !out) return fail("swb_score_batch_vs_reference: null pointer");
+  if (qo[0] != 0) return fail("swb_score_batch_vs_reference: offsets must start at 0");
   CUDA_TRY(cudaSetDevice(c->device));
   static const uint8_t empty = 0;
-  return score_host_batch(c, "swb_score_batch_vs_reference", q ? q : &empty, qo, nullptr, nullptr, win_start, win_len, n_pairs, out);
+  const RefSrc ref = resident_ref(c);
+  return score_host_batch(c, "swb_score_batch_vs_reference", q ? q : &empty, qo, nullptr, nullptr, win_start, win_len, &ref, n_pairs, out);
+}
+
+// ---- reads against windows that are RANGES of one host buffer (they may overlap, repeat, come in any order) ----
+// What a read mapper hands over: candidate windows of a genome, many of them sharing bases.  The covered part of the buffer
+// crosses PCIe once per call -- not once per window -- is packed once, and the reads are pipelined against it like against
+// the resident reference.  1 M windows of 500 bp in a 16 Mbase buffer: 16 MB on the wire instead of 500 MB.
+int swb_score_batch_ranges(swb_ctx* c, const uint8_t* q, const uint64_t* qo, uint64_t n_pairs,
+                           const uint8_t* w_bytes, uint64_t w_total, const uint64_t* win_start, const uint32_t* win_len, swb_result* out)
+{
+  if (!c) return fail("null ctx");
+  if (n_pairs == 0) return 0;
+  if (!qo || !win_start || !win_len || !out || (w_total && !w_bytes)) return fail("swb_score_batch_ranges: null pointer");
+  if (qo[0] != 0) return fail("swb_score_batch_ranges: offsets must start at 0");
+  CUDA_TRY(cudaSetDevice(c->device));
+  uint64_t lo = w_total, hi = 0, sum = 0;                 // the part of the buffer the windows touch
+  for (uint64_t k = 0; k < n_pairs; ++k) {
+    const uint64_t s = win_start[k], n = win_len[k];
+    if (s > w_total || n > w_total - s) return fail("swb_score_batch_ranges: window outside the buffer");
+    if (n) { lo = std::min(lo, s); hi = std::max(hi, s + n); sum += n; }
+  }
+  if (hi <= lo) { lo = 0; hi = 0; }
+  lo &= ~511ull;                                          // one bitmap word = 32 packed words = 512 bases
+  const uint64_t n = hi - lo, nw = (n + 15) / 16;
+  if (c->call_ref_bytes.reserve(n + 64) || c->call_ref_pk.reserve(nw * 4 + 64) || c->call_ref_bad.reserve((nw + 31) / 32 * 4 + 64)) return 1;
+  if (!c->call_ref_ready) CUDA_TRY(cudaEventCreateWithFlags(&c->call_ref_ready, cudaEventDisableTiming));
+  cudaStream_t st = c->st;                                // lane 0: the first chunk follows on the same stream
+  if (n) CUDA_TRY(cudaMemcpyAsync(c->call_ref_bytes.p, w_bytes + lo, n, cudaMemcpyHostToDevice, st));
+  swb::launch_pack2bit(c->call_ref_bytes.as<uint8_t>(), n, c->call_ref_pk.as<uint32_t>(), c->call_ref_bad.as<uint32_t>(), st);
+  CUDA_TRY(cudaEventRecord(c->call_ref_ready, st));
+  RefSrc ref;
+  ref.bytes = c->call_ref_bytes.as<uint8_t>(); ref.pk = c->call_ref_pk.as<uint32_t>(); ref.bad = c->call_ref_bad.as<uint32_t>();
+  ref.len = w_total; ref.base = lo; ref.ready = c->call_ref_ready;
+  c->last_ranges_uploaded = n; c->last_ranges_window_bytes = sum;
+  static const uint8_t empty = 0;
+  const int rc = score_host_batch(c, "swb_score_batch_ranges", q ? q : &empty, qo, nullptr, nullptr, win_start, win_len, &ref, n_pairs, out);
+  if (rc == 0) c->last_kernels += n ? 1 : 0;
+  return rc;
+}
+
+int swb_last_ranges_info(swb_ctx* c, uint64_t* bytes_uploaded, uint64_t* window_bytes)
+{
+  if (!c) return fail("null ctx");
+  if (bytes_uploaded) *bytes_uploaded = c->last_ranges_uploaded;
+  if (window_bytes) *window_bytes = c->last_ranges_window_bytes;
+  return 0;
 }
 
 // ---- FASTQ.gz (BGZF) -> scores entirely on the device ----
@@ -632,8 +724,9 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
     const uint64_t n = std::min(batch, R - a);
     k += swb::launch_fq_windows(file_index, first_read + a, n, c->ref_len, window_len, d_beg + a, d_end + a, c->win_beg.as<uint64_t>(),
                                 c->win_end.as<uint64_t>(), st);
+    const RefSrc rref = resident_ref(c);
     if (run_device_pipeline(c, c, c->ev, d_text, d_beg + a, end, c->ref_bytes.as<uint8_t>(), c->win_beg.as<uint64_t>(),
-                            c->win_end.as<uint64_t>(), 0, true, n, 0xffffffffu, window_len, c->out.as<swb_result>(), &k, d_end + a, true)) return 1;
+                            c->win_end.as<uint64_t>(), 0, &rref, n, 0xffffffffu, window_len, c->out.as<swb_result>(), &k, d_end + a, true)) return 1;
     k += swb::launch_fq_reduce(c->out.as<swb_result>(), d_beg + a, d_end + a, n, reinterpret_cast<unsigned long long*>(d_scal + 2), st);
   }
   if (dbg) cudaEventRecord(te[4], st);
@@ -894,6 +987,17 @@ int swb_synth_device(swb_ctx* c, uint64_t first_pair, uint64_t n_pairs, uint32_t
   return 0;
 }
 
+int swb_synth_device_ref(swb_ctx* c, const uint8_t* d_ref, uint64_t ref_len, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len,
+                         uint32_t window_len, int distribution, uint8_t* d_q, uint64_t* d_qo, uint8_t* d_r, uint64_t* d_ro, uint64_t* d_win_start)
+{
+  if (!c) return fail("null ctx");
+  if (!d_ref || window_len == 0 || window_len > ref_len) return fail("swb_synth_device_ref: the window must fit the reference");
+  CUDA_TRY(cudaSetDevice(c->device));
+  swb::launch_synth_ref(d_ref, ref_len, first_pair, n_pairs, read_len, window_len, distribution, d_q, d_qo, d_r, d_ro, d_win_start, c->st);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 // raw device / pinned memory for callers without a CUDA runtime of their own (CLI, ctypes tests)
 int swb_malloc_device(swb_ctx* c, uint64_t bytes, void** out)
 {
@@ -925,6 +1029,162 @@ int swb_memcpy_h2d(swb_ctx* c, void* dst, const void* src, uint64_t bytes)
   CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->st));
   CUDA_TRY(cudaStreamSynchronize(c->st));
   return 0;
+}
+
+// =====================================================================================
+// Several devices behind one handle (north_star: "each chunk is partitioned across the 8 GPUs of one box with per-GPU
+// streams"; the reference drives devices[0] only, gpu.rs:117-131, main.rs:95).  One persistent host thread per device owns
+// that device's swb_ctx (three pipeline streams each); a batch is cut into contiguous slices of pairs of about equal
+// bytes, every slice is scored by its device into its own part of the caller's result array -- no inter-GPU traffic, no
+// collective.  The contexts are created by their threads, i.e. concurrently.
+// =====================================================================================
+}  // extern "C"
+
+struct swb_multi {
+  struct Worker {
+    int device = 0; swb_ctx* ctx = nullptr;
+    std::thread th; std::mutex mu; std::condition_variable cv;
+    std::function<int(swb_ctx*)> job; bool has_job = false, done = false, quit = false;
+    int rc = 0; std::string err;
+  };
+  std::vector<Worker*> w;
+  // run fn(k, ctx) on every worker concurrently; returns the first failure
+  int run(const std::function<int(int, swb_ctx*)>& fn)
+  {
+    for (size_t k = 0; k < w.size(); ++k) {
+      Worker* x = w[k];
+      std::lock_guard<std::mutex> lk(x->mu);
+      x->job = [fn, k](swb_ctx* c) { return fn((int)k, c); };
+      x->has_job = true; x->done = false;
+      x->cv.notify_all();
+    }
+    int rc = 0;
+    for (Worker* x : w) {
+      std::unique_lock<std::mutex> lk(x->mu);
+      x->cv.wait(lk, [x] { return x->done; });
+      if (x->rc && !rc) { rc = x->rc; g_err = "device " + std::to_string(x->device) + ": " + x->err; }
+    }
+    return rc;
+  }
+  static void loop(Worker* x)
+  {
+    for (;;) {
+      std::function<int(swb_ctx*)> job;
+      {
+        std::unique_lock<std::mutex> lk(x->mu);
+        x->cv.wait(lk, [x] { return x->has_job || x->quit; });
+        if (x->quit) return;
+        job = x->job; x->has_job = false;
+      }
+      const int rc = job(x->ctx);
+      std::lock_guard<std::mutex> lk(x->mu);
+      x->rc = rc; x->err = rc ? std::string(swb_last_error()) : std::string();
+      x->done = true;
+      x->cv.notify_all();
+    }
+  }
+};
+
+// pair index where the first `part` of `parts` equal shares of the batch's bytes ends (offsets are monotone)
+static uint64_t split_point(const uint64_t* qo, const uint64_t* ro, uint64_t n_pairs, uint64_t part, uint64_t parts)
+{
+  if (part == 0) return 0;
+  if (part >= parts) return n_pairs;
+  auto bytes_before = [&](uint64_t k) { return (qo[k] - qo[0]) + (ro ? ro[k] - ro[0] : 0); };
+  const uint64_t total = bytes_before(n_pairs);
+  if (total == 0) return n_pairs * part / parts;
+  const uint64_t want = (uint64_t)((unsigned __int128)total * part / parts);
+  uint64_t lo = 0, hi = n_pairs;
+  while (lo < hi) { const uint64_t mid = (lo + hi) / 2; if (bytes_before(mid) < want) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+extern "C" {
+
+int swb_create_multi(swb_multi** out, const int* device_ids, int n_devices, const swb_params* params)
+{
+  if (!out) return fail("swb_create_multi: null out pointer");
+  *out = nullptr;
+  const int visible = swb_device_count();
+  if (visible <= 0) return fail("error: gpu acceleration is required and no compatible gpu was found");   // main.rs:161
+  if (n_devices <= 0 || !device_ids) { n_devices = visible; device_ids = nullptr; }                      // all visible devices
+  if (n_devices > 64) return fail("swb_create_multi: at most 64 devices");
+  for (int k = 0; k < n_devices; ++k) {
+    const int d = device_ids ? device_ids[k] : k;
+    if (d < 0 || d >= visible) return fail("swb_create_multi: no such device");
+    for (int j = 0; j < k; ++j) if ((device_ids ? device_ids[j] : j) == d) return fail("swb_create_multi: a device is listed twice");
+  }
+  swb_multi* m = new swb_multi();
+  const swb_params pcopy = params ? *params : swb_params{swb::kMatch, swb::kMismatch, swb::kGap};
+  for (int k = 0; k < n_devices; ++k) {
+    auto* x = new swb_multi::Worker();
+    x->device = device_ids ? device_ids[k] : k;
+    m->w.push_back(x);
+    x->th = std::thread(swb_multi::loop, x);
+  }
+  // every worker creates its own context: CUDA context creation, streams and module load run concurrently per device
+  const int rc = m->run([m, pcopy](int k, swb_ctx*) { return swb_create(&m->w[k]->ctx, m->w[k]->device, &pcopy); });
+  if (rc) { const std::string keep = g_err; swb_destroy_multi(m); g_err = keep; return 1; }
+  *out = m;
+  return 0;
+}
+
+void swb_destroy_multi(swb_multi* m)
+{
+  if (!m) return;
+  for (auto* x : m->w) {
+    { std::lock_guard<std::mutex> lk(x->mu); x->quit = true; x->cv.notify_all(); }
+    if (x->th.joinable()) x->th.join();
+    if (x->ctx) swb_destroy(x->ctx);
+    delete x;
+  }
+  delete m;
+}
+
+int swb_multi_device_count(swb_multi* m) { return m ? (int)m->w.size() : 0; }
+swb_ctx* swb_multi_ctx(swb_multi* m, int k) { return (m && k >= 0 && k < (int)m->w.size()) ? m->w[k]->ctx : nullptr; }
+
+int swb_multi_score_batch(swb_multi* m, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro,
+                          uint64_t n_pairs, swb_result* out)
+{
+  if (!m) return fail("null ctx");
+  if (n_pairs == 0) return 0;
+  if (!qo || !ro || !out) return fail("swb_multi_score_batch: null pointer");
+  if (qo[0] != 0 || ro[0] != 0) return fail("swb_multi_score_batch: offsets must start at 0");
+  const uint64_t parts = m->w.size();
+  static const uint8_t empty = 0;
+  const uint8_t* qq = q ? q : &empty; const uint8_t* rr = r ? r : &empty;
+  return m->run([=](int k, swb_ctx* c) -> int {
+    const uint64_t lo = split_point(qo, ro, n_pairs, (uint64_t)k, parts), hi = split_point(qo, ro, n_pairs, (uint64_t)k + 1, parts);
+    if (hi <= lo) return 0;
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail("cudaSetDevice failed");
+    return score_host_batch(c, "swb_multi_score_batch", qq, qo + lo, rr, ro + lo, nullptr, nullptr, nullptr, hi - lo, out + lo);
+  });
+}
+
+int swb_multi_set_reference(swb_multi* m, const uint8_t* ref, uint64_t n)
+{
+  if (!m) return fail("null ctx");
+  return m->run([=](int, swb_ctx* c) { return swb_set_reference(c, ref, n); });
+}
+
+int swb_multi_score_batch_vs_reference(swb_multi* m, const uint8_t* q, const uint64_t* qo, uint64_t n_pairs,
+                                       const uint64_t* win_start, const uint32_t* win_len, swb_result* out)
+{
+  if (!m) return fail("null ctx");
+  if (n_pairs == 0) return 0;
+  if (!qo || !win_start || !win_len || !out) return fail("swb_multi_score_batch_vs_reference: null pointer");
+  if (qo[0] != 0) return fail("swb_multi_score_batch_vs_reference: offsets must start at 0");
+  const uint64_t parts = m->w.size();
+  static const uint8_t empty = 0;
+  const uint8_t* qq = q ? q : &empty;
+  return m->run([=](int k, swb_ctx* c) -> int {
+    const uint64_t lo = split_point(qo, nullptr, n_pairs, (uint64_t)k, parts), hi = split_point(qo, nullptr, n_pairs, (uint64_t)k + 1, parts);
+    if (hi <= lo) return 0;
+    if (cudaSetDevice(c->device) != cudaSuccess) return fail("cudaSetDevice failed");
+    const RefSrc ref = resident_ref(c);
+    return score_host_batch(c, "swb_multi_score_batch_vs_reference", qq, qo + lo, nullptr, nullptr, win_start + lo, win_len + lo, &ref, hi - lo, out + lo);
+  });
 }
 
 }  // extern "C"

@@ -117,6 +117,10 @@ classify_kernel(BatchView b)
     if (n == 0 || mm == 0) {                               // aligner.rs:413-416: empty input scores 0
       cls = CLASS_EMPTY;
       b.out[k] = swb_result{0, -1, -1};
+    } else if (mm > b.max_window) {                        // longer than the bound the scratch rows were sized for (a wrong
+      cls = CLASS_EMPTY;                                   //  max_r_len of swb_score_batch_device): not scored, reported
+      b.out[k] = swb_result{INT32_MIN, -1, -1};
+      atomicAdd(&b.counters->n_overflow, 1u);
     } else if (n <= kShortMaxRead && mm <= kShortMaxWindow &&
                !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1)) {
       cls = CLASS_SHORT; m = (uint32_t)mm;
@@ -167,25 +171,26 @@ classify_kernel(BatchView b)
 __global__ void __launch_bounds__(256)
 chunk_prepare_kernel(uint64_t* __restrict__ off_a, uint64_t n_a, uint64_t base_a, uint64_t len_a,
                      uint64_t* __restrict__ off_b, uint64_t n_b, uint64_t base_b, uint64_t len_b,
-                     const uint64_t* __restrict__ win_beg, const uint32_t* __restrict__ win_len,
-                     uint64_t* __restrict__ win_end, uint64_t n_w)
+                     uint64_t* __restrict__ win_beg, const uint32_t* __restrict__ win_len, uint32_t len_w,
+                     uint64_t* __restrict__ win_end, uint64_t n_w, uint64_t win_base)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_a || k < n_b || k < n_w; k += stride) {
     if (k < n_a) off_a[k] = len_a ? k * len_a : off_a[k] - base_a;
     if (k < n_b) off_b[k] = len_b ? k * len_b : off_b[k] - base_b;
-    if (k < n_w) win_end[k] = win_beg[k] + win_len[k];
+    if (k < n_w) { const uint64_t w0 = win_beg[k] - win_base; win_beg[k] = w0; win_end[k] = w0 + (len_w ? len_w : win_len[k]); }
   }
 }
 
 int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_t len_a, uint64_t* off_b, uint64_t n_b, uint64_t base_b,
-                         uint64_t len_b, const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st)
+                         uint64_t len_b, uint64_t* win_beg, const uint32_t* win_len, uint32_t len_w, uint64_t* win_end, uint64_t n_w, uint64_t win_base,
+                         cudaStream_t st)
 {
   const uint64_t n = n_a > n_b ? (n_a > n_w ? n_a : n_w) : (n_b > n_w ? n_b : n_w);
   if (n == 0) return 0;
   uint64_t blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  chunk_prepare_kernel<<<(unsigned)blocks, 256, 0, st>>>(off_a, n_a, base_a, len_a, off_b, n_b, base_b, len_b, win_beg, win_len, win_end, n_w);
+  chunk_prepare_kernel<<<(unsigned)blocks, 256, 0, st>>>(off_a, n_a, base_a, len_a, off_b, n_b, base_b, len_b, win_beg, win_len, len_w, win_end, n_w, win_base);
   return 1;
 }
 
@@ -221,6 +226,7 @@ int launch_classify(const BatchView& b, cudaStream_t st)
 // 32-bit key per pair  H<<21 | (255-i)<<13 | (8191-NPAD-j)  whose maximum is exactly
 // (max H, then min i, then min j).
 // =====================================================================================
+#ifdef SWB_ALL_VARIANTS      // sw_short_kernel: test build only (an independent implementation the parity tests cross-check)
 struct ShortArgs {
   const uint32_t* q_pk; const uint64_t* q_beg; const uint64_t* q_end;
   const uint32_t* r_pk; const uint64_t* r_beg; const uint64_t* r_end;
@@ -371,7 +377,7 @@ sw_short_kernel(ShortArgs a)
 }
 
 template <int G, int K, bool SPLIT>
-static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t st)
+static int launch_short_t(const BatchView& b, uint32_t window_cap, LaunchCfg& lc, int slot, cudaStream_t st)
 {
   constexpr int NPAD = G * K, GPW = 32 / G;
   ShortArgs a;
@@ -381,11 +387,9 @@ static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t 
   const uint32_t n_iters = (NPAD + a.w_pad + K - 1) / K;
   a.wbuf_stride = (NPAD + n_iters * K + 15) & ~15u;
   const size_t smem = (size_t)a.wbuf_stride * 4 * GPW;
-  static bool attr_set[64] = {};                         // function attributes are per device
-  int dev_id = 0; cudaGetDevice(&dev_id);
-  if (!attr_set[dev_id & 63]) {
+  if (!lc.attr_set[slot]) {                              // function attributes are per device: once per context
     cudaFuncSetAttribute(sw_short_kernel<G, K, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set[dev_id & 63] = true;
+    lc.attr_set[slot] = true;
   }
   // the grid covers the worst case (every pair short); surplus groups read n_short and leave
   const uint64_t n_pp = (b.n_pairs + 1) / 2;
@@ -394,26 +398,54 @@ static int launch_short_t(const BatchView& b, uint32_t window_cap, cudaStream_t 
   return 1;
 }
 
-template <int G, int K, int MINB, int FLAGS> static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st);
+#endif  // SWB_ALL_VARIANTS
 
-// variant 4..6: streaming kernel; else bit0: 0 = G8/K20, 1 = G16/K10 ; bit1: split tracking (VIADD + VIMNMX) instead of VIADDMNMX
-int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st)
+template <int G, int K, int MINB, int FLAGS> static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStream_t st);
+
+void launch_cfg_init(LaunchCfg& lc, int sm_count)
+{
+  lc = LaunchCfg();
+  lc.sm_count = sm_count;
+  if (const char* v = getenv("SWB_STREAM_CTAS_PER_SM")) lc.stream_ctas_per_sm = atoi(v);
+  if (const char* v = getenv("SWB_STREAM_GRID")) lc.stream_grid = atol(v);
+  if (const char* v = getenv("SWB_LONG_K")) lc.long_k = atoi(v);
+  lc.debug = getenv("SWB_DEBUG") != nullptr;
+}
+
+// Short-read kernel variants.  9 (default): sw_stream_kernel<16 lanes x 10 rows, 4 CTAs/SM> with the two-step tracker and
+// dynamic couple distribution.  The others exist only in builds with -DSWB_ALL_VARIANTS (tests/native target: the parity
+// tests cross-check every one of them; the product library carries the default only): 4 = the round-1 stream kernel,
+// 5 / 6 = 5 CTAs per SM / 8 lanes x 20 rows, 7 = two-step tracker only, 8 = dynamic distribution only, 10 / 11 = 8 / 9 at
+// 5 CTAs per SM, 0..3 = sw_short_kernel (bit0: 0 = G8/K20, 1 = G16/K10; bit1: split tracking).
+int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg& lc, cudaStream_t st)
 {
   if (b.n_pairs == 0) return 0;
-  if ((variant & 15) == 4) return launch_stream_t<16, 10, 4, 0>(b, sm_count, st);
-  if ((variant & 15) == 5) return launch_stream_t<16, 10, 5, 0>(b, sm_count, st);
-  if ((variant & 15) == 6) return launch_stream_t<8, 20, 3, 0>(b, sm_count, st);
-  if ((variant & 15) == 7) return launch_stream_t<16, 10, 4, 1>(b, sm_count, st);     // two-step tracker
-  if ((variant & 15) == 8) return launch_stream_t<16, 10, 4, 2>(b, sm_count, st);    // dynamic couple distribution
-  if ((variant & 15) == 9) return launch_stream_t<16, 10, 4, 3>(b, sm_count, st);    // both
-  if ((variant & 15) == 10) return launch_stream_t<16, 10, 5, 2>(b, sm_count, st);   // dynamic, five CTAs per SM
-  if ((variant & 15) == 11) return launch_stream_t<16, 10, 5, 3>(b, sm_count, st);
-  switch (variant & 3) {
-    case 0: return launch_short_t<8, 20, false>(b, window_cap, st);
-    case 1: return launch_short_t<16, 10, false>(b, window_cap, st);
-    case 2: return launch_short_t<8, 20, true>(b, window_cap, st);
-    default: return launch_short_t<16, 10, true>(b, window_cap, st);
+  (void)window_cap;
+  switch (variant & 15) {
+#ifdef SWB_ALL_VARIANTS
+    case 0: return launch_short_t<8, 20, false>(b, window_cap, lc, 0, st);
+    case 1: return launch_short_t<16, 10, false>(b, window_cap, lc, 1, st);
+    case 2: return launch_short_t<8, 20, true>(b, window_cap, lc, 2, st);
+    case 3: return launch_short_t<16, 10, true>(b, window_cap, lc, 3, st);
+    case 4: return launch_stream_t<16, 10, 4, 0>(b, lc, 4, st);
+    case 5: return launch_stream_t<16, 10, 5, 0>(b, lc, 5, st);
+    case 6: return launch_stream_t<8, 20, 3, 0>(b, lc, 6, st);
+    case 7: return launch_stream_t<16, 10, 4, 1>(b, lc, 7, st);
+    case 8: return launch_stream_t<16, 10, 4, 2>(b, lc, 8, st);
+    case 10: return launch_stream_t<16, 10, 5, 2>(b, lc, 10, st);
+    case 11: return launch_stream_t<16, 10, 5, 3>(b, lc, 11, st);
+#endif
+    default: return launch_stream_t<16, 10, 4, 3>(b, lc, 9, st);
   }
+}
+
+bool short_variant_available(int variant)
+{
+#ifdef SWB_ALL_VARIANTS
+  return variant >= 0 && variant <= 11;
+#else
+  return variant == 9;
+#endif
 }
 
 // =====================================================================================
@@ -724,8 +756,9 @@ sw_stream_kernel(StreamArgs a)
         if (u & 1) B[m] = h; else A[m] = h;
 #if SWB_ABLATE != 2
         if (TRK) {                                       // two steps per tracker update: x = h + e is a plain add (FMA pipe)
-          if (u & 1) cur[m] = __vimax3_s16x2(cur[m], X[m], h + e);
-          else       X[m] = h + e;
+          const uint32_t xe = h + e;
+          if (u & 1) cur[m] = __vimax3_s16x2(cur[m], X[m], xe);
+          else       X[m] = xe;
         } else {
           cur[m] = __viaddmax_s16x2(h, e, cur[m]);
         }
@@ -744,27 +777,25 @@ sw_stream_kernel(StreamArgs a)
 }
 
 template <int G, int K, int MINB, int FLAGS>
-static int launch_stream_t(const BatchView& b, int sm_count, cudaStream_t st)
+static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStream_t st)
 {
   constexpr int GPW = 32 / G;
   constexpr int GSTRIDE = 4 * G * K * 2 + 128;
   StreamArgs a;
   a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.desc = b.short_desc; a.counters = b.counters; a.out = b.out;
   const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4 + (size_t)4 * GPW * 8 * 4;
-  static int resident_by_device[64] = {};                // CTAs of this kernel one SM holds (asked once per device)
-  int dev_id = 0; cudaGetDevice(&dev_id);
-  int& resident = resident_by_device[dev_id & 63];
+  int& resident = lc.resident[slot];                     // CTAs of this kernel one SM holds (asked once per context)
   if (!resident) {
     cudaFuncSetAttribute(sw_stream_kernel<G, K, MINB, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, sw_stream_kernel<G, K, MINB, FLAGS>, 128, smem) != cudaSuccess || resident < 1)
       resident = 1;
-    if (const char* v = getenv("SWB_STREAM_CTAS_PER_SM")) { const int w = atoi(v); if (w >= 1 && w <= resident) resident = w; }
-    if (getenv("SWB_DEBUG")) fprintf(stderr, "sw_stream_kernel<%d,%d,%d,%d>: %d resident CTAs/SM, %zu B smem\n", G, K, MINB, FLAGS, resident, smem);
+    if (lc.stream_ctas_per_sm >= 1 && lc.stream_ctas_per_sm <= resident) resident = lc.stream_ctas_per_sm;
+    if (lc.debug) fprintf(stderr, "sw_stream_kernel<%d,%d,%d,%d>: %d resident CTAs/SM, %zu B smem\n", G, K, MINB, FLAGS, resident, smem);
   }
   // persistent grid: every resident CTA slot of every SM; never more groups than pair couples in the worst case
   const uint64_t n_pp = (b.n_pairs + 1) / 2;
-  uint64_t blocks = (uint64_t)sm_count * resident;
-  if (const char* v = getenv("SWB_STREAM_GRID")) { const long w = atol(v); if (w >= 1) blocks = (uint64_t)w; }
+  uint64_t blocks = (uint64_t)lc.sm_count * resident;
+  if (lc.stream_grid >= 1) blocks = (uint64_t)lc.stream_grid;
   const uint64_t need = (n_pp + 4 * GPW - 1) / (4 * GPW);
   if (blocks > need) blocks = need;
   sw_stream_kernel<G, K, MINB, FLAGS><<<(unsigned)blocks, 128, smem, st>>>(a);
@@ -1086,7 +1117,7 @@ sw_long_kernel(LongArgs a)
 }
 
 template <int K, int MINB, bool BYTES>
-static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
+static int launch_long_t(const BatchView& b, int ctas, LaunchCfg& lc, int slot, cudaStream_t st)
 {
   LongArgs a;
   a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.q_bytes = b.q_bytes; a.r_bytes = b.r_bytes;
@@ -1095,11 +1126,9 @@ static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
   a.scratch = b.scratch; a.scratch_stride = b.scratch_stride;
   constexpr size_t RING = 4 * 32 * K;
   const size_t smem = 9 * 128 + 4 * (RING * 6 + 16 * sizeof(LongJob)) + (size_t)2 * K * 128 * 4;
-  static bool attr_set[64] = {};                         // function attributes are per device
-  int dev_id = 0; cudaGetDevice(&dev_id);
-  if (!attr_set[dev_id & 63]) {
+  if (!lc.attr_set[slot]) {                              // function attributes are per device: once per context
     cudaFuncSetAttribute(sw_long_kernel<K, MINB, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set[dev_id & 63] = true;
+    lc.attr_set[slot] = true;
   }
   sw_long_kernel<K, MINB, BYTES><<<ctas, 128, smem, st>>>(a);
   return 1;
@@ -1108,21 +1137,22 @@ static int launch_long_t(const BatchView& b, int ctas, cudaStream_t st)
 // persistent grids (ctas = a multiple of the SM count unless the scratch clamp reduced it), work-stealing over the long /
 // the bytes list; the two launches use disjoint scratch halves
 // max_read_len <= 192: every job is a single band, 32 x 6 rows waste fewer lanes than 32 x 10 on 150 bp reads
-int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st)
+int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, LaunchCfg& lc, cudaStream_t st)
 {
-  if (max_read_len <= 192) return launch_long_t<6, 4, false>(b, ctas, st);
-  static int k_env = -1;                                 // SWB_LONG_K: rows per lane (tuning experiments)
-  if (k_env < 0) { const char* v = getenv("SWB_LONG_K"); k_env = v ? atoi(v) : 0; }
-  switch (k_env) {                                       // measured on 10 kb pairs: K=10 4019, 12 4113, 14 3959, 16 3658 GCUPS
-    case 10: return launch_long_t<10, 4, false>(b, ctas, st);
-    case 14: return launch_long_t<14, 4, false>(b, ctas, st);
-    case 16: return launch_long_t<16, 3, false>(b, ctas * 3 / 4, st);
-    default: return launch_long_t<12, 4, false>(b, ctas, st);
+  if (max_read_len <= 192) return launch_long_t<6, 4, false>(b, ctas, lc, 16, st);
+#ifdef SWB_ALL_VARIANTS
+  switch (lc.long_k) {                                   // SWB_LONG_K, measured on 10 kb pairs: K=10 4019, 12 4113, 14 3959, 16 3658 GCUPS
+    case 10: return launch_long_t<10, 4, false>(b, ctas, lc, 17, st);
+    case 14: return launch_long_t<14, 4, false>(b, ctas, lc, 18, st);
+    case 16: return launch_long_t<16, 3, false>(b, ctas * 3 / 4, lc, 19, st);
+    default: break;
   }
+#endif
+  return launch_long_t<12, 4, false>(b, ctas, lc, 20, st);
 }
-int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st)
+int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, LaunchCfg& lc, cudaStream_t st)
 {
-  return max_read_len <= 192 ? launch_long_t<6, 4, true>(b, ctas, st) : launch_long_t<10, 4, true>(b, ctas, st);
+  return max_read_len <= 192 ? launch_long_t<6, 4, true>(b, ctas, lc, 21, st) : launch_long_t<10, 4, true>(b, ctas, lc, 22, st);
 }
 
 // =====================================================================================
@@ -1230,7 +1260,7 @@ int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cud
 
 __global__ void single_pair_setup_kernel(Counters* c, uint32_t* list)
 {
-  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; list[0] = 0;
+  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; c->stream_cursor = 0; c->n_overflow = 0; list[0] = 0;
 }
 
 // exposed for the C API: run the generic kernel on a prepared single-pair view
@@ -1288,6 +1318,8 @@ int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32
 // x = draw(0xB201, 1+i):  x%1000 == 0 -> 1-base insertion (random base, cursor stays),
 // x%1000 == 1 -> 1-base deletion (cursor skips one), and (x>>10)%100 == 0 -> substitution.
 // Distribution 1 (unrelated): read base i = 2 bits of draw(0xB201, 1 + i/32).
+// With a reference (launch_synth_ref) the window of pair p is instead cut from it at draw(0xB202, 0) % (ref_len - W + 1)
+// -- windows of neighbouring reads overlap, as in a genome -- and the read is made from that window by the same rule.
 // =====================================================================================
 __host__ __device__ __forceinline__ uint64_t splitmix_at(uint64_t seed, uint64_t p, uint64_t k)
 {
@@ -1303,19 +1335,25 @@ __device__ __forceinline__ uint32_t window_code(uint64_t p, uint32_t j)
 }
 
 __global__ void synth_window_kernel(uint64_t first_pair, uint64_t n_pairs, uint32_t wlen,
-                                    uint8_t* __restrict__ r_bytes, uint64_t* __restrict__ r_off)
+                                    uint8_t* __restrict__ r_bytes, uint64_t* __restrict__ r_off,
+                                    const uint8_t* __restrict__ ref, uint64_t ref_len, uint64_t* __restrict__ win_start)
 {
   const uint64_t total = n_pairs * wlen;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += stride) {
     const uint64_t k = x / wlen; const uint32_t j = (uint32_t)(x - k * wlen);
-    r_bytes[x] = "ACGT"[window_code(first_pair + k, j)];
+    if (ref) r_bytes[x] = ref[splitmix_at(0xB202ull, first_pair + k, 0) % (ref_len - wlen + 1) + j];
+    else     r_bytes[x] = "ACGT"[window_code(first_pair + k, j)];
   }
-  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_pairs; k += stride) r_off[k] = k * wlen;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_pairs; k += stride) {
+    r_off[k] = k * wlen;
+    if (ref && win_start && k < n_pairs) win_start[k] = splitmix_at(0xB202ull, first_pair + k, 0) % (ref_len - wlen + 1);
+  }
 }
 
+// the read of pair k is made from ITS window as synth_window_kernel wrote it (w_bytes + k*wlen), whatever filled it
 __global__ void synth_read_kernel(uint64_t first_pair, uint64_t n_pairs, uint32_t rlen, uint32_t wlen, int dist,
-                                  uint8_t* __restrict__ q_bytes, uint64_t* __restrict__ q_off)
+                                  uint8_t* __restrict__ q_bytes, uint64_t* __restrict__ q_off, const uint8_t* __restrict__ w_bytes)
 {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k <= n_pairs; k += stride) {
@@ -1337,7 +1375,8 @@ __global__ void synth_read_kernel(uint64_t first_pair, uint64_t n_pairs, uint32_
           code = (uint32_t)(x >> 32) & 3u;                       // insertion: cursor stays
         } else {
           if (ev == 1) ++c;                                      // deletion: skip one window base
-          code = c < wlen ? window_code(p, c) : ((uint32_t)(x >> 34) & 3u);
+          if (c < wlen) { const uint32_t t = ((uint32_t)w_bytes[k * wlen + c] >> 1) & 3u; code = t ^ (t >> 1); }   // A C G T -> 0 1 2 3
+          else code = (uint32_t)(x >> 34) & 3u;
           ++c;
           if ((uint32_t)((x >> 10) % 100u) == 0) code = (code + 1u + (uint32_t)((x >> 20) % 3u)) & 3u;
         }
@@ -1350,8 +1389,16 @@ __global__ void synth_read_kernel(uint64_t first_pair, uint64_t n_pairs, uint32_
 int launch_synth(uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len, int distribution,
                  uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, cudaStream_t st)
 {
-  synth_window_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, window_len, r_bytes, r_off);
-  synth_read_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, read_len, window_len, distribution, q_bytes, q_off);
+  synth_window_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, window_len, r_bytes, r_off, nullptr, 0, nullptr);
+  synth_read_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, read_len, window_len, distribution, q_bytes, q_off, r_bytes);
+  return 2;
+}
+
+int launch_synth_ref(const uint8_t* ref, uint64_t ref_len, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len,
+                     int distribution, uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, uint64_t* win_start, cudaStream_t st)
+{
+  synth_window_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, window_len, r_bytes, r_off, ref, ref_len, win_start);
+  synth_read_kernel<<<148 * 8, 256, 0, st>>>(first_pair, n_pairs, read_len, window_len, distribution, q_bytes, q_off, r_bytes);
   return 2;
 }
 

@@ -28,7 +28,8 @@ struct Counters {             // device-resident, zeroed per batch
   uint32_t n_bytes;           // pairs touching a non-ACGT byte (any length below kLongMaxLen): the same kernel on raw bytes
   uint32_t bytes_cursor;
   uint32_t stream_cursor;     // sw_stream_kernel: couples handed out beyond every group's static ones
-  uint32_t pad_[3];
+  uint32_t n_overflow;        // pairs whose window is longer than BatchView::max_window (result INT32_MIN): the caller's bound was wrong
+  uint32_t pad_[2];
 };
 
 struct ShortDesc {            // one entry per short-listed pair, written by classify_kernel (32 B, 16-aligned)
@@ -55,6 +56,7 @@ struct BatchView {            // everything the kernels need about one batch (de
   swb_result*     out;
   int32_t*        scratch;      // generic kernel: one boundary row per resident warp
   uint64_t        scratch_stride;
+  uint32_t        max_window;   // windows longer than this are refused (the scratch rows hold scratch_stride >= max_window columns)
 };
 
 #if defined(__CUDACC__)
@@ -73,19 +75,35 @@ __device__ __forceinline__ uint32_t pack4(uint32_t x, uint32_t& bad)
 }
 #endif
 
+// Launch state of one context (function attributes set, occupancy asked, tuning knobs from the environment): owned by the
+// swb_ctx, which one thread uses at a time -- no process-wide mutable state in the launchers.
+struct LaunchCfg {
+  int  sm_count = 0;
+  int  resident[16] = {};          // sw_stream_kernel variant -> resident CTAs per SM (0 = not asked yet)
+  bool attr_set[32] = {};          // kernel slot -> cudaFuncSetAttribute done
+  int  stream_ctas_per_sm = 0;     // SWB_STREAM_CTAS_PER_SM
+  long stream_grid = 0;            // SWB_STREAM_GRID
+  int  long_k = 0;                 // SWB_LONG_K (builds with -DSWB_ALL_VARIANTS)
+  bool debug = false;              // SWB_DEBUG
+};
+void launch_cfg_init(LaunchCfg& lc, int sm_count);
+bool short_variant_available(int variant);
+
 // launchers (all asynchronous on `st`); each returns the number of kernels it launched
 int launch_pack2bit(const uint8_t* bytes, uint64_t n, uint32_t* words, uint32_t* bitmap, cudaStream_t st);
 int launch_classify(const BatchView& b, cudaStream_t st);
 int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_t len_a, uint64_t* off_b, uint64_t n_b, uint64_t base_b,
-                         uint64_t len_b, const uint64_t* win_beg, const uint32_t* win_len, uint64_t* win_end, uint64_t n_w, cudaStream_t st);
-int launch_short(const BatchView& b, uint32_t window_cap, int variant, int sm_count, cudaStream_t st);
+                         uint64_t len_b, uint64_t* win_beg, const uint32_t* win_len, uint32_t len_w, uint64_t* win_end, uint64_t n_w, uint64_t win_base, cudaStream_t st);
+int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg& lc, cudaStream_t st);
 int launch_generic(const BatchView& b, int sm_count, int warps_resident, cudaStream_t st);
-int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st);
-int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, cudaStream_t st);
+int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, LaunchCfg& lc, cudaStream_t st);
+int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, LaunchCfg& lc, cudaStream_t st);
 int launch_ref_compat(const uint8_t* s1, const uint8_t* s2, uint64_t len, uint32_t wgs, uint64_t groups,
                       int32_t* result, cudaStream_t st);
 int launch_synth(uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len, int distribution,
                  uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, cudaStream_t st);
+int launch_synth_ref(const uint8_t* ref, uint64_t ref_len, uint64_t first_pair, uint64_t n_pairs, uint32_t read_len, uint32_t window_len,
+                     int distribution, uint8_t* q_bytes, uint64_t* q_off, uint8_t* r_bytes, uint64_t* r_off, uint64_t* win_start, cudaStream_t st);
 // alignments behind the scores (swb_traceback.cu)
 struct TracebackArgs {
   const uint8_t* q; const uint64_t* qo; const uint8_t* r; const uint64_t* ro;     // CSR pairs (device)

@@ -35,8 +35,8 @@ def to_csr(seqs):
 
 
 class Engine:
-    def __init__(self, device=0):
-        self._lib = load_library()
+    def __init__(self, device=0, lib=None):
+        self._lib = lib if lib is not None else load_library()      # lib: another build of the library (tests: the all-variants build)
         h = ctypes.c_void_p()
         if self._lib.swb_create(ctypes.byref(h), int(device), None) != 0:
             raise SwbError(self._err())
@@ -142,6 +142,27 @@ class Engine:
                                                                win_start.ctypes.data, win_len.ctypes.data, out.ctypes.data))
         return out
 
+    def score_batch_ranges(self, q_bytes, q_off, w_bytes, win_start, win_len):
+        """Windows are ranges of ONE host buffer (they may overlap / repeat): swb_score_batch_ranges."""
+        q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        w_bytes = np.ascontiguousarray(w_bytes, dtype=np.uint8)
+        win_start = np.ascontiguousarray(win_start, dtype=np.uint64)
+        win_len = np.ascontiguousarray(win_len, dtype=np.uint32)
+        n = q_off.size - 1
+        if win_start.size != n or win_len.size != n:
+            raise ValueError("q_off, win_start and win_len must describe the same number of pairs")
+        out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
+        if n > 0:
+            self._check(self._lib.swb_score_batch_ranges(self._h, q_bytes.ctypes.data, q_off.ctypes.data, n, w_bytes.ctypes.data, w_bytes.size,
+                                                         win_start.ctypes.data, win_len.ctypes.data, out.ctypes.data))
+        return out
+
+    def last_ranges_info(self):
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._lib.swb_last_ranges_info(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return {"bytes_uploaded": int(a.value), "window_bytes": int(b.value)}
+
     def fastq_bgzf_score(self, comp, blocks, carry=b"", final=True, file_index=0, first_read=0, window_len=500, carry_cap=1 << 16):
         """swb_fastq_bgzf_score: one segment of whole BGZF blocks -> (score sum, reads, bases, new carry, status).
         `blocks` is a sequence of (payload offset in comp, payload length, inflated length)."""
@@ -199,6 +220,10 @@ class Engine:
         self._check(self._lib.swb_synth_device(self._h, first_pair, n_pairs, read_len, window_len, distribution,
                                                d_q, d_qo, d_r, d_ro))
 
+    def synth_device_ref(self, d_ref, ref_len, first_pair, n_pairs, read_len, window_len, distribution, d_q, d_qo, d_r, d_ro, d_ws):
+        self._check(self._lib.swb_synth_device_ref(self._h, d_ref, ref_len, first_pair, n_pairs, read_len, window_len, distribution,
+                                                   d_q, d_qo, d_r, d_ro, d_ws))
+
     def set_short_variant(self, v):
         self._check(self._lib.swb_set_short_variant(self._h, int(v)))
 
@@ -242,3 +267,61 @@ class Engine:
 
     def h2d(self, d_dst, src_array, nbytes):
         self._check(self._lib.swb_memcpy_h2d(self._h, d_dst, src_array.ctypes.data, int(nbytes)))
+
+
+class MultiEngine:
+    """Several GPUs behind one handle (swb_create_multi): a host batch is split into contiguous slices, one per device."""
+
+    def __init__(self, devices=None):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        if devices is None:
+            rc = self._lib.swb_create_multi(ctypes.byref(h), None, 0, None)
+        else:
+            ids = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.swb_create_multi(ctypes.byref(h), ids, len(devices), None)
+        if rc != 0:
+            raise SwbError(self._lib.swb_last_error().decode("utf-8", "replace"))
+        self._h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise SwbError(self._lib.swb_last_error().decode("utf-8", "replace"))
+
+    @property
+    def n_devices(self):
+        return int(self._lib.swb_multi_device_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.swb_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def score_batch_csr(self, q_bytes, q_off, r_bytes, r_off):
+        q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8); r_bytes = np.ascontiguousarray(r_bytes, dtype=np.uint8)
+        q_off = np.ascontiguousarray(q_off, dtype=np.uint64); r_off = np.ascontiguousarray(r_off, dtype=np.uint64)
+        n = q_off.size - 1
+        out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
+        if n > 0:
+            self._check(self._lib.swb_multi_score_batch(self._h, q_bytes.ctypes.data, q_off.ctypes.data, r_bytes.ctypes.data, r_off.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def set_reference(self, ref):
+        a = _as_bytes_array(ref)
+        self._check(self._lib.swb_multi_set_reference(self._h, a.ctypes.data, a.size))
+
+    def score_batch_vs_reference(self, q_bytes, q_off, win_start, win_len):
+        q_bytes = np.ascontiguousarray(q_bytes, dtype=np.uint8); q_off = np.ascontiguousarray(q_off, dtype=np.uint64)
+        win_start = np.ascontiguousarray(win_start, dtype=np.uint64); win_len = np.ascontiguousarray(win_len, dtype=np.uint32)
+        n = q_off.size - 1
+        out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
+        if n > 0:
+            self._check(self._lib.swb_multi_score_batch_vs_reference(self._h, q_bytes.ctypes.data, q_off.ctypes.data, n, win_start.ctypes.data,
+                                                                     win_len.ctypes.data, out.ctypes.data))
+        return out

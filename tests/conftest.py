@@ -21,3 +21,17 @@ def engine():
     eng = mp.Engine(0)
     yield eng
     eng.close()
+
+
+@pytest.fixture(scope="session")
+def engine_variants():
+    """An engine on the TEST build of the library (tests/native/libswb200_variants.so, -DSWB_ALL_VARIANTS): every
+    short-read kernel variant, cross-checked against the oracle.  The product library carries the default only."""
+    import mini_parallel_b200 as mp
+    from mini_parallel_b200 import _lib
+    path = os.path.join(ROOT, "tests", "native", "libswb200_variants.so")
+    if not os.path.exists(path):
+        pytest.fail("tests/native/libswb200_variants.so is missing: make variants (or __graft_entry__.build())")
+    eng = mp.Engine(0, lib=_lib.bind(path))
+    yield eng
+    eng.close()

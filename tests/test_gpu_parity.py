@@ -13,7 +13,13 @@ from mini_parallel_b200.engine import to_csr
 
 pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sw_vectors.json")))["vectors"]
+PRODUCT = "product"        # the default variant on the PRODUCT library; the numbered ones run on the test build
 ALL_VARIANTS = (0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11)
+DEFAULT_VARIANT = 9          # sw_stream_kernel with the two-step tracker and dynamic couple distribution
+
+
+def _vnum(variant):
+    return DEFAULT_VARIANT if variant == PRODUCT else variant
 
 
 def _rand(rng, n, alphabet=b"ACGT"):
@@ -57,47 +63,62 @@ def test_golden_vectors(engine, v):
     assert engine.ref_compat_align(a, b, 256) == v["ref_compat_256"]
 
 
-def test_golden_vectors_as_one_batch(engine):
+def test_golden_vectors_as_one_batch(engine, engine_variants):
     reads = [v["seq1"].encode("latin1") for v in GOLD]
     wins = [v["seq2"].encode("latin1") for v in GOLD]
-    for variant in ALL_VARIANTS:
-        engine.set_short_variant(variant)
-        got = engine.score_batch(reads, wins)
-        for g, v in zip(got, GOLD):
-            assert (int(g["score"]), int(g["end_i"]), int(g["end_j"])) == (v["score"], v["end_i"], v["end_j"]), v["name"]
-    engine.set_short_variant(4)
+    for eng, variants in ((engine, (DEFAULT_VARIANT,)), (engine_variants, ALL_VARIANTS)):
+        for variant in variants:
+            eng.set_short_variant(variant)
+            got = eng.score_batch(reads, wins)
+            for g, v in zip(got, GOLD):
+                assert (int(g["score"]), int(g["end_i"]), int(g["end_j"])) == (v["score"], v["end_i"], v["end_j"]), v["name"]
+        eng.set_short_variant(DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", ALL_VARIANTS)
-def test_short_path_uniform_150x500(engine, variant):
-    rng = np.random.default_rng(100 + variant)
-    engine.set_short_variant(variant)
+def test_product_library_carries_the_default_variant_only(engine):
+    for v in ALL_VARIANTS:
+        if v != DEFAULT_VARIANT:
+            with pytest.raises(mp.SwbError, match="not in this build"):
+                engine.set_short_variant(v)
+    engine.set_short_variant(DEFAULT_VARIANT)
+
+
+@pytest.mark.parametrize("variant", (PRODUCT,) + ALL_VARIANTS)
+def test_short_path_uniform_150x500(engine, engine_variants, variant):
+    if variant != PRODUCT:
+        engine = engine_variants
+    rng = np.random.default_rng(100 + _vnum(variant))
+    engine.set_short_variant(_vnum(variant))
     _assert_parity(engine, *_pairs(rng, 4001, (150, 150), (500, 500)))           # odd count: last group holds one pair
     assert engine.last_routing() == {"short": 4001, "generic": 0, "long": 0}
     _assert_parity(engine, *_pairs(rng, 2000, (150, 150), (500, 500), related=False))
-    engine.set_short_variant(4)
+    engine.set_short_variant(DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", ALL_VARIANTS)
-def test_short_path_ragged_lengths(engine, variant):
-    rng = np.random.default_rng(200 + variant)
-    engine.set_short_variant(variant)
+@pytest.mark.parametrize("variant", (PRODUCT,) + ALL_VARIANTS)
+def test_short_path_ragged_lengths(engine, engine_variants, variant):
+    if variant != PRODUCT:
+        engine = engine_variants
+    rng = np.random.default_rng(200 + _vnum(variant))
+    engine.set_short_variant(_vnum(variant))
     _assert_parity(engine, *_pairs(rng, 6000, (1, 160), (1, 900)))
     _assert_parity(engine, *_pairs(rng, 1500, (140, 160), (1, 60), related=False))   # window shorter than the read
-    engine.set_short_variant(4)
+    engine.set_short_variant(DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", ALL_VARIANTS)
-def test_short_path_many_way_ties(engine, variant):
+@pytest.mark.parametrize("variant", (PRODUCT,) + ALL_VARIANTS)
+def test_short_path_many_way_ties(engine, engine_variants, variant):
+    if variant != PRODUCT:
+        engine = engine_variants
     """Homopolymers and short repeats: every tie-break decision (min i, then min j) is exercised."""
-    rng = np.random.default_rng(300 + variant)
-    engine.set_short_variant(variant)
+    rng = np.random.default_rng(300 + _vnum(variant))
+    engine.set_short_variant(_vnum(variant))
     _assert_parity(engine, *_pairs(rng, 1500, (1, 160), (1, 400), alphabet=b"A"))
     _assert_parity(engine, *_pairs(rng, 1500, (1, 160), (1, 400), related=False, alphabet=b"AC"))
     reads = [b"ACG" * 50] * 64 + [b"AT" * 80] * 64
     wins = [b"ACG" * 160] * 64 + [b"TA" * 250] * 64
     _assert_parity(engine, reads, wins)
-    engine.set_short_variant(4)
+    engine.set_short_variant(DEFAULT_VARIANT)
 
 
 def test_short_path_window_limits(engine):
