@@ -18,6 +18,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <filesystem>
+#include <system_error>
 #include <vector>
 
 namespace {
@@ -32,13 +34,17 @@ bool ref_compat_mode()
 }
 
 // ---- process-wide context per device: the OPENCL_CONTEXT singleton of gpu.rs:13-14, :97-115 ----
-std::mutex g_ctx_mu;
+// One lock PER ORDINAL: the --full-wgs driver's per-GPU threads build their contexts (CUDA context, six streams, module
+// load: ~1 s each) at the same time instead of one after another.  g_use_mu serialises the callers that SHARE a
+// process-wide context (rsm_gpu_align*, like the reference's Mutex around its one queue).
+std::mutex g_ctx_mu[64];
+std::mutex g_use_mu[64];
 swb_ctx* g_ctx[64] = {};
 
 swb_ctx* context_for(int ordinal)
 {
-  std::lock_guard<std::mutex> lk(g_ctx_mu);
   if (ordinal < 0 || ordinal >= 64) { g_err = "Failed to get GPU context: bad device ordinal"; return nullptr; }
+  std::lock_guard<std::mutex> lk(g_ctx_mu[ordinal]);
   if (!g_ctx[ordinal]) {
     swb_ctx* c = nullptr;
     if (swb_create(&c, ordinal, nullptr) != 0) { g_err = std::string("Failed to get GPU context: ") + swb_last_error(); return nullptr; }
@@ -831,6 +837,7 @@ int rsm_gpu_align_ex(const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t
   if (len == 0) return 0;                                            // aligner.rs:413-416
   swb_ctx* c = context_for(dev ? dev->ordinal : 0);
   if (!c) return 1;
+  std::lock_guard<std::mutex> use(g_use_mu[dev ? dev->ordinal : 0]);   // gpu.rs:13-14: callers of the shared context take turns
   if (ref_compat_mode()) {
     int32_t v = 0;
     const uint32_t wg = dev ? (uint32_t)std::min<uint64_t>(dev->max_work_group_size, 0xffffffffull) : 1024u;
@@ -894,6 +901,7 @@ int rsm_gpu_align_pair(const char* file1, const char* file2, const rsm_gpu_devic
     // Smith-Waterman mode: read k of file1 against read k of file2 (mates), one batch per chunk
     swb_ctx* c = context_for(dev ? dev->ordinal : 0);
     if (!c) return 1;
+    std::lock_guard<std::mutex> use(g_use_mu[dev ? dev->ordinal : 0]);
     FastqReader r1, r2; if (r1.open(file1) || r2.open(file2)) return 1;
     bool eof1 = false, eof2 = false; std::vector<swb_result> res;
     while (!eof1 && !eof2) {
@@ -1040,7 +1048,7 @@ int rsm_checkpoint_load(const char* path, char* run_id, size_t run_id_cap, rsm_f
     else { if (!c.scalar(&val)) return bad(); if (key == "total_files") tot = std::strtoull(val.c_str(), nullptr, 10); }
   }
   if (run_id && run_id_cap) std::snprintf(run_id, run_id_cap, "%s", rid.c_str());
-  if (n_files) *n_files = n;
+  if (n_files) *n_files = files ? std::min(n, cap) : n;         // entries written (files == NULL: entries in the file)
   if (total_files) *total_files = tot;
   return 0;
 }
@@ -1189,8 +1197,9 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
     const uint64_t w = compat ? 0 : window_len;
     std::string dir = "benchmark_results";
     if (const char* d = std::getenv("WGS_CHECKPOINT_DIR")) if (*d) dir = std::string(d) + "/benchmark_results";
-    const std::string mk = "mkdir -p '" + dir + "'";
-    if (std::system(mk.c_str()) == 0) {
+    std::error_code mk_ec;
+    std::filesystem::create_directories(dir, mk_ec);            // no shell: the path comes from the environment
+    if (!mk_ec) {
       const std::string path = dir + "/run_" + book.run_id + "_benchmark_results.json";
       if (FILE* fp = std::fopen(path.c_str(), "w")) {
         std::fprintf(fp, "{\n  \"timestamp\": \"%s\",\n  \"run_id\": \"%s\",\n  \"mode\": \"full_wgs\",\n  \"files_processed\": %zu,\n"

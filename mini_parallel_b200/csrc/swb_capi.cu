@@ -58,7 +58,7 @@ struct Lane {
 constexpr int kLanes = 6;                  // pipeline lanes a context owns; a host batch uses the first n_lanes of them
                                            // (chunks in flight: H2D / kernels / D2H overlap)
 
-struct ChunkEvents { cudaEvent_t ev[8]; };
+struct ChunkEvents { cudaEvent_t ev[8]; cudaEvent_t copied; };   // ev: stage boundaries (timed); copied: the chunk's host-to-device copies are done
 
 // The packed text the windows of a batch are cut from: the resident reference (swb_set_reference) or the window buffer of
 // one swb_score_batch_ranges call.  Window coordinates are relative to `base` (the first byte that was uploaded).
@@ -190,7 +190,7 @@ void swb_destroy(swb_ctx* c)
     for (DevBuf* b : {&sl.comp, &sl.blocks, &sl.out_off, &sl.text, &sl.fail}) b->release();
     if (sl.done) cudaEventDestroy(sl.done);
   }
-  for (auto& ce : c->chunk_ev) for (auto& e : ce.ev) cudaEventDestroy(e);
+  for (auto& ce : c->chunk_ev) { for (auto& e : ce.ev) cudaEventDestroy(e); cudaEventDestroy(ce.copied); }
   if (c->h_counters) cudaFreeHost(c->h_counters);
   delete c;
 }
@@ -350,6 +350,7 @@ static int ensure_chunk_slots(swb_ctx* c, size_t n_chunks)
   while (c->chunk_ev.size() < n_chunks) {
     ChunkEvents ce;
     for (auto& e : ce.ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaEventCreateWithFlags(&ce.copied, cudaEventDisableTiming));
     c->chunk_ev.push_back(ce);
   }
   if (c->h_counters_cap < n_chunks) {
@@ -410,6 +411,7 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
   const uint64_t n_chunks = bounds.size() - 1;
   if (ensure_chunk_slots(c, n_chunks)) return 1;
   c->last_kernels = 0;
+  uint64_t win_bytes = 0;
 
   for (uint64_t ch = 0; ch < n_chunks; ++ch) {
     const uint64_t p0 = bounds[ch], p1 = bounds[ch + 1], n = p1 - p0;
@@ -429,9 +431,11 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
       max_q = std::max<uint32_t>(max_q, (uint32_t)(qo[k + 1] - qo[k]));
       q_uniform &= qo[k + 1] - qo[k] == q_len0;
       if (ref_windows) {
-        if (win_start[k] > ref->len || win_len[k] > ref->len - win_start[k]) return fail(std::string(who) + ": window outside the reference");
+        if (win_start[k] > ref->len || win_len[k] > ref->len - win_start[k])
+          return fail(std::string(who) + (ref->ready ? ": window outside the buffer" : ": window outside the reference"));
         max_r = std::max<uint32_t>(max_r, win_len[k]);
         w_uniform &= win_len[k] == w_len0;
+        win_bytes += win_len[k];
       } else {
         if (ro[k + 1] < ro[k]) return fail(std::string(who) + ": offsets must be non-decreasing");
         if (ro[k + 1] - ro[k] > 0x7fffffffull) return fail("Sequence too large (more than 2^31-1 bytes)");
@@ -444,6 +448,10 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
     if (ref_windows) { if (l->win_beg.reserve(n * 8) || l->win_end.reserve(n * 8) || l->win_len.reserve(n * 4)) return 1; }
     else             { if (l->r_bytes.reserve(rb + 64) || l->r_off.reserve((n + 1) * 8)) return 1; }
 
+    // One chunk's copies at a time, in chunk order.  Copies of different streams otherwise share the link and finish
+    // together, their kernels then start together, and the lanes march in step -- copy, compute, copy, compute, nothing
+    // overlapping (measured: 12.0 instead of 10.5 ms per million pairs when the three lanes start on one event).
+    if (ch > 0) CUDA_TRY(cudaStreamWaitEvent(st, c->chunk_ev[ch - 1].copied, 0));
     CUDA_TRY(cudaEventRecord(ev[4], st));
     if (qb) CUDA_TRY(cudaMemcpyAsync(l->q_bytes.p, q + qo[p0], qb, cudaMemcpyHostToDevice, st));
     if (!q_uniform) CUDA_TRY(cudaMemcpyAsync(l->q_off.p, qo + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -451,11 +459,13 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
     if (ref_windows) {
       CUDA_TRY(cudaMemcpyAsync(l->win_beg.p, win_start + p0, n * 8, cudaMemcpyHostToDevice, st));
       if (!w_uniform) CUDA_TRY(cudaMemcpyAsync(l->win_len.p, win_len + p0, n * 4, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaEventRecord(c->chunk_ev[ch].copied, st));
       k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], q_uniform ? q_len0 : 0, nullptr, 0, 0, 0,
                                      l->win_beg.as<uint64_t>(), l->win_len.as<uint32_t>(), w_uniform ? w_len0 : 0, l->win_end.as<uint64_t>(), n, ref->base, st);
     } else {
       if (rb) CUDA_TRY(cudaMemcpyAsync(l->r_bytes.p, r + ro[p0], rb, cudaMemcpyHostToDevice, st));
       if (!r_uniform) CUDA_TRY(cudaMemcpyAsync(l->r_off.p, ro + p0, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaEventRecord(c->chunk_ev[ch].copied, st));
       k += swb::launch_chunk_prepare(l->q_off.as<uint64_t>(), n + 1, qo[p0], q_uniform ? q_len0 : 0, l->r_off.as<uint64_t>(), n + 1, ro[p0],
                                      r_uniform ? r_len0 : 0, nullptr, nullptr, 0, nullptr, 0, 0, st);
     }
@@ -478,6 +488,7 @@ static int score_host_batch_enqueue(swb_ctx* c, const char* who, const uint8_t* 
   for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamSynchronize(c->lane(i)->st));
   CUDA_TRY(cudaGetLastError());
   c->host_path = true; c->last_chunks = (size_t)n_chunks; c->timings_pending = true;
+  c->last_ranges_window_bytes = win_bytes;
   return 0;
 }
 
@@ -550,13 +561,19 @@ int swb_score_batch_ranges(swb_ctx* c, const uint8_t* q, const uint64_t* qo, uin
   if (!qo || !win_start || !win_len || !out || (w_total && !w_bytes)) return fail("swb_score_batch_ranges: null pointer");
   if (qo[0] != 0) return fail("swb_score_batch_ranges: offsets must start at 0");
   CUDA_TRY(cudaSetDevice(c->device));
-  uint64_t lo = w_total, hi = 0, sum = 0;                 // the part of the buffer the windows touch
-  for (uint64_t k = 0; k < n_pairs; ++k) {
-    const uint64_t s = win_start[k], n = win_len[k];
-    if (s > w_total || n > w_total - s) return fail("swb_score_batch_ranges: window outside the buffer");
-    if (n) { lo = std::min(lo, s); hi = std::max(hi, s + n); sum += n; }
+  // Which part of the buffer do the windows touch?  Finding out is a pass over the coordinates on the host with the GPU
+  // idle, ~1 ns per pair -- the time in which PCIe moves ~64 bytes -- so a buffer of fewer than 64 bytes per pair goes up
+  // whole; the windows are still validated chunk by chunk while the GPU works.
+  uint64_t lo = 0, hi = w_total, sum = 0;
+  if (w_total / 64 > n_pairs) {
+    lo = w_total; hi = 0;
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+      const uint64_t s = win_start[k], n = win_len[k];
+      if (s > w_total || n > w_total - s) return fail("swb_score_batch_ranges: window outside the buffer");
+      if (n) { lo = std::min(lo, s); hi = std::max(hi, s + n); sum += n; }
+    }
+    if (hi <= lo) { lo = 0; hi = 0; }
   }
-  if (hi <= lo) { lo = 0; hi = 0; }
   lo &= ~511ull;                                          // one bitmap word = 32 packed words = 512 bases
   const uint64_t n = hi - lo, nw = (n + 15) / 16;
   if (c->call_ref_bytes.reserve(n + 64) || c->call_ref_pk.reserve(nw * 4 + 64) || c->call_ref_bad.reserve((nw + 31) / 32 * 4 + 64)) return 1;
@@ -568,10 +585,10 @@ int swb_score_batch_ranges(swb_ctx* c, const uint8_t* q, const uint64_t* qo, uin
   RefSrc ref;
   ref.bytes = c->call_ref_bytes.as<uint8_t>(); ref.pk = c->call_ref_pk.as<uint32_t>(); ref.bad = c->call_ref_bad.as<uint32_t>();
   ref.len = w_total; ref.base = lo; ref.ready = c->call_ref_ready;
-  c->last_ranges_uploaded = n; c->last_ranges_window_bytes = sum;
   static const uint8_t empty = 0;
   const int rc = score_host_batch(c, "swb_score_batch_ranges", q ? q : &empty, qo, nullptr, nullptr, win_start, win_len, &ref, n_pairs, out);
   if (rc == 0) c->last_kernels += n ? 1 : 0;
+  c->last_ranges_uploaded = n;                            // (the window bytes were summed while the chunks were validated)
   return rc;
 }
 

@@ -434,6 +434,9 @@ int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg
     case 8: return launch_stream_t<16, 10, 4, 2>(b, lc, 8, st);
     case 10: return launch_stream_t<16, 10, 5, 2>(b, lc, 10, st);
     case 11: return launch_stream_t<16, 10, 5, 3>(b, lc, 11, st);
+    case 12: return launch_stream_t<16, 10, 4, 3 + (6 << 4)>(b, lc, 12, st);     // two-step tracker on 6 / 7 / 8 of a lane's 10 rows
+    case 13: return launch_stream_t<16, 10, 4, 3 + (7 << 4)>(b, lc, 13, st);
+    case 14: return launch_stream_t<16, 10, 4, 3 + (8 << 4)>(b, lc, 14, st);
 #endif
     default: return launch_stream_t<16, 10, 4, 3>(b, lc, 9, st);
   }
@@ -442,7 +445,7 @@ int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg
 bool short_variant_available(int variant)
 {
 #ifdef SWB_ALL_VARIANTS
-  return variant >= 0 && variant <= 11;
+  return variant >= 0 && variant <= 14;
 #else
   return variant == 9;
 #endif
@@ -512,6 +515,9 @@ __global__ void __launch_bounds__(128, MINB)
 sw_stream_kernel(StreamArgs a)
 {
   constexpr bool TRK = (FLAGS & 1) != 0;                 // two-step tracker (x = h + e as a plain add, one VIMNMX3 per two steps)
+  // rows of a lane that use it; the others keep the one-instruction VIADDMNMX tracker.  The two-step form trades half an
+  // ALU-pipe instruction for a whole FMA-pipe one: all rows when the ALU pipe is the limit, fewer when the issue slots are
+  constexpr int TRKROWS = TRK ? ((FLAGS >> 4) ? (FLAGS >> 4) : K) : 0;
   constexpr bool DYN = (FLAGS & 2) != 0;                 // couples beyond a group's first kStaticCouples come from a device-wide cursor
   constexpr uint32_t NSTAT = 5;                          // couples per group assigned statically; the cursor is read NSTAT ahead
   static_assert(K % 2 == 0 && K <= 32, "K even, at most 32 codes per 64-bit code word");
@@ -633,6 +639,7 @@ sw_stream_kernel(StreamArgs a)
   // h_half + e_half >= tag >= 0 and the carry out of the low half cancels the borrow of a negative e_half
   // exactly when e is held as e_half * 65537 (two's complement)
   uint32_t e = TRK ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
+  uint32_t e16 = (uint32_t)(BLOCK - 1) * 0x00010001u;    // the packed-halves form, for the rows on the VIADDMNMX tracker
   int32_t blockStart = 0;
   int32_t pairBase = 0;                                  // first stream column of the lane's current pair
   uint32_t fin_n = 0;
@@ -666,6 +673,7 @@ sw_stream_kernel(StreamArgs a)
       upPrev = __vsub2(upPrev, REBASE);
       floor_ = 0; fm1 = 0xFF80FF80u;
       e = TRK ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
+      e16 = (uint32_t)(BLOCK - 1) * 0x00010001u;
       blockStart += BLOCK;
     }
     if (it == stage_it) {                                // refill the ring one chunk ahead (all lanes)
@@ -755,12 +763,12 @@ sw_stream_kernel(StreamArgs a)
         const uint32_t h  = __vimax3_s16x2(t1, l, floor_);
         if (u & 1) B[m] = h; else A[m] = h;
 #if SWB_ABLATE != 2
-        if (TRK) {                                       // two steps per tracker update: x = h + e is a plain add (FMA pipe)
+        if (m < TRKROWS) {                               // two steps per tracker update: x = h + e is a plain add (FMA pipe)
           const uint32_t xe = h + e;
           if (u & 1) cur[m] = __vimax3_s16x2(cur[m], X[m], xe);
           else       X[m] = xe;
         } else {
-          cur[m] = __viaddmax_s16x2(h, e, cur[m]);
+          cur[m] = __viaddmax_s16x2(h, TRK ? e16 : e, cur[m]);
         }
 #else
         cur[m] |= h;
@@ -771,6 +779,7 @@ sw_stream_kernel(StreamArgs a)
       fm1 = floor_;
       floor_ += 0x00800080u;
       e = TRK ? e - 129u * 65537u : __vsub2(e, 0x00810081u);
+      if (TRK && TRKROWS < K) e16 = __vsub2(e16, 0x00810081u);
 #endif
     }
   }

@@ -36,7 +36,11 @@ def synth_reference(n):
 
 
 def make_file(args):
-    path, fi, n_reads, ref_len, rl, wl, level, blocked, noisy = args
+    """One FASTQ file (or, with a 10th / 11th field, the slice [first_read, first_read + n_reads) of one: BGZF files are
+    concatenations of independent blocks, so the slices of a file are made by different processes and joined)."""
+    path, fi, n_reads, ref_len, rl, wl, level, blocked, noisy = args[:9]
+    first_read = args[9] if len(args) > 9 else 0
+    write_eof = args[10] if len(args) > 10 else True
     ref = synth_reference(ref_len)
     if blocked:                                    # BGZF: independent <= 64 KiB members with a 'BC' size field (bgzip / BCL Convert)
         sys.path.insert(0, ROOT)
@@ -44,8 +48,8 @@ def make_file(args):
     co = None if blocked else zlib.compressobj(level, zlib.DEFLATED, 31)
     step = 100_000
     with open(path, "wb") as f:
-        for a in range(0, n_reads, step):
-            m = min(step, n_reads - a)
+        for a in range(first_read, first_read + n_reads, step):
+            m = min(step, first_read + n_reads - a)
             k = np.arange(a, a + m, dtype=np.uint64)
             with np.errstate(over="ignore"):
                 g = (np.uint64(fi) << np.uint64(40)) + k
@@ -73,7 +77,8 @@ def make_file(args):
                 f.write(bgzf.compress(rec.tobytes(), level, 65280, eof=False))     # blocks may end anywhere inside a record
             else:
                 f.write(co.compress(rec.tobytes()))
-        f.write(bgzf.EOF_BLOCK if blocked else co.flush())
+        if write_eof:
+            f.write(bgzf.EOF_BLOCK if blocked else co.flush())
     return os.path.getsize(path), n_reads * rec.shape[1]
 
 
@@ -98,8 +103,34 @@ def main():
             jobs.append((os.path.join(args.dir, f"SYN_L{lane:03d}_R{rd}_001.fastq.gz"), fi, args.reads_per_file, args.ref_bases, 150, 500, args.level, args.bgzf, args.quals == "noisy"))
             fi += 1
     t0 = time.time()
+    rec_len = 12 + 150 + 3 + 150 + 1
     if args.reuse and all(os.path.exists(j[0]) for j in jobs):     # files of an earlier run with the same parameters
-        rec_len = 12 + 150 + 3 + 150 + 1
+        sizes = [(os.path.getsize(j[0]), args.reads_per_file * rec_len) for j in jobs]
+    elif args.bgzf and (os.cpu_count() or 1) >= 2 * len(jobs):     # more cores than files: every file in slices, joined afterwards
+        parts = max(1, (os.cpu_count() or 1) // len(jobs))
+        per = (args.reads_per_file + parts - 1) // parts
+        pjobs = []
+        for j in jobs:
+            for k in range(parts):
+                a, b = k * per, min(args.reads_per_file, (k + 1) * per)
+                if b > a:
+                    pjobs.append((j[0] + f".part{k}",) + j[1:2] + (b - a,) + j[3:] + (a, False))
+        with ProcessPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+            list(ex.map(make_file, pjobs))
+        sys.path.insert(0, ROOT)
+        from mini_parallel_b200 import bgzf as _bgzf
+        for j in jobs:
+            with open(j[0], "wb") as out:
+                for pj in pjobs:
+                    if pj[0].startswith(j[0] + ".part"):
+                        with open(pj[0], "rb") as src:
+                            while True:
+                                blk = src.read(64 << 20)
+                                if not blk:
+                                    break
+                                out.write(blk)
+                        os.unlink(pj[0])
+                out.write(_bgzf.EOF_BLOCK)
         sizes = [(os.path.getsize(j[0]), args.reads_per_file * rec_len) for j in jobs]
     else:
         with ProcessPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
@@ -129,7 +160,9 @@ def main():
         "gz_mb_per_s": round(gz_bytes / wall / 1e6, 1), "fastq_text_mb_per_s": round(text_bytes / wall / 1e6, 1),
         "slowest_file_s": max(file_s) if file_s else None,
         "pipeline_reads_per_s": round(n_reads / max(file_s), 1) if file_s else None,      # all files run concurrently: excludes process + CUDA context start-up
-        "pipeline_gcups": round(n_reads * 150 * 500 / max(file_s) / 1e9, 1) if file_s else None, "host_cores": os.cpu_count(), "generate_s": round(gen_s, 1),
+        "pipeline_gcups": round(n_reads * 150 * 500 / max(file_s) / 1e9, 1) if file_s else None,
+        "startup_s": round(wall - max(file_s), 3) if file_s else None,                    # process start, CUDA contexts, reference upload: everything before / after the files
+        "host_cores": os.cpu_count(), "generate_s": round(gen_s, 1),
         "mean_score_per_read": round(sum(scores) / n_reads, 2), "files_done": len(scores)}))
 
 
