@@ -308,7 +308,8 @@ def leg_bgzf(args, eng, lib, mp):
     tmp = tempfile.mkdtemp(prefix="swb_bgzf_")
     jobs = [(os.path.join(tmp, f"part{k}.fastq.gz"), k, per, ref_len) for k in range(parts)]
     t0 = time.perf_counter()
-    with ProcessPoolExecutor(max_workers=min(parts, os.cpu_count() or 1)) as ex:
+    import multiprocessing
+    with ProcessPoolExecutor(max_workers=min(parts, os.cpu_count() or 1), mp_context=multiprocessing.get_context("spawn")) as ex:   # no fork of a CUDA process
         paths = list(ex.map(_bgzf_part, jobs))
     gen_s = time.perf_counter() - t0
     segs = []

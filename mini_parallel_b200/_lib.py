@@ -50,6 +50,8 @@ SIGNATURES = {
     "swb_synth_device": (_int, [_vp, _u64, _u64, _u32, _u32, _int, _vp, _vp, _vp, _vp]),
     "swb_last_timings": (_int, [_vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_int)]),
     "swb_last_routing": (_int, [_vp, ctypes.POINTER(_u64)]),
+    "swb_last_routing_ex": (_int, [_vp, ctypes.POINTER(_u64)]),
+    "swb_set_mid_path": (_int, [_vp, _int]),
     "swb_set_short_variant": (_int, [_vp, _int]),
     "swb_traceback_batch": (_int, [_vp, _u8p, _vp, _u8p, _vp, _u64, _vp, _vp, _vp, _u64, ctypes.POINTER(_u64)]),
     "swb_set_chunking": (_int, [_vp, _u64, _u64]),

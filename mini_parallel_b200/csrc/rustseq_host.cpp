@@ -27,6 +27,14 @@ namespace {
 thread_local std::string g_err;
 int fail(const std::string& m) { g_err = m; return 1; }
 
+// SWB_DEBUG: seconds since the library was loaded (~ process start), for the start-up / tear-down accounting of the CLI
+const std::chrono::steady_clock::time_point g_loaded = std::chrono::steady_clock::now();
+void dbg_stamp(const char* what)
+{
+  if (std::getenv("SWB_DEBUG"))
+    std::fprintf(stderr, "[main] %-36s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - g_loaded).count());
+}
+
 bool ref_compat_mode()
 {
   const char* m = std::getenv("SWB_GPU_ALIGN_MODE");
@@ -1097,6 +1105,7 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   std::vector<uint8_t> ref; uint32_t window_len = 500;
   if (!compat) {
     if (load_reference(ref)) return 1;
+    stamp("reference in host memory");
     uint64_t w = 500; if (!parse_usize(env_or("WGS_WINDOW_LEN", "500"), &w, &why) && w >= 1) window_len = (uint32_t)std::min<uint64_t>(w, ref.size());
     std::printf("Reference: %zu bases, window %u bp, %zu GPU(s)\n", ref.size(), window_len, order.size());
   }
@@ -1161,6 +1170,7 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
       else if (swb_create(&ctx, ord, nullptr) == 0) own_ctx[w] = ctx;
       else { g_err = std::string("Failed to get GPU context: ") + swb_last_error(); ctx = nullptr; }
       if (!ctx) { werr[w] = g_err; return; }
+      stamp("context created");
       if (swb_set_reference(ctx, ref.data(), ref.size())) { werr[w] = swb_last_error(); return; }
       stamp("context + reference on device");
       std::vector<size_t> mine;
@@ -1173,8 +1183,8 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   for (auto& t : workers) t.join();
   double mem_used_mb = 0;
   { uint64_t fr = 0, to = 0; if (swb_memory_info(first, &fr, &to) == 0) mem_used_mb = (double)(to - fr) / 1048576.0; }
-  for (swb_ctx* x : own_ctx) if (x) swb_destroy(x);
   stamp("all files done");
+  for (swb_ctx* x : own_ctx) if (x) swb_destroy(x);
   for (const auto& e : werr) if (!e.empty()) return fail(e);
   int n = 0;
   for (size_t i = 0; i < total; ++i) {
@@ -1236,6 +1246,8 @@ static void usage()
 
 int rsm_main(int argc, char** argv)
 {
+  dbg_stamp("main entered");
+  std::atexit([] { dbg_stamp("atexit (before static destructors)"); });
   load_dotenv();                                                     // main.rs:50
   std::string seq1, seq2; bool has1 = false, has2 = false, files = false, gpu = false, test_wgs = false, full_wgs = false;
   for (int i = 1; i < argc; ++i) {
@@ -1265,13 +1277,17 @@ int rsm_main(int argc, char** argv)
       std::fprintf(stderr, "error: gpu acceleration is required for full WGS processing\n");   // main.rs:77
       return 1;
     }
+    dbg_stamp("gpu available");
     rsm_gpu_device devs[64];
     const int nd = rsm_get_gpu_devices(devs, 64);
+    dbg_stamp("devices listed");
     std::printf("GPU acceleration enabled\n");
     for (int d = 0; d < nd && d < 64; ++d) std::printf("  Found GPU: %s (%g GB)\n", devs[d].name, devs[d].memory_gb);
     std::vector<rsm_alignment_result> res(4096);
     int n = 0;
-    if (rsm_process_full_wgs_dataset(&devs[0], res.data(), (int)res.size(), &n)) {
+    const int wgs_rc = rsm_process_full_wgs_dataset(&devs[0], res.data(), (int)res.size(), &n);
+    dbg_stamp("full wgs returned");
+    if (wgs_rc) {
       std::fprintf(stderr, "Full WGS processing error: %s\n", rsm_last_error());               // main.rs:115
       return 1;
     }
@@ -1282,6 +1298,7 @@ int rsm_main(int argc, char** argv)
     std::printf("Total reads processed: %llu\nTotal base pairs: %llu\n", (unsigned long long)reads, (unsigned long long)bases);
     std::printf("Total processing time: %.2f seconds\n", ms / 1000.0);
     for (int i = 0; i < n; ++i) std::printf("File %d: Score=%lld, Time=%.2fs\n", i + 1, (long long)res[i].score64, res[i].processing_time_ms / 1000.0);
+    dbg_stamp("main returns");
     return 0;
   }
 

@@ -47,11 +47,12 @@ struct DevBuf {
 struct Lane {
   cudaStream_t st = nullptr;
   cudaEvent_t ev[8] = {};
+  DevBuf mid_desc;
   DevBuf q_bytes, r_bytes, q_off, r_off, q_pk, r_pk, q_bad, r_bad, short_list, short_desc, generic_list, long_list, bytes_list, long_scratch, bytes_scratch, counters, out, scratch, misc;
   DevBuf win_beg, win_end, win_len;
   void release_all() {
     for (DevBuf* b : {&q_bytes, &r_bytes, &q_off, &r_off, &q_pk, &r_pk, &q_bad, &r_bad, &short_list, &short_desc,
-                      &generic_list, &long_list, &bytes_list, &long_scratch, &bytes_scratch, &counters, &out, &scratch, &misc, &win_beg, &win_end, &win_len}) b->release();
+                      &generic_list, &long_list, &bytes_list, &long_scratch, &bytes_scratch, &counters, &out, &scratch, &misc, &win_beg, &win_end, &win_len, &mid_desc}) b->release();
   }
 };
 
@@ -105,6 +106,8 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   uint64_t last_routing[3] = {0, 0, 0};
   bool timings_pending = false, host_path = false;
   int variant = 9;                         // sw_stream_kernel<16,10,4, two-step tracker + dynamic couple distribution>
+  bool mid_path = true;                    // SWB_MID_PATH=0: reads of 161..320 bp go to the 32-bit long-pair kernel (tests / comparison)
+  uint64_t last_routing5[5] = {0, 0, 0, 0, 0};
   int force_bytes = 0;                     // SWB_FORCE_BYTES=1: every non-short pair through the byte-compare kernel (bench / tests)
 };
 
@@ -163,6 +166,7 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   }
   if (const char* v = std::getenv("SWB_SHORT_VARIANT")) { const int w = std::atoi(v) & 15; if (swb::short_variant_available(w)) c->variant = w; }
   if (const char* v = std::getenv("SWB_FORCE_BYTES")) c->force_bytes = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SWB_MID_PATH")) c->mid_path = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_UNIFORM_OFFSETS")) c->uniform_offsets = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_LANES")) c->n_lanes = std::min(kLanes, std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("SWB_CHUNK_RAMP")) c->chunk_ramp = std::min(2, std::max(0, std::atoi(v)));
@@ -279,6 +283,7 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   if (l->q_pk.reserve(qw * 4 + 64) || l->r_pk.reserve(rw * 4 + 64) ||
       l->q_bad.reserve((qw + 31) / 32 * 4 + 64) || l->r_bad.reserve((rw + 31) / 32 * 4 + 64) ||
       l->short_list.reserve(n_pairs * 4 + 64) || l->short_desc.reserve(n_pairs * sizeof(swb::ShortDesc) + 64) ||
+      (max_q_len > swb::kShortMaxRead && l->mid_desc.reserve(n_pairs * sizeof(swb::ShortDesc) + 64)) ||
       l->generic_list.reserve(n_pairs * 4 + 64) || l->long_list.reserve(n_pairs * 4 + 64) || l->bytes_list.reserve(n_pairs * 4 + 64) ||
       l->counters.reserve(sizeof(swb::Counters))) return 1;
   // generic kernel: persistent grid, one boundary row of max_r_len ints per resident warp
@@ -295,6 +300,7 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   b.r_bad = ref_windows ? ref->bad : l->r_bad.as<uint32_t>();
   b.n_pairs = n_pairs;
   b.short_list = l->short_list.as<uint32_t>(); b.short_desc = l->short_desc.as<swb::ShortDesc>();
+  b.mid_desc = (max_q_len > swb::kShortMaxRead && c->mid_path) ? l->mid_desc.as<swb::ShortDesc>() : nullptr;   // no read beyond 160 bp: no mid list, no launch
   b.generic_list = l->generic_list.as<uint32_t>(); b.long_list = l->long_list.as<uint32_t>(); b.bytes_list = l->bytes_list.as<uint32_t>();
   b.force_bytes = c->force_bytes;
   b.counters = l->counters.as<swb::Counters>(); b.out = d_out;
@@ -311,6 +317,7 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   CUDA_TRY(cudaEventRecord(ev[1], st));
   const uint32_t wcap = std::min<uint32_t>(std::max<uint32_t>(max_r_len, 1), swb::kShortMaxWindow);
   k += swb::launch_short(b, wcap, c->variant, c->lc, st);
+  k += swb::launch_mid(b, c->lc, st);
   CUDA_TRY(cudaEventRecord(ev[2], st));
   k += swb::launch_generic(b, ctas / 4 > 0 ? ctas / 4 : 1, 0, st);
   {
@@ -862,6 +869,7 @@ int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
     for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamSynchronize(c->lane(i)->st));
     for (float& v : c->last_ms) v = 0;
     c->last_routing[0] = c->last_routing[1] = c->last_routing[2] = 0;
+    for (auto& v : c->last_routing5) v = 0;
     if (!c->host_path) {
       cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
       cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
@@ -869,7 +877,8 @@ int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
       cudaEventElapsedTime(&c->last_ms[3], c->ev[0], c->ev[3]);
       swb::Counters h;
       CUDA_TRY(cudaMemcpy(&h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
-      c->last_routing[0] = h.n_short; c->last_routing[1] = h.n_generic + h.n_bytes; c->last_routing[2] = h.n_long;
+      c->last_routing[0] = h.n_short + h.n_mid; c->last_routing[1] = h.n_generic + h.n_bytes; c->last_routing[2] = h.n_long;
+      c->last_routing5[0] = h.n_short; c->last_routing5[1] = h.n_mid; c->last_routing5[2] = h.n_long; c->last_routing5[3] = h.n_bytes; c->last_routing5[4] = h.n_generic;
     } else {
       // sums over the chunks of the call (chunks overlap in time, so [3] is the span first event -> last event)
       for (size_t ch = 0; ch < c->last_chunks; ++ch) {
@@ -880,8 +889,9 @@ int swb_last_timings(swb_ctx* c, float* ms, int* kernels)
         cudaEventElapsedTime(&t, ev[2], ev[3]); c->last_ms[2] += t;
         cudaEventElapsedTime(&t, ev[4], ev[5]); c->last_ms[4] += t;
         cudaEventElapsedTime(&t, ev[6], ev[7]); c->last_ms[5] += t;
-        c->last_routing[0] += c->h_counters[ch].n_short; c->last_routing[1] += c->h_counters[ch].n_generic + c->h_counters[ch].n_bytes;
-        c->last_routing[2] += c->h_counters[ch].n_long;
+        const swb::Counters& hc = c->h_counters[ch];
+        c->last_routing[0] += hc.n_short + hc.n_mid; c->last_routing[1] += hc.n_generic + hc.n_bytes; c->last_routing[2] += hc.n_long;
+        c->last_routing5[0] += hc.n_short; c->last_routing5[1] += hc.n_mid; c->last_routing5[2] += hc.n_long; c->last_routing5[3] += hc.n_bytes; c->last_routing5[4] += hc.n_generic;
       }
       if (std::getenv("SWB_DEBUG_TIMELINE")) {                 // per chunk, ms since the first event of the call
         for (size_t ch = 0; ch < c->last_chunks; ++ch) {
@@ -914,6 +924,16 @@ int swb_last_routing(swb_ctx* c, uint64_t* counts)
   counts[0] = c->last_routing[0]; counts[1] = c->last_routing[1]; counts[2] = c->last_routing[2];
   return 0;
 }
+
+int swb_last_routing_ex(swb_ctx* c, uint64_t* counts)
+{
+  if (!c || !counts) return fail("null pointer");
+  if (swb_last_timings(c, nullptr, nullptr)) return 1;
+  for (int k = 0; k < 5; ++k) counts[k] = c->last_routing5[k];
+  return 0;
+}
+
+int swb_set_mid_path(swb_ctx* c, int on) { if (!c) return fail("null ctx"); c->mid_path = on != 0; return 0; }
 
 int swb_ref_compat_align(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2,
                          uint32_t dev_max_wg, int32_t* out)

@@ -121,12 +121,11 @@ classify_kernel(BatchView b)
       cls = CLASS_EMPTY;                                   //  max_r_len of swb_score_batch_device): not scored, reported
       b.out[k] = swb_result{INT32_MIN, -1, -1};
       atomicAdd(&b.counters->n_overflow, 1u);
-    } else if (n <= kShortMaxRead && mm <= kShortMaxWindow &&
-               !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1)) {
-      cls = CLASS_SHORT; m = (uint32_t)mm;
     } else if (n <= kLongMaxLen && mm <= kLongMaxLen) {
-      const bool acgt = !b.force_bytes && !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1);
-      cls = acgt ? CLASS_LONG : CLASS_BYTES;
+      const bool acgt = !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1);
+      if (acgt && n <= kShortMaxRead && mm <= kShortMaxWindow) { cls = CLASS_SHORT; m = (uint32_t)mm; }
+      else if (acgt && n <= kMidMaxRead && mm <= kShortMaxWindow && b.mid_desc && !b.force_bytes) { cls = CLASS_MID; m = (uint32_t)mm; }
+      else cls = (acgt && !b.force_bytes) ? CLASS_LONG : CLASS_BYTES;
     } else {
       cls = CLASS_GENERIC;
     }
@@ -137,17 +136,20 @@ classify_kernel(BatchView b)
   const uint32_t mg = __ballot_sync(0xffffffffu, cls == CLASS_GENERIC);
   const uint32_t ml = __ballot_sync(0xffffffffu, cls == CLASS_LONG);
   const uint32_t mb = __ballot_sync(0xffffffffu, cls == CLASS_BYTES);
-  uint32_t base_s = 0, base_g = 0, base_l = 0, base_b = 0;
+  const uint32_t mm_ = __ballot_sync(0xffffffffu, cls == CLASS_MID);
+  uint32_t base_s = 0, base_g = 0, base_l = 0, base_b = 0, base_m = 0;
   if (lane == 0) {
     if (ms) base_s = atomicAdd(&b.counters->n_short, __popc(ms));
     if (mg) base_g = atomicAdd(&b.counters->n_generic, __popc(mg));
     if (ml) base_l = atomicAdd(&b.counters->n_long, __popc(ml));
     if (mb) base_b = atomicAdd(&b.counters->n_bytes, __popc(mb));
+    if (mm_) base_m = atomicAdd(&b.counters->n_mid, __popc(mm_));
   }
   base_s = __shfl_sync(0xffffffffu, base_s, 0);
   base_g = __shfl_sync(0xffffffffu, base_g, 0);
   base_l = __shfl_sync(0xffffffffu, base_l, 0);
   base_b = __shfl_sync(0xffffffffu, base_b, 0);
+  base_m = __shfl_sync(0xffffffffu, base_m, 0);
   const uint32_t below = (1u << lane) - 1;
   if (cls == CLASS_SHORT) {
     const uint32_t slot = base_s + __popc(ms & below);
@@ -157,12 +159,20 @@ classify_kernel(BatchView b)
     d[0] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)r0, (uint32_t)(r0 >> 32));
     d[1] = make_uint4((uint32_t)(b.q_end[k] - q0), m, (uint32_t)k, 0u);
   }
+  if (cls == CLASS_MID) {
+    const uint32_t slot = base_m + __popc(mm_ & below);
+    const uint64_t q0 = b.q_beg[k], r0 = b.r_beg[k];
+    uint4* d = reinterpret_cast<uint4*>(b.mid_desc + slot);
+    d[0] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)r0, (uint32_t)(r0 >> 32));
+    d[1] = make_uint4((uint32_t)(b.q_end[k] - q0), m, (uint32_t)k, 0u);
+  }
   if (cls == CLASS_GENERIC) b.generic_list[base_g + __popc(mg & below)] = (uint32_t)k;
   if (cls == CLASS_LONG)    b.long_list[base_l + __popc(ml & below)] = (uint32_t)k;
   if (cls == CLASS_BYTES)   b.bytes_list[base_b + __popc(mb & below)] = (uint32_t)k;
-  uint32_t wm = m;
-  for (int o = 16; o; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+  uint32_t wm = cls == CLASS_SHORT ? m : 0u, wmid = cls == CLASS_MID ? m : 0u;
+  for (int o = 16; o; o >>= 1) { wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o)); wmid = max(wmid, __shfl_xor_sync(0xffffffffu, wmid, o)); }
   if (lane == 0 && wm) atomicMax(&b.counters->max_short_window, wm);
+  if (lane == 0 && wmid) atomicMax(&b.counters->max_mid_window, wmid);
 }
 
 // Chunk preparation of the host path: CSR offsets arrive as absolute positions in the caller's arrays and are
@@ -434,18 +444,22 @@ int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg
     case 8: return launch_stream_t<16, 10, 4, 2>(b, lc, 8, st);
     case 10: return launch_stream_t<16, 10, 5, 2>(b, lc, 10, st);
     case 11: return launch_stream_t<16, 10, 5, 3>(b, lc, 11, st);
-    case 12: return launch_stream_t<16, 10, 4, 3 + (6 << 4)>(b, lc, 12, st);     // two-step tracker on 6 / 7 / 8 of a lane's 10 rows
-    case 13: return launch_stream_t<16, 10, 4, 3 + (7 << 4)>(b, lc, 13, st);
-    case 14: return launch_stream_t<16, 10, 4, 3 + (8 << 4)>(b, lc, 14, st);
 #endif
     default: return launch_stream_t<16, 10, 4, 3>(b, lc, 9, st);
   }
 }
 
+// reads of 161..320 bp: one group of 32 lanes x 10 rows per warp, value scale 32 (two-step tracker, dynamic distribution)
+int launch_mid(const BatchView& b, LaunchCfg& lc, cudaStream_t st)
+{
+  if (b.n_pairs == 0 || !b.mid_desc) return 0;
+  return launch_stream_t<32, 10, 4, 3 + 8>(b, lc, 15, st);
+}
+
 bool short_variant_available(int variant)
 {
 #ifdef SWB_ALL_VARIANTS
-  return variant >= 0 && variant <= 14;
+  return variant >= 0 && variant <= 11;
 #else
   return variant == 9;
 #endif
@@ -485,7 +499,10 @@ template <int G> __device__ __forceinline__ uint32_t ring_skew_t(uint32_t g) { r
 
 struct StreamArgs {
   const uint32_t* q_pk; const uint32_t* r_pk;
-  const ShortDesc* desc; const Counters* counters;
+  const ShortDesc* desc;                    // the listed pairs, in list order
+  const uint32_t* n_list;                   // how many (device-side count)
+  const uint32_t* max_window;               // longest window among them
+  uint32_t* cursor;                         // couples handed out beyond every group's static ones (zeroed per batch)
   swb_result* out;
 };
 
@@ -515,17 +532,26 @@ __global__ void __launch_bounds__(128, MINB)
 sw_stream_kernel(StreamArgs a)
 {
   constexpr bool TRK = (FLAGS & 1) != 0;                 // two-step tracker (x = h + e as a plain add, one VIMNMX3 per two steps)
-  // rows of a lane that use it; the others keep the one-instruction VIADDMNMX tracker.  The two-step form trades half an
-  // ALU-pipe instruction for a whole FMA-pipe one: all rows when the ALU pipe is the limit, fewer when the issue slots are
-  constexpr int TRKROWS = TRK ? ((FLAGS >> 4) ? (FLAGS >> 4) : K) : 0;
   constexpr bool DYN = (FLAGS & 2) != 0;                 // couples beyond a group's first kStaticCouples come from a device-wide cursor
   constexpr uint32_t NSTAT = 5;                          // couples per group assigned statically; the cursor is read NSTAT ahead
   static_assert(K % 2 == 0 && K <= 32, "K even, at most 32 codes per 64-bit code word");
   static_assert(32 % G == 0, "G must divide the warp");
   constexpr int NPAD  = G * K;
-  constexpr int BLOCK = (62 / K) * K;
+  // Value scale.  V = SC * (H + 2*tau) must stay inside int16: SC = 64 (6 tag bits, blocks of 60 steps) holds H <= 2*160 + the
+  // block's bias; the 320-row instantiation (FLAGS & 8: reads of 161..320 bp, H <= 640) runs at SC = 32 with 5 tag bits and
+  // blocks of 30 steps: 32 * (640 + 2*29) = 22 336.  Keys: H << HSHIFT | (RMAX - i) << 13 | (8191 - NPAD - j).
+  constexpr int TB    = (FLAGS & 8) ? 5 : 6;
+  constexpr uint32_t SC = 1u << TB;
+  constexpr int BLOCK = (((1 << TB) - 2) / K) * K;
   constexpr int IPB   = BLOCK / K;                       // iterations per block
-  constexpr uint32_t REBASE = (uint32_t)(128 * BLOCK) * 0x00010001u;
+  constexpr uint32_t P2 = 0x00010001u;                   // both halves
+  constexpr uint32_t REBASE = (2u * SC * BLOCK) * P2;
+  constexpr int ROWBITS = NPAD > 256 ? 9 : 8;
+  constexpr int HSHIFT = 13 + ROWBITS;
+  constexpr uint32_t RMAX = (1u << ROWBITS) - 1u;
+  constexpr uint32_t FOLDM = 1u << (HSHIFT - TB);        // key = c * FOLDM - tag * (FOLDM - 1) + position
+  static_assert(NPAD <= 320 && (NPAD <= 160 || TB == 5), "int16 range: 160 rows at scale 64, 320 rows at scale 32");
+  constexpr uint32_t V0A = (0u - 4u * SC) & 0xFFFFu, V0B = (0u - 2u * SC) & 0xFFFFu;   // image of H = 0 two steps / one step before tau = 0
   constexpr int GPW = 32 / G;
   constexpr int RSLOTS = 4 * G;                          // ring = RSLOTS slots of K columns
   constexpr int RING = RSLOTS * K;                       // uint16 entries
@@ -536,19 +562,19 @@ sw_stream_kernel(StreamArgs a)
   uint32_t* lut = reinterpret_cast<uint32_t*>(smem);
   for (uint32_t x = threadIdx.x; x < kLutEntries * 32; x += blockDim.x) {
     const uint32_t idx = x >> 5, ia = idx / 9, ib = idx % 9;
-    lut[x] = ((ia == 3 ? 384u : 192u) << 16) | (ib == 3 ? 384u : 192u);
+    lut[x] = ((ia == 3 ? 6u * SC : 3u * SC) << 16) | (ib == 3 ? 6u * SC : 3u * SC);
   }
   __syncthreads();
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t g = lane / G, L = lane % G;
-  const uint32_t n_list = a.counters->n_short;
+  const uint32_t n_list = *a.n_list;
   const uint32_t n_pp = (n_list + 1) >> 1;
   const uint32_t NG = gridDim.x * 4 * GPW;
   const uint32_t gidx0 = (blockIdx.x * 4 + warp) * GPW, gidx = gidx0 + g;
   if (gidx0 >= n_pp) return;                             // no pair couple for any group of this warp
   const uint32_t warpN = (n_pp - 1 - gidx0) / NG + 1;    // static distribution: the warp's first group has the longest run
-  uint32_t Wp = (a.counters->max_short_window + 2 * K - 2) / K * K;
+  uint32_t Wp = (*a.max_window + 2 * K - 2) / K * K;
   if (Wp < NPAD + K) Wp = NPAD + K;                      // at most two pairs in flight per group
   const uint32_t ipp = Wp / K;                           // iterations per pair
 
@@ -632,27 +658,26 @@ sw_stream_kernel(StreamArgs a)
 
   uint32_t A[K], B[K], W[K], cur[K], X[K];
 #pragma unroll
-  for (int m = 0; m < K; ++m) { A[m] = 0xFF00FF00u; B[m] = 0xFF80FF80u; W[m] = WPADV; cur[m] = 0; X[m] = 0; }
+  for (int m = 0; m < K; ++m) { A[m] = V0A * P2; B[m] = V0B * P2; W[m] = WPADV; cur[m] = 0; X[m] = 0; }
   uint32_t recA = 0, recB = 0, prevA = 0, prevB = 0;
-  uint32_t floor_ = 0, fm1 = 0xFF80FF80u, upPrev = 0xFF00FF00u;
+  uint32_t floor_ = 0, fm1 = V0B * P2, upPrev = V0A * P2;
   // e = tag - floor per half.  TRK == 1 adds it to h as ONE 32-bit integer: both halves of h are >= floor, so
   // h_half + e_half >= tag >= 0 and the carry out of the low half cancels the borrow of a negative e_half
   // exactly when e is held as e_half * 65537 (two's complement)
-  uint32_t e = TRK ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
-  uint32_t e16 = (uint32_t)(BLOCK - 1) * 0x00010001u;    // the packed-halves form, for the rows on the VIADDMNMX tracker
+  uint32_t e = (uint32_t)(BLOCK - 1) * P2;               // (BLOCK-1) * 65537 == (BLOCK-1) * 0x00010001: both forms start equal
   int32_t blockStart = 0;
   int32_t pairBase = 0;                                  // first stream column of the lane's current pair
   uint32_t fin_n = 0;
   uint32_t sw_it = ipp + L, fin_it = ipp + G - 1, stage_it = 0, stage_k = 1;
   int bit = 0;
 
-  // fold the K row trackers into the two per-pair keys  H<<21 | (255-i)<<13 | (8191-NPAD-j)
+  // fold the K row trackers into the two per-pair keys  H<<HSHIFT | (RMAX-i)<<13 | (8191-NPAD-j)
   auto fold_word = [&](uint32_t c, int32_t Pm, uint32_t& ra, uint32_t& rb) {
     const uint32_t hi = c >> 16, lo = c & 0xFFFFu;
-    ra = max(ra, hi * 32768u - (hi & 63u) * 32767u + (uint32_t)Pm);
-    rb = max(rb, lo * 32768u - (lo & 63u) * 32767u + (uint32_t)Pm);
+    ra = max(ra, hi * FOLDM - (hi & (SC - 1u)) * (FOLDM - 1u) + (uint32_t)Pm);
+    rb = max(rb, lo * FOLDM - (lo & (SC - 1u)) * (FOLDM - 1u) + (uint32_t)Pm);
   };
-  const int32_t Pconst = (int32_t)(((255u - K * L) << 13) + K * L) + (8192 - NPAD - BLOCK);
+  const int32_t Pconst = (int32_t)(((RMAX - K * L) << 13) + K * L) + (8192 - NPAD - BLOCK);
 
   const uint32_t n_iters = DYN ? 0xFFFFFFFFu : warpN * ipp + G;
   for (uint32_t it = 0; it < n_iters; ++it) {
@@ -671,9 +696,8 @@ sw_stream_kernel(StreamArgs a)
         A[m] = __vsub2(A[m], REBASE); B[m] = __vsub2(B[m], REBASE);
       }
       upPrev = __vsub2(upPrev, REBASE);
-      floor_ = 0; fm1 = 0xFF80FF80u;
-      e = TRK ? (uint32_t)(BLOCK - 1) * 65537u : (uint32_t)(BLOCK - 1) * 0x00010001u;
-      e16 = (uint32_t)(BLOCK - 1) * 0x00010001u;
+      floor_ = 0; fm1 = V0B * P2;
+      e = (uint32_t)(BLOCK - 1) * P2;
       blockStart += BLOCK;
     }
     if (it == stage_it) {                                // refill the ring one chunk ahead (all lanes)
@@ -684,7 +708,7 @@ sw_stream_kernel(StreamArgs a)
     if (it == sw_it) {                                   // this lane moves on to its next pair (one lane per group:
       prevA = recA; prevB = recB; recA = 0; recB = 0;    //  divergent, so it only parks / fetches / resets)
       pairBase += (int32_t)Wp; sw_it += ipp;
-      const uint32_t z2 = __vsub2(floor_, 0x01000100u);
+      const uint32_t z2 = __vsub2(floor_, (4u * SC) * P2);
 #pragma unroll
       for (int m = 0; m < K; ++m) {
         csave[m * 128] = cur[m]; cur[m] = 0;
@@ -709,10 +733,10 @@ sw_stream_kernel(StreamArgs a)
       }
       const uint32_t pp = couple_of(fin_n);
       if (L == 0 && pp < n_pp) {
-        const uint32_t sA = ka >> 21, sB = kb >> 21;
+        const uint32_t sA = ka >> HSHIFT, sB = kb >> HSHIFT;
         swb_result ra{0, -1, -1}, rb{0, -1, -1};
-        if (sA) ra = swb_result{(int32_t)sA, 255 - (int32_t)((ka >> 13) & 255u), 8191 - NPAD - (int32_t)(ka & 8191u)};
-        if (sB) rb = swb_result{(int32_t)sB, 255 - (int32_t)((kb >> 13) & 255u), 8191 - NPAD - (int32_t)(kb & 8191u)};
+        if (sA) ra = swb_result{(int32_t)sA, (int32_t)RMAX - (int32_t)((ka >> 13) & RMAX), 8191 - NPAD - (int32_t)(ka & 8191u)};
+        if (sB) rb = swb_result{(int32_t)sB, (int32_t)RMAX - (int32_t)((kb >> 13) & RMAX), 8191 - NPAD - (int32_t)(kb & 8191u)};
         a.out[a.desc[2 * (uint64_t)pp].pair] = ra;
         if (2 * pp + 1 < n_list) a.out[a.desc[2 * (uint64_t)pp + 1].pair] = rb;
       }
@@ -720,7 +744,7 @@ sw_stream_kernel(StreamArgs a)
       if (DYN) {
         // one cursor read per warp and couple period: the id of each group's couple fin_n + NSTAT
         uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(const_cast<uint32_t*>(&a.counters->stream_cursor), (uint32_t)GPW);
+        if (lane == 0) base = atomicAdd(a.cursor, (uint32_t)GPW);
         base = __shfl_sync(0xffffffffu, base, 0);
         const uint32_t next_valid = couple_of(fin_n + 1) < n_pp;
         __syncwarp();
@@ -763,12 +787,12 @@ sw_stream_kernel(StreamArgs a)
         const uint32_t h  = __vimax3_s16x2(t1, l, floor_);
         if (u & 1) B[m] = h; else A[m] = h;
 #if SWB_ABLATE != 2
-        if (m < TRKROWS) {                               // two steps per tracker update: x = h + e is a plain add (FMA pipe)
+        if (TRK) {                                       // two steps per tracker update: x = h + e is a plain add (FMA pipe)
           const uint32_t xe = h + e;
           if (u & 1) cur[m] = __vimax3_s16x2(cur[m], X[m], xe);
           else       X[m] = xe;
         } else {
-          cur[m] = __viaddmax_s16x2(h, TRK ? e16 : e, cur[m]);
+          cur[m] = __viaddmax_s16x2(h, e, cur[m]);
         }
 #else
         cur[m] |= h;
@@ -777,9 +801,8 @@ sw_stream_kernel(StreamArgs a)
       upPrev = up;
 #if SWB_ABLATE != 6
       fm1 = floor_;
-      floor_ += 0x00800080u;
-      e = TRK ? e - 129u * 65537u : __vsub2(e, 0x00810081u);
-      if (TRK && TRKROWS < K) e16 = __vsub2(e16, 0x00810081u);
+      floor_ += (2u * SC) * P2;
+      e = TRK ? e - (2u * SC + 1u) * 65537u : __vsub2(e, (2u * SC + 1u) * P2);
 #endif
     }
   }
@@ -788,10 +811,15 @@ sw_stream_kernel(StreamArgs a)
 template <int G, int K, int MINB, int FLAGS>
 static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStream_t st)
 {
+  constexpr bool MID = (FLAGS & 8) != 0;                 // the 320-row instantiation scores the mid list
   constexpr int GPW = 32 / G;
   constexpr int GSTRIDE = 4 * G * K * 2 + 128;
   StreamArgs a;
-  a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.desc = b.short_desc; a.counters = b.counters; a.out = b.out;
+  a.q_pk = b.q_pk; a.r_pk = b.r_pk; a.out = b.out;
+  a.desc = MID ? b.mid_desc : b.short_desc;
+  a.n_list = MID ? &b.counters->n_mid : &b.counters->n_short;
+  a.max_window = MID ? &b.counters->max_mid_window : &b.counters->max_short_window;
+  a.cursor = MID ? &b.counters->mid_cursor : &b.counters->stream_cursor;
   const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4 + (size_t)4 * GPW * 8 * 4;
   int& resident = lc.resident[slot];                     // CTAs of this kernel one SM holds (asked once per context)
   if (!resident) {
@@ -1269,7 +1297,7 @@ int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cud
 
 __global__ void single_pair_setup_kernel(Counters* c, uint32_t* list)
 {
-  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; c->stream_cursor = 0; c->n_overflow = 0; list[0] = 0;
+  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; c->stream_cursor = 0; c->n_overflow = 0; c->n_mid = 0; c->max_mid_window = 0; c->mid_cursor = 0; list[0] = 0;
 }
 
 // exposed for the C API: run the generic kernel on a prepared single-pair view

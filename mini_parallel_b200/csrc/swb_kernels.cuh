@@ -11,10 +11,11 @@ constexpr int kMatch = 2, kMismatch = -1, kGap = -2;
 constexpr int kGapAbs = -kGap;
 
 // ---- routing classes written by classify_pairs ----
-enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2, CLASS_LONG = 3, CLASS_BYTES = 4 };
+enum : uint8_t { CLASS_EMPTY = 0, CLASS_SHORT = 1, CLASS_GENERIC = 2, CLASS_LONG = 3, CLASS_BYTES = 4, CLASS_MID = 5 };
 
 // Limits of the int16x2 inter-task kernel (see sw_short_kernel).
 constexpr uint32_t kShortMaxRead   = 160;    // rows held by one lane group (G x K)
+constexpr uint32_t kMidMaxRead     = 320;    // rows of the one-group-per-warp instantiation (value scale 32, see sw_stream_kernel)
 constexpr uint32_t kShortMaxWindow = 4096;   // columns staged in shared memory per group
 constexpr uint32_t kLongMaxLen = (1u << 20) - 4096;   // rows / columns the 64-bit end-cell key of sw_long_kernel can hold
 
@@ -29,7 +30,10 @@ struct Counters {             // device-resident, zeroed per batch
   uint32_t bytes_cursor;
   uint32_t stream_cursor;     // sw_stream_kernel: couples handed out beyond every group's static ones
   uint32_t n_overflow;        // pairs whose window is longer than BatchView::max_window (result INT32_MIN): the caller's bound was wrong
-  uint32_t pad_[2];
+  uint32_t n_mid;             // ACGT-only pairs with reads of 161..320 bp: the 320-row int16x2 instantiation of sw_stream_kernel
+  uint32_t max_mid_window;    // longest window among them
+  uint32_t mid_cursor;        // its couple cursor
+  uint32_t pad_[3];
 };
 
 struct ShortDesc {            // one entry per short-listed pair, written by classify_kernel (32 B, 16-aligned)
@@ -48,6 +52,7 @@ struct BatchView {            // everything the kernels need about one batch (de
   uint64_t        n_pairs;
   uint32_t*       short_list;   // pair ids, n_short entries
   ShortDesc*      short_desc;   // descriptors, same order as short_list
+  ShortDesc*      mid_desc;     // descriptors of the 161..320 bp reads (n_mid entries); nullptr: no such path, they go to the long kernel
   uint32_t*       generic_list; // pair ids, n_generic entries
   uint32_t*       long_list;    // pair ids, n_long entries
   uint32_t*       bytes_list;   // pair ids, n_bytes entries
@@ -95,6 +100,7 @@ int launch_classify(const BatchView& b, cudaStream_t st);
 int launch_chunk_prepare(uint64_t* off_a, uint64_t n_a, uint64_t base_a, uint64_t len_a, uint64_t* off_b, uint64_t n_b, uint64_t base_b,
                          uint64_t len_b, uint64_t* win_beg, const uint32_t* win_len, uint32_t len_w, uint64_t* win_end, uint64_t n_w, uint64_t win_base, cudaStream_t st);
 int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg& lc, cudaStream_t st);
+int launch_mid(const BatchView& b, LaunchCfg& lc, cudaStream_t st);
 int launch_generic(const BatchView& b, int sm_count, int warps_resident, cudaStream_t st);
 int launch_long(const BatchView& b, int ctas, uint32_t max_read_len, LaunchCfg& lc, cudaStream_t st);
 int launch_long_bytes(const BatchView& b, int ctas, uint32_t max_read_len, LaunchCfg& lc, cudaStream_t st);

@@ -249,6 +249,14 @@ class Engine:
         self._check(self._lib.swb_last_routing(self._h, c))
         return {"short": int(c[0]), "generic": int(c[1]), "long": int(c[2])}
 
+    def last_routing_ex(self):
+        c = (ctypes.c_uint64 * 5)()
+        self._check(self._lib.swb_last_routing_ex(self._h, c))
+        return dict(zip(("short", "mid", "long", "bytes", "generic"), (int(v) for v in c)))
+
+    def set_mid_path(self, on):
+        self._check(self._lib.swb_set_mid_path(self._h, int(bool(on))))
+
     @property
     def stream(self):
         return self._lib.swb_stream(self._h)

@@ -154,7 +154,9 @@ def test_mixed_batch_routing_and_empties(engine):
     got = _assert_parity(engine, reads, wins)
     routing = engine.last_routing()
     assert routing["short"] + routing["generic"] + routing["long"] == len(reads) - 3
-    assert routing["short"] >= 200 and routing["generic"] >= 25 and routing["long"] >= 25   # N-flags are per 16-base word: neighbours of an N read may go generic too
+    ex = engine.last_routing_ex()                                                           # r2: reads of 161..320 bp -> mid, 321..400 -> long
+    assert ex["short"] >= 200 and ex["bytes"] >= 25 and ex["mid"] >= 20 and ex["long"] >= 8  # N-flags are per 16-base word: neighbours of an N read may go to the byte kernel too
+    assert ex["short"] + ex["mid"] == routing["short"] and ex["bytes"] + ex["generic"] == routing["generic"] and ex["long"] == routing["long"]
     for k, (a, b) in enumerate(zip(reads, wins)):
         if len(a) == 0 or len(b) == 0:
             assert tuple(got[k]) == (0, -1, -1)                                                 # aligner.rs:413-416
@@ -166,6 +168,14 @@ def test_long_kernel_band_and_stride_edges(engine):
     shorter / longer than the minimum column stride (3 wavefronts), tall-and-narrow and short-and-wide pairs, many
     pairs per warp (work stealing), ties."""
     rng = np.random.default_rng(750)
+    engine.set_mid_path(False)                                                      # reads of 161..320 bp through the long kernel too
+    try:
+        _long_kernel_edges(engine, rng)
+    finally:
+        engine.set_mid_path(True)
+
+
+def _long_kernel_edges(engine, rng):
     _assert_parity(engine, *_pairs(rng, 40, (161, 170), (1, 400)))                  # one band, window < stride
     assert engine.last_routing()["long"] == 40
     _assert_parity(engine, *_pairs(rng, 60, (318, 323), (900, 1100)))               # band boundary 320, stride boundary 970
@@ -183,6 +193,49 @@ def test_long_kernel_band_and_stride_edges(engine):
     reads = [b"ACG" * 400] * 8 + [b"AT" * 500] * 8
     wins = [b"ACG" * 700] * 8 + [b"TA" * 900] * 8
     _assert_parity(engine, reads, wins)
+
+
+def test_mid_path_reads_161_to_320(engine):
+    """Reads of 161..320 bp: the 320-row instantiation of sw_stream_kernel (one group of 32 lanes x 10 rows per warp, value
+    scale 32, 5 tag bits, blocks of 30 steps, keys with 9 row bits) -- the 2 x 250 / 2 x 300 bp read lengths."""
+    rng = np.random.default_rng(760)
+    _assert_parity(engine, *_pairs(rng, 3001, (250, 250), (500, 500)))              # odd count: the last couple holds one pair
+    assert engine.last_routing_ex() == {"short": 0, "mid": 3001, "long": 0, "bytes": 0, "generic": 0}
+    _assert_parity(engine, *_pairs(rng, 2000, (300, 300), (1000, 1000), related=False))
+    _assert_parity(engine, *_pairs(rng, 5000, (161, 320), (1, 1200)))               # ragged: windows shorter than the read, than a wavefront
+    assert engine.last_routing_ex()["mid"] == 5000
+    _assert_parity(engine, *_pairs(rng, 300, (310, 320), (3900, 4096)))             # the longest windows the path takes
+    assert engine.last_routing_ex()["mid"] == 300
+    _assert_parity(engine, *_pairs(rng, 40, (310, 320), (4097, 4200)))              # one past: long-pair kernel
+    assert engine.last_routing_ex() == {"short": 0, "mid": 0, "long": 40, "bytes": 0, "generic": 0}
+    _assert_parity(engine, *_pairs(rng, 40, (321, 330), (500, 600)))                # one row past
+    assert engine.last_routing_ex()["long"] == 40
+    _assert_parity(engine, *_pairs(rng, 1500, (161, 320), (1, 700), alphabet=b"A"))                   # all ties: min i, then min j
+    _assert_parity(engine, *_pairs(rng, 1500, (161, 320), (1, 700), related=False, alphabet=b"AC"))
+    reads = [b"ACG" * 100] * 33 + [b"AT" * 160] * 33 + [b"G" * 320] * 3
+    wins = [b"ACG" * 300] * 33 + [b"TA" * 400] * 33 + [b"G" * 4096] * 3
+    got = _assert_parity(engine, reads, wins)
+    assert tuple(got[-1]) == (640, 319, 319)                                        # the highest score the path can see
+    # short, mid, long and byte-kernel pairs in one batch, shuffled
+    r1, w1 = _pairs(rng, 700, (100, 160), (200, 600))
+    r2, w2 = _pairs(rng, 700, (161, 320), (200, 900))
+    r3, w3 = _pairs(rng, 50, (321, 600), (200, 900))
+    r4, w4 = _pairs(rng, 50, (200, 300), (300, 600), alphabet=b"ACGTN")
+    reads, wins = r1 + r2 + r3 + r4, w1 + w2 + w3 + w4
+    order = rng.permutation(len(reads))
+    _assert_parity(engine, [reads[k] for k in order], [wins[k] for k in order])
+    ex = engine.last_routing_ex()
+    # (the N-flags are per 16-base word of the concatenated arrays: a neighbour of an N read may take the byte kernel too)
+    assert sum(ex.values()) == 1500 and ex["short"] >= 600 and ex["mid"] >= 600 and ex["long"] >= 40 and 50 <= ex["bytes"] <= 250 and ex["generic"] == 0
+    # the same pairs through the long kernel give the same results (two independent implementations)
+    a = engine.score_batch(r2, w2)
+    engine.set_mid_path(False)
+    try:
+        b = engine.score_batch(r2, w2)
+        assert engine.last_routing_ex()["long"] == 700
+    finally:
+        engine.set_mid_path(True)
+    assert np.array_equal(a, b)
 
 
 def test_long_identical_pair_needs_32bit(engine):

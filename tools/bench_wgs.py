@@ -146,7 +146,8 @@ def main():
     r = subprocess.run([cli, "--full-wgs", "--gpu"], env=env, capture_output=True, text=True)
     wall = time.time() - t0
     if os.environ.get("SWB_DEBUG"):
-        print(r.stderr[-3000:], file=sys.stderr)
+        print("\n".join(l for l in r.stderr.splitlines() if l.startswith("[main]") or l.startswith("[wgs]")), file=sys.stderr)
+        print(r.stderr[-1500:], file=sys.stderr)
     if r.returncode != 0:
         print(r.stdout[-2000:], r.stderr[-2000:], file=sys.stderr)
         raise SystemExit("rustseq_mini --full-wgs failed")
