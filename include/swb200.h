@@ -106,6 +106,8 @@ typedef struct { uint64_t in_off; uint32_t in_len; uint32_t out_len; } swb_bgzf_
 /* Optional: start copying and inflating the NEXT segment on a second stream while the current one is being scored.  The
  * buffers must stay untouched until swb_fastq_bgzf_score is called with the same comp pointer and returns. */
 int  swb_fastq_bgzf_prefetch(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks);
+/* A prefetched segment that will NOT be scored after all: waits for its copy and frees the slot (the buffer may then be reused). */
+int  swb_fastq_bgzf_cancel(swb_ctx*, const uint8_t* comp);
 int  swb_fastq_bgzf_score(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
                           const uint8_t* carry, uint64_t carry_len, int final_segment,
                           uint64_t file_index, uint64_t first_read, uint32_t window_len,

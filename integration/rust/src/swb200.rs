@@ -90,9 +90,19 @@ impl Engine {
         if rc != 0 { Err(last_error()) } else { Ok(r) }
     }
 
+    /// The C ABI trusts CSR offsets to stay inside the byte slice: a safe function checks that before it hands out pointers.
+    fn check_csr(bytes: &[u8], off: &[u64], what: &str) -> Result<(), String> {
+        if off.is_empty() || off[0] != 0 { return Err(format!("{what}: offsets must start at 0")); }
+        if off.windows(2).any(|w| w[1] < w[0]) { return Err(format!("{what}: offsets must be non-decreasing")); }
+        if *off.last().unwrap() > bytes.len() as u64 { return Err(format!("{what}: the last offset is past the end of the byte slice")); }
+        Ok(())
+    }
+
     /// One chunk of reads (what process_fastq_file_in_chunks hands its callback) against their windows.
     pub fn score_batch(&mut self, reads: &[u8], read_off: &[u64], windows: &[u8], window_off: &[u64]) -> Result<Vec<SwbResult>, String> {
-        assert_eq!(read_off.len(), window_off.len());
+        if read_off.len() != window_off.len() { return Err("read_off and window_off must describe the same number of pairs".into()); }
+        Self::check_csr(reads, read_off, "reads")?;
+        Self::check_csr(windows, window_off, "windows")?;
         let n = read_off.len().saturating_sub(1);
         let mut out = vec![SwbResult::default(); n];
         let rc = unsafe {
@@ -106,6 +116,9 @@ impl Engine {
     pub fn traceback_batch(&mut self, reads: &[u8], read_off: &[u64], windows: &[u8], window_off: &[u64], results: &[SwbResult])
                            -> Result<(Vec<SwbAlignment>, Vec<u32>), String> {
         let n = results.len();
+        if read_off.len() != n + 1 || window_off.len() != n + 1 { return Err("offsets and results must describe the same number of pairs".into()); }
+        Self::check_csr(reads, read_off, "reads")?;
+        Self::check_csr(windows, window_off, "windows")?;
         let mut out = vec![SwbAlignment::default(); n];
         let mut cigar = vec![0u32; 8 * n + 1024];
         let mut used = 0u64;

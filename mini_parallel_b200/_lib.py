@@ -57,6 +57,7 @@ SIGNATURES = {
     "swb_set_chunking": (_int, [_vp, _u64, _u64]),
     "swb_set_chunk_ramp": (_int, [_vp, _int]),
     "swb_fastq_bgzf_prefetch": (_int, [_vp, _u8p, _u64, _vp, _u64]),
+    "swb_fastq_bgzf_cancel": (_int, [_vp, _u8p]),
     "swb_fastq_bgzf_score": (_int, [_vp, _u8p, _u64, _vp, _u64, _u8p, _u64, _int, _u64, _u64, _u32,
                                     ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64),
                                     _u8p, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_int)]),

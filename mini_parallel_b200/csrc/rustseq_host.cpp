@@ -171,7 +171,7 @@ class FastqReader {
           const size_t n = len_ - pos_;
           std::vector<uint8_t> last(buf_.begin() + pos_, buf_.begin() + pos_ + n);
           pos_ = len_ = 0;
-          if (handle_line(last.data(), n, bases, offs)) return 1;
+          if (handle_line(last.data(), n, bases, offs, false)) return 1;
           if (chunk_full(max_reads, max_bases, bases, offs)) return 0;
         }
         *eof = true;
@@ -190,9 +190,9 @@ class FastqReader {
     return n >= max_reads || (max_bases && bases.size() >= max_bases);   // aligner.rs:143 (+ GPU_CHUNK_SIZE_BASES)
   }
   template <class VB, class VO>
-  int handle_line(const uint8_t* p, size_t n, VB& bases, VO& offs)
+  int handle_line(const uint8_t* p, size_t n, VB& bases, VO& offs, bool terminated = true)
   {
-    if (n && p[n - 1] == '\r') --n;                // lines() strips "\r\n" too
+    if (terminated && n && p[n - 1] == '\r') --n;  // lines() strips "\n" and "\r\n"; a last line without '\n' keeps its '\r'
     if (!valid_utf8(p, n)) {                       // lines() yields Err for invalid UTF-8 (aligner.rs:155-163)
       ++error_count;
       if (error_count <= 5) std::printf("    Warning: Error reading line %llu: stream did not contain valid UTF-8\n", (unsigned long long)line_count);
@@ -716,7 +716,10 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
                         (unsigned long long)cr, (long long)f->score);
         }
       }
-      if (c->comp) { pool.release(c->comp); c->comp = nullptr; }
+      if (c->comp) {
+        if (f->gpu_path_failed || abort_run) swb_fastq_bgzf_cancel(ctx, c->comp->data());   // dropped, perhaps after it was prefetched
+        pool.release(c->comp); c->comp = nullptr;
+      }
       std::lock_guard<std::mutex> lk(gate.mu);
       f->spare.push_back(c);
       gate.cv.notify_all();

@@ -652,7 +652,35 @@ int swb_fastq_bgzf_prefetch(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes
   return 0;                                               // both slots busy: the segment is inflated when it is scored
 }
 
-int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
+// a segment that was prefetched but will not be scored (the file fell back to the host reader, the run was aborted): wait
+// for its copy and release the slot, so that the pinned buffer can be reused and no later segment at the same address is
+// taken for this one
+int swb_fastq_bgzf_cancel(swb_ctx* c, const uint8_t* comp)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (auto& s : c->fq_slot)
+    if (s.pending && s.key == comp) {
+      CUDA_TRY(cudaStreamSynchronize(c->lane(1)->st));
+      s.pending = false; s.key = nullptr;
+    }
+  return 0;
+}
+
+// nothing may still be reading the caller's buffers when a call returns with an error
+static int drain_after_error(swb_ctx* c, int rc)
+{
+  if (rc != 0 && c) {
+    const std::string keep = g_err;
+    for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(c->lane(i)->st);
+    cudaGetLastError();
+    for (auto& s : c->fq_slot) { s.pending = false; s.key = nullptr; }
+    g_err = keep;
+  }
+  return rc;
+}
+
+static int fastq_bgzf_score_impl(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
                          const uint8_t* carry, uint64_t carry_len, int final_segment,
                          uint64_t file_index, uint64_t first_read, uint32_t window_len,
                          int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases, uint64_t* n_lines,
@@ -697,7 +725,7 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   if (dbg) for (auto& e : te) cudaEventCreate(&e);
   if (dbg) cudaEventRecord(te[0], st);
   if (dbg) cudaEventRecord(te[1], st);
-  k += swb::launch_fq_index(d_text, begin, end, c->fq_tile_count.as<uint32_t>(), c->fq_tile_prefix.as<uint64_t>(), d_scal, d_fail + 1, st);
+  k += swb::launch_fq_index(d_text, begin, end, c->fq_tile_count.as<uint32_t>(), c->fq_tile_prefix.as<uint64_t>(), d_scal, d_fail + 1, final_segment, st);
   if (dbg) cudaEventRecord(te[2], st);
   uint64_t h_scal[8] = {};
   uint32_t h_fail[4] = {};
@@ -782,8 +810,18 @@ int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, c
   return 0;
 }
 
+int swb_fastq_bgzf_score(swb_ctx* c, const uint8_t* comp, uint64_t comp_bytes, const swb_bgzf_block* blocks, uint64_t n_blocks,
+                         const uint8_t* carry, uint64_t carry_len, int final_segment,
+                         uint64_t file_index, uint64_t first_read, uint32_t window_len,
+                         int64_t* score_sum, uint64_t* n_reads, uint64_t* n_bases, uint64_t* n_lines,
+                         uint8_t* carry_out, uint64_t carry_cap, uint64_t* carry_out_len, int* status)
+{
+  return drain_after_error(c, fastq_bgzf_score_impl(c, comp, comp_bytes, blocks, n_blocks, carry, carry_len, final_segment, file_index, first_read,
+                                                    window_len, score_sum, n_reads, n_bases, n_lines, carry_out, carry_cap, carry_out_len, status));
+}
+
 // ---- alignments behind the scores ----
-int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro, uint64_t n_pairs,
+static int traceback_batch_impl(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro, uint64_t n_pairs,
                         const swb_result* results, swb_alignment* out, uint32_t* cigar, uint64_t cigar_cap, uint64_t* cigar_used)
 {
   if (!c) return fail("null ctx");
@@ -852,6 +890,12 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
   if (h_cursor[1]) CUDA_TRY(cudaMemcpy(cigar, c->tb_cigar.p, h_cursor[1] * 4, cudaMemcpyDeviceToHost));
   c->host_path = false; c->timings_pending = false;
   return 0;
+}
+
+int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const uint8_t* r, const uint64_t* ro, uint64_t n_pairs,
+                        const swb_result* results, swb_alignment* out, uint32_t* cigar, uint64_t cigar_cap, uint64_t* cigar_used)
+{
+  return drain_after_error(c, traceback_batch_impl(c, q, qo, r, ro, n_pairs, results, out, cigar, cigar_cap, cigar_used));
 }
 
 int swb_score_pair(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, swb_result* out)

@@ -82,11 +82,25 @@ __device__ __forceinline__ FqChunk fq_load(const uint8_t* __restrict__ text, uin
 }
 
 __global__ void __launch_bounds__(256)
-fq_count_kernel(const uint8_t* __restrict__ text, uint64_t begin, uint64_t end, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ flags)
+fq_count_kernel(const uint8_t* __restrict__ text, uint64_t begin, uint64_t end, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ flags,
+                int final_segment)
 {
   const uint64_t pos = fq_tile0(begin) + (uint64_t)blockIdx.x * kTile + threadIdx.x * 16;
   const FqChunk c = fq_load(text, pos, begin, end);
   uint32_t n = __popc(c.nl), hi = (c.w[0] | c.w[1] | c.w[2] | c.w[3]) & 0x80808080u;
+  // A '\r' that is not the first half of "\r\n" (mid-line, or ending an unterminated last line) is a byte of its line for
+  // BufRead::lines; the in-place masking below only knows line terminators, so such a file is left to the host reader.
+  const uint32_t cr = flags_to_nibble(eq_flags(c.w[0], 0x0D0D0D0Du)) | (flags_to_nibble(eq_flags(c.w[1], 0x0D0D0D0Du)) << 4) |
+                      (flags_to_nibble(eq_flags(c.w[2], 0x0D0D0D0Du)) << 8) | (flags_to_nibble(eq_flags(c.w[3], 0x0D0D0D0Du)) << 12);
+  if (cr) {
+    uint32_t stray = cr & ~(c.nl >> 1) & 0x7FFFu;           // bytes 0..14: the next byte is in this chunk
+    if (cr & 0x8000u) {                                     // byte 15: the next byte is the neighbour's (text is still untouched here)
+      if (pos + 16 < end) stray |= text[pos + 16] != '\n';
+      else stray |= final_segment ? 1u : 0u;                // last byte of the text: of a non-final segment it is carried and seen again
+    }
+    if (pos + 16 > end && !final_segment) stray &= (1u << (uint32_t)(end - 1 - pos)) - 1u;   // same for a chunk the text ends in
+    if (stray) hi |= 0x80u;                                 // (the extra '\r' check after the last real byte sees filler 'A', not '\n')
+  }
   __shared__ uint32_t wsum[8];
   n = __reduce_add_sync(0xffffffffu, n); hi = __reduce_or_sync(0xffffffffu, hi);
   if ((threadIdx.x & 31) == 0) { wsum[threadIdx.x >> 5] = n; if (hi) atomicOr(flags, 1u); }   // not ASCII: host path
@@ -209,11 +223,11 @@ fq_extract_kernel(uint8_t* __restrict__ text, uint64_t begin, uint64_t end, cons
 }
 
 int launch_fq_index(const uint8_t* text, uint64_t begin, uint64_t end, uint32_t* tile_count, uint64_t* tile_prefix, uint64_t* total,
-                    uint32_t* flags, cudaStream_t st)
+                    uint32_t* flags, int final_segment, cudaStream_t st)
 {
   if (end <= begin) return 0;
   const uint64_t n_tiles = fq_tiles(begin, end);
-  fq_count_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(text, begin, end, tile_count, flags);
+  fq_count_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(text, begin, end, tile_count, flags, final_segment);
   fq_scan_kernel<<<1, 1024, 0, st>>>(tile_count, n_tiles, tile_prefix, total);
   return 2;
 }

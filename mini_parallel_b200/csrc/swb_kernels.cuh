@@ -131,7 +131,7 @@ uint64_t fq_tiles(uint64_t begin, uint64_t end);
 int launch_inflate_bgzf(const uint8_t* comp, const swb_bgzf_block* blocks, uint64_t n_blocks, const uint64_t* out_off, uint8_t* text,
                         uint32_t* n_failed, cudaStream_t st);
 int launch_fq_index(const uint8_t* text, uint64_t begin, uint64_t end, uint32_t* tile_count, uint64_t* tile_prefix, uint64_t* total,
-                    uint32_t* flags, cudaStream_t st);
+                    uint32_t* flags, int final_segment, cudaStream_t st);
 int launch_fq_extract(uint8_t* text, uint64_t begin, uint64_t end, const uint32_t* tile_count, const uint64_t* tile_prefix, const uint64_t* n_newlines, uint64_t* seq_beg,
                       uint64_t* seq_end, uint64_t n_records_cap, unsigned long long* tail_start, int final_segment, uint32_t* pk_words,
                       uint32_t* pk_bitmap, cudaStream_t st);

@@ -34,6 +34,17 @@ def to_csr(seqs):
     return np.ascontiguousarray(data, dtype=np.uint8), off
 
 
+def _check_csr(data, off, what):
+    """The C ABI trusts that offsets stay inside the byte array it is handed (it only checks their order while it walks
+    them): a safe wrapper must not let a bad offset array make the library read past the buffer."""
+    if off.size == 0 or int(off[0]) != 0:
+        raise ValueError(f"{what}: offsets must start at 0")
+    if off.size > 1 and bool(np.any(off[1:] < off[:-1])):
+        raise ValueError(f"{what}: offsets must be non-decreasing")
+    if int(off[-1]) > data.size:
+        raise ValueError(f"{what}: the last offset ({int(off[-1])}) is past the end of the {data.size}-byte array")
+
+
 class Engine:
     def __init__(self, device=0, lib=None):
         self._lib = lib if lib is not None else load_library()      # lib: another build of the library (tests: the all-variants build)
@@ -82,6 +93,8 @@ class Engine:
         n = q_off.size - 1
         if r_off.size - 1 != n:
             raise ValueError("q_off and r_off must describe the same number of pairs")
+        if int(q_off[-1]) > q_bytes.size or int(r_off[-1]) > r_bytes.size or int(q_off[0]) != 0 or int(r_off[0]) != 0:
+            _check_csr(q_bytes, q_off, "reads"); _check_csr(r_bytes, r_off, "windows")      # (order is checked by the library, with its own message)
         out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
         if n > 0:
             self._check(self._lib.swb_score_batch(self._h, q_bytes.ctypes.data, q_off.ctypes.data,
@@ -107,6 +120,7 @@ class Engine:
         n = q_off.size - 1
         if r_off.size - 1 != n or results.size != n:
             raise ValueError("offsets and results must describe the same number of pairs")
+        _check_csr(q_bytes, q_off, "reads"); _check_csr(r_bytes, r_off, "windows")
         out = np.zeros(max(n, 0), dtype=ALIGNMENT_DTYPE)
         cap = int(cigar_cap) if cigar_cap is not None else 8 * max(n, 1) + 1024
         used = ctypes.c_uint64()
@@ -136,6 +150,9 @@ class Engine:
         win_start = np.ascontiguousarray(win_start, dtype=np.uint64)
         win_len = np.ascontiguousarray(win_len, dtype=np.uint32)
         n = q_off.size - 1
+        if win_start.size != n or win_len.size != n:
+            raise ValueError("q_off, win_start and win_len must describe the same number of pairs")
+        _check_csr(q_bytes, q_off, "reads")
         out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
         if n > 0:
             self._check(self._lib.swb_score_batch_vs_reference(self._h, q_bytes.ctypes.data, q_off.ctypes.data, n,
@@ -152,6 +169,7 @@ class Engine:
         n = q_off.size - 1
         if win_start.size != n or win_len.size != n:
             raise ValueError("q_off, win_start and win_len must describe the same number of pairs")
+        _check_csr(q_bytes, q_off, "reads")
         out = np.zeros(max(n, 0), dtype=RESULT_DTYPE)
         if n > 0:
             self._check(self._lib.swb_score_batch_ranges(self._h, q_bytes.ctypes.data, q_off.ctypes.data, n, w_bytes.ctypes.data, w_bytes.size,

@@ -166,3 +166,33 @@ def test_random_fastq_shapes_agree_with_the_host_path(engine, seed):
         tot = _run_segments(engine, gz, int(rng.integers(1, 40)), file_index=7, w=w)
         assert {k: tot[k] for k in exp} == exp
         assert tot["lines"] == 4 * len(reads)
+
+
+def test_stray_carriage_returns_are_left_to_the_host_reader(engine):
+    """a '\\r' that is not the first half of "\\r\\n" -- in the middle of a sequence line, or ending a last line
+    that has no '\\n' -- is a byte of its line for BufRead::lines (a mismatching base), not a terminator.  The in-place
+    masking of the GPU path only knows terminators, so it must decline such text (status 1), at every position of the index
+    kernel's 16-byte chunks; plain CRLF text, also cut between '\\r' and '\\n' by a segment boundary, stays on the GPU."""
+    rng = np.random.default_rng(80)
+    ref = ACGT[rng.integers(0, 4, 50_000)]
+    engine.set_reference(ref)
+    reads, text = _make(rng, ref, 120, eol=b"\r\n", with_n=False)
+    exp_score, exp_bases = _expected(reads, ref, 0, 0, 500)
+    tot = _run_segments(engine, bgzf.compress(text, 1, 777), 3)                       # small blocks: segment ends fall everywhere, also after a '\r'
+    assert {k: tot[k] for k in ("score_sum", "reads", "bases")} == {"score_sum": exp_score, "reads": 120, "bases": exp_bases}
+    seq_line = text.index(b"\r\n") + 2                                                # first byte of the first sequence line
+    for off in range(0, 40):                                                          # a stray '\r' at 40 consecutive positions
+        bad = bytearray(text)
+        bad[seq_line + 200 + off] = 0x0D
+        if bytes(bad[seq_line + 200 + off:seq_line + 202 + off]) == b"\r\n":
+            continue
+        gz = bgzf.compress(bytes(bad), 1)
+        out = engine.fastq_bgzf_score(np.frombuffer(gz, dtype=np.uint8), bgzf.walk(gz)[0], b"", True, 0, 0, 500)
+        assert out["status"] == 1 and out["reads"] == 0, off
+    for pad in range(0, 17):                                                          # the text ENDS in '\r' (no '\n'), at every chunk offset
+        t = text[: text.rfind(b"\r\n+\r\n")] + b"A" * pad + b"\r"
+        gz = bgzf.compress(t, 1)
+        out = engine.fastq_bgzf_score(np.frombuffer(gz, dtype=np.uint8), bgzf.walk(gz)[0], b"", True, 0, 0, 500)
+        assert out["status"] == 1, pad
+    tot = _run_segments(engine, bgzf.compress(text, 1), 100)                          # and the context still works
+    assert tot["reads"] == 120

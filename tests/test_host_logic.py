@@ -73,6 +73,20 @@ def test_chunk_reader_no_trailing_newline_and_partial_record(tmp_path, clean_env
     assert got == [b"ACGT", b"GGCC"]
 
 
+def test_chunk_reader_carriage_returns_follow_bufread_lines(tmp_path, clean_env):
+    """BufRead::lines strips "\n" and "\r\n" (aligner.rs:133): a '\r' in the middle of a line is a byte of the line, and a last
+    line WITHOUT '\n' keeps a trailing '\r'."""
+    p = tmp_path / "cr.fastq"
+    p.write_bytes(b"@a\r\nAC\rGT\r\n+\r\nIIIII\r\n@b\r\nACGT\r")           # record 2 is cut after its sequence line, which ends in '\r'
+    got = []
+    aligner.process_fastq_file_in_chunks(p, 10, lambda ch: got.extend(ch))
+    assert got == [b"AC\rGT", b"ACGT\r"]
+    p.write_bytes(b"@a\r\nACGT\r\n+\r\nIIII\r\n")
+    got = []
+    aligner.process_fastq_file_in_chunks(p, 10, lambda ch: got.extend(ch))
+    assert got == [b"ACGT"]
+
+
 def test_chunk_reader_bases_cap(tmp_path, clean_env):
     reads = ["A" * 150] * 10
     p = tmp_path / "z.fastq"

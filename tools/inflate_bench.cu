@@ -79,7 +79,7 @@ int main(int argc, char** argv)
     float ms_index = 0, ms_em = 0;
     for (int it = 0; it < 3; ++it) {
       cudaEventRecord(e0);
-      swb::launch_fq_index(d_text, begin, end, d_tc, d_tp, d_scal, reinterpret_cast<uint32_t*>(d_scal + 4) + 1, 0);
+      swb::launch_fq_index(d_text, begin, end, d_tc, d_tp, d_scal, reinterpret_cast<uint32_t*>(d_scal + 4) + 1, 1, 0);
       cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_index, e0, e1);
     }
     uint32_t *d_pk, *d_bm;
