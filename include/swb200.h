@@ -165,6 +165,12 @@ int  swb_last_routing_ex(swb_ctx*, uint64_t* counts /* 5 */);
 /* on = 0: reads of 161..320 bp take the 32-bit long-pair kernel instead of the 320-row int16x2 one (comparison, tests). */
 int  swb_set_mid_path(swb_ctx*, int on);
 
+/* Debugging aid (compute-sanitizer is not available on every box).  With SWB_GUARD=1 in the environment when the library
+ * is loaded, every device arena is allocated exactly (no geometric over-allocation, the documented 64 B of read slack only)
+ * between two 4 KiB zones of a known pattern; this call synchronises the device and returns how many zones of the
+ * context's device have been written into (0 = none), -1 when guard mode is off.  *n_arenas = arenas checked. */
+int  swb_debug_guard_check(swb_ctx*, char* report, uint64_t report_cap, uint64_t* n_arenas);
+
 /* The packing stage alone on device-resident bytes (bench: HBM roofline of the packing kernel). */
 int  swb_pack2bit_device(swb_ctx*, const uint8_t* d_bytes, uint64_t n, uint32_t* d_words, uint32_t* d_bitmap);
 

@@ -31,7 +31,7 @@ int fail(const std::string& m) { g_err = m; return 1; }
 const std::chrono::steady_clock::time_point g_loaded = std::chrono::steady_clock::now();
 void dbg_stamp(const char* what)
 {
-  if (std::getenv("SWB_DEBUG"))
+  if (std::getenv("SWB_DEBUG") || std::getenv("SWB_STAMPS"))
     std::fprintf(stderr, "[main] %-36s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - g_loaded).count());
 }
 
@@ -1103,7 +1103,7 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
 
   const auto t_start = std::chrono::steady_clock::now();
   auto stamp = [&](const char* what) {
-    if (std::getenv("SWB_DEBUG")) std::fprintf(stderr, "[wgs] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+    if (std::getenv("SWB_DEBUG") || std::getenv("SWB_STAMPS")) std::fprintf(stderr, "[wgs] %-28s %.3f s\n", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
   };
   std::vector<uint8_t> ref; uint32_t window_len = 500;
   if (!compat) {

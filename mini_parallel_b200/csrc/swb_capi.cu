@@ -28,18 +28,45 @@ static int fail(const std::string& m) { g_err = m; return 1; }
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
   return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
 
+// SWB_GUARD=1 (debugging aid; compute-sanitizer is not available on every box): every arena is allocated with a 4 KiB
+// zone of 0xA5 before and after it and WITHOUT the geometric over-allocation, and swb_debug_guard_check() reports every
+// zone a kernel or copy wrote into.  A write past an arena then shows up as a damaged zone instead of as silent
+// corruption of the neighbouring allocation; reads of the documented 64 B slack stay legal.
+static const bool g_guard = [] { const char* v = std::getenv("SWB_GUARD"); return v && *v && *v != '0'; }();
+constexpr size_t kGuardBytes = 4096;
+struct GuardEntry { uint8_t* base; size_t cap; int device; };
+static std::mutex g_guard_mu;
+static std::vector<GuardEntry> g_guard_list;
+
 struct DevBuf {
   void* p = nullptr; size_t cap = 0;
   int reserve(size_t bytes) {
     if (bytes <= cap) return 0;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    size_t want = bytes + bytes / 8 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
+    release();
+    size_t want = g_guard ? ((bytes + 255) & ~(size_t)255) + 256 : bytes + bytes / 8 + 256;
+    void* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, want + (g_guard ? 2 * kGuardBytes : 0));
     if (e != cudaSuccess) { g_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return 1; }
-    cap = want; return 0;
+    if (g_guard) {
+      int dev = 0; cudaGetDevice(&dev);
+      cudaMemset(base, 0xA5, kGuardBytes);
+      cudaMemset(static_cast<uint8_t*>(base) + kGuardBytes + want, 0xA5, kGuardBytes);
+      cudaDeviceSynchronize();
+      std::lock_guard<std::mutex> lk(g_guard_mu);
+      g_guard_list.push_back({static_cast<uint8_t*>(base), want, dev});
+      base = static_cast<uint8_t*>(base) + kGuardBytes;
+    }
+    p = base; cap = want; return 0;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() {
+    if (p && g_guard) {
+      uint8_t* base = static_cast<uint8_t*>(p) - kGuardBytes;
+      { std::lock_guard<std::mutex> lk(g_guard_mu);
+        for (size_t k = 0; k < g_guard_list.size(); ++k) if (g_guard_list[k].base == base) { g_guard_list.erase(g_guard_list.begin() + k); break; } }
+      cudaFree(base);
+    } else if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+  }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -896,6 +923,40 @@ int swb_traceback_batch(swb_ctx* c, const uint8_t* q, const uint64_t* qo, const 
                         const swb_result* results, swb_alignment* out, uint32_t* cigar, uint64_t cigar_cap, uint64_t* cigar_used)
 {
   return drain_after_error(c, traceback_batch_impl(c, q, qo, r, ro, n_pairs, results, out, cigar, cigar_cap, cigar_used));
+}
+
+// SWB_GUARD: how many guard zones of this process's arenas on the context's device are damaged (0 = none; -1 = guard mode
+// is off).  Synchronises the device.  `report` receives one line per damaged zone.
+int swb_debug_guard_check(swb_ctx* c, char* report, uint64_t report_cap, uint64_t* n_arenas)
+{
+  if (report && report_cap) report[0] = 0;
+  if (n_arenas) *n_arenas = 0;
+  if (!g_guard) return -1;
+  if (!c) return -1;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  std::vector<GuardEntry> list;
+  { std::lock_guard<std::mutex> lk(g_guard_mu); list = g_guard_list; }
+  std::vector<uint8_t> h(kGuardBytes);
+  int bad = 0; std::string rep; uint64_t seen = 0;
+  for (const GuardEntry& ge : list) {
+    if (ge.device != c->device) continue;
+    ++seen;
+    for (int side = 0; side < 2; ++side) {
+      const uint8_t* z = side ? ge.base + kGuardBytes + ge.cap : ge.base;
+      if (cudaMemcpy(h.data(), z, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess) { ++bad; rep += "guard zone unreadable\n"; continue; }
+      size_t first = kGuardBytes, n = 0;
+      for (size_t k = 0; k < kGuardBytes; ++k) if (h[k] != 0xA5) { if (first == kGuardBytes) first = k; ++n; }
+      if (n) {
+        ++bad;
+        rep += std::string(side ? "after" : "before") + " an arena of " + std::to_string(ge.cap) + " bytes: " + std::to_string(n) +
+               " bytes damaged, first at zone offset " + std::to_string(first) + "\n";
+      }
+    }
+  }
+  if (n_arenas) *n_arenas = seen;
+  if (report && report_cap) std::snprintf(report, report_cap, "%s", rep.c_str());
+  return bad;
 }
 
 int swb_score_pair(swb_ctx* c, const uint8_t* s1, uint64_t n1, const uint8_t* s2, uint64_t n2, swb_result* out)

@@ -176,6 +176,13 @@ class Engine:
                                                          win_start.ctypes.data, win_len.ctypes.data, out.ctypes.data))
         return out
 
+    def guard_check(self):
+        """SWB_GUARD=1 debugging aid (swb_debug_guard_check): (damaged guard zones, arenas checked, report); (-1, 0, "") when off."""
+        buf = ctypes.create_string_buffer(4096)
+        n = ctypes.c_uint64()
+        bad = self._lib.swb_debug_guard_check(self._h, buf, 4096, ctypes.byref(n))
+        return int(bad), int(n.value), buf.value.decode()
+
     def last_ranges_info(self):
         a, b = ctypes.c_uint64(), ctypes.c_uint64()
         self._check(self._lib.swb_last_ranges_info(self._h, ctypes.byref(a), ctypes.byref(b)))

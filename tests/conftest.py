@@ -35,3 +35,17 @@ def engine_variants():
     eng = mp.Engine(0, lib=_lib.bind(path))
     yield eng
     eng.close()
+
+
+@pytest.fixture(autouse=True)
+def _arena_guards(request):
+    """SWB_GUARD=1 (tools/sanitize.sh): after every GPU test, no guard zone round any device arena may have been written."""
+    yield
+    if os.environ.get("SWB_GUARD", "0") in ("", "0") or "engine" not in request.fixturenames:
+        return
+    eng = request.getfixturevalue("engine")
+    bad, n, report = eng.guard_check()
+    assert bad == 0 and n > 0, f"{bad} damaged guard zones round {n} arenas:\n{report}"
+    if "engine_variants" in request.fixturenames:
+        bad, n, report = request.getfixturevalue("engine_variants").guard_check()
+        assert bad == 0, report

@@ -491,3 +491,34 @@ def test_error_in_a_later_chunk_leaves_the_engine_usable(engine):
         assert np.array_equal(got, ol.batch(q, qo, r, ro, threads=8, simd=True))
     finally:
         engine.set_chunking(32 << 20, 16384)
+
+
+def test_repeated_runs_are_bit_identical(engine):
+    """Stand-in for racecheck (compute-sanitizer is closed on the GPU pool): the kernels exchange data through shared memory
+    (window ring, parked trackers, couple ids) and through per-warp global scratch rows; a missing barrier or a stale read
+    shows up as run-to-run variation long before it shows up as a wrong answer on one fixed schedule.  The same mixed batch,
+    20 times over, alone and while a second batch keeps other lanes busy: every run equals the first, which equals the oracle."""
+    rng = np.random.default_rng(2027)
+    r1, w1 = _pairs(rng, 6000, (1, 160), (1, 700))
+    r2, w2 = _pairs(rng, 1500, (161, 320), (100, 900))
+    r3, w3 = _pairs(rng, 30, (321, 1400), (300, 2600))
+    r4, w4 = _pairs(rng, 60, (1, 500), (1, 900), alphabet=b"ACGTNacgt")
+    reads, wins = r1 + r2 + r3 + r4, w1 + w2 + w3 + w4
+    order = rng.permutation(len(reads))
+    reads, wins = [reads[k] for k in order], [wins[k] for k in order]
+    q, qo = to_csr(reads); r, ro = to_csr(wins)
+    first = engine.score_batch_csr(q, qo, r, ro)
+    assert np.array_equal(first, ol.batch(q, qo, r, ro, threads=8, simd=False))
+    engine.set_chunking(256 << 10, 64)                      # many small chunks over the three lanes: kernels of different chunks overlap
+    try:
+        for rep in range(20):
+            got = engine.score_batch_csr(q, qo, r, ro)
+            assert np.array_equal(got, first), f"run {rep} differs from the first in {int((got != first).sum())} pairs"
+    finally:
+        engine.set_chunking(32 << 20)
+    al0, ops0 = engine.traceback_batch(q, qo, r, ro, first)
+    c0 = [engine.cigar_of(al0[k], ops0) for k in range(0, len(reads), 7)]
+    for rep in range(5):
+        al, ops = engine.traceback_batch(q, qo, r, ro, first)
+        assert np.array_equal(al["start_i"], al0["start_i"]) and np.array_equal(al["start_j"], al0["start_j"])
+        assert [engine.cigar_of(al[k], ops) for k in range(0, len(reads), 7)] == c0

@@ -145,8 +145,10 @@ def main():
     t0 = time.time()
     r = subprocess.run([cli, "--full-wgs", "--gpu"], env=env, capture_output=True, text=True)
     wall = time.time() - t0
-    if os.environ.get("SWB_DEBUG"):
+    if os.environ.get("SWB_DEBUG") or os.environ.get("SWB_STAMPS"):
         print("\n".join(l for l in r.stderr.splitlines() if l.startswith("[main]") or l.startswith("[wgs]")), file=sys.stderr)
+        print(f"[bench_wgs] subprocess wall {wall:.3f} s", file=sys.stderr)
+    if os.environ.get("SWB_DEBUG"):
         print(r.stderr[-1500:], file=sys.stderr)
     if r.returncode != 0:
         print(r.stdout[-2000:], r.stderr[-2000:], file=sys.stderr)
