@@ -3,6 +3,9 @@
 // through the C ABI of swb200.h; there is no CPU scoring code in this file.
 #include "../../include/rustseq_host.h"
 #include <zlib.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include <algorithm>
 #include <cerrno>
 #include <chrono>
@@ -372,6 +375,8 @@ struct WgsChunk {
   // BGZF files: a segment of whole compressed blocks for swb_fastq_bgzf_score (the GPU inflates and parses)
   bool bgzf = false, final_segment = false;
   pinned_vector<uint8_t>* comp = nullptr; uint64_t comp_len = 0;     // a buffer of the consumer's CompPool while the segment is in flight
+  uint64_t comp_off = 0;                                              // the segment's first block starts here in *comp
+  const uint8_t* comp_data() const { return comp->data() + comp_off; }
   std::vector<swb_bgzf_block> blocks;
 };
 
@@ -382,6 +387,7 @@ struct WgsChunk {
 // the current one, so a half-empty last wave leaves no SM idle.)  Smaller files use segments of their own size (pinned
 // memory is slow to allocate).
 constexpr uint64_t kBgzfSegmentMax = 112ull << 20;
+constexpr uint64_t kBgzfSegmentMulti = 32ull << 20;      // when the process drives more than one GPU (see wgs_device_pipeline)
 
 // Is this a blocked-gzip file (first member carries a 'BC' extra field)?  SWB_GPU_INFLATE=0 keeps every file on the host.
 bool file_is_bgzf(const std::string& path)
@@ -435,6 +441,7 @@ struct DeviceGate { std::mutex mu; std::condition_variable cv; };   // wakes the
 // Pinned staging buffers for compressed BGZF segments, shared by all files of one consumer: the consumer works on one
 // segment at a time, so three buffers keep it fed however many files it serves (page-locking 112 MiB per file and per
 // pipeline slot would cost seconds).
+std::atomic<uint64_t> g_pin_us{0}, g_pin_bytes{0};     // SWB_STAMPS: time spent page-locking segment buffers (summed over threads)
 struct CompPool {
   std::mutex mu; std::condition_variable cv;
   std::vector<std::unique_ptr<pinned_vector<uint8_t>>> all;
@@ -449,7 +456,10 @@ struct CompPool {
         all.push_back(std::make_unique<pinned_vector<uint8_t>>());
         auto* b = all.back().get();
         lk.unlock();
+        const auto t0 = std::chrono::steady_clock::now();
         b->resize(bytes);                           // the slow part, outside the lock
+        g_pin_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        g_pin_bytes += bytes;
         return b;
       }
       cv.wait(lk);
@@ -471,51 +481,83 @@ struct WgsFile {
   bool bgzf = false, gpu_path_failed = false;  // BGZF: inflated and parsed on the GPU; failed -> the file is redone on the host
   std::vector<uint8_t> carry; uint64_t lines = 0;
   uint64_t seg_bytes = 0; CompPool* comp_pool = nullptr;
+  // several readers per file (wgs_bgzf_reader_thread): segment k may take its buffers once k-1 has, and is walked after k-1
+  int fd = -1; uint64_t file_bytes = 0, n_segments = 0;
+  unsigned n_readers = 1, live_readers = 0;
+  uint64_t next_acquire = 0, next_walk = 0;    // guarded by gate->mu
+  std::vector<uint8_t> left;                   // the partial block at the end of the last walked segment (owned by the walker in turn)
+  int reader_rc = 0; std::string reader_err;   // first failure among the readers, guarded by gate->mu
 };
 
-// BGZF files: the reader only moves compressed bytes and walks block headers; inflate + parse happen on the GPU.
-void wgs_bgzf_reader_thread(WgsFile* f)
+// BGZF files: the readers only move compressed bytes and walk block headers; inflate + parse happen on the GPU.
+// A file has n_readers of these threads (reader r takes segments r, r + n_readers, ...): the bytes of segment k are the
+// fixed file range [k * seg_bytes, (k+1) * seg_bytes), so several pread()s of one file run at once -- one thread copying out
+// of the page cache delivers 1-3 GB/s, a B200 inflates and scores ~3.7 GB/s of compressed FASTQ, and a box has more cores
+// than files.  Only the cheap part is ordered: segment k takes its chunk and its pinned buffer after segment k-1 has taken
+// its own (so the segment the consumer needs next is never the one left without a buffer), and its block headers are
+// walked after k-1's, because the first block of k starts where the last whole block of k-1 ended; the bytes in between
+// (`left`, less than one block) are copied in front of the range (kBgzfFront bytes of room).
+constexpr uint64_t kBgzfFront = 128u << 10;
+
+void wgs_bgzf_reader_thread(WgsFile* f, unsigned r)
 {
-  FILE* fp = std::fopen(f->path.c_str(), "rb");
   int rc = 0; std::string err;
-  if (!fp) { rc = 1; err = "Failed to open file " + f->path + ": " + std::strerror(errno); }
-  std::vector<uint8_t> left;                                  // a partial block at the end of the previous segment
-  const uint64_t seg_bytes = f->seg_bytes;
-  bool eof = false;
-  while (rc == 0 && !eof) {
+  const uint64_t S = f->seg_bytes;
+  for (uint64_t k = r; k < f->n_segments && rc == 0; k += f->n_readers) {
     WgsChunk* c = nullptr;
     {
       std::unique_lock<std::mutex> lk(f->gate->mu);
-      f->gate->cv.wait(lk, [&] { return !f->spare.empty() || f->gpu_path_failed; });
-      if (f->gpu_path_failed) break;
+      f->gate->cv.wait(lk, [&] { return (f->next_acquire == k && !f->spare.empty()) || f->gpu_path_failed || f->reader_rc; });
+      if (f->gpu_path_failed || f->reader_rc) break;
       c = f->spare.front(); f->spare.pop_front();
     }
     bool push = false;
     try {
       c->bgzf = true; c->blocks.clear();
       c->comp = f->comp_pool->acquire();
-      uint8_t* buf = c->comp->data();
-      std::memcpy(buf, left.data(), left.size());
-      const size_t got = std::fread(buf + left.size(), 1, seg_bytes, fp);
-      eof = got < seg_bytes;
-      const uint64_t have = left.size() + got;
-      const uint64_t used = walk_bgzf(buf, have, c->blocks);
-      if (used == ~0ull || (eof && used != have)) { rc = 2; err = "not a BGZF stream"; }      // -> host path
-      else {
-        left.assign(buf + used, buf + have);
-        c->comp_len = used; c->final_segment = eof;
-        push = true;
+      { std::lock_guard<std::mutex> lk(f->gate->mu); ++f->next_acquire; }
+      f->gate->cv.notify_all();
+      uint8_t* buf = c->comp->data() + kBgzfFront;
+      uint64_t got = 0;
+      while (got < S) {
+        const ssize_t n = ::pread(f->fd, buf + got, (size_t)std::min<uint64_t>(S - got, 1u << 30), (off_t)(k * S + got));
+        if (n < 0) { if (errno == EINTR) continue; rc = 1; err = "Failed to read file " + f->path + ": " + std::strerror(errno); break; }
+        if (n == 0) break;
+        got += (uint64_t)n;
+      }
+      {
+        std::unique_lock<std::mutex> lk(f->gate->mu);
+        f->gate->cv.wait(lk, [&] { return f->next_walk == k || f->gpu_path_failed || f->reader_rc; });
+        if (f->gpu_path_failed || f->reader_rc) rc = rc ? rc : 3;
+      }
+      if (rc == 0) {                                            // this thread's turn: nobody else touches f->left
+        const bool last = k + 1 == f->n_segments;
+        const uint64_t nl = f->left.size();
+        uint8_t* start = buf - nl;
+        std::memcpy(start, f->left.data(), nl);
+        const uint64_t have = nl + got;
+        const uint64_t used = walk_bgzf(start, have, c->blocks);
+        if (used == ~0ull || (last && used != have)) { rc = 2; err = "not a BGZF stream"; }      // -> host path
+        else {
+          f->left.assign(start + used, start + have);
+          if (f->left.size() > kBgzfFront) { rc = 2; err = "not a BGZF stream"; }
+          c->comp_off = kBgzfFront - nl; c->comp_len = used; c->final_segment = last;
+          push = rc == 0;
+        }
       }
     } catch (const std::bad_alloc&) { rc = 1; err = "out of pinned host memory"; }
     if (!push && c->comp) { f->comp_pool->release(c->comp); c->comp = nullptr; }
     std::lock_guard<std::mutex> lk(f->gate->mu);
-    if (push) f->ready.push_back(c); else f->spare.push_back(c);
+    if (push) { f->ready.push_back(c); ++f->next_walk; } else f->spare.push_back(c);
     if (rc == 2) f->gpu_path_failed = true;
+    else if (rc == 1 && !f->reader_rc) { f->reader_rc = 1; f->reader_err = err; }
     f->gate->cv.notify_all();
   }
-  if (fp) std::fclose(fp);
   std::lock_guard<std::mutex> lk(f->gate->mu);
-  f->rc = rc == 2 ? 0 : rc; f->err = err; f->closed = true;
+  if (--f->live_readers == 0) {
+    if (f->fd >= 0) { ::close(f->fd); f->fd = -1; }
+    f->rc = f->reader_rc; f->err = f->reader_err; f->closed = true;
+  }
   f->gate->cv.notify_all();
 }
 
@@ -585,10 +627,11 @@ void wgs_finish_file(WgsFile* f, size_t total, uint64_t chunk_reads, const rsm_g
 // All files of one GPU: readers in parallel, one consumer (this thread) scoring whatever is ready.
 void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std::string>& files, size_t total, uint64_t chunk_reads,
                          uint64_t chunk_bases, const rsm_gpu_device* dev, swb_ctx* ctx, uint64_t ref_len, uint32_t window_len,
-                         std::vector<FileOutcome>* outcomes)
+                         std::vector<FileOutcome>* outcomes, unsigned readers_per_file, size_t n_devices)
 {
   DeviceGate gate;
   CompPool pool;
+  size_t bgzf_files = 0;
   if (const char* v = std::getenv("SWB_BGZF_POOL")) { const long n = std::atol(v); if (n >= 2 && n <= 16) pool.max_buffers = (size_t)n; }
   std::vector<std::unique_ptr<WgsFile>> fs;
   const size_t depth = 3;
@@ -598,18 +641,30 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
     f->bgzf = file_is_bgzf(files[i]);
     if (f->bgzf) {
       f->comp_pool = &pool;
-      f->seg_bytes = kBgzfSegmentMax;
+      // Page-locking the segment buffers is the expensive part of start-up, and a process that drives several GPUs pays
+      // more per byte (the pages are mapped for every device, all threads pin under one mm lock: 2.8 GB took 12 thread-seconds
+      // on eight GPUs, 0.35 GB 0.3 s on one): smaller segments there (8 GPUs, 128 M reads: 76 -> 133-154 M reads/s in the
+      // pipeline; one GPU alone loses 2 % with them and keeps the large ones).
+      const uint64_t seg_max = n_devices > 1 ? kBgzfSegmentMulti : kBgzfSegmentMax;
+      f->seg_bytes = seg_max;
       if (FILE* fp = std::fopen(files[i].c_str(), "rb")) {
         if (std::fseek(fp, 0, SEEK_END) == 0) {
           const long sz = std::ftell(fp);
-          if (sz > 0) f->seg_bytes = std::min<uint64_t>(kBgzfSegmentMax, (((uint64_t)sz + 1) / 2 + (1u << 16) + 4095) & ~4095ull);   // at least two segments
+          if (sz > 0) f->seg_bytes = std::min<uint64_t>(seg_max, (((uint64_t)sz + 1) / 2 + (1u << 16) + 4095) & ~4095ull);   // at least two segments
         }
         std::fclose(fp);
       }
       if (const char* v = std::getenv("SWB_BGZF_SEGMENT_MB")) { const long mb = std::atol(v); if (mb > 0) f->seg_bytes = (uint64_t)mb << 20; }
-      pool.bytes = std::max<uint64_t>(pool.bytes, f->seg_bytes + (1u << 17));
+      if (const char* v = std::getenv("SWB_BGZF_SEGMENT_KB")) { const long kb = std::atol(v); if (kb >= 128) f->seg_bytes = (uint64_t)kb << 10; }   // tests: many segments of a small file
+      pool.bytes = std::max<uint64_t>(pool.bytes, kBgzfFront + f->seg_bytes + 64);
+      f->fd = ::open(files[i].c_str(), O_RDONLY);
+      struct stat sb;
+      if (f->fd >= 0 && ::fstat(f->fd, &sb) == 0) f->file_bytes = (uint64_t)sb.st_size;
+      f->n_segments = std::max<uint64_t>(1, (f->file_bytes + f->seg_bytes - 1) / f->seg_bytes);
+      f->n_readers = (unsigned)std::min<uint64_t>(std::max(1u, readers_per_file), f->n_segments);
+      ++bgzf_files;
     }
-    for (size_t d = 0; d < (f->bgzf ? 2 : depth); ++d) {
+    for (size_t d = 0; d < (f->bgzf ? 1 + f->n_readers : depth); ++d) {
       f->pool.push_back(std::make_unique<WgsChunk>());
       WgsChunk* c = f->pool.back().get();
       if (!f->bgzf) {
@@ -627,9 +682,19 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
     if (f->bgzf) std::printf("    Blocked gzip (BGZF): inflate + FASTQ parsing on the GPU\n");
     fs.push_back(std::move(f));
   }
+  // pinned segment buffers of this GPU: the one being scored, the one being prefetched, and one per reader
+  if (!std::getenv("SWB_BGZF_POOL") && readers_per_file > 1) pool.max_buffers = std::min<size_t>(16, 2 + bgzf_files * readers_per_file);
   std::vector<std::thread> readers;
   for (auto& f : fs) {
-    if (f->bgzf) readers.emplace_back(wgs_bgzf_reader_thread, f.get());
+    if (f->bgzf) {
+      if (f->fd < 0) {                                       // unreadable: reported like the host reader would
+        std::lock_guard<std::mutex> lk(gate.mu);
+        f->rc = 1; f->err = "Failed to open file " + f->path + ": " + std::strerror(errno); f->closed = true;
+        continue;
+      }
+      f->live_readers = f->n_readers;
+      for (unsigned r = 0; r < f->n_readers; ++r) readers.emplace_back(wgs_bgzf_reader_thread, f.get(), r);
+    }
     else readers.emplace_back(wgs_reader_thread, f.get(), chunk_reads, chunk_bases, ref_len, window_len);
   }
   std::vector<uint8_t> carry_out(1 << 20);
@@ -660,7 +725,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
           if (g->bgzf && !g->gpu_path_failed && !g->ready.empty() && g->ready.front()->bgzf) { nf = g; nc = g->ready.front(); }
         }
     }
-    if (nc && !abort_run && swb_fastq_bgzf_prefetch(ctx, nc->comp->data(), nc->comp_len, nc->blocks.data(), nc->blocks.size()) == 0) {
+    if (nc && !abort_run && swb_fastq_bgzf_prefetch(ctx, nc->comp_data(), nc->comp_len, nc->blocks.data(), nc->blocks.size()) == 0) {
       pre_f = nf; pre_c = nc;                                      // copied in and inflated on a second stream while `c` is scored
     }
     if (finished && f->bgzf && f->gpu_path_failed && f->rc == 0 && !abort_run) {
@@ -697,7 +762,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
         int64_t ssum = 0; uint64_t nr = 0, nb = 0, nl = 0, ncarry = 0; int status = 0;
         const uint32_t w = (uint32_t)std::min<uint64_t>(window_len, ref_len);
         const auto tc0 = std::chrono::steady_clock::now();
-        const int crc = swb_fastq_bgzf_score(ctx, c->comp->data(), c->comp_len, c->blocks.data(), c->blocks.size(), f->carry.data(), f->carry.size(),
+        const int crc = swb_fastq_bgzf_score(ctx, c->comp_data(), c->comp_len, c->blocks.data(), c->blocks.size(), f->carry.data(), f->carry.size(),
                                              c->final_segment ? 1 : 0, f->index, f->reads, w, &ssum, &nr, &nb, &nl, carry_out.data(),
                                              carry_out.size(), &ncarry, &status);
         g_gpu_call_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tc0).count();
@@ -717,7 +782,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
         }
       }
       if (c->comp) {
-        if (f->gpu_path_failed || abort_run) swb_fastq_bgzf_cancel(ctx, c->comp->data());   // dropped, perhaps after it was prefetched
+        if (f->gpu_path_failed || abort_run) swb_fastq_bgzf_cancel(ctx, c->comp_data());   // dropped, perhaps after it was prefetched
         pool.release(c->comp); c->comp = nullptr;
       }
       std::lock_guard<std::mutex> lk(gate.mu);
@@ -1155,6 +1220,10 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   if (const char* v = std::getenv("SWB_CONSUMERS_PER_GPU")) if (parse_usize(v, &per_gpu, &why) || per_gpu < 1 || per_gpu > 8) per_gpu = 1;
   if (compat) per_gpu = 1;
   const size_t n_workers = std::min<size_t>(order.size() * per_gpu, todo.size());      // nothing left to do: no worker, no context
+  // BGZF files are read by several threads each when the box has more cores than files (SWB_READERS_PER_FILE overrides)
+  uint64_t rpf = todo.empty() ? 1 : std::max<uint64_t>(1, std::min<uint64_t>(2, std::thread::hardware_concurrency() / todo.size()));
+  if (const char* v = std::getenv("SWB_READERS_PER_FILE")) if (parse_usize(v, &rpf, &why) || rpf < 1 || rpf > 16) rpf = 1;
+  const unsigned readers_per_file = (unsigned)rpf;
   std::vector<std::string> werr(n_workers);
   std::vector<swb_ctx*> own_ctx(n_workers, nullptr);
   for (size_t w = 0; w < n_workers; ++w) {
@@ -1179,7 +1248,8 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
       std::vector<size_t> mine;
       for (size_t t = w; t < todo.size(); t += n_workers) mine.push_back(todo[t]);
       if (mine.empty()) return;
-      wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes);
+      wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes, readers_per_file, order.size());
+      stamp("a device's files done");
     });
   }
   stamp("reference + workers started");
@@ -1187,6 +1257,8 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   double mem_used_mb = 0;
   { uint64_t fr = 0, to = 0; if (swb_memory_info(first, &fr, &to) == 0) mem_used_mb = (double)(to - fr) / 1048576.0; }
   stamp("all files done");
+  if (std::getenv("SWB_DEBUG") || std::getenv("SWB_STAMPS"))
+    std::fprintf(stderr, "[wgs] pinned segment buffers: %.1f MB page-locked in %.3f thread-seconds\n", g_pin_bytes.load() / 1e6, g_pin_us.load() / 1e6);
   for (swb_ctx* x : own_ctx) if (x) swb_destroy(x);
   for (const auto& e : werr) if (!e.empty()) return fail(e);
   int n = 0;
@@ -1252,6 +1324,16 @@ int rsm_main(int argc, char** argv)
   dbg_stamp("main entered");
   std::atexit([] { dbg_stamp("atexit (before static destructors)"); });
   load_dotenv();                                                     // main.rs:50
+  // SWB_NUM_DEVICES=n (use the first n GPUs) is known before the driver is: hide the others from it, so that a run on one
+  // GPU of an eight-GPU box does not pay for initialising eight
+  if (const char* v = std::getenv("SWB_NUM_DEVICES")) {
+    const long n = std::atol(v);
+    if (n >= 1 && n < 64 && !std::getenv("CUDA_VISIBLE_DEVICES")) {
+      std::string list;
+      for (long d = 0; d < n; ++d) list += (d ? "," : "") + std::to_string(d);
+      setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 0);
+    }
+  }
   std::string seq1, seq2; bool has1 = false, has2 = false, files = false, gpu = false, test_wgs = false, full_wgs = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];

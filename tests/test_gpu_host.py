@@ -211,6 +211,13 @@ def test_full_wgs_bgzf_files_take_the_gpu_ingest_path(tmp_path, device, monkeypa
         assert ("inflate + FASTQ parsing on the GPU" in out) == (fmt == "bgzf")
         assert "Total lines read: %d" % (4 * n_reads) in out
     assert results["gzip"] == results["bgzf"] and results["gzip"][0][1] == n_reads
+    # several readers per file (each pread()s its own segments, block headers walked in order), many small segments
+    for readers, seg_kb in ((1, 128), (3, 128), (4, 200), (16, 129)):
+        monkeypatch.setenv("SWB_READERS_PER_FILE", str(readers)); monkeypatch.setenv("SWB_BGZF_SEGMENT_KB", str(seg_kb))
+        res = aligner.process_full_wgs_dataset(device)
+        assert [(r.score64, r.total_reads, r.total_bases) for r in res] == results["gzip"], (readers, seg_kb)
+        assert "inflate + FASTQ parsing on the GPU" in capfd.readouterr().out
+    monkeypatch.delenv("SWB_BGZF_SEGMENT_KB")
     # a block with a damaged payload: the GPU path declines, the host reader takes over and fails like zlib does
     d = tmp_path / "bad"
     d.mkdir()
@@ -222,9 +229,12 @@ def test_full_wgs_bgzf_files_take_the_gpu_ingest_path(tmp_path, device, monkeypa
                 gz[k] ^= 0xA5
         (d / f"SYN_L{lane:03d}_R{rd}_001.fastq.gz").write_bytes(bytes(gz))
     monkeypatch.setenv("WGS_DATA_DIR", str(d))
-    with pytest.raises(aligner.AlignerError):
-        aligner.process_full_wgs_dataset(device)
-    assert "falling back to the host reader" in capfd.readouterr().out
+    for readers in (3, 1):
+        monkeypatch.setenv("SWB_READERS_PER_FILE", str(readers))
+        with pytest.raises(aligner.AlignerError):
+            aligner.process_full_wgs_dataset(device)
+        assert "falling back to the host reader" in capfd.readouterr().out
+    monkeypatch.delenv("SWB_READERS_PER_FILE")
 
 
 def test_full_wgs_checkpoint_resume(tmp_path, device, monkeypatch, capfd):

@@ -82,6 +82,42 @@ def make_file(args):
     return os.path.getsize(path), n_reads * rec.shape[1]
 
 
+def io_ceiling(paths, gz_bytes):
+    """What the host can deliver at all: threads that do nothing but pread() the compressed files in 112 MiB segments into
+    their own buffers (no GPU, no parsing), 1 / 2 / 4 threads per file, segments dealt round-robin like the driver's readers."""
+    import threading
+    seg = 112 << 20
+    out = {"what": "pread() of the compressed files only, 112 MiB segments, MB/s over all files", "files": len(paths), "gz_mb": round(gz_bytes / 1e6, 1),
+           "host_cores": os.cpu_count()}
+
+    def reader(path, r, nr, buf):
+        fd = os.open(path, os.O_RDONLY)
+        size = os.fstat(fd).st_size
+        k = r
+        while k * seg < size:
+            got, want = 0, min(seg, size - k * seg)
+            mv = memoryview(buf)
+            while got < want:
+                n = os.preadv(fd, [mv[got:want]], k * seg + got)
+                if n <= 0:
+                    break
+                got += n
+            k += nr
+        os.close(fd)
+    for nr in (1, 2, 4, 1):
+        bufs = [bytearray(min(seg, os.path.getsize(p))) for p in paths for r in range(nr)]      # allocated (and touched) outside the timed region
+        th = [threading.Thread(target=reader, args=(p, r, nr, bufs[i * nr + r])) for i, p in enumerate(paths) for r in range(nr)]
+        t0 = time.time()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        dt = time.time() - t0
+        key = f"threads_per_file_{nr}" + ("_again" if f"threads_per_file_{nr}" in out else "")
+        out[key] = {"seconds": round(dt, 3), "mb_per_s": round(gz_bytes / dt / 1e6, 1)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads-per-file", type=int, default=250_000)
@@ -93,6 +129,12 @@ def main():
     ap.add_argument("--level", type=int, default=1)
     ap.add_argument("--reuse", action="store_true", help="keep the files already in --dir (same parameters) instead of regenerating them")
     ap.add_argument("--bgzf", action="store_true", help="write blocked gzip (BGZF): the driver inflates and parses it on the GPU")
+    ap.add_argument("--clone-files", action="store_true",
+                    help="generate the first file only and copy it to the other 15 names (the driver pairs every read with a window by "
+                         "(file index, read index), so the files still score differently): a full-size data set in a fraction of the time")
+    ap.add_argument("--io-ceiling", action="store_true",
+                    help="do not score: only pread() the files with 1, 2 and 4 threads per file (the host-side ceiling of the ingest)")
+    ap.add_argument("--readers", type=int, default=0, help="SWB_READERS_PER_FILE for the run (0: the driver's default)")
     ap.add_argument("--quals", default="constant", choices=["constant", "noisy"], help="quality strings: all 'I', or four binned values at random")
     args = ap.parse_args()
     os.makedirs(args.dir, exist_ok=True)
@@ -104,6 +146,9 @@ def main():
             fi += 1
     t0 = time.time()
     rec_len = 12 + 150 + 3 + 150 + 1
+    all_jobs = jobs
+    if args.clone_files and not (args.reuse and all(os.path.exists(j[0]) for j in jobs)):
+        jobs = jobs[:1]
     if args.reuse and all(os.path.exists(j[0]) for j in jobs):     # files of an earlier run with the same parameters
         sizes = [(os.path.getsize(j[0]), args.reads_per_file * rec_len) for j in jobs]
     elif args.bgzf and (os.cpu_count() or 1) >= 2 * len(jobs):     # more cores than files: every file in slices, joined afterwards
@@ -135,11 +180,23 @@ def main():
     else:
         with ProcessPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
             sizes = list(ex.map(make_file, jobs))
+    if len(all_jobs) > len(jobs):                                   # --clone-files
+        import shutil
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            list(ex.map(lambda j: shutil.copyfile(jobs[0][0], j[0]), all_jobs[1:]))
+        sizes = [sizes[0]] * len(all_jobs)
+    jobs = all_jobs
     gen_s = time.time() - t0
     gz_bytes = sum(s[0] for s in sizes); text_bytes = sum(s[1] for s in sizes)
+    if args.io_ceiling:
+        print(json.dumps(io_ceiling([j[0] for j in jobs], gz_bytes)))
+        return
     env = dict(os.environ, GPU_CHUNK_SIZE_READS=str(args.chunk_reads), WGS_DATA_DIR=args.dir, WGS_SAMPLE_ID="SYN", WGS_LANES=str(args.lanes),
                WGS_READS_PER_LANE="2", WGS_SYNTH_REFERENCE_BASES=str(args.ref_bases), SWB_NUM_DEVICES=str(args.devices), WGS_CHECKPOINT_DIR=args.dir)
     env.pop("SWB_GPU_ALIGN_MODE", None)
+    if args.readers:
+        env["SWB_READERS_PER_FILE"] = str(args.readers)
     cli = os.path.join(ROOT, "build", "rustseq_mini")
     subprocess.run([cli, "-1", "ACGT", "-2", "ACGT", "--gpu"], env=env, capture_output=True)      # warm the driver / context creation
     t0 = time.time()
@@ -165,6 +222,7 @@ def main():
         "pipeline_reads_per_s": round(n_reads / max(file_s), 1) if file_s else None,      # all files run concurrently: excludes process + CUDA context start-up
         "pipeline_gcups": round(n_reads * 150 * 500 / max(file_s) / 1e9, 1) if file_s else None,
         "startup_s": round(wall - max(file_s), 3) if file_s else None,                    # process start, CUDA contexts, reference upload: everything before / after the files
+        "readers_per_file": args.readers or "default (cores / files, 1..4)",
         "host_cores": os.cpu_count(), "generate_s": round(gen_s, 1),
         "mean_score_per_read": round(sum(scores) / n_reads, 2), "files_done": len(scores)}))
 
