@@ -7,6 +7,12 @@ pub struct SwbCtx {
     _private: [u8; 0],
 }
 
+/// swb_multi: several devices behind one handle (the reference uses devices[0] only, gpu.rs:117-131, main.rs:95).
+#[repr(C)]
+pub struct SwbMulti {
+    _private: [u8; 0],
+}
+
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
 pub struct SwbResult {
@@ -49,6 +55,17 @@ extern "C" {
     pub fn swb_set_reference(ctx: *mut SwbCtx, reference: *const u8, n: u64) -> c_int;
     pub fn swb_score_batch_vs_reference(ctx: *mut SwbCtx, q: *const u8, q_off: *const u64, n_pairs: u64, win_start: *const u64,
                                         win_len: *const u32, out: *mut SwbResult) -> c_int;
+    pub fn swb_score_batch_ranges(ctx: *mut SwbCtx, q: *const u8, q_off: *const u64, n_pairs: u64, w_bytes: *const u8, w_total: u64,
+                                  win_start: *const u64, win_len: *const u32, out: *mut SwbResult) -> c_int;
+    pub fn swb_create_multi(out: *mut *mut SwbMulti, device_ids: *const c_int, n_devices: c_int, params: *const c_void) -> c_int;
+    pub fn swb_destroy_multi(m: *mut SwbMulti);
+    pub fn swb_multi_device_count(m: *mut SwbMulti) -> c_int;
+    pub fn swb_multi_score_batch(m: *mut SwbMulti, q: *const u8, q_off: *const u64, r: *const u8, r_off: *const u64, n_pairs: u64,
+                                 out: *mut SwbResult) -> c_int;
+    pub fn swb_multi_set_reference(m: *mut SwbMulti, reference: *const u8, n: u64) -> c_int;
+    pub fn swb_multi_score_batch_vs_reference(m: *mut SwbMulti, q: *const u8, q_off: *const u64, n_pairs: u64, win_start: *const u64,
+                                              win_len: *const u32, out: *mut SwbResult) -> c_int;
+    pub fn swb_fastq_bgzf_cancel(ctx: *mut SwbCtx, comp: *const u8) -> c_int;
     pub fn swb_fastq_bgzf_prefetch(ctx: *mut SwbCtx, comp: *const u8, comp_bytes: u64, blocks: *const SwbBgzfBlock, n_blocks: u64) -> c_int;
     pub fn swb_fastq_bgzf_score(ctx: *mut SwbCtx, comp: *const u8, comp_bytes: u64, blocks: *const SwbBgzfBlock, n_blocks: u64,
                                 carry: *const u8, carry_len: u64, final_segment: c_int, file_index: u64, first_read: u64,
@@ -111,6 +128,21 @@ impl Engine {
         if rc != 0 { Err(last_error()) } else { Ok(out) }
     }
 
+    /// Reads against windows that are ranges of ONE buffer (candidate windows of a genome: they overlap); the covered part of
+    /// the buffer is uploaded once per call.  Same results as `score_batch` on the materialised windows.
+    pub fn score_batch_ranges(&mut self, reads: &[u8], read_off: &[u64], buffer: &[u8], win_start: &[u64], win_len: &[u32])
+                              -> Result<Vec<SwbResult>, String> {
+        Self::check_csr(reads, read_off, "reads")?;
+        let n = read_off.len() - 1;
+        if win_start.len() != n || win_len.len() != n { return Err("read_off, win_start and win_len must describe the same number of pairs".into()); }
+        let mut out = vec![SwbResult::default(); n];
+        let rc = unsafe {
+            swb_score_batch_ranges(self.ctx, reads.as_ptr(), read_off.as_ptr(), n as u64, buffer.as_ptr(), buffer.len() as u64,
+                                   win_start.as_ptr(), win_len.as_ptr(), out.as_mut_ptr())
+        };
+        if rc != 0 { Err(last_error()) } else { Ok(out) }
+    }
+
     /// Start cell and CIGAR behind the results of `score_batch` on the same pairs; grows the operation buffer once if the
     /// first guess was too small (the library reports how much the batch needs).
     pub fn traceback_batch(&mut self, reads: &[u8], read_off: &[u64], windows: &[u8], window_off: &[u64], results: &[SwbResult])
@@ -159,4 +191,59 @@ pub fn gpu_align(seq1: &str, seq2: &str, engine: &mut Engine) -> Result<i32, Str
         return Ok(0);
     }
     engine.score_pair(seq1.as_bytes(), seq2.as_bytes()).map(|r| r.score)
+}
+
+
+/// Every GPU of the box behind one handle: a batch is cut into contiguous slices, one per device, each written by its own
+/// host thread into its slice of the result vector.
+pub struct MultiEngine {
+    m: *mut SwbMulti,
+}
+
+unsafe impl Send for MultiEngine {}
+
+impl MultiEngine {
+    /// `devices` empty = every visible device.
+    pub fn new(devices: &[i32]) -> Result<Self, String> {
+        let mut m: *mut SwbMulti = std::ptr::null_mut();
+        let ids = if devices.is_empty() { std::ptr::null() } else { devices.as_ptr() };
+        if unsafe { swb_create_multi(&mut m, ids, devices.len() as c_int, std::ptr::null()) } != 0 { return Err(last_error()); }
+        Ok(Self { m })
+    }
+
+    pub fn n_devices(&self) -> usize { unsafe { swb_multi_device_count(self.m) as usize } }
+
+    pub fn set_reference(&mut self, reference: &[u8]) -> Result<(), String> {
+        if unsafe { swb_multi_set_reference(self.m, reference.as_ptr(), reference.len() as u64) } != 0 { Err(last_error()) } else { Ok(()) }
+    }
+
+    pub fn score_batch(&mut self, reads: &[u8], read_off: &[u64], windows: &[u8], window_off: &[u64]) -> Result<Vec<SwbResult>, String> {
+        if read_off.len() != window_off.len() { return Err("read_off and window_off must describe the same number of pairs".into()); }
+        Engine::check_csr(reads, read_off, "reads")?;
+        Engine::check_csr(windows, window_off, "windows")?;
+        let n = read_off.len() - 1;
+        let mut out = vec![SwbResult::default(); n];
+        let rc = unsafe {
+            swb_multi_score_batch(self.m, reads.as_ptr(), read_off.as_ptr(), windows.as_ptr(), window_off.as_ptr(), n as u64, out.as_mut_ptr())
+        };
+        if rc != 0 { Err(last_error()) } else { Ok(out) }
+    }
+
+    pub fn score_batch_vs_reference(&mut self, reads: &[u8], read_off: &[u64], win_start: &[u64], win_len: &[u32]) -> Result<Vec<SwbResult>, String> {
+        Engine::check_csr(reads, read_off, "reads")?;
+        let n = read_off.len() - 1;
+        if win_start.len() != n || win_len.len() != n { return Err("read_off, win_start and win_len must describe the same number of pairs".into()); }
+        let mut out = vec![SwbResult::default(); n];
+        let rc = unsafe {
+            swb_multi_score_batch_vs_reference(self.m, reads.as_ptr(), read_off.as_ptr(), n as u64, win_start.as_ptr(), win_len.as_ptr(),
+                                               out.as_mut_ptr())
+        };
+        if rc != 0 { Err(last_error()) } else { Ok(out) }
+    }
+}
+
+impl Drop for MultiEngine {
+    fn drop(&mut self) {
+        unsafe { swb_destroy_multi(self.m) }
+    }
 }
