@@ -26,14 +26,16 @@ def main():
     rng = np.random.default_rng(args.seed)
     alphabets = [b"ACGT"] * 6 + [b"A", b"AC", b"ACGTN", b"ACGTacgtN", bytes(range(256))]
     t_end = time.time() + args.seconds
-    rounds, pairs_total, routes = 0, 0, {"short": 0, "generic": 0, "long": 0}
+    rounds, pairs_total, routes = 0, 0, {"short": 0, "mid": 0, "long": 0, "bytes": 0, "generic": 0}
+    tb_checked = 0
     while time.time() < t_end:
-        shape = rng.integers(0, 6)
+        shape = rng.integers(0, 7)
         if shape == 0:   n, rl, wl = int(rng.integers(1, 30000)), (1, 160), (1, 900)
         elif shape == 1: n, rl, wl = int(rng.integers(1, 30000)), (150, 150), (500, 500)
         elif shape == 2: n, rl, wl = int(rng.integers(1, 3000)), (1, 200), (1, 4200)
         elif shape == 3: n, rl, wl = int(rng.integers(1, 400)), (100, 1500), (1, 2500)
         elif shape == 4: n, rl, wl = int(rng.integers(1, 40)), (300, 6000), (300, 6000)
+        elif shape == 6: n, rl, wl = int(rng.integers(1, 6000)), (150, 330), (1, 1300)       # round 2: the 320-row int16x2 path and its edges
         else:            n, rl, wl = int(rng.integers(1, 8000)), (140, 160), (400, 1100)
         al = np.frombuffer(alphabets[int(rng.integers(0, len(alphabets)))], dtype=np.uint8)
         related = bool(rng.integers(0, 2))
@@ -51,10 +53,18 @@ def main():
                 r = al[rng.integers(0, al.size, a)]
             reads.append(r)
         q, qo = to_csr(reads); r, ro = to_csr(wins)
-        variant = int(rng.choice([4, 4, 4, 5, 6, 1]))
+        variant = 9                                        # the product library carries the default stream kernel only
         chunk = (int(rng.choice([1 << 14, 1 << 17, 1 << 20, 32 << 20])), int(rng.choice([1, 256, 16384])))
-        eng.set_short_variant(variant); eng.set_chunking(*chunk)
-        got = eng.score_batch_csr(q, qo, r, ro)
+        eng.set_chunking(*chunk)
+        eng.set_mid_path(bool(rng.integers(0, 4)))         # one batch in four: reads of 161..320 bp through the 32-bit kernel instead
+        api = int(rng.integers(0, 3))
+        if api == 0 or r.size == 0:
+            got = eng.score_batch_csr(q, qo, r, ro)
+        elif api == 1:                                     # the same windows as ranges of one host buffer
+            got = eng.score_batch_ranges(q, qo, r, ro[:-1].copy(), np.diff(ro).astype(np.uint32))
+        else:                                              # ... and of the resident reference
+            eng.set_reference(r)
+            got = eng.score_batch_vs_reference(q, qo, ro[:-1].copy(), np.diff(ro).astype(np.uint32))
         exp = ol.batch(q, qo, r, ro, threads=os.cpu_count() or 8, simd=True)
         bad = np.nonzero(got != exp)[0]
         if bad.size:
@@ -62,11 +72,22 @@ def main():
             print(f"MISMATCH seed={args.seed} round={rounds} shape={shape} n={n} variant={variant} chunk={chunk} pair={k} "
                   f"n1={n1[k]} n2={n2[k]} got={got[k]} exp={exp[k]} ({bad.size} pairs differ)")
             return 1
-        rt = eng.last_routing()
+        rt = eng.last_routing_ex()
         for kk in routes:
             routes[kk] += rt[kk]
+        if rounds % 5 == 0:                                # the alignments behind a sample of the scores
+            m = min(n, 200)
+            al_, ops = eng.traceback_batch(q[:int(qo[m])], qo[:m + 1], r[:int(ro[m])], ro[:m + 1], got[:m])
+            for k in range(0, m, 9):
+                a1 = q[int(qo[k]):int(qo[k + 1])].tobytes(); b1 = r[int(ro[k]):int(ro[k + 1])].tobytes()
+                e = ol.traceback(a1, b1, int(got[k]["end_i"]), int(got[k]["end_j"]))
+                g = (int(al_[k]["start_i"]), int(al_[k]["start_j"]), eng.cigar_of(al_[k], ops))
+                if g != e:
+                    print(f"TRACEBACK MISMATCH seed={args.seed} round={rounds} pair={k} got={g} exp={e}")
+                    return 1
+                tb_checked += 1
         rounds += 1; pairs_total += n
-    print(f"fuzz ok: {rounds} batches, {pairs_total} pairs, routing {routes}, seed {args.seed}")
+    print(f"fuzz ok: {rounds} batches, {pairs_total} pairs, routing {routes}, {tb_checked} tracebacks, seed {args.seed}")
     return 0
 
 
