@@ -219,6 +219,10 @@ int  swb_set_chunk_ramp(swb_ctx*, int ramp);
 int  swb_malloc_device(swb_ctx*, uint64_t bytes, void** out);
 int  swb_free_device(swb_ctx*, void* p);
 int  swb_malloc_pinned(uint64_t bytes, void** out);
+/* Makes the context's device the calling thread's current device.  A helper thread that allocates pinned memory for a
+ * context (swb_malloc_pinned page-locks under the CURRENT device's context lock) should call this first: left on the
+ * default device 0, the page-locking of every thread of a multi-GPU process stalls device 0's own launches. */
+int  swb_bind_thread(swb_ctx*);
 int  swb_free_pinned(void* p);
 int  swb_memcpy_h2d(swb_ctx*, void* d_dst, const void* h_src, uint64_t bytes);
 int  swb_memcpy_d2h(swb_ctx*, void* h_dst, const void* d_src, uint64_t bytes);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "swb_score_batch_vs_reference": (_int, [_vp, _u8p, _vp, _u64, _vp, _vp, _vp]),
     "swb_score_batch_ranges": (_int, [_vp, _u8p, _vp, _u64, _u8p, _u64, _vp, _vp, _vp]),
     "swb_last_ranges_info": (_int, [_vp, ctypes.POINTER(_u64), ctypes.POINTER(_u64)]),
+    "swb_bind_thread": (_int, [_vp]),
     "swb_debug_guard_check": (_int, [_vp, ctypes.c_char_p, _u64, ctypes.POINTER(_u64)]),
     "swb_create_multi": (_int, [ctypes.POINTER(_vp), _vp, _int, _vp]),
     "swb_destroy_multi": (None, [_vp]),

@@ -482,6 +482,7 @@ struct WgsFile {
   std::vector<uint8_t> carry; uint64_t lines = 0;
   uint64_t seg_bytes = 0; CompPool* comp_pool = nullptr;
   // several readers per file (wgs_bgzf_reader_thread): segment k may take its buffers once k-1 has, and is walked after k-1
+  swb_ctx* ctx = nullptr;                      // the consumer's context: readers make its device current before they page-lock buffers
   int fd = -1; uint64_t file_bytes = 0, n_segments = 0;
   unsigned n_readers = 1, live_readers = 0;
   uint64_t next_acquire = 0, next_walk = 0;    // guarded by gate->mu
@@ -502,6 +503,10 @@ constexpr uint64_t kBgzfFront = 128u << 10;
 void wgs_bgzf_reader_thread(WgsFile* f, unsigned r)
 {
   int rc = 0; std::string err;
+  // Page-locking runs under the current device's context lock, and a new thread's current device is 0: without this the
+  // readers of ALL GPUs pin under device 0's lock and its consumer's launches wait behind them (8 GPUs, 32 MiB segments:
+  // 22 ms per call on device 0 against 9.5 ms on the other seven, profiles/wgs_8gpu_consumer_accounting_r02.txt).
+  if (f->ctx) swb_bind_thread(f->ctx);
   const uint64_t S = f->seg_bytes;
   for (uint64_t k = r; k < f->n_segments && rc == 0; k += f->n_readers) {
     WgsChunk* c = nullptr;
@@ -637,7 +642,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
   const size_t depth = 3;
   for (size_t i : mine) {
     auto f = std::make_unique<WgsFile>();
-    f->index = i; f->path = files[i]; f->gate = &gate; f->t0 = std::chrono::steady_clock::now();
+    f->index = i; f->path = files[i]; f->gate = &gate; f->t0 = std::chrono::steady_clock::now(); f->ctx = ctx;
     f->bgzf = file_is_bgzf(files[i]);
     if (f->bgzf) {
       f->comp_pool = &pool;
@@ -702,6 +707,8 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
   for (auto& f : fs) active.push_back(f.get());
   bool abort_run = false;
   size_t rr = 0;
+  uint64_t st_wait_us = 0, st_call_us = 0, st_segments = 0, st_prefetched = 0;      // SWB_STAMPS: where this consumer's time went
+  const auto st_t0 = std::chrono::steady_clock::now();
   WgsFile* pre_f = nullptr; WgsChunk* pre_c = nullptr;             // the BGZF segment already being inflated (prefetch)
   while (!active.empty()) {
     WgsFile* f = nullptr; WgsChunk* c = nullptr; bool finished = false;
@@ -716,7 +723,9 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
           else if (g->closed) { f = g; finished = true; }
         }
         if (f) break;
+        const auto tw0 = std::chrono::steady_clock::now();
         gate.cv.wait(lk);
+        st_wait_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tw0).count();
       }
       ++rr;
       if (!finished && c->bgzf && !f->gpu_path_failed)            // the next BGZF segment, whichever file has one ready
@@ -727,6 +736,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
     }
     if (nc && !abort_run && swb_fastq_bgzf_prefetch(ctx, nc->comp_data(), nc->comp_len, nc->blocks.data(), nc->blocks.size()) == 0) {
       pre_f = nf; pre_c = nc;                                      // copied in and inflated on a second stream while `c` is scored
+      ++st_prefetched;
     }
     if (finished && f->bgzf && f->gpu_path_failed && f->rc == 0 && !abort_run) {
       // the GPU path declined the file (not really BGZF, a corrupt block, non-ASCII text, a giant record): redo it with
@@ -765,7 +775,8 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
         const int crc = swb_fastq_bgzf_score(ctx, c->comp_data(), c->comp_len, c->blocks.data(), c->blocks.size(), f->carry.data(), f->carry.size(),
                                              c->final_segment ? 1 : 0, f->index, f->reads, w, &ssum, &nr, &nb, &nl, carry_out.data(),
                                              carry_out.size(), &ncarry, &status);
-        g_gpu_call_us += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tc0).count();
+        const uint64_t call_us = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - tc0).count();
+        g_gpu_call_us += call_us; st_call_us += call_us; ++st_segments;
         if (crc != 0 || status != 0) {
           if (crc) std::printf("    Warning: GPU FASTQ path failed on %s: %s\n", base_name(f->path).c_str(), swb_last_error());
           std::lock_guard<std::mutex> lk(gate.mu);
@@ -814,6 +825,10 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
     gate.cv.notify_all();
   }
   for (auto& t : readers) t.join();
+  if (std::getenv("SWB_STAMPS") && st_segments)
+    std::fprintf(stderr, "[wgs] device consumer: %.3f s in all, %.3f s waiting for a segment, %.3f s inside %llu GPU calls (%.2f ms each), %llu prefetched\n",
+                 std::chrono::duration<double>(std::chrono::steady_clock::now() - st_t0).count(), st_wait_us / 1e6, st_call_us / 1e6,
+                 (unsigned long long)st_segments, st_call_us / 1e3 / (double)st_segments, (unsigned long long)st_prefetched);
 }
 
 void load_dotenv()
@@ -1221,7 +1236,10 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
   if (compat) per_gpu = 1;
   const size_t n_workers = std::min<size_t>(order.size() * per_gpu, todo.size());      // nothing left to do: no worker, no context
   // BGZF files are read by several threads each when the box has more cores than files (SWB_READERS_PER_FILE overrides)
-  uint64_t rpf = todo.empty() ? 1 : std::max<uint64_t>(1, std::min<uint64_t>(2, std::thread::hardware_concurrency() / todo.size()));
+  // Default: one reader per file, two when a GPU serves a single file.  Every reader costs a page-locked segment buffer, and
+  // page-locking is what a short run spends its time on (8 GPUs x 2 files, 256 M reads: 259 M reads/s with one reader per
+  // file, 174-187 with two; profiles/wgs_8gpu_consumer_accounting_r02.txt).
+  uint64_t rpf = (!todo.empty() && todo.size() < 2 * n_workers && std::thread::hardware_concurrency() >= 2 * todo.size()) ? 2 : 1;
   if (const char* v = std::getenv("SWB_READERS_PER_FILE")) if (parse_usize(v, &rpf, &why) || rpf < 1 || rpf > 16) rpf = 1;
   const unsigned readers_per_file = (unsigned)rpf;
   std::vector<std::string> werr(n_workers);

@@ -180,6 +180,9 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   if (n <= 0) return fail("error: gpu acceleration is required and no compatible gpu was found");   // main.rs:161
   if (device_id < 0 || device_id >= n) return fail("swb_create: no such device");
   CUDA_TRY(cudaSetDevice(device_id));
+  // SWB_BLOCKING_SYNC=1: host threads sleep in cudaStreamSynchronize instead of spinning (a process that drives eight GPUs and
+  // reads 16 files has more busy threads than a 32-core box has cores)
+  if (const char* v = std::getenv("SWB_BLOCKING_SYNC")) if (std::atoi(v) != 0) { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); }
   swb_ctx* c = new swb_ctx();
   c->device = device_id;
   cudaDeviceProp p;
@@ -1149,6 +1152,13 @@ int swb_malloc_device(swb_ctx* c, uint64_t bytes, void** out)
   return 0;
 }
 int swb_free_device(swb_ctx* c, void* p) { if (c) cudaSetDevice(c->device); cudaFree(p); return 0; }
+int swb_bind_thread(swb_ctx* c)
+{
+  if (!c) return fail("null ctx");
+  CUDA_TRY(cudaSetDevice(c->device));
+  return 0;
+}
+
 int swb_malloc_pinned(uint64_t bytes, void** out)
 {
   if (!out) return fail("null pointer");
