@@ -42,6 +42,11 @@ typedef int (*rsm_chunk_fn)(void* user, const uint8_t* bases, const uint64_t* of
 int  rsm_process_fastq_file_in_chunks(const char* filepath, uint64_t chunk_size_reads, rsm_chunk_fn processor, void* user);
 
 int  rsm_count_bases_in_fastq(const char* filepath, uint64_t* out);  /* aligner.rs:535-544 */
+/* Test hook, needs no GPU: the BGZF readers of the --full-wgs driver (several pread() threads per file, ordered hand-off of
+ * segments) against a consumer that only takes the segments in order.  *hash covers every block's compressed payload and
+ * inflated size in stream order: the same for every reader count, segment size and pool size.  *status: 0 ok, 2 not BGZF. */
+int  rsm_debug_bgzf_segments(const char* path, unsigned readers, uint64_t seg_bytes, unsigned pool_buffers, uint64_t* n_segments,
+                             uint64_t* n_blocks, uint64_t* text_bytes, uint64_t* hash, int* status);
 
 /* aligner.rs:410-532  gpu_align(seq1, seq2, device) -> Result<i32, String> */
 int  rsm_gpu_align(const uint8_t* seq1, uint64_t n1, const uint8_t* seq2, uint64_t n2, const rsm_gpu_device* device, int32_t* score);

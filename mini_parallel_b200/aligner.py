@@ -59,6 +59,8 @@ def _lib():
         lib.rsm_get_chunk_size_bases.argtypes = [u64p]
         lib.rsm_process_fastq_file_in_chunks.argtypes = [ctypes.c_char_p, ctypes.c_uint64, _CHUNK_FN, ctypes.c_void_p]
         lib.rsm_count_bases_in_fastq.argtypes = [ctypes.c_char_p, u64p]
+        lib.rsm_debug_bgzf_segments.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint, u64p, u64p, u64p, u64p,
+                                                ctypes.POINTER(ctypes.c_int)]
         lib.rsm_gpu_align.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
                                       ctypes.POINTER(GpuDevice), ctypes.POINTER(ctypes.c_int32)]
         lib.rsm_gpu_align_ex.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
@@ -130,6 +132,16 @@ def process_fastq_file_in_chunks(filepath, chunk_size_reads, processor):
     if err:
         raise err[0]
     _check(rc)
+
+
+def debug_bgzf_segments(filepath, readers, seg_bytes, pool_buffers):
+    """rsm_debug_bgzf_segments (test hook, no GPU): the --full-wgs BGZF readers against a consumer that only takes the segments
+    in order -> dict(segments, blocks, text_bytes, hash, status)."""
+    a, b, c, h = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    st = ctypes.c_int()
+    _check(_lib().rsm_debug_bgzf_segments(str(filepath).encode(), int(readers), int(seg_bytes), int(pool_buffers), ctypes.byref(a),
+                                          ctypes.byref(b), ctypes.byref(c), ctypes.byref(h), ctypes.byref(st)))
+    return {"segments": int(a.value), "blocks": int(b.value), "text_bytes": int(c.value), "hash": int(h.value), "status": int(st.value)}
 
 
 def count_bases_in_fastq(filepath):

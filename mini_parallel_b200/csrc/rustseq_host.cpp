@@ -108,12 +108,25 @@ bool valid_utf8(const uint8_t* p, size_t n)
 
 // Host memory the GPU can copy from asynchronously (USE_PINNED_MEMORY, aligner.rs:466-475): std::vector over
 // swb_malloc_pinned.  The WGS pipeline keeps its chunk buffers in it so H2D overlaps inflate and scoring.
+// (rsm_debug_bgzf_segments walks a file with the readers alone, no GPU in sight: its buffers are plain memory.)
+std::atomic<int> g_plain_buffers{0};
 template <class T> struct PinnedAlloc {
   using value_type = T;
   PinnedAlloc() = default;
   template <class U> PinnedAlloc(const PinnedAlloc<U>&) {}
-  T* allocate(size_t n) { void* p = nullptr; if (swb_malloc_pinned(n * sizeof(T), &p) != 0 || !p) throw std::bad_alloc(); return (T*)p; }
-  void deallocate(T* p, size_t) { swb_free_pinned(p); }
+  T* allocate(size_t n)
+  {
+    void* p = nullptr;
+    if (g_plain_buffers.load()) { p = std::malloc(n * sizeof(T) + 16); if (!p) throw std::bad_alloc(); *(uint64_t*)p = 0x504C41494E; return (T*)((char*)p + 16); }
+    if (swb_malloc_pinned(n * sizeof(T) + 16, &p) != 0 || !p) throw std::bad_alloc();
+    *(uint64_t*)p = 0;
+    return (T*)((char*)p + 16);
+  }
+  void deallocate(T* p, size_t)
+  {
+    void* base = (char*)p - 16;
+    if (*(uint64_t*)base == 0x504C41494E) std::free(base); else swb_free_pinned(base);
+  }
   template <class U> bool operator==(const PinnedAlloc<U>&) const { return true; }
   template <class U> bool operator!=(const PinnedAlloc<U>&) const { return false; }
 };
@@ -912,6 +925,60 @@ int rsm_process_fastq_file_in_chunks(const char* filepath, uint64_t chunk_size_r
 }
 
 static int count_cb(void* user, const uint8_t*, const uint64_t* offs, uint64_t n) { *(uint64_t*)user += offs[n]; return 0; }
+
+// Test hook (no GPU): runs the BGZF readers of the --full-wgs driver on one file -- `readers` threads, segments of seg_bytes,
+// `pool_buffers` segment buffers -- against a consumer that only takes the segments in order, and reports what it saw: the
+// blocks, their inflated bytes, and an FNV-1a hash over every block's compressed payload and inflated size in stream order
+// (identical for every reader count / segment size / pool size, or the hand-off protocol is broken).  status: 0 ok, 2 the
+// file is not BGZF (the driver would fall back to the host reader), 1 error (rsm_last_error()).
+int rsm_debug_bgzf_segments(const char* path, unsigned readers, uint64_t seg_bytes, unsigned pool_buffers, uint64_t* n_segments,
+                            uint64_t* n_blocks, uint64_t* text_bytes, uint64_t* hash, int* status)
+{
+  if (!path || !n_segments || !n_blocks || !text_bytes || !hash || !status) return fail("rsm_debug_bgzf_segments: null pointer");
+  *n_segments = *n_blocks = *text_bytes = 0; *hash = 1469598103934665603ull; *status = 0;
+  if (seg_bytes < (128u << 10)) return fail("rsm_debug_bgzf_segments: segments of at least 128 KiB");
+  struct PlainGuard { PlainGuard() { ++g_plain_buffers; } ~PlainGuard() { --g_plain_buffers; } } plain;
+  DeviceGate gate; CompPool pool;
+  pool.max_buffers = std::max(2u, pool_buffers); pool.bytes = kBgzfFront + seg_bytes + 64;
+  WgsFile f;
+  f.path = path; f.gate = &gate; f.bgzf = true; f.comp_pool = &pool; f.seg_bytes = seg_bytes;
+  f.fd = ::open(path, O_RDONLY);
+  if (f.fd < 0) return fail(std::string("Failed to open file ") + path + ": " + std::strerror(errno));
+  struct stat sb;
+  if (::fstat(f.fd, &sb) == 0) f.file_bytes = (uint64_t)sb.st_size;
+  f.n_segments = std::max<uint64_t>(1, (f.file_bytes + seg_bytes - 1) / seg_bytes);
+  f.n_readers = (unsigned)std::min<uint64_t>(std::max(1u, readers), f.n_segments);
+  for (unsigned d = 0; d < 1 + f.n_readers; ++d) { f.pool.push_back(std::make_unique<WgsChunk>()); f.spare.push_back(f.pool.back().get()); }
+  f.live_readers = f.n_readers;
+  std::vector<std::thread> th;
+  for (unsigned r = 0; r < f.n_readers; ++r) th.emplace_back(wgs_bgzf_reader_thread, &f, r);
+  for (;;) {
+    WgsChunk* c = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(gate.mu);
+      gate.cv.wait(lk, [&] { return !f.ready.empty() || f.closed; });
+      if (f.ready.empty()) break;
+      c = f.ready.front(); f.ready.pop_front();
+    }
+    ++*n_segments;
+    const uint8_t* base = c->comp_data();
+    for (const swb_bgzf_block& b : c->blocks) {
+      ++*n_blocks; *text_bytes += b.out_len;
+      uint64_t h = *hash;
+      for (uint32_t k = 0; k < b.in_len; ++k) { h ^= base[b.in_off + k]; h *= 1099511628211ull; }
+      h ^= b.out_len; h *= 1099511628211ull;
+      *hash = h;
+    }
+    pool.release(c->comp); c->comp = nullptr;
+    std::lock_guard<std::mutex> lk(gate.mu);
+    f.spare.push_back(c);
+    gate.cv.notify_all();
+  }
+  for (auto& t : th) t.join();
+  if (f.gpu_path_failed) *status = 2;
+  if (f.rc) { *status = 1; return fail(f.err); }
+  return 0;
+}
 
 int rsm_count_bases_in_fastq(const char* filepath, uint64_t* out)
 {

@@ -235,3 +235,45 @@ def test_checkpoint_round_trip_and_serde_layout(tmp_path, clean_env):
     path.write_text("{ not json")
     with pytest.raises(aligner.AlignerError, match="Failed to parse checkpoint"):
         aligner.checkpoint_load(path)
+
+
+def test_bgzf_readers_hand_segments_over_in_order(tmp_path):
+    """The --full-wgs driver reads a BGZF file with several pread() threads (reader r takes segments r, r+R, ...): a segment
+    takes its buffers after its predecessor did and is walked after it, because its first block starts where the last whole
+    block of the predecessor ended.  Whatever the reader count, the segment size and the number of buffers, the consumer must
+    see every block exactly once, in stream order (rsm_debug_bgzf_segments hashes payloads + sizes in the order it gets them)."""
+    from mini_parallel_b200 import bgzf
+    rng = np.random.default_rng(91)
+    text = b"".join(b"@r%d\n" % k + bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, int(rng.integers(30, 200)))]) + b"\n+\n" +
+                    b"I" * 40 + b"\n" for k in range(60_000))
+    gz = bgzf.compress(text, 1, 30_000)                      # blocks of ~9 KB: hundreds per segment, many segments
+    blocks, used = bgzf.walk(gz)
+    assert used == len(gz)
+    path = tmp_path / "a.fastq.gz"
+    path.write_bytes(gz)
+    h = 1469598103934665603
+    for off, n, m in blocks:                                 # the same FNV-1a, straight over the file
+        for byte in gz[off:off + n]:
+            h = ((h ^ byte) * 1099511628211) & ((1 << 64) - 1)
+        h = ((h ^ m) * 1099511628211) & ((1 << 64) - 1)
+    seen = set()
+    for readers, seg_kb, pool in ((1, 128, 2), (1, 4096, 3), (2, 128, 3), (3, 200, 4), (4, 131, 2), (8, 128, 9), (16, 257, 5), (2, 1 << 20, 3)):
+        out = aligner.debug_bgzf_segments(path, readers, seg_kb << 10, pool)
+        assert out["status"] == 0 and out["blocks"] == len(blocks) and out["text_bytes"] == len(text), (readers, seg_kb, pool, out)
+        assert out["hash"] == h, (readers, seg_kb, pool)
+        assert out["segments"] == max(1, -(-len(gz) // (seg_kb << 10)))
+        seen.add(out["segments"])
+    assert len(seen) >= 4
+    # a file that stops being BGZF half way: status 2 (the driver then hands the file to the host reader), no hang
+    bad = bytearray(gz)
+    bad[blocks[len(blocks) // 2][0] - 18] ^= 0xFF                      # first magic byte of a block header in the middle
+    (tmp_path / "b.fastq.gz").write_bytes(bytes(bad))
+    for readers in (1, 3):
+        assert aligner.debug_bgzf_segments(tmp_path / "b.fastq.gz", readers, 128 << 10, 3)["status"] == 2
+    # a truncated file (cut inside a block) is not a whole BGZF stream either
+    (tmp_path / "c.fastq.gz").write_bytes(gz[: blocks[-1][0] + 5])
+    assert aligner.debug_bgzf_segments(tmp_path / "c.fastq.gz", 2, 128 << 10, 3)["status"] == 2
+    # empty file: one empty final segment, nothing to walk
+    (tmp_path / "d.fastq.gz").write_bytes(b"")
+    out = aligner.debug_bgzf_segments(tmp_path / "d.fastq.gz", 2, 128 << 10, 3)
+    assert out["status"] == 0 and out["blocks"] == 0 and out["segments"] == 1
