@@ -45,6 +45,9 @@ int  rsm_count_bases_in_fastq(const char* filepath, uint64_t* out);  /* aligner.
 /* Test hook, needs no GPU: the BGZF readers of the --full-wgs driver (several pread() threads per file, ordered hand-off of
  * segments) against a consumer that only takes the segments in order.  *hash covers every block's compressed payload and
  * inflated size in stream order: the same for every reader count, segment size and pool size.  *status: 0 ok, 2 not BGZF. */
+/* Test hook: a .gz file through the host gzip reader of the FASTQ path (csrc/host_gunzip.h; use_zlib = 1: zlib's gzread, the
+ * behaviour it keeps) in read() calls of read_cap bytes.  *n = bytes delivered, *failed = 1 on corrupt data. */
+int  rsm_debug_gunzip(const char* path, uint64_t read_cap, int use_zlib, uint8_t* out, uint64_t out_cap, uint64_t* n, int* failed);
 int  rsm_debug_bgzf_segments(const char* path, unsigned readers, uint64_t seg_bytes, unsigned pool_buffers, uint64_t* n_segments,
                              uint64_t* n_blocks, uint64_t* text_bytes, uint64_t* hash, int* status);
 

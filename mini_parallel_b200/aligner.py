@@ -59,6 +59,8 @@ def _lib():
         lib.rsm_get_chunk_size_bases.argtypes = [u64p]
         lib.rsm_process_fastq_file_in_chunks.argtypes = [ctypes.c_char_p, ctypes.c_uint64, _CHUNK_FN, ctypes.c_void_p]
         lib.rsm_count_bases_in_fastq.argtypes = [ctypes.c_char_p, u64p]
+        lib.rsm_debug_gunzip.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, u64p,
+                                         ctypes.POINTER(ctypes.c_int)]
         lib.rsm_debug_bgzf_segments.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint, u64p, u64p, u64p, u64p,
                                                 ctypes.POINTER(ctypes.c_int)]
         lib.rsm_gpu_align.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
@@ -132,6 +134,17 @@ def process_fastq_file_in_chunks(filepath, chunk_size_reads, processor):
     if err:
         raise err[0]
     _check(rc)
+
+
+def debug_gunzip(filepath, read_cap=1 << 20, use_zlib=False, out_cap=None):
+    """rsm_debug_gunzip (test hook): the file through the host gzip reader -> (bytes, n_delivered, failed)."""
+    import os
+    cap = int(out_cap) if out_cap is not None else max(1 << 16, 64 * os.path.getsize(filepath) + (1 << 20))
+    buf = np.empty(cap, dtype=np.uint8)
+    n = ctypes.c_uint64(); failed = ctypes.c_int()
+    _check(_lib().rsm_debug_gunzip(str(filepath).encode(), int(read_cap), int(bool(use_zlib)), buf.ctypes.data, cap, ctypes.byref(n),
+                                   ctypes.byref(failed)))
+    return buf[: min(cap, int(n.value))].tobytes(), int(n.value), bool(failed.value)
 
 
 def debug_bgzf_segments(filepath, readers, seg_bytes, pool_buffers):

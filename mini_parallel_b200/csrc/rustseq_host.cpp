@@ -2,6 +2,7 @@
 // (smith_waterman/src/aligner.rs, gpu.rs, main.rs).  See include/rustseq_host.h.  All scoring goes
 // through the C ABI of swb200.h; there is no CPU scoring code in this file.
 #include "../../include/rustseq_host.h"
+#include "host_gunzip.h"
 #include <zlib.h>
 #include <fcntl.h>
 #include <unistd.h>
@@ -140,8 +141,14 @@ class FastqReader {
   {
     path_ = path;
     const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;   // aligner.rs:109
-    if (gz) {
-      gz_ = gzopen(path.c_str(), "rb");            // in-process inflate instead of a `zcat` child (aligner.rs:111-120)
+    const char* how = std::getenv("SWB_HOST_INFLATE");
+    if (gz && !(how && std::string(how) == "zlib")) {
+      // in-process inflate instead of a `zcat` child (aligner.rs:111-120): this repository's decoder (host_gunzip.h), 1.6-1.7x
+      // zlib on FASTQ text and the same behaviour at the edges; SWB_HOST_INFLATE=zlib selects gzread
+      if (!hz_.open(path.c_str())) return fail("Failed to open file " + path + ": " + std::strerror(errno));
+      use_hz_ = true;
+    } else if (gz) {
+      gz_ = gzopen(path.c_str(), "rb");
       if (!gz_) return fail("Failed to open file " + path + ": " + std::strerror(errno));
       gzbuffer(gz_, 1 << 20);
     } else {
@@ -151,7 +158,7 @@ class FastqReader {
     buf_.resize(4 << 20);
     return 0;
   }
-  void close() { if (gz_) gzclose(gz_); if (fp_) std::fclose(fp_); gz_ = nullptr; fp_ = nullptr; }
+  void close() { if (gz_) gzclose(gz_); if (fp_) std::fclose(fp_); gz_ = nullptr; fp_ = nullptr; hz_.close(); use_hz_ = false; }
 
   // Appends up to max_reads sequence lines (and at most max_bases bases, 0 = no cap) to bases/offs.
   // Returns 0 ok, 1 error; *eof set when the input is exhausted.
@@ -176,7 +183,8 @@ class FastqReader {
       if (len_ == buf_.size()) buf_.resize(buf_.size() * 2);
       long got = 0;
       if (!at_eof_) {
-        got = gz_ ? gzread(gz_, buf_.data() + len_, (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30))
+        got = use_hz_ ? hz_.read(buf_.data() + len_, buf_.size() - len_)
+            : gz_ ? gzread(gz_, buf_.data() + len_, (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30))
                   : (long)std::fread(buf_.data() + len_, 1, buf_.size() - len_, fp_);
         if (got < 0) return fail("Failed to read " + path_ + ": gzip stream error");
         if (got == 0) at_eof_ = true;
@@ -228,6 +236,7 @@ class FastqReader {
   }
   std::string path_;
   gzFile gz_ = nullptr; FILE* fp_ = nullptr;
+  hgz::GunzipStream hz_; bool use_hz_ = false;
   std::vector<uint8_t> buf_;
   size_t pos_ = 0, len_ = 0;
   bool at_eof_ = false;
@@ -925,6 +934,41 @@ int rsm_process_fastq_file_in_chunks(const char* filepath, uint64_t chunk_size_r
 }
 
 static int count_cb(void* user, const uint8_t*, const uint64_t* offs, uint64_t n) { *(uint64_t*)user += offs[n]; return 0; }
+
+// Test hook: a whole .gz file through the host gzip reader (hgz::GunzipStream, or gzread with use_zlib) in read() calls of
+// read_cap bytes.  *n = bytes delivered (the first out_cap of them are in out), *failed = 1 when the reader reported corrupt data.
+int rsm_debug_gunzip(const char* path, uint64_t read_cap, int use_zlib, uint8_t* out, uint64_t out_cap, uint64_t* n, int* failed)
+{
+  if (!path || !n || !failed || read_cap == 0) return fail("rsm_debug_gunzip: bad argument");
+  *n = 0; *failed = 0;
+  std::vector<uint8_t> buf(read_cap);
+  auto deliver = [&](long got) {
+    if (*n < out_cap && out) std::memcpy(out + *n, buf.data(), (size_t)std::min<uint64_t>((uint64_t)got, out_cap - *n));
+    *n += (uint64_t)got;
+  };
+  if (use_zlib) {
+    gzFile g = gzopen(path, "rb");
+    if (!g) return fail(std::string("Failed to open file ") + path);
+    gzbuffer(g, 1 << 20);
+    for (;;) {
+      const long got = gzread(g, buf.data(), (unsigned)std::min<uint64_t>(read_cap, 1u << 30));
+      if (got < 0) { *failed = 1; break; }
+      if (got == 0) break;
+      deliver(got);
+    }
+    gzclose(g);
+    return 0;
+  }
+  hgz::GunzipStream gs;
+  if (!gs.open(path)) return fail(std::string("Failed to open file ") + path);
+  for (;;) {
+    const long got = gs.read(buf.data(), (size_t)read_cap);
+    if (got < 0) { *failed = 1; g_err = gs.error(); break; }
+    if (got == 0) break;
+    deliver(got);
+  }
+  return 0;
+}
 
 // Test hook (no GPU): runs the BGZF readers of the --full-wgs driver on one file -- `readers` threads, segments of seg_bytes,
 // `pool_buffers` segment buffers -- against a consumer that only takes the segments in order, and reports what it saw: the
