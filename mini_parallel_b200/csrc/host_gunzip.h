@@ -5,7 +5,7 @@
 // 88 % of a reader thread in inflate() at ~285 MB/s of FASTQ text per core.  This decoder is the usual modern design -- a
 // 64-bit bit buffer refilled with one unaligned load, an 11-bit literal/length table and an 8-bit distance table whose
 // entries carry base value, extra-bit count and code length, sub-tables for longer codes, word-wise match copies with a
-// broadcast path for distance 1 (quality strings) -- and keeps gzread's behaviour at the edges (listed at GunzipStream).
+// broadcast path for distance 1 (quality strings), the CRC-32 folded with PCLMULQDQ -- and keeps gzread's behaviour at the edges (listed at GunzipStream).
 // Host only; the device decoder is swb_inflate.cuh.  Checked against zlib on every level / strategy, random read sizes,
 // multi-member files, corrupt and truncated input (tests/test_host_gunzip.py).
 #pragma once
@@ -17,11 +17,99 @@
 #include <zlib.h>          // crc32() only
 #include <string>
 #include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 namespace hgz {
 
+// ---- CRC-32 of the inflated text ----
+// zlib's crc32 runs at ~2.3 GB/s, a fifth of this reader's time.  On x86-64 with PCLMULQDQ the checksum is folded 64 bytes
+// at a time with carry-less multiplications (the fold-by-4 scheme of Intel's "Fast CRC Computation for Generic Polynomials
+// Using PCLMULQDQ", constants for the reflected IEEE polynomial); heads, tails and other CPUs use zlib.  The first use checks
+// the folded result against zlib's on a test pattern and falls back for good if they differ.
+#if defined(__x86_64__)
+__attribute__((target("pclmul,sse4.1")))
+static inline uint32_t crc32_fold(const uint8_t* buf, size_t len /* >= 64, multiple of 16 */, uint32_t crc /* inverted */)
+{
+  alignas(16) static const uint64_t k1k2[2] = {0x0154442bd4ull, 0x01c6e41596ull};
+  alignas(16) static const uint64_t k3k4[2] = {0x01751997d0ull, 0x00ccaa009eull};
+  alignas(16) static const uint64_t k5k0[2] = {0x0163cd6124ull, 0};
+  alignas(16) static const uint64_t poly[2] = {0x01db710641ull, 0x01f7011641ull};
+  __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8;
+  x1 = _mm_loadu_si128((const __m128i*)(buf + 0));  x2 = _mm_loadu_si128((const __m128i*)(buf + 16));
+  x3 = _mm_loadu_si128((const __m128i*)(buf + 32)); x4 = _mm_loadu_si128((const __m128i*)(buf + 48));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+  x0 = _mm_load_si128((const __m128i*)k1k2);
+  buf += 64; len -= 64;
+  while (len >= 64) {
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00); x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11); x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), _mm_loadu_si128((const __m128i*)(buf + 0)));
+    x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), _mm_loadu_si128((const __m128i*)(buf + 16)));
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), _mm_loadu_si128((const __m128i*)(buf + 32)));
+    x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), _mm_loadu_si128((const __m128i*)(buf + 48)));
+    buf += 64; len -= 64;
+  }
+  x0 = _mm_load_si128((const __m128i*)k3k4);                        // four lanes into one
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (len >= 16) {
+    x2 = _mm_loadu_si128((const __m128i*)buf);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16; len -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10);                          // 128 -> 64 bits
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_xor_si128(_mm_srli_si128(x1, 8), x2);
+  x0 = _mm_loadl_epi64((const __m128i*)k5k0);
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_xor_si128(_mm_clmulepi64_si128(_mm_and_si128(x1, x3), x0, 0x00), x2);
+  x0 = _mm_load_si128((const __m128i*)poly);                        // Barrett reduction to 32 bits
+  x2 = _mm_clmulepi64_si128(_mm_and_si128(x1, x3), x0, 0x10);
+  x2 = _mm_clmulepi64_si128(_mm_and_si128(x2, x3), x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#endif
+
+static inline bool crc32_fold_usable()
+{
+#if defined(__x86_64__)
+  static const bool ok = [] {
+    if (!__builtin_cpu_supports("pclmul") || !__builtin_cpu_supports("sse4.1")) return false;
+    uint8_t t[1024 + 48];
+    for (size_t i = 0; i < sizeof t; ++i) t[i] = (uint8_t)(i * 131u + (i >> 3) * 7u + 5u);
+    for (size_t len : {(size_t)64, (size_t)80, (size_t)256, (size_t)1024, (size_t)1072}) {
+      const uint32_t seed = 0x1234567u * (uint32_t)len;
+      if (~crc32_fold(t, len, ~seed) != (uint32_t)crc32_z(seed, t, len)) return false;
+    }
+    return true;
+  }();
+  return ok;
+#else
+  return false;
+#endif
+}
+
+static inline uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n)
+{
+#if defined(__x86_64__)
+  if (n >= 256 && crc32_fold_usable()) {
+    const size_t body = n & ~(size_t)15;
+    crc = ~crc32_fold(p, body, ~crc);
+    p += body; n -= body;
+  }
+#endif
+  return n ? (uint32_t)crc32_z(crc, p, n) : crc;
+}
+
 constexpr int LIT_TB = 11, DIST_TB = 8;
-constexpr uint32_t K_LIT = 0x8000u, K_EXC = 0x4000u, K_SUB = 0x2000u;     // entry: value<<16 | kind | extra<<8 | bits
+constexpr uint32_t K_LIT = 0x8000u, K_EXC = 0x4000u, K_SUB = 0x2000u;     // entry: value<<16 | kind | extra<<8 | bits, where `bits` is what the
+                                                                          // symbol consumes: its code AND its extra bits (one shift per symbol)
 constexpr uint32_t V_EOB = 0, V_BAD = 1;
 
 static inline uint64_t load64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
@@ -98,12 +186,14 @@ static inline bool build_table(const uint8_t* lens, int n, Alphabet a, int tb, u
     if (!len) continue;
     const uint32_t rev = bitrev(next[len]++, len);
     if (len <= tb) {
-      const uint32_t e = symbol_entry(a, s) | (uint32_t)len;
+      const uint32_t se = symbol_entry(a, s), xb = (se & (K_LIT | K_EXC)) ? 0u : (se >> 8) & 15u;
+      const uint32_t e = se | ((uint32_t)len + xb);
       for (uint32_t i = rev; i < (uint32_t)main_size; i += 1u << len) table[i] = e;
     } else {
       const uint32_t pre = rev & (uint32_t)(main_size - 1), head = table[pre];
       const uint32_t off = head >> 16, sb = (head >> 8) & 15u;
-      const uint32_t e = symbol_entry(a, s) | (uint32_t)(len - tb);
+      const uint32_t se = symbol_entry(a, s), xb = (se & (K_LIT | K_EXC)) ? 0u : (se >> 8) & 15u;
+      const uint32_t e = se | ((uint32_t)(len - tb) + xb);
       for (uint32_t i = rev >> tb; i < (1u << sb); i += 1u << (len - tb)) table[off + i] = e;
     }
   }
@@ -168,7 +258,7 @@ struct Inflater {
     while (i < nlit + ndist) {
       if (bc < 14) refill_safe(bb, bc, in, in_end);                  // a code (<= 7 bits) and its extra bits (<= 7)
       const uint32_t e = clen[bb & 127u];
-      const int bits = (int)(e & 15u);
+      const int bits = (int)(e & 255u);
       if (bits > bc) return starve();
       if (e & K_EXC) { error = "invalid code lengths set"; return ERROR; }
       bb >>= bits; bc -= bits;
@@ -244,62 +334,80 @@ struct Inflater {
         continue;
       }
       // ---- huffman symbols ----
-      // fast loop: >= 16 input bytes and >= 258 + 16 output bytes in hand, no bounds checks inside
+      // fast loop: >= 16 input bytes and >= 258 + 16 output bytes in hand, no bounds checks inside.  The table entry of the
+      // NEXT symbol is fetched before the copy of a match runs (the load's latency hides behind the copy), and literals run
+      // three to a refill.
       bool ended = false;
-      while (in_end - in >= 16 && out_end - out >= 280) {
+      if (in_end - in >= 16 && out_end - out >= 280) {
         refill_fast(bb, bc, in);
         uint32_t e = lit[bb & ((1u << LIT_TB) - 1)];
-        if (e & K_LIT) {
-          bb >>= (e & 15u); bc -= (int)(e & 15u); *out++ = (uint8_t)(e >> 16);
-          e = lit[bb & ((1u << LIT_TB) - 1)];
+        for (;;) {
           if (e & K_LIT) {
-            bb >>= (e & 15u); bc -= (int)(e & 15u); *out++ = (uint8_t)(e >> 16);
+            bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
             e = lit[bb & ((1u << LIT_TB) - 1)];
-            if (e & K_LIT) { bb >>= (e & 15u); bc -= (int)(e & 15u); *out++ = (uint8_t)(e >> 16); continue; }
-          }
-          refill_fast(bb, bc, in);
-        }
-        if (e & K_EXC) {
-          if (e & K_SUB) {
-            bb >>= LIT_TB; bc -= LIT_TB;
-            e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 8) & 15u)) - 1))];
-            if (e & K_LIT) { bb >>= (e & 15u); bc -= (int)(e & 15u); *out++ = (uint8_t)(e >> 16); continue; }
+            if (e & K_LIT) {
+              bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
+              e = lit[bb & ((1u << LIT_TB) - 1)];
+              if (e & K_LIT) {
+                bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
+                e = lit[bb & ((1u << LIT_TB) - 1)];
+              }
+            }
+            if (!(in_end - in >= 16 && out_end - out >= 280)) break;
+            refill_fast(bb, bc, in);                                 // (e looked at the low bits only: still the entry of the next symbol)
+            continue;
           }
           if (e & K_EXC) {
-            bb >>= (e & 15u); bc -= (int)(e & 15u);
-            if ((e >> 16) == V_EOB && !(e & K_SUB)) { ended = true; break; }
-            error = "invalid literal/length code"; save(); return ERROR;
+            if (e & K_SUB) {
+              bb >>= LIT_TB; bc -= LIT_TB;
+              e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 8) & 15u)) - 1))];
+              if (e & K_LIT) {
+                bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
+                if (!(in_end - in >= 16 && out_end - out >= 280)) break;
+                refill_fast(bb, bc, in);
+                e = lit[bb & ((1u << LIT_TB) - 1)];
+                continue;
+              }
+            }
+            if (e & K_EXC) {
+              bb >>= (e & 255u); bc -= (int)(e & 255u);
+              if ((e >> 16) == V_EOB && !(e & K_SUB)) { ended = true; break; }
+              error = "invalid literal/length code"; save(); return ERROR;
+            }
           }
+          // a length: base + extra bits, then the distance
+          const uint64_t lsaved = bb;
+          bb >>= (e & 255u); bc -= (int)(e & 255u);                  // code and extra bits in one shift; the extra bits come from lsaved
+          uint32_t d = dist[bb & ((1u << DIST_TB) - 1)];
+          const uint32_t lxb = (e >> 8) & 15u;
+          const uint32_t len = (e >> 16) + ((uint32_t)(lsaved >> ((e & 255u) - lxb)) & ((1u << lxb) - 1));
+          if (d & K_EXC) {
+            if (!(d & K_SUB)) { error = "invalid distance code"; save(); return ERROR; }
+            bb >>= DIST_TB; bc -= DIST_TB;
+            d = dist[(d >> 16) + (uint32_t)(bb & ((1u << ((d >> 8) & 15u)) - 1))];
+            if (d & K_EXC) { error = "invalid distance code"; save(); return ERROR; }
+          }
+          const uint64_t dsaved = bb;
+          bb >>= (d & 255u); bc -= (int)(d & 255u);
+          const uint32_t dxb = (d >> 8) & 15u;
+          const uint32_t dd = (d >> 16) + ((uint32_t)(dsaved >> ((d & 255u) - dxb)) & ((1u << dxb) - 1));
+          if (dd > hist + (uint64_t)(out - out_start)) { error = "invalid distance too far back"; save(); return ERROR; }
+          const uint8_t* src = out - dd;
+          uint8_t* const end = out + len;
+          const bool more = in_end - in >= 16 && out_end - end >= 280;
+          if (more) { refill_fast(bb, bc, in); e = lit[bb & ((1u << LIT_TB) - 1)]; }      // the next symbol's entry, before the copy
+          if (dd >= 8) {
+            store64(out, load64(src)); store64(out + 8, load64(src + 8));          // len >= 3; up to 16 bytes at once
+            if (len > 16) { uint8_t* o = out + 16; src += 16; do { store64(o, load64(src)); o += 8; src += 8; } while (o < end); }
+          } else if (dd == 1) {
+            const uint64_t v = 0x0101010101010101ull * src[0];
+            uint8_t* o = out; do { store64(o, v); o += 8; } while (o < end);
+          } else {
+            uint8_t* o = out; do { *o++ = *src++; } while (o < end);
+          }
+          out = end;
+          if (!more) break;
         }
-        // a length: base + extra bits, then the distance
-        bb >>= (e & 15u); bc -= (int)(e & 15u);
-        const uint32_t lxb = (e >> 8) & 15u;
-        const uint32_t len = (e >> 16) + (uint32_t)(bb & ((1u << lxb) - 1));
-        bb >>= lxb; bc -= (int)lxb;
-        uint32_t d = dist[bb & ((1u << DIST_TB) - 1)];
-        if (d & K_EXC) {
-          if (!(d & K_SUB)) { error = "invalid distance code"; save(); return ERROR; }
-          bb >>= DIST_TB; bc -= DIST_TB;
-          d = dist[(d >> 16) + (uint32_t)(bb & ((1u << ((d >> 8) & 15u)) - 1))];
-          if (d & K_EXC) { error = "invalid distance code"; save(); return ERROR; }
-        }
-        bb >>= (d & 15u); bc -= (int)(d & 15u);
-        const uint32_t dxb = (d >> 8) & 15u;
-        const uint32_t dd = (d >> 16) + (uint32_t)(bb & ((1u << dxb) - 1));
-        bb >>= dxb; bc -= (int)dxb;
-        if (dd > hist + (uint64_t)(out - out_start)) { error = "invalid distance too far back"; save(); return ERROR; }
-        const uint8_t* src = out - dd;
-        uint8_t* const end = out + len;
-        if (dd >= 8) {
-          store64(out, load64(src)); store64(out + 8, load64(src + 8));          // len >= 3; up to 16 bytes at once
-          if (len > 16) { uint8_t* o = out + 16; src += 16; do { store64(o, load64(src)); o += 8; src += 8; } while (o < end); }
-        } else if (dd == 1) {
-          const uint64_t v = 0x0101010101010101ull * src[0];
-          uint8_t* o = out; do { store64(o, v); o += 8; } while (o < end);
-        } else {
-          uint8_t* o = out; do { *o++ = *src++; } while (o < end);
-        }
-        out = end;
       }
       if (ended) { state = last_block ? 3 : 0; continue; }
       // careful loop near the ends of the buffers: one symbol at a time, every step checked.  A whole symbol (length code,
@@ -316,9 +424,12 @@ struct Inflater {
           b2 >>= LIT_TB; used += LIT_TB;
           e = lit[(e >> 16) + (uint32_t)(b2 & ((1u << ((e >> 8) & 15u)) - 1))];
         }
-        used += (int)(e & 15u);
+        const uint32_t lxb = (e & (K_LIT | K_EXC)) ? 0u : (e >> 8) & 15u;
+        const uint32_t lcode = (e & 255u) - lxb;                       // bits of the code alone
+        used += (int)(e & 255u);
         if (used > bc || ((e & K_EXC) && (e >> 16) == V_BAD && bc < 15)) { starve(); goto out_of_loop; }
-        b2 >>= (e & 15u);
+        const uint32_t len = (e >> 16) + ((uint32_t)(b2 >> lcode) & ((1u << lxb) - 1));
+        b2 >>= (e & 255u);
         if (e & K_LIT) {
           if (out >= out_end) { res = NEED_OUTPUT; goto out_of_loop; }
           *out++ = (uint8_t)(e >> 16); bb = b2; bc -= used;
@@ -329,21 +440,17 @@ struct Inflater {
           if ((e >> 16) == V_EOB) { bb = b2; bc -= used; state = last_block ? 3 : 0; break; }
           error = "invalid literal/length code"; save(); return ERROR;
         }
-        const uint32_t lxb = (e >> 8) & 15u;
-        const uint32_t len = (e >> 16) + (uint32_t)(b2 & ((1u << lxb) - 1));
-        b2 >>= lxb; used += (int)lxb;
         uint32_t d = dist[b2 & ((1u << DIST_TB) - 1)];
         if ((d & (K_EXC | K_SUB)) == (K_EXC | K_SUB)) {
           b2 >>= DIST_TB; used += DIST_TB;
           d = dist[(d >> 16) + (uint32_t)(b2 & ((1u << ((d >> 8) & 15u)) - 1))];
         }
-        const uint32_t dxb = (d >> 8) & 15u;
-        used += (int)(d & 15u) + (int)dxb;
+        const uint32_t dxb = (d & K_EXC) ? 0u : (d >> 8) & 15u;
+        used += (int)(d & 255u);
         if (used > bc || ((d & K_EXC) && bc < 48)) { starve(); goto out_of_loop; }
         if (d & K_EXC) { error = "invalid distance code"; save(); return ERROR; }
-        b2 >>= (d & 15u);
-        const uint32_t dd = (d >> 16) + (uint32_t)(b2 & ((1u << dxb) - 1));
-        b2 >>= dxb;
+        const uint32_t dd = (d >> 16) + ((uint32_t)(b2 >> ((d & 255u) - dxb)) & ((1u << dxb) - 1));
+        b2 >>= (d & 255u);
         if ((uint64_t)(out_end - out) < len) { res = NEED_OUTPUT; goto out_of_loop; }      // the symbol is not consumed: decoded again later
         if (dd > hist + (uint64_t)(out - out_start)) { error = "invalid distance too far back"; save(); return ERROR; }
         bb = b2; bc -= used;
@@ -379,6 +486,7 @@ class GunzipStream {
   }
   void close() { if (fd_ >= 0) ::close(fd_); fd_ = -1; }
   const std::string& error() const { return err_; }
+  void set_verify(bool on) { verify_ = on; }                 // benchmarks only: skip the CRC-32 / length check of the trailer
 
   // up to cap bytes of inflated text; 0 at the end of the data, -1 on corrupt input
   long read(uint8_t* dst, size_t cap)
@@ -441,7 +549,7 @@ class GunzipStream {
       const Inflater::Result r = inf_.run(in, in_end_, eof_in_, out, out0 + kOut, hist_);
       in_ = in;
       const size_t n = (size_t)(out - out0);
-      if (n) { crc_ = (uint32_t)crc32_z(crc_, out0, n); isize_ += (uint32_t)n; hist_ = std::min<uint64_t>(kHist, hist_ + n); w_have_ = kHist + n; }
+      if (n) { if (verify_) crc_ = crc32_update(crc_, out0, n); isize_ += (uint32_t)n; hist_ = std::min<uint64_t>(kHist, hist_ + n); w_have_ = kHist + n; }
       if (r == Inflater::ERROR) { err_ = inf_.error ? inf_.error : "invalid deflate data"; return n != 0; }
       if (r == Inflater::NEED_INPUT) {
         if (eof_in_ && n == 0) { done_ = true; return false; }          // truncated: what was decoded has been delivered (gzread: Z_BUF_ERROR)
@@ -460,7 +568,7 @@ class GunzipStream {
       want(8);
       if (avail() < 4) { done_ = true; return false; }      // truncated inside the trailer: like any early end
       const uint32_t crc = (uint32_t)in_[0] | ((uint32_t)in_[1] << 8) | ((uint32_t)in_[2] << 16) | ((uint32_t)in_[3] << 24);
-      if (crc != crc_) { err_ = "incorrect data check"; return false; }      // (zlib, too, checks the CRC as soon as its four bytes are there)
+      if (verify_ && crc != crc_) { err_ = "incorrect data check"; return false; }      // (zlib, too, checks the CRC as soon as its four bytes are there)
       if (avail() < 8) { done_ = true; return false; }
       const uint32_t isz = (uint32_t)in_[4] | ((uint32_t)in_[5] << 8) | ((uint32_t)in_[6] << 16) | ((uint32_t)in_[7] << 24);
       in_ += 8;
@@ -502,7 +610,7 @@ class GunzipStream {
   int fd_ = -1;
   std::vector<uint8_t> ibuf_, wbuf_;
   const uint8_t* in_ = nullptr; const uint8_t* in_end_ = nullptr;
-  bool eof_in_ = false, done_ = false, first_member_ = true;
+  bool eof_in_ = false, done_ = false, first_member_ = true, verify_ = true;
   size_t w_have_ = 0, w_read_ = 0;
   uint64_t hist_ = 0;
   int mode_ = 0;                      // 0 member start, 1 deflate data, 2 trailer, 3 transparent
