@@ -158,8 +158,8 @@ int  swb_last_timings(swb_ctx*, float* ms /* 6 */, int* kernels_launched);
 /* Pairs routed to each path by the last call: [0] short-read int16x2 kernel, [1] generic 32-bit byte-compare kernel
  * (any bytes, any length), [2] long-pair 32-bit banded wavefront kernel (ACGT-only pairs beyond the short limits). */
 int  swb_last_routing(swb_ctx*, uint64_t* counts /* 3 */);
-/* The same by kernel: [0] int16x2 stream kernel, reads <= 160 bp; [1] its 320-row instantiation, reads of 161..320 bp
- * (value scale 32); [2] long-pair kernel on 2-bit codes; [3] long-pair kernel on raw bytes (a non-ACGT byte in the pair);
+/* The same by kernel: [0] int16x2 stream kernel, reads <= 160 bp; [1] its 256- / 320-row instantiations, reads of 161..320 bp
+ * (value scale 32; 256 rows when no read of the list is longer than 256 bp); [2] long-pair kernel on 2-bit codes; [3] long-pair kernel on raw bytes (a non-ACGT byte in the pair);
  * [4] generic kernel (beyond 2^20 rows or columns).  [0] + [1] is swb_last_routing's [0], [3] + [4] its [1]. */
 int  swb_last_routing_ex(swb_ctx*, uint64_t* counts /* 5 */);
 /* on = 0: reads of 161..320 bp take the 32-bit long-pair kernel instead of the 320-row int16x2 one (comparison, tests). */

@@ -170,9 +170,14 @@ classify_kernel(BatchView b)
   if (cls == CLASS_LONG)    b.long_list[base_l + __popc(ml & below)] = (uint32_t)k;
   if (cls == CLASS_BYTES)   b.bytes_list[base_b + __popc(mb & below)] = (uint32_t)k;
   uint32_t wm = cls == CLASS_SHORT ? m : 0u, wmid = cls == CLASS_MID ? m : 0u;
-  for (int o = 16; o; o >>= 1) { wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o)); wmid = max(wmid, __shfl_xor_sync(0xffffffffu, wmid, o)); }
+  uint32_t rmid = cls == CLASS_MID ? (uint32_t)(b.q_end[k] - b.q_beg[k]) : 0u;
+  for (int o = 16; o; o >>= 1) {
+    wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o)); wmid = max(wmid, __shfl_xor_sync(0xffffffffu, wmid, o));
+    rmid = max(rmid, __shfl_xor_sync(0xffffffffu, rmid, o));
+  }
   if (lane == 0 && wm) atomicMax(&b.counters->max_short_window, wm);
   if (lane == 0 && wmid) atomicMax(&b.counters->max_mid_window, wmid);
+  if (lane == 0 && rmid) atomicMax(&b.counters->max_mid_read, rmid);
 }
 
 // Chunk preparation of the host path: CSR offsets arrive as absolute positions in the caller's arrays and are
@@ -410,7 +415,8 @@ static int launch_short_t(const BatchView& b, uint32_t window_cap, LaunchCfg& lc
 
 #endif  // SWB_ALL_VARIANTS
 
-template <int G, int K, int MINB, int FLAGS> static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStream_t st);
+template <int G, int K, int MINB, int FLAGS> static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStream_t st,
+                                                                        uint32_t sel_lo = 0, uint32_t sel_hi = 0);
 
 void launch_cfg_init(LaunchCfg& lc, int sm_count)
 {
@@ -453,7 +459,9 @@ int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg
 int launch_mid(const BatchView& b, LaunchCfg& lc, cudaStream_t st)
 {
   if (b.n_pairs == 0 || !b.mid_desc) return 0;
-  return launch_stream_t<32, 10, 4, 3 + 8>(b, lc, 15, st);
+  // the list's longest read decides on the device: up to 256 bp the 32 x 8-row instantiation (250 bp reads: 2 % pad rows
+  // instead of 22 %), beyond that the 32 x 10-row one; the other launch returns at once
+  return launch_stream_t<32, 8, 4, 3 + 8>(b, lc, 14, st, 0, 256) + launch_stream_t<32, 10, 4, 3 + 8>(b, lc, 15, st, 256, kMidMaxRead);
 }
 
 bool short_variant_available(int variant)
@@ -504,6 +512,9 @@ struct StreamArgs {
   const uint32_t* max_window;               // longest window among them
   uint32_t* cursor;                         // couples handed out beyond every group's static ones (zeroed per batch)
   swb_result* out;
+  // Two instantiations can be launched on one list and decide on the device which of them runs (no host round trip for a
+  // count): the kernel leaves at once unless sel_lo < *sel_value <= sel_hi.  sel_value == nullptr: always runs.
+  const uint32_t* sel_value; uint32_t sel_lo, sel_hi;
 };
 
 // 2-bit codes of bases [pos, pos+32) of a packed array, code k in bits 2k..2k+1
@@ -558,6 +569,7 @@ sw_stream_kernel(StreamArgs a)
   constexpr int GSTRIDE = RING * 2 + 128;                // bytes between group rings (a multiple of 128, room for ring_skew)
   constexpr uint32_t WPADV = (9u * 4u + 4u) << 7;        // ring value of a pad column
 
+  if (a.sel_value) { const uint32_t v = *a.sel_value; if (v <= a.sel_lo || v > a.sel_hi) return; }      // (the whole grid alike, before any barrier)
   extern __shared__ __align__(16) uint8_t smem[];
   uint32_t* lut = reinterpret_cast<uint32_t*>(smem);
   for (uint32_t x = threadIdx.x; x < kLutEntries * 32; x += blockDim.x) {
@@ -809,7 +821,7 @@ sw_stream_kernel(StreamArgs a)
 }
 
 template <int G, int K, int MINB, int FLAGS>
-static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStream_t st)
+static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStream_t st, uint32_t sel_lo, uint32_t sel_hi)
 {
   constexpr bool MID = (FLAGS & 8) != 0;                 // the 320-row instantiation scores the mid list
   constexpr int GPW = 32 / G;
@@ -820,6 +832,7 @@ static int launch_stream_t(const BatchView& b, LaunchCfg& lc, int slot, cudaStre
   a.n_list = MID ? &b.counters->n_mid : &b.counters->n_short;
   a.max_window = MID ? &b.counters->max_mid_window : &b.counters->max_short_window;
   a.cursor = MID ? &b.counters->mid_cursor : &b.counters->stream_cursor;
+  a.sel_value = (MID && sel_hi) ? &b.counters->max_mid_read : nullptr; a.sel_lo = sel_lo; a.sel_hi = sel_hi;
   const size_t smem = kLutBytes + (size_t)GSTRIDE * 4 * GPW + (size_t)2 * K * 128 * 4 + (size_t)4 * GPW * 8 * 4;
   int& resident = lc.resident[slot];                     // CTAs of this kernel one SM holds (asked once per context)
   if (!resident) {
@@ -1297,7 +1310,7 @@ int launch_generic(const BatchView& b, int sm_count, int /*warps_resident*/, cud
 
 __global__ void single_pair_setup_kernel(Counters* c, uint32_t* list)
 {
-  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; c->stream_cursor = 0; c->n_overflow = 0; c->n_mid = 0; c->max_mid_window = 0; c->mid_cursor = 0; list[0] = 0;
+  c->n_short = 0; c->n_generic = 1; c->max_short_window = 0; c->generic_cursor = 0; c->n_long = 0; c->long_cursor = 0; c->n_bytes = 0; c->bytes_cursor = 0; c->stream_cursor = 0; c->n_overflow = 0; c->n_mid = 0; c->max_mid_window = 0; c->mid_cursor = 0; c->max_mid_read = 0; list[0] = 0;
 }
 
 // exposed for the C API: run the generic kernel on a prepared single-pair view

@@ -33,7 +33,8 @@ struct Counters {             // device-resident, zeroed per batch
   uint32_t n_mid;             // ACGT-only pairs with reads of 161..320 bp: the 320-row int16x2 instantiation of sw_stream_kernel
   uint32_t max_mid_window;    // longest window among them
   uint32_t mid_cursor;        // its couple cursor
-  uint32_t pad_[3];
+  uint32_t max_mid_read;      // longest read among them: <= 256 bp and the 256-row instantiation scores the list, else the 320-row one
+  uint32_t pad_[2];
 };
 
 struct ShortDesc {            // one entry per short-listed pair, written by classify_kernel (32 B, 16-aligned)

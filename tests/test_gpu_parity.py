@@ -204,6 +204,17 @@ def test_mid_path_reads_161_to_320(engine):
     _assert_parity(engine, *_pairs(rng, 2000, (300, 300), (1000, 1000), related=False))
     _assert_parity(engine, *_pairs(rng, 5000, (161, 320), (1, 1200)))               # ragged: windows shorter than the read, than a wavefront
     assert engine.last_routing_ex()["mid"] == 5000
+    # the list's longest read picks the instantiation on the device: <= 256 bp the 32 x 8-row one (256 rows), else 32 x 10 (320)
+    _assert_parity(engine, *_pairs(rng, 4001, (161, 256), (1, 1200)))               # 256-row kernel, ragged
+    assert engine.last_routing_ex()["mid"] == 4001
+    _assert_parity(engine, *_pairs(rng, 1000, (256, 256), (300, 700)))              # its last row in use
+    _assert_parity(engine, *_pairs(rng, 1000, (161, 256), (1, 600), alphabet=b"A"))             # all ties on 256 rows
+    r_a, w_a = _pairs(rng, 999, (161, 256), (200, 900))
+    r_b, w_b = _pairs(rng, 1, (257, 257), (400, 400))                               # one read of 257 bp: the whole list moves to 320 rows
+    _assert_parity(engine, r_a + r_b, w_a + w_b)
+    reads256 = [b"G" * 256] * 3 + [b"AC" * 128] * 30
+    got256 = _assert_parity(engine, reads256, [b"G" * 4096] * 3 + [b"CA" * 600] * 30)
+    assert tuple(got256[0]) == (512, 255, 255)                                       # the highest score the 256-row kernel can see
     _assert_parity(engine, *_pairs(rng, 300, (310, 320), (3900, 4096)))             # the longest windows the path takes
     assert engine.last_routing_ex()["mid"] == 300
     _assert_parity(engine, *_pairs(rng, 40, (310, 320), (4097, 4200)))              # one past: long-pair kernel

@@ -7,7 +7,7 @@ import torch
 import mini_parallel_b200 as mp
 eng = mp.Engine(0); dev = torch.device("cuda", 0)
 out = {}
-for rl, wl in ((250, 500), (300, 1000), (161, 500), (320, 500)):
+for rl, wl in ((250, 500), (256, 500), (200, 500), (300, 1000), (161, 500), (320, 500)):
     n = 500_000
     d_q = torch.empty(n * rl, dtype=torch.uint8, device=dev); d_r = torch.empty(n * wl, dtype=torch.uint8, device=dev)
     d_qo = torch.empty(n + 1, dtype=torch.int64, device=dev); d_ro = torch.empty(n + 1, dtype=torch.int64, device=dev)
