@@ -119,7 +119,8 @@ int  swb_fastq_bgzf_score(swb_ctx*, const uint8_t* comp, uint64_t comp_bytes, co
  * max_r_len is a HARD upper bound of the window lengths (the boundary-row scratch of the long-pair kernels is sized from
  * it before the device has seen the offsets): a pair whose window is longer is not scored -- its result is
  * (INT32_MIN, -1, -1) -- and swb_sync() / swb_last_routing() fail saying how many there were.  max_q_len is a hint only
- * (0 = unknown): it picks the long-pair kernel's band height. */
+ * (0 = unknown): it picks the row count of the kernel instantiations (128 rows for reads <= 128 bp, the 161..320 bp list,
+ * the long-pair kernel's band height); a read longer than the hint is still scored exactly, by a slower kernel. */
 int  swb_score_batch_device(swb_ctx*, const uint8_t* d_q_bytes, const uint64_t* d_q_off, uint64_t q_total_bytes,
                             const uint8_t* d_r_bytes, const uint64_t* d_r_off, uint64_t r_total_bytes,
                             uint64_t n_pairs, uint32_t max_q_len, uint32_t max_r_len, swb_result* d_out);

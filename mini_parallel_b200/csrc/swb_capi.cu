@@ -133,6 +133,7 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
   uint64_t last_routing[3] = {0, 0, 0};
   bool timings_pending = false, host_path = false;
   int variant = 9;                         // sw_stream_kernel<16,10,4, two-step tracker + dynamic couple distribution>
+  bool rows128 = true;                     // SWB_ROWS128=0: reads <= 128 bp also take the 160-row instantiation (comparison)
   bool mid_path = true;                    // SWB_MID_PATH=0: reads of 161..320 bp go to the 32-bit long-pair kernel (tests / comparison)
   uint64_t last_routing5[5] = {0, 0, 0, 0, 0};
   int force_bytes = 0;                     // SWB_FORCE_BYTES=1: every non-short pair through the byte-compare kernel (bench / tests)
@@ -197,6 +198,7 @@ int swb_create(swb_ctx** out, int device_id, const swb_params* params)
   if (const char* v = std::getenv("SWB_SHORT_VARIANT")) { const int w = std::atoi(v) & 15; if (swb::short_variant_available(w)) c->variant = w; }
   if (const char* v = std::getenv("SWB_FORCE_BYTES")) c->force_bytes = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_MID_PATH")) c->mid_path = std::atoi(v) != 0;
+  if (const char* v = std::getenv("SWB_ROWS128")) c->rows128 = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_UNIFORM_OFFSETS")) c->uniform_offsets = std::atoi(v) != 0;
   if (const char* v = std::getenv("SWB_LANES")) c->n_lanes = std::min(kLanes, std::max(1, std::atoi(v)));
   if (const char* v = std::getenv("SWB_CHUNK_RAMP")) c->chunk_ramp = std::min(2, std::max(0, std::atoi(v)));
@@ -333,6 +335,9 @@ static int run_device_pipeline(swb_ctx* c, Lane* l, cudaEvent_t* ev, const uint8
   b.mid_desc = (max_q_len > swb::kShortMaxRead && c->mid_path) ? l->mid_desc.as<swb::ShortDesc>() : nullptr;   // no read beyond 160 bp: no mid list, no launch
   b.generic_list = l->generic_list.as<uint32_t>(); b.long_list = l->long_list.as<uint32_t>(); b.bytes_list = l->bytes_list.as<uint32_t>();
   b.force_bytes = c->force_bytes;
+  // max_q_len is exact on the host paths and the caller's bound on the device path; a read longer than it is still scored
+  // (classify_kernel routes it to a kernel without the row limit), a wrong bound only costs speed
+  b.short_max_read = (max_q_len >= 1 && max_q_len <= 128 && c->variant == 9 && c->rows128) ? 128u : swb::kShortMaxRead;   // 0 = unknown
   b.counters = l->counters.as<swb::Counters>(); b.out = d_out;
   b.scratch = l->scratch.as<int32_t>(); b.scratch_stride = stride; b.max_window = max_r_len;
 

@@ -123,7 +123,7 @@ classify_kernel(BatchView b)
       atomicAdd(&b.counters->n_overflow, 1u);
     } else if (n <= kLongMaxLen && mm <= kLongMaxLen) {
       const bool acgt = !range_flagged(b.q_bad, q0, q1) && !range_flagged(b.r_bad, r0, r1);
-      if (acgt && n <= kShortMaxRead && mm <= kShortMaxWindow) { cls = CLASS_SHORT; m = (uint32_t)mm; }
+      if (acgt && n <= b.short_max_read && mm <= kShortMaxWindow) { cls = CLASS_SHORT; m = (uint32_t)mm; }
       else if (acgt && n <= kMidMaxRead && mm <= kShortMaxWindow && b.mid_desc && !b.force_bytes) { cls = CLASS_MID; m = (uint32_t)mm; }
       else cls = (acgt && !b.force_bytes) ? CLASS_LONG : CLASS_BYTES;
     } else {
@@ -451,7 +451,10 @@ int launch_short(const BatchView& b, uint32_t window_cap, int variant, LaunchCfg
     case 10: return launch_stream_t<16, 10, 5, 2>(b, lc, 10, st);
     case 11: return launch_stream_t<16, 10, 5, 3>(b, lc, 11, st);
 #endif
-    default: return launch_stream_t<16, 10, 4, 3>(b, lc, 9, st);
+    default:
+      // 16 lanes x 8 rows when no read of the batch is longer than 128 bp (125 bp reads: 2 % pad rows instead of 22 %)
+      if (b.short_max_read <= 128) return launch_stream_t<16, 8, 4, 3>(b, lc, 13, st);
+      return launch_stream_t<16, 10, 4, 3>(b, lc, 9, st);
   }
 }
 

@@ -58,6 +58,8 @@ struct BatchView {            // everything the kernels need about one batch (de
   uint32_t*       long_list;    // pair ids, n_long entries
   uint32_t*       bytes_list;   // pair ids, n_bytes entries
   int             force_bytes;  // debug/bench knob: route every non-short pair to the byte-compare kernel
+  uint32_t        short_max_read;   // rows of the stream-kernel instantiation this batch uses: 160, or 128 when the caller's bound on
+                                    // the read length allows it (2 x 100 / 2 x 125 bp runs); longer reads are routed past it
   Counters*       counters;
   swb_result*     out;
   int32_t*        scratch;      // generic kernel: one boundary row per resident warp

@@ -121,6 +121,41 @@ def test_short_path_many_way_ties(engine, engine_variants, variant):
     engine.set_short_variant(DEFAULT_VARIANT)
 
 
+def test_short_path_128_row_instantiation(engine):
+    """No read of the batch longer than 128 bp (2 x 100 / 2 x 125 bp runs): the 16 lanes x 8 rows instantiation of the stream
+    kernel.  The choice follows the longest read of each chunk on the host paths and the caller's bound on the device path,
+    where a read beyond the bound is routed past the kernel instead of losing its last rows."""
+    rng = np.random.default_rng(128)
+    for rl, wl in (((100, 100), (500, 500)), ((125, 125), (500, 500)), ((128, 128), (300, 700)), ((1, 128), (1, 900))):
+        _assert_parity(engine, *_pairs(rng, 3001, rl, wl))
+        assert engine.last_routing_ex()["short"] == 3001
+    _assert_parity(engine, *_pairs(rng, 1500, (1, 128), (1, 600), alphabet=b"A"))                    # all ties
+    _assert_parity(engine, *_pairs(rng, 1500, (1, 128), (1, 600), related=False, alphabet=b"AC"))
+    got = _assert_parity(engine, [b"G" * 128] * 3 + [b"AC" * 64] * 30, [b"G" * 4096] * 3 + [b"CA" * 600] * 30)
+    assert tuple(got[0]) == (256, 127, 127)
+    r_a, w_a = _pairs(rng, 999, (90, 128), (200, 900))
+    r_b, w_b = _pairs(rng, 1, (129, 129), (400, 400))                                            # one read of 129 bp: this batch runs on 160 rows
+    _assert_parity(engine, r_a + r_b, w_a + w_b)
+    assert engine.last_routing_ex()["short"] == 1000
+    # device path with a bound that is too small: 150 bp reads declared as <= 100 are still scored exactly (by the long-pair kernel)
+    reads, wins = _pairs(rng, 64, (150, 150), (500, 500))
+    q, qo = to_csr(reads); r, ro = to_csr(wins)
+    exp = ol.batch(q, qo, r, ro, threads=4, simd=True)
+    dq, dqo, dr, dro, dout = (engine.malloc_device(x) for x in (q.size, qo.nbytes, r.size, ro.nbytes, 64 * 12))
+    try:
+        engine.h2d(dq, q, q.size); engine.h2d(dqo, qo, qo.nbytes); engine.h2d(dr, r, r.size); engine.h2d(dro, ro, ro.nbytes)
+        out = np.zeros(64, dtype=mp.RESULT_DTYPE)
+        for bound, path in ((100, "long"), (150, "short"), (0, "short")):
+            engine.score_batch_device(dq, dqo, q.size, dr, dro, r.size, 64, bound, 500, dout)
+            engine.sync()
+            engine.d2h(out, dout, out.nbytes)
+            assert np.array_equal(out, exp), bound
+            assert engine.last_routing_ex()[path] == 64, (bound, engine.last_routing_ex())
+    finally:
+        for p in (dq, dqo, dr, dro, dout):
+            engine.free_device(p)
+
+
 def test_short_path_window_limits(engine):
     rng = np.random.default_rng(400)
     _assert_parity(engine, *_pairs(rng, 64, (150, 160), (4000, 4096)))               # longest window the short path takes
