@@ -15,7 +15,11 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <zlib.h>          // crc32() only
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -617,6 +621,91 @@ class GunzipStream {
   uint32_t crc_ = 0, isize_ = 0;
   Inflater inf_;
   std::string err_;
+};
+
+// The same reader with the inflating on a thread of its own: the caller's thread parses lines while the next 4 MiB are being
+// decoded (a plain gzip stream cannot be split, but inflate and parse can overlap: 0.55 + 0.2 s per 316 MB of FASTQ text
+// become max(0.55, 0.2)).  Worth it only where cores are spare -- FastqReader asks for it when the box has at least two per
+// file.  Same read() contract as GunzipStream, including "what was decoded first, the error on the next call".
+class AsyncGunzip {
+ public:
+  ~AsyncGunzip() { close(); }
+  bool open(const char* path)
+  {
+    close();
+    if (!gs_.open(path)) return false;
+    for (auto& b : bufs_) { b.data.resize(kBuf); b.n = 0; }
+    free_.clear(); ready_.clear();
+    for (size_t i = 0; i < kBufs; ++i) free_.push_back(i);
+    stop_ = false; cur_ = kNone; cur_pos_ = 0; ended_ = false; failed_ = false;
+    th_ = std::thread([this] { produce(); });
+    return true;
+  }
+  void close()
+  {
+    if (th_.joinable()) {
+      { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+      cv_.notify_all();
+      th_.join();
+    }
+    gs_.close();
+  }
+  const std::string& error() const { return gs_.error(); }
+
+  long read(uint8_t* dst, size_t cap)
+  {
+    size_t got = 0;
+    while (got < cap) {
+      if (cur_ == kNone) {
+        if (ended_) break;
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !ready_.empty(); });
+        cur_ = ready_.front(); ready_.erase(ready_.begin()); cur_pos_ = 0;
+      }
+      Buf& b = bufs_[cur_];
+      if (b.n <= 0) {                                        // the producer's last word: end of data (0) or corrupt data (-1)
+        ended_ = true; failed_ = b.n < 0; cur_ = kNone;
+        break;
+      }
+      const size_t n = std::min(cap - got, (size_t)b.n - cur_pos_);
+      memcpy(dst + got, b.data.data() + cur_pos_, n); got += n; cur_pos_ += n;
+      if (cur_pos_ == (size_t)b.n) {
+        { std::lock_guard<std::mutex> lk(mu_); free_.push_back(cur_); }
+        cv_.notify_all();
+        cur_ = kNone;
+      }
+    }
+    if (got == 0 && failed_) return -1;
+    return (long)got;
+  }
+
+ private:
+  static constexpr size_t kBuf = 4 << 20, kBufs = 3, kNone = ~(size_t)0;
+  struct Buf { std::vector<uint8_t> data; long n = 0; };
+  void produce()
+  {
+    for (;;) {
+      size_t i;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || !free_.empty(); });
+        if (stop_) return;
+        i = free_.back(); free_.pop_back();
+      }
+      bufs_[i].n = gs_.read(bufs_[i].data.data(), kBuf);
+      const bool last = bufs_[i].n <= 0;
+      { std::lock_guard<std::mutex> lk(mu_); ready_.push_back(i); }
+      cv_.notify_all();
+      if (last) return;
+    }
+  }
+  GunzipStream gs_;
+  Buf bufs_[kBufs];
+  std::vector<size_t> free_, ready_;
+  std::mutex mu_; std::condition_variable cv_;
+  std::thread th_;
+  bool stop_ = false, ended_ = false, failed_ = false;
+  size_t cur_ = kNone, cur_pos_ = 0;
 };
 
 }  // namespace hgz

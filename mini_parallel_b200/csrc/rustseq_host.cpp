@@ -137,16 +137,23 @@ template <class T> using pinned_vector = std::vector<T, PinnedAlloc<T>>;
 class FastqReader {
  public:
   ~FastqReader() { close(); }
-  int open(const std::string& path)
+  // spare_core: a second thread may inflate while this one parses (plain .gz only; SWB_ASYNC_INFLATE=0/1 overrides)
+  int open(const std::string& path, bool spare_core = false)
   {
     path_ = path;
+    if (const char* v = std::getenv("SWB_ASYNC_INFLATE")) spare_core = std::atoi(v) != 0;
     const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;   // aligner.rs:109
     const char* how = std::getenv("SWB_HOST_INFLATE");
     if (gz && !(how && std::string(how) == "zlib")) {
       // in-process inflate instead of a `zcat` child (aligner.rs:111-120): this repository's decoder (host_gunzip.h), 1.6-1.7x
       // zlib on FASTQ text and the same behaviour at the edges; SWB_HOST_INFLATE=zlib selects gzread
-      if (!hz_.open(path.c_str())) return fail("Failed to open file " + path + ": " + std::strerror(errno));
-      use_hz_ = true;
+      if (spare_core) {
+        if (!az_.open(path.c_str())) return fail("Failed to open file " + path + ": " + std::strerror(errno));
+        use_az_ = true;
+      } else {
+        if (!hz_.open(path.c_str())) return fail("Failed to open file " + path + ": " + std::strerror(errno));
+        use_hz_ = true;
+      }
     } else if (gz) {
       gz_ = gzopen(path.c_str(), "rb");
       if (!gz_) return fail("Failed to open file " + path + ": " + std::strerror(errno));
@@ -158,7 +165,7 @@ class FastqReader {
     buf_.resize(4 << 20);
     return 0;
   }
-  void close() { if (gz_) gzclose(gz_); if (fp_) std::fclose(fp_); gz_ = nullptr; fp_ = nullptr; hz_.close(); use_hz_ = false; }
+  void close() { if (gz_) gzclose(gz_); if (fp_) std::fclose(fp_); gz_ = nullptr; fp_ = nullptr; hz_.close(); use_hz_ = false; az_.close(); use_az_ = false; }
 
   // Appends up to max_reads sequence lines (and at most max_bases bases, 0 = no cap) to bases/offs.
   // Returns 0 ok, 1 error; *eof set when the input is exhausted.
@@ -183,7 +190,8 @@ class FastqReader {
       if (len_ == buf_.size()) buf_.resize(buf_.size() * 2);
       long got = 0;
       if (!at_eof_) {
-        got = use_hz_ ? hz_.read(buf_.data() + len_, buf_.size() - len_)
+        got = use_az_ ? az_.read(buf_.data() + len_, buf_.size() - len_)
+            : use_hz_ ? hz_.read(buf_.data() + len_, buf_.size() - len_)
             : gz_ ? gzread(gz_, buf_.data() + len_, (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30))
                   : (long)std::fread(buf_.data() + len_, 1, buf_.size() - len_, fp_);
         if (got < 0) return fail("Failed to read " + path_ + ": gzip stream error");
@@ -237,6 +245,7 @@ class FastqReader {
   std::string path_;
   gzFile gz_ = nullptr; FILE* fp_ = nullptr;
   hgz::GunzipStream hz_; bool use_hz_ = false;
+  hgz::AsyncGunzip az_; bool use_az_ = false;
   std::vector<uint8_t> buf_;
   size_t pos_ = 0, len_ = 0;
   bool at_eof_ = false;
@@ -504,6 +513,7 @@ struct WgsFile {
   std::vector<uint8_t> carry; uint64_t lines = 0;
   uint64_t seg_bytes = 0; CompPool* comp_pool = nullptr;
   // several readers per file (wgs_bgzf_reader_thread): segment k may take its buffers once k-1 has, and is walked after k-1
+  bool spare_core = false;                     // plain .gz: the box has a second core for this file (inflate and parse on two threads)
   swb_ctx* ctx = nullptr;                      // the consumer's context: readers make its device current before they page-lock buffers
   int fd = -1; uint64_t file_bytes = 0, n_segments = 0;
   unsigned n_readers = 1, live_readers = 0;
@@ -591,7 +601,7 @@ void wgs_bgzf_reader_thread(WgsFile* f, unsigned r)
 void wgs_reader_thread(WgsFile* f, uint64_t chunk_reads, uint64_t chunk_bases, uint64_t ref_len, uint32_t window_len)
 {
   FastqReader rd;
-  int rc = rd.open(f->path);
+  int rc = rd.open(f->path, f->spare_core);
   std::string err = rc ? g_err : "";
   bool eof = false; uint64_t first = 0, in_chunk_reads = 0, in_chunk_bases = 0;
   while (rc == 0 && !eof) {
@@ -654,7 +664,7 @@ void wgs_finish_file(WgsFile* f, size_t total, uint64_t chunk_reads, const rsm_g
 // All files of one GPU: readers in parallel, one consumer (this thread) scoring whatever is ready.
 void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std::string>& files, size_t total, uint64_t chunk_reads,
                          uint64_t chunk_bases, const rsm_gpu_device* dev, swb_ctx* ctx, uint64_t ref_len, uint32_t window_len,
-                         std::vector<FileOutcome>* outcomes, unsigned readers_per_file, size_t n_devices)
+                         std::vector<FileOutcome>* outcomes, unsigned readers_per_file, size_t n_devices, bool spare_cores)
 {
   DeviceGate gate;
   CompPool pool;
@@ -665,6 +675,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
   for (size_t i : mine) {
     auto f = std::make_unique<WgsFile>();
     f->index = i; f->path = files[i]; f->gate = &gate; f->t0 = std::chrono::steady_clock::now(); f->ctx = ctx;
+    f->spare_core = spare_cores;
     f->bgzf = file_is_bgzf(files[i]);
     if (f->bgzf) {
       f->comp_pool = &pool;
@@ -919,7 +930,7 @@ int rsm_process_fastq_file_in_chunks(const char* filepath, uint64_t chunk_size_r
   uint64_t max_bases = 0;
   if (rsm_get_chunk_size_bases(&max_bases)) return 1;
   FastqReader rd;
-  if (rd.open(filepath)) return 1;
+  if (rd.open(filepath, std::thread::hardware_concurrency() >= 2)) return 1;      // one file: a second core may inflate while this one parses
   std::vector<uint8_t> bases; std::vector<uint64_t> offs;
   bool eof = false;
   while (!eof) {
@@ -1377,7 +1388,8 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
       std::vector<size_t> mine;
       for (size_t t = w; t < todo.size(); t += n_workers) mine.push_back(todo[t]);
       if (mine.empty()) return;
-      wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes, readers_per_file, order.size());
+      wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes, readers_per_file, order.size(),
+                          std::thread::hardware_concurrency() >= 2 * todo.size() + n_workers);
       stamp("a device's files done");
     });
   }

@@ -186,3 +186,41 @@ def test_fastq_reader_uses_it_and_agrees_with_the_zlib_path(tmp_path, monkeypatc
             monkeypatch.delenv("SWB_HOST_INFLATE", raising=False)
         with pytest.raises(aligner.AlignerError, match="gzip stream error"):
             aligner.process_fastq_file_in_chunks(tmp_path / "bad.fastq.gz", 700, lambda ch: None)
+
+
+def test_inflate_on_its_own_thread_reads_the_same(tmp_path, monkeypatch):
+    """SWB_ASYNC_INFLATE: the gzip stream decoded by a second thread while the reader's thread parses (used where the box has
+    two cores per file): the same reads, the same error behaviour, no thread left behind when a file is abandoned early."""
+    rng = np.random.default_rng(12)
+    reads = [ACGT[rng.integers(0, 4, int(rng.integers(1, 200)))].tobytes() for _ in range(120_000)]      # ~25 MB of text: many 4 MiB buffers
+    text = b"".join(b"@r%d\n%s\n+\n%s\n" % (k, r, b"I" * len(r)) for k, r in enumerate(reads))
+    p = tmp_path / "r.fastq.gz"
+    p.write_bytes(gz(text, 1))
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("SWB_ASYNC_INFLATE", mode)
+        out = []
+        aligner.process_fastq_file_in_chunks(p, 5000, lambda ch: out.extend(ch))
+        got[mode] = out
+    assert got["0"] == got["1"] == reads
+    monkeypatch.setenv("SWB_ASYNC_INFLATE", "1")
+    bad = bytearray(gz(text, 6)); bad[len(bad) // 2] ^= 0xFF
+    (tmp_path / "bad.fastq.gz").write_bytes(bytes(bad))
+    seen = []
+    with pytest.raises(aligner.AlignerError, match="gzip stream error"):
+        aligner.process_fastq_file_in_chunks(tmp_path / "bad.fastq.gz", 5000, lambda ch: seen.extend(ch))
+    assert 50_000 < len(seen) < len(reads) and seen[:50_000] == reads[:50_000]        # what preceded the damage was delivered (a flipped
+                                                                                       # bit decodes to wrong text for a while before a check trips)
+    (tmp_path / "cut.fastq.gz").write_bytes(gz(text, 1)[:200_000])                     # truncated: ends early, no error
+    seen = []
+    aligner.process_fastq_file_in_chunks(tmp_path / "cut.fastq.gz", 5000, lambda ch: seen.extend(ch))
+    assert 0 < len(seen) < len(reads) and seen[:-1] == reads[: len(seen) - 1]
+    # a callback that gives up after the first chunk: the reader is closed with its producer blocked on a full queue
+    class Stop(Exception):
+        pass
+
+    def once(ch):
+        raise Stop()
+    for _ in range(5):
+        with pytest.raises(Stop):
+            aligner.process_fastq_file_in_chunks(p, 100, once)
