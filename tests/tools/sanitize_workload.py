@@ -82,7 +82,9 @@ def main():
     parity(eng, *pairs(rng, n_of(3000), (1, 160), (1, 700)), "stream ragged")
     parity(eng, *pairs(rng, n_of(800), (1, 160), (1, 600), alphabet=b"A"), "stream ties")
     parity(eng, *pairs(rng, n_of(64), (100, 160), (3900, 4096)), "stream widest windows")
-    # the 320-row instantiation
+    parity(eng, *pairs(rng, n_of(2000), (1, 128), (1, 700)), "stream 128-row instantiation")
+    # the 256- and 320-row instantiations
+    parity(eng, *pairs(rng, n_of(800), (161, 256), (1, 900)), "mid 161..256 (256 rows)")
     parity(eng, *pairs(rng, n_of(800), (161, 320), (1, 900)), "mid 161..320")
     # sw_long_kernel (32-bit bands), its byte variant, the generic kernel
     parity(eng, *pairs(rng, n_of(40), (321, 1500), (200, 3000)), "long bands")
