@@ -600,6 +600,7 @@ void wgs_bgzf_reader_thread(WgsFile* f, unsigned r)
 
 void wgs_reader_thread(WgsFile* f, uint64_t chunk_reads, uint64_t chunk_bases, uint64_t ref_len, uint32_t window_len)
 {
+  if (f->ctx) swb_bind_thread(f->ctx);          // a chunk buffer that grows is page-locked by this thread: under its own GPU's context lock
   FastqReader rd;
   int rc = rd.open(f->path, f->spare_core);
   std::string err = rc ? g_err : "";
