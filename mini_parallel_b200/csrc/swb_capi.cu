@@ -115,6 +115,10 @@ struct swb_ctx : Lane {                    // lane 0 is the context itself (devi
     cudaEvent_t done = nullptr; bool pending = false;
   } fq_slot[2];
   DevBuf fq_tile_count, fq_tile_prefix, fq_seq_beg, fq_seq_end, fq_scal;
+  // longest read of the last segment of every file (by file_index): the next segment's bound on the read length, which picks
+  // the 128-row instantiation for files of <= 128 bp reads.  A bound only: a longer read is still scored exactly (classify
+  // routes it past the kernel), and the following segment runs on 160 rows again.
+  std::vector<std::pair<uint64_t, uint32_t>> fq_read_hint;
   DevBuf tb_scratch, tb_res, tb_out, tb_cigar, tb_cursor, tb_handled;   // swb_traceback_batch
   uint64_t ref_len = 0;
   std::vector<ChunkEvents> chunk_ev;       // host path: one event set per chunk of the last call
@@ -812,8 +816,10 @@ static int fastq_bgzf_score_impl(swb_ctx* c, const uint8_t* comp, uint64_t comp_
     k += swb::launch_fq_windows(file_index, first_read + a, n, c->ref_len, window_len, d_beg + a, d_end + a, c->win_beg.as<uint64_t>(),
                                 c->win_end.as<uint64_t>(), st);
     const RefSrc rref = resident_ref(c);
+    uint32_t read_bound = 0xffffffffu;                            // unknown: 160 rows, mid and long lists
+    for (const auto& h : c->fq_read_hint) if (h.first == file_index && h.second >= 1 && h.second <= 128) read_bound = 128;
     if (run_device_pipeline(c, c, c->ev, d_text, d_beg + a, end, c->ref_bytes.as<uint8_t>(), c->win_beg.as<uint64_t>(),
-                            c->win_end.as<uint64_t>(), 0, &rref, n, 0xffffffffu, window_len, c->out.as<swb_result>(), &k, d_end + a, true)) return 1;
+                            c->win_end.as<uint64_t>(), 0, &rref, n, read_bound, window_len, c->out.as<swb_result>(), &k, d_end + a, true)) return 1;
     k += swb::launch_fq_reduce(c->out.as<swb_result>(), d_beg + a, d_end + a, n, reinterpret_cast<unsigned long long*>(d_scal + 2), st);
   }
   if (dbg) cudaEventRecord(te[4], st);
@@ -838,6 +844,12 @@ static int fastq_bgzf_score_impl(swb_ctx* c, const uint8_t* comp, uint64_t comp_
       CUDA_TRY(cudaStreamSynchronize(st));
     }
     *carry_out_len = tl;
+  }
+  if (R) {                                                       // this segment's longest read: the next one's bound
+    const uint32_t longest = (uint32_t)std::min<uint64_t>(h_scal[6], 0xffffffffull);
+    bool found = false;
+    for (auto& h : c->fq_read_hint) if (h.first == file_index) { h.second = longest; found = true; }
+    if (!found) { if (c->fq_read_hint.size() >= 64) c->fq_read_hint.erase(c->fq_read_hint.begin()); c->fq_read_hint.emplace_back(file_index, longest); }
   }
   *score_sum = (int64_t)h_scal[2]; *n_reads = R; *n_bases = h_scal[3];
   *n_lines = final_segment ? lines : 4 * R;               // lines of the records scored here (the carried ones count next time)

@@ -272,14 +272,18 @@ fq_windows_kernel(uint64_t file_index, uint64_t first_read, uint64_t n, uint64_t
 
 __global__ void __launch_bounds__(256)
 fq_reduce_kernel(const swb_result* __restrict__ res, const uint64_t* __restrict__ seq_beg, const uint64_t* __restrict__ seq_end, uint64_t n,
-                 unsigned long long* __restrict__ sums /* [0] score sum, [1] bases */)
+                 unsigned long long* __restrict__ sums /* [0] score sum, [1] bases, [4] longest read */)
 {
-  unsigned long long sc = 0, bs = 0;
+  unsigned long long sc = 0, bs = 0, mx = 0;
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
-    sc += (unsigned long long)(long long)res[k].score; bs += seq_end[k] - seq_beg[k];
+    const unsigned long long len = seq_end[k] - seq_beg[k];
+    sc += (unsigned long long)(long long)res[k].score; bs += len; mx = len > mx ? len : mx;
   }
-  for (int o = 16; o; o >>= 1) { sc += __shfl_xor_sync(0xffffffffu, sc, o); bs += __shfl_xor_sync(0xffffffffu, bs, o); }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], sc); atomicAdd(&sums[1], bs); }
+  for (int o = 16; o; o >>= 1) {
+    sc += __shfl_xor_sync(0xffffffffu, sc, o); bs += __shfl_xor_sync(0xffffffffu, bs, o);
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, mx, o); mx = other > mx ? other : mx;
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], sc); atomicAdd(&sums[1], bs); if (mx) atomicMax(&sums[4], mx); }
 }
 
 int launch_fq_windows(uint64_t file_index, uint64_t first_read, uint64_t n, uint64_t ref_len, uint32_t w, uint64_t* seq_beg, uint64_t* seq_end,

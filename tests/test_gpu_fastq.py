@@ -196,3 +196,38 @@ def test_stray_carriage_returns_are_left_to_the_host_reader(engine):
         assert out["status"] == 1, pad
     tot = _run_segments(engine, bgzf.compress(text, 1), 100)                          # and the context still works
     assert tot["reads"] == 120
+
+
+def test_files_of_short_reads_move_to_the_128_row_kernel_and_back(engine):
+    """A file's segments carry the longest read of the previous one as the next one's bound: files of <= 128 bp reads (2 x 100,
+    2 x 125 runs) are scored on 128 rows from their second segment on.  The bound is a hint: a later segment with longer reads
+    is still exact (those reads are routed past the kernel), and the segment after it is back on 160 rows."""
+    rng = np.random.default_rng(81)
+    ref = ACGT[rng.integers(0, 4, 60_000)]
+    engine.set_reference(ref)
+
+    def make(lengths, file_index, first):
+        reads, recs = [], []
+        for k, ln in enumerate(lengths):
+            s = splitmix64(((file_index << 40) + first + k) ^ 0xB202) % (len(ref) - 500 + 1)
+            o = int(rng.integers(0, 500 - ln + 1))
+            r = ref[s + o:s + o + ln].copy()
+            m = rng.random(ln) < 0.02
+            r[m] = ACGT[rng.integers(0, 4, int(m.sum()))]
+            reads.append(r.tobytes())
+            recs.append(b"@r%d\n" % (first + k) + reads[-1] + b"\n+\n" + b"I" * ln + b"\n")
+        return reads, b"".join(recs)
+    fi, first, total = 9, 0, 0
+    plan = [[100] * 900, [100] * 900, list(rng.integers(60, 129, 900)), [100] * 450 + [150] * 450, [150] * 900, [125] * 900, [125] * 900]
+    for seg, lengths in enumerate(plan):
+        reads, text = make([int(x) for x in lengths], fi, first)
+        gz = bgzf.compress(text, 1, 30000)
+        blocks, used = bgzf.walk(gz)
+        out = engine.fastq_bgzf_score(np.frombuffer(gz, dtype=np.uint8), blocks, b"", True, fi, first, 500)
+        assert out["status"] == 0 and out["reads"] == len(reads), seg
+        q, qo = to_csr(reads)
+        starts = [splitmix64(((fi << 40) + first + k) ^ 0xB202) % (len(ref) - 500 + 1) for k in range(len(reads))]
+        r, ro = to_csr([ref[s:s + 500] for s in starts])
+        exp = ol.batch(q, qo, r, ro, threads=8, simd=True)
+        assert out["score_sum"] == int(exp["score"].astype(np.int64).sum()), seg
+        first += len(reads); total += len(reads)           # (segment 3 runs with the bound 128 of segment 2 and 150 bp reads: the long-pair kernel)
