@@ -638,7 +638,8 @@ class AsyncGunzip {
     free_.clear(); ready_.clear();
     for (size_t i = 0; i < kBufs; ++i) free_.push_back(i);
     stop_ = false; cur_ = kNone; cur_pos_ = 0; ended_ = false; failed_ = false;
-    th_ = std::thread([this] { produce(); });
+    try { th_ = std::thread([this] { produce(); }); }
+    catch (const std::exception&) { gs_.close(); errno = EAGAIN; return false; }      // no thread to be had: the caller reports the file as unopenable
     return true;
   }
   void close()

@@ -697,6 +697,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
       if (const char* v = std::getenv("SWB_BGZF_SEGMENT_KB")) { const long kb = std::atol(v); if (kb >= 128) f->seg_bytes = (uint64_t)kb << 10; }   // tests: many segments of a small file
       pool.bytes = std::max<uint64_t>(pool.bytes, kBgzfFront + f->seg_bytes + 64);
       f->fd = ::open(files[i].c_str(), O_RDONLY);
+      if (f->fd < 0) f->err = "Failed to open file " + f->path + ": " + std::strerror(errno);      // (errno is this call's only here)
       struct stat sb;
       if (f->fd >= 0 && ::fstat(f->fd, &sb) == 0) f->file_bytes = (uint64_t)sb.st_size;
       f->n_segments = std::max<uint64_t>(1, (f->file_bytes + f->seg_bytes - 1) / f->seg_bytes);
@@ -728,7 +729,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
     if (f->bgzf) {
       if (f->fd < 0) {                                       // unreadable: reported like the host reader would
         std::lock_guard<std::mutex> lk(gate.mu);
-        f->rc = 1; f->err = "Failed to open file " + f->path + ": " + std::strerror(errno); f->closed = true;
+        f->rc = 1; f->closed = true;
         continue;
       }
       f->live_readers = f->n_readers;
@@ -953,6 +954,7 @@ int rsm_debug_gunzip(const char* path, uint64_t read_cap, int use_zlib, uint8_t*
 {
   if (!path || !n || !failed || read_cap == 0) return fail("rsm_debug_gunzip: bad argument");
   *n = 0; *failed = 0;
+  read_cap = std::min<uint64_t>(read_cap, 1ull << 28);               // a test hook: no gigabyte read buffers
   std::vector<uint8_t> buf(read_cap);
   auto deliver = [&](long got) {
     if (*n < out_cap && out) std::memcpy(out + *n, buf.data(), (size_t)std::min<uint64_t>((uint64_t)got, out_cap - *n));
@@ -1005,9 +1007,19 @@ int rsm_debug_bgzf_segments(const char* path, unsigned readers, uint64_t seg_byt
   f.n_segments = std::max<uint64_t>(1, (f.file_bytes + seg_bytes - 1) / seg_bytes);
   f.n_readers = (unsigned)std::min<uint64_t>(std::max(1u, readers), f.n_segments);
   for (unsigned d = 0; d < 1 + f.n_readers; ++d) { f.pool.push_back(std::make_unique<WgsChunk>()); f.spare.push_back(f.pool.back().get()); }
-  f.live_readers = f.n_readers;
+  f.live_readers = f.n_readers;                                        // all of them before the first one runs: the last to leave closes the file
   std::vector<std::thread> th;
-  for (unsigned r = 0; r < f.n_readers; ++r) th.emplace_back(wgs_bgzf_reader_thread, &f, r);
+  try {
+    for (unsigned r = 0; r < f.n_readers; ++r) th.emplace_back(wgs_bgzf_reader_thread, &f, r);
+  } catch (const std::exception& e) {                                  // no exception leaves through the C ABI
+    {
+      std::lock_guard<std::mutex> lk(gate.mu);
+      f.reader_rc = 1; f.reader_err = std::string("cannot start a reader thread: ") + e.what();      // the ones that run stop at their next step
+      f.live_readers -= f.n_readers - (unsigned)th.size();
+      if (th.empty()) { f.rc = 1; f.err = f.reader_err; f.closed = true; ::close(f.fd); f.fd = -1; }
+    }
+    gate.cv.notify_all();
+  }
   for (;;) {
     WgsChunk* c = nullptr;
     {
