@@ -76,6 +76,8 @@ extern "C" {
     pub fn swb_set_chunking(ctx: *mut SwbCtx, chunk_bytes: u64, min_chunk_pairs: u64) -> c_int;
     pub fn swb_last_routing(ctx: *mut SwbCtx, counts: *mut u64) -> c_int;
     pub fn swb_malloc_pinned(bytes: u64, out: *mut *mut c_void) -> c_int;
+    pub fn swb_bind_thread(ctx: *mut SwbCtx) -> c_int;          // a helper thread that page-locks buffers for `ctx` calls this first
+    pub fn swb_debug_guard_check(ctx: *mut SwbCtx, report: *mut c_char, report_cap: u64, n_arenas: *mut u64) -> c_int;   // SWB_GUARD=1
     pub fn swb_free_pinned(p: *mut c_void) -> c_int;
     pub fn swb_last_error() -> *const c_char;
 }
