@@ -224,3 +224,22 @@ def test_inflate_on_its_own_thread_reads_the_same(tmp_path, monkeypatch):
     for _ in range(5):
         with pytest.raises(Stop):
             aligner.process_fastq_file_in_chunks(p, 100, once)
+
+
+def test_flush_points_and_empty_stored_blocks(tmp_path):
+    """Streams written with Z_SYNC_FLUSH / Z_FULL_FLUSH (pigz, network writers) carry empty stored blocks and byte-aligned
+    restarts in the middle of the data."""
+    rng = np.random.default_rng(13)
+    raw = fastq(rng, 6000, "noisy")
+    for level in (1, 6):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31)
+        parts, pos = [], 0
+        while pos < len(raw):
+            n = int(rng.integers(1, 70_000))
+            parts.append(c.compress(raw[pos:pos + n]))
+            parts.append(c.flush(zlib.Z_SYNC_FLUSH if rng.integers(0, 2) else zlib.Z_FULL_FLUSH))
+            if rng.integers(0, 4) == 0:
+                parts.append(c.flush(zlib.Z_SYNC_FLUSH))                 # two flushes in a row: consecutive empty stored blocks
+            pos += n
+        parts.append(c.flush())
+        same_as_zlib(tmp_path, f"flush{level}.gz", b"".join(parts), raw, caps=(1 << 20, 333))
