@@ -196,6 +196,8 @@ class FastqReader {
                   : (long)std::fread(buf_.data() + len_, 1, buf_.size() - len_, fp_);
         if (got < 0) return fail("Failed to read " + path_ + ": gzip stream error");
         if (got == 0) at_eof_ = true;
+        // the kept partial line came out of the previous buffer: ASCII if that one was, as a whole
+        buf_ascii_ = (len_ == 0 || buf_ascii_) && all_ascii(buf_.data() + len_, (size_t)got);
         len_ += (size_t)got;
       }
       if (at_eof_ && got == 0) {
@@ -225,7 +227,8 @@ class FastqReader {
   int handle_line(const uint8_t* p, size_t n, VB& bases, VO& offs, bool terminated = true)
   {
     if (terminated && n && p[n - 1] == '\r') --n;  // lines() strips "\n" and "\r\n"; a last line without '\n' keeps its '\r'
-    if (!valid_utf8(p, n)) {                       // lines() yields Err for invalid UTF-8 (aligner.rs:155-163)
+    if (!buf_ascii_ && !valid_utf8(p, n)) {        // lines() yields Err for invalid UTF-8 (aligner.rs:155-163); a buffer that is
+                                                   // ASCII as a whole (one wide pass when it was read) needs no check per line
       ++error_count;
       if (error_count <= 5) std::printf("    Warning: Error reading line %llu: stream did not contain valid UTF-8\n", (unsigned long long)line_count);
       if (error_count > 10) return fail("Too many read errors (>10), stopping at line " + std::to_string(line_count));
@@ -244,6 +247,14 @@ class FastqReader {
   }
   std::string path_;
   gzFile gz_ = nullptr; FILE* fp_ = nullptr;
+  static bool all_ascii(const uint8_t* p, size_t n)
+  {
+    uint64_t acc = 0; size_t i = 0;
+    for (; i + 32 <= n; i += 32) { uint64_t w[4]; std::memcpy(w, p + i, 32); acc |= w[0] | w[1] | w[2] | w[3]; }
+    for (; i < n; ++i) acc |= p[i];
+    return (acc & 0x8080808080808080ull) == 0;
+  }
+  bool buf_ascii_ = false;
   hgz::GunzipStream hz_; bool use_hz_ = false;
   hgz::AsyncGunzip az_; bool use_az_ = false;
   std::vector<uint8_t> buf_;
