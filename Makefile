@@ -7,14 +7,14 @@ LIB       := mini_parallel_b200/libswb200.so
 
 all: $(LIB) variants build/rustseq_mini build/issue_rate_bench build/cell_loop_bench build/inflate_bench oracle
 
-$(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh $(CSRC)/host_gunzip.h include/swb200.h include/rustseq_host.h
+$(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh $(CSRC)/host_gunzip.h $(CSRC)/host_pgunzip.h include/swb200.h include/rustseq_host.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
 
 # TEST-ONLY build with every short-read / long-pair kernel variant (-DSWB_ALL_VARIANTS): the parity tests load it beside
 # the product library and cross-check the variants against the oracle.  Nothing in the product loads it.
 VARLIB := tests/native/libswb200_variants.so
 variants: $(VARLIB)
-$(VARLIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh $(CSRC)/host_gunzip.h include/swb200.h include/rustseq_host.h
+$(VARLIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh $(CSRC)/host_gunzip.h $(CSRC)/host_pgunzip.h include/swb200.h include/rustseq_host.h
 	mkdir -p tests/native
 	$(NVCC) $(NVCCFLAGS) -DSWB_ALL_VARIANTS -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
 

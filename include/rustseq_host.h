@@ -48,6 +48,11 @@ int  rsm_count_bases_in_fastq(const char* filepath, uint64_t* out);  /* aligner.
 /* Test hook: a .gz file through the host gzip reader of the FASTQ path (csrc/host_gunzip.h; use_zlib = 1: zlib's gzread, the
  * behaviour it keeps) in read() calls of read_cap bytes.  *n = bytes delivered, *failed = 1 on corrupt data. */
 int  rsm_debug_gunzip(const char* path, uint64_t read_cap, int use_zlib, uint8_t* out, uint64_t out_cap, uint64_t* n, int* failed);
+/* Test hook: the same file through the parallel reader (csrc/host_pgunzip.h: `threads` decoder threads on chunks of chunk_bytes
+ * compressed bytes, 0 = 1 MiB).  *parallel = 0 when the file went to the serial reader; *accepted / *serial_stretches = chunks
+ * taken from the decoder threads / stretches the calling thread decoded itself. */
+int  rsm_debug_pgunzip(const char* path, uint64_t read_cap, unsigned threads, uint64_t chunk_bytes, uint8_t* out, uint64_t out_cap, uint64_t* n,
+                       int* failed, int* parallel, uint64_t* accepted, uint64_t* serial_stretches);
 int  rsm_debug_bgzf_segments(const char* path, unsigned readers, uint64_t seg_bytes, unsigned pool_buffers, uint64_t* n_segments,
                              uint64_t* n_blocks, uint64_t* text_bytes, uint64_t* hash, int* status);
 

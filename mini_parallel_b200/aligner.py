@@ -61,6 +61,8 @@ def _lib():
         lib.rsm_count_bases_in_fastq.argtypes = [ctypes.c_char_p, u64p]
         lib.rsm_debug_gunzip.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, u64p,
                                          ctypes.POINTER(ctypes.c_int)]
+        lib.rsm_debug_pgunzip.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, u64p,
+                                          ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), u64p, u64p]
         lib.rsm_debug_bgzf_segments.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_uint64, ctypes.c_uint, u64p, u64p, u64p, u64p,
                                                 ctypes.POINTER(ctypes.c_int)]
         lib.rsm_gpu_align.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
@@ -145,6 +147,20 @@ def debug_gunzip(filepath, read_cap=1 << 20, use_zlib=False, out_cap=None):
     _check(_lib().rsm_debug_gunzip(str(filepath).encode(), int(read_cap), int(bool(use_zlib)), buf.ctypes.data, cap, ctypes.byref(n),
                                    ctypes.byref(failed)))
     return buf[: min(cap, int(n.value))].tobytes(), int(n.value), bool(failed.value)
+
+
+def debug_pgunzip(filepath, threads, chunk_bytes=0, read_cap=1 << 20, out_cap=None):
+    """rsm_debug_pgunzip (test hook): the file through the parallel host gzip reader ->
+    (bytes, n_delivered, failed, dict(parallel, accepted, serial_stretches))."""
+    import os
+    cap = int(out_cap) if out_cap is not None else max(1 << 16, 64 * os.path.getsize(filepath) + (1 << 20))
+    buf = np.empty(cap, dtype=np.uint8)
+    n, acc, ser = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+    failed, par = ctypes.c_int(), ctypes.c_int()
+    _check(_lib().rsm_debug_pgunzip(str(filepath).encode(), int(read_cap), int(threads), int(chunk_bytes), buf.ctypes.data, cap, ctypes.byref(n),
+                                    ctypes.byref(failed), ctypes.byref(par), ctypes.byref(acc), ctypes.byref(ser)))
+    return (buf[: min(cap, int(n.value))].tobytes(), int(n.value), bool(failed.value),
+            {"parallel": bool(par.value), "accepted": int(acc.value), "serial_stretches": int(ser.value)})
 
 
 def debug_bgzf_segments(filepath, readers, seg_bytes, pool_buffers):

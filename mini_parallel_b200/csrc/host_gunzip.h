@@ -217,10 +217,23 @@ struct Inflater {
   uint32_t clen[1 << 7];
   const char* error = nullptr;
   bool starved = false;              // the FINAL input ended inside the stream: nothing more can be decoded, ever
+  // Optional stop at a block boundary (the parallel reader, host_pgunzip.h): with pos_base set, run() returns BOUNDARY in front
+  // of the first block header whose bit position -- counted from pos_base -- is >= stop_bit, and leaves it in boundary_bit.
+  const uint8_t* pos_base = nullptr;
+  uint64_t stop_bit = ~0ull, boundary_bit = 0;
 
-  void reset() { bitbuf = 0; bitcnt = 0; state = 0; last_block = false; stored_left = 0; error = nullptr; starved = false; }
+  void reset() { bitbuf = 0; bitcnt = 0; state = 0; last_block = false; stored_left = 0; error = nullptr; starved = false; pos_base = nullptr; stop_bit = ~0ull; }
+  // start in the middle of a byte: the stream's next bit is bit (bit & 7) of base[bit >> 3]; returns the input cursor for run()
+  const uint8_t* start_at_bit(const uint8_t* base, uint64_t bit)
+  {
+    reset();
+    const uint8_t* in = base + (bit >> 3);
+    const int r = (int)(bit & 7);
+    if (r) { bitbuf = (uint64_t)(*in++ >> r); bitcnt = 8 - r; }
+    return in;
+  }
 
-  enum Result { NEED_INPUT, NEED_OUTPUT, DONE, ERROR };
+  enum Result { NEED_INPUT, NEED_OUTPUT, DONE, ERROR, BOUNDARY };
 
   static inline void refill_fast(uint64_t& bb, int& bc, const uint8_t*& in)
   {
@@ -295,6 +308,10 @@ struct Inflater {
     for (;;) {
       if (state == 3) { res = DONE; break; }
       if (state == 0) {                                                // ---- block header ----
+        if (pos_base) {
+          const uint64_t bp = (uint64_t)(in - pos_base) * 8 - (uint64_t)bc;
+          if (bp >= stop_bit) { boundary_bit = bp; res = BOUNDARY; break; }
+        }
         // a dynamic header is parsed in one go: wait until it is certainly all there
         if (!final_input && (in_end - in) < 1024) { res = NEED_INPUT; break; }
         refill_safe(bb, bc, in, in_end);
@@ -340,20 +357,21 @@ struct Inflater {
       // ---- huffman symbols ----
       // fast loop: >= 16 input bytes and >= 258 + 16 output bytes in hand, no bounds checks inside.  The table entry of the
       // NEXT symbol is fetched before the copy of a match runs (the load's latency hides behind the copy), and literals run
-      // three to a refill.
+      // three to a refill.  (Shift counts are written `& 63`: an entry's bit count is below 64, and a 64-bit shift takes its
+      // count modulo 64 anyway, so the mask costs no instruction where `& 255` put one on the critical path.)
       bool ended = false;
       if (in_end - in >= 16 && out_end - out >= 280) {
         refill_fast(bb, bc, in);
         uint32_t e = lit[bb & ((1u << LIT_TB) - 1)];
         for (;;) {
           if (e & K_LIT) {
-            bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
+            bb >>= (e & 63u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
             e = lit[bb & ((1u << LIT_TB) - 1)];
             if (e & K_LIT) {
-              bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
+              bb >>= (e & 63u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
               e = lit[bb & ((1u << LIT_TB) - 1)];
               if (e & K_LIT) {
-                bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
+                bb >>= (e & 63u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
                 e = lit[bb & ((1u << LIT_TB) - 1)];
               }
             }
@@ -366,7 +384,7 @@ struct Inflater {
               bb >>= LIT_TB; bc -= LIT_TB;
               e = lit[(e >> 16) + (uint32_t)(bb & ((1u << ((e >> 8) & 15u)) - 1))];
               if (e & K_LIT) {
-                bb >>= (e & 255u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
+                bb >>= (e & 63u); bc -= (int)(e & 255u); *out++ = (uint8_t)(e >> 16);
                 if (!(in_end - in >= 16 && out_end - out >= 280)) break;
                 refill_fast(bb, bc, in);
                 e = lit[bb & ((1u << LIT_TB) - 1)];
@@ -374,14 +392,14 @@ struct Inflater {
               }
             }
             if (e & K_EXC) {
-              bb >>= (e & 255u); bc -= (int)(e & 255u);
+              bb >>= (e & 63u); bc -= (int)(e & 255u);
               if ((e >> 16) == V_EOB && !(e & K_SUB)) { ended = true; break; }
               error = "invalid literal/length code"; save(); return ERROR;
             }
           }
           // a length: base + extra bits, then the distance
           const uint64_t lsaved = bb;
-          bb >>= (e & 255u); bc -= (int)(e & 255u);                  // code and extra bits in one shift; the extra bits come from lsaved
+          bb >>= (e & 63u); bc -= (int)(e & 255u);                  // code and extra bits in one shift; the extra bits come from lsaved
           uint32_t d = dist[bb & ((1u << DIST_TB) - 1)];
           const uint32_t lxb = (e >> 8) & 15u;
           const uint32_t len = (e >> 16) + ((uint32_t)(lsaved >> ((e & 255u) - lxb)) & ((1u << lxb) - 1));
@@ -392,14 +410,20 @@ struct Inflater {
             if (d & K_EXC) { error = "invalid distance code"; save(); return ERROR; }
           }
           const uint64_t dsaved = bb;
-          bb >>= (d & 255u); bc -= (int)(d & 255u);
+          bb >>= (d & 63u); bc -= (int)(d & 255u);
           const uint32_t dxb = (d >> 8) & 15u;
           const uint32_t dd = (d >> 16) + ((uint32_t)(dsaved >> ((d & 255u) - dxb)) & ((1u << dxb) - 1));
           if (dd > hist + (uint64_t)(out - out_start)) { error = "invalid distance too far back"; save(); return ERROR; }
           const uint8_t* src = out - dd;
           uint8_t* const end = out + len;
           const bool more = in_end - in >= 16 && out_end - end >= 280;
-          if (more) { refill_fast(bb, bc, in); e = lit[bb & ((1u << LIT_TB) - 1)]; }      // the next symbol's entry, before the copy
+          // The next symbol's entry, before the copy.  A refill only adds bits above the bc valid ones, so with a table index
+          // worth of bits in hand the look-up does not wait for the refill's load -- whose address hangs on this match's bit
+          // count -- and the two dependency chains (table look-ups, input pointer) run side by side instead of end to end.
+          if (more) {
+            if (bc >= LIT_TB) { e = lit[bb & ((1u << LIT_TB) - 1)]; refill_fast(bb, bc, in); }
+            else { refill_fast(bb, bc, in); e = lit[bb & ((1u << LIT_TB) - 1)]; }
+          }
           if (dd >= 8) {
             store64(out, load64(src)); store64(out + 8, load64(src + 8));          // len >= 3; up to 16 bytes at once
             if (len > 16) { uint8_t* o = out + 16; src += 16; do { store64(o, load64(src)); o += 8; src += 8; } while (o < end); }

@@ -3,6 +3,7 @@
 // through the C ABI of swb200.h; there is no CPU scoring code in this file.
 #include "../../include/rustseq_host.h"
 #include "host_gunzip.h"
+#include "host_pgunzip.h"
 #include <zlib.h>
 #include <fcntl.h>
 #include <unistd.h>
@@ -133,21 +134,31 @@ template <class T> struct PinnedAlloc {
 };
 template <class T> using pinned_vector = std::vector<T, PinnedAlloc<T>>;
 
+// Beyond this many decoder threads a file's single parsing thread is the limit (it splits lines at ~2 GB/s of text).
+constexpr unsigned kMaxInflateThreads = 12;
+
 // ---- streaming FASTQ reader: the body of process_fastq_file_in_chunks (aligner.rs:107-178), pull style ----
 class FastqReader {
  public:
   ~FastqReader() { close(); }
-  // spare_core: a second thread may inflate while this one parses (plain .gz only; SWB_ASYNC_INFLATE=0/1 overrides)
-  int open(const std::string& path, bool spare_core = false)
+  // spare_threads: threads this file may use beside the caller's, which parses (plain .gz only): 0 = inflate here, 1-2 = one
+  // thread inflates ahead (hgz::AsyncGunzip), >= 3 = that many decode chunks of the file side by side (hgz::ParallelGunzip).
+  // SWB_INFLATE_THREADS=n overrides the caller's figure, SWB_ASYNC_INFLATE=0/1 is the older switch between 0 and 1.
+  int open(const std::string& path, unsigned spare_threads = 0)
   {
     path_ = path;
-    if (const char* v = std::getenv("SWB_ASYNC_INFLATE")) spare_core = std::atoi(v) != 0;
+    if (const char* v = std::getenv("SWB_ASYNC_INFLATE")) spare_threads = std::atoi(v) != 0 ? 1 : 0;
+    if (const char* v = std::getenv("SWB_INFLATE_THREADS")) { const int n = std::atoi(v); spare_threads = n < 0 ? 0u : (unsigned)std::min(n, 64); }
     const bool gz = path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0;   // aligner.rs:109
     const char* how = std::getenv("SWB_HOST_INFLATE");
     if (gz && !(how && std::string(how) == "zlib")) {
       // in-process inflate instead of a `zcat` child (aligner.rs:111-120): this repository's decoder (host_gunzip.h), 1.6-1.7x
       // zlib on FASTQ text and the same behaviour at the edges; SWB_HOST_INFLATE=zlib selects gzread
-      if (spare_core) {
+      if (spare_threads >= 3) {
+        pz_.set_threads(spare_threads);
+        if (!pz_.open(path.c_str())) return fail("Failed to open file " + path + ": " + std::strerror(errno));
+        use_pz_ = true;
+      } else if (spare_threads) {
         if (!az_.open(path.c_str())) return fail("Failed to open file " + path + ": " + std::strerror(errno));
         use_az_ = true;
       } else {
@@ -165,7 +176,7 @@ class FastqReader {
     buf_.resize(4 << 20);
     return 0;
   }
-  void close() { if (gz_) gzclose(gz_); if (fp_) std::fclose(fp_); gz_ = nullptr; fp_ = nullptr; hz_.close(); use_hz_ = false; az_.close(); use_az_ = false; }
+  void close() { if (gz_) gzclose(gz_); if (fp_) std::fclose(fp_); gz_ = nullptr; fp_ = nullptr; hz_.close(); use_hz_ = false; az_.close(); use_az_ = false; pz_.close(); use_pz_ = false; }
 
   // Appends up to max_reads sequence lines (and at most max_bases bases, 0 = no cap) to bases/offs.
   // Returns 0 ok, 1 error; *eof set when the input is exhausted.
@@ -190,7 +201,8 @@ class FastqReader {
       if (len_ == buf_.size()) buf_.resize(buf_.size() * 2);
       long got = 0;
       if (!at_eof_) {
-        got = use_az_ ? az_.read(buf_.data() + len_, buf_.size() - len_)
+        got = use_pz_ ? pz_.read(buf_.data() + len_, buf_.size() - len_)
+            : use_az_ ? az_.read(buf_.data() + len_, buf_.size() - len_)
             : use_hz_ ? hz_.read(buf_.data() + len_, buf_.size() - len_)
             : gz_ ? gzread(gz_, buf_.data() + len_, (unsigned)std::min<size_t>(buf_.size() - len_, 1u << 30))
                   : (long)std::fread(buf_.data() + len_, 1, buf_.size() - len_, fp_);
@@ -257,6 +269,7 @@ class FastqReader {
   bool buf_ascii_ = false;
   hgz::GunzipStream hz_; bool use_hz_ = false;
   hgz::AsyncGunzip az_; bool use_az_ = false;
+  hgz::ParallelGunzip pz_; bool use_pz_ = false;
   std::vector<uint8_t> buf_;
   size_t pos_ = 0, len_ = 0;
   bool at_eof_ = false;
@@ -524,7 +537,7 @@ struct WgsFile {
   std::vector<uint8_t> carry; uint64_t lines = 0;
   uint64_t seg_bytes = 0; CompPool* comp_pool = nullptr;
   // several readers per file (wgs_bgzf_reader_thread): segment k may take its buffers once k-1 has, and is walked after k-1
-  bool spare_core = false;                     // plain .gz: the box has a second core for this file (inflate and parse on two threads)
+  unsigned spare_threads = 0;                  // plain .gz: threads the box has for this file beside its parsing thread (FastqReader::open)
   swb_ctx* ctx = nullptr;                      // the consumer's context: readers make its device current before they page-lock buffers
   int fd = -1; uint64_t file_bytes = 0, n_segments = 0;
   unsigned n_readers = 1, live_readers = 0;
@@ -613,7 +626,7 @@ void wgs_reader_thread(WgsFile* f, uint64_t chunk_reads, uint64_t chunk_bases, u
 {
   if (f->ctx) swb_bind_thread(f->ctx);          // a chunk buffer that grows is page-locked by this thread: under its own GPU's context lock
   FastqReader rd;
-  int rc = rd.open(f->path, f->spare_core);
+  int rc = rd.open(f->path, f->spare_threads);
   std::string err = rc ? g_err : "";
   bool eof = false; uint64_t first = 0, in_chunk_reads = 0, in_chunk_bases = 0;
   while (rc == 0 && !eof) {
@@ -676,7 +689,7 @@ void wgs_finish_file(WgsFile* f, size_t total, uint64_t chunk_reads, const rsm_g
 // All files of one GPU: readers in parallel, one consumer (this thread) scoring whatever is ready.
 void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std::string>& files, size_t total, uint64_t chunk_reads,
                          uint64_t chunk_bases, const rsm_gpu_device* dev, swb_ctx* ctx, uint64_t ref_len, uint32_t window_len,
-                         std::vector<FileOutcome>* outcomes, unsigned readers_per_file, size_t n_devices, bool spare_cores)
+                         std::vector<FileOutcome>* outcomes, unsigned readers_per_file, size_t n_devices, unsigned spare_threads)
 {
   DeviceGate gate;
   CompPool pool;
@@ -687,7 +700,7 @@ void wgs_device_pipeline(const std::vector<size_t>& mine, const std::vector<std:
   for (size_t i : mine) {
     auto f = std::make_unique<WgsFile>();
     f->index = i; f->path = files[i]; f->gate = &gate; f->t0 = std::chrono::steady_clock::now(); f->ctx = ctx;
-    f->spare_core = spare_cores;
+    f->spare_threads = spare_threads;
     f->bgzf = file_is_bgzf(files[i]);
     if (f->bgzf) {
       f->comp_pool = &pool;
@@ -943,7 +956,8 @@ int rsm_process_fastq_file_in_chunks(const char* filepath, uint64_t chunk_size_r
   uint64_t max_bases = 0;
   if (rsm_get_chunk_size_bases(&max_bases)) return 1;
   FastqReader rd;
-  if (rd.open(filepath, std::thread::hardware_concurrency() >= 2)) return 1;      // one file: a second core may inflate while this one parses
+  // one file: every other core may inflate while this thread parses
+  if (rd.open(filepath, std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()) - 1, kMaxInflateThreads))) return 1;
   std::vector<uint8_t> bases; std::vector<uint64_t> offs;
   bool eof = false;
   while (!eof) {
@@ -992,6 +1006,35 @@ int rsm_debug_gunzip(const char* path, uint64_t read_cap, int use_zlib, uint8_t*
     if (got == 0) break;
     deliver(got);
   }
+  return 0;
+}
+
+// Test hook: the same through hgz::ParallelGunzip (host_pgunzip.h) with `threads` decoder threads and chunks of chunk_bytes
+// compressed bytes (0 = the default, 1 MiB).  *parallel = 0 when the file went to the serial reader (too small, not gzip, not a
+// regular file), *accepted / *serial_stretches = chunks taken from the workers / stretches the caller's thread decoded itself.
+int rsm_debug_pgunzip(const char* path, uint64_t read_cap, unsigned threads, uint64_t chunk_bytes, uint8_t* out, uint64_t out_cap, uint64_t* n,
+                      int* failed, int* parallel, uint64_t* accepted, uint64_t* serial_stretches)
+{
+  if (!path || !n || !failed || read_cap == 0) return fail("rsm_debug_pgunzip: bad argument");
+  *n = 0; *failed = 0;
+  try {
+    read_cap = std::min<uint64_t>(read_cap, 1ull << 28);
+    std::vector<uint8_t> buf(read_cap);
+    hgz::ParallelGunzip pz;
+    pz.set_threads(threads);
+    if (chunk_bytes) pz.set_chunk_bytes(chunk_bytes);
+    if (!pz.open(path)) return fail(std::string("Failed to open file ") + path);
+    for (;;) {
+      const long got = pz.read(buf.data(), (size_t)read_cap);
+      if (got < 0) { *failed = 1; g_err = pz.error(); break; }
+      if (got == 0) break;
+      if (*n < out_cap && out) std::memcpy(out + *n, buf.data(), (size_t)std::min<uint64_t>((uint64_t)got, out_cap - *n));
+      *n += (uint64_t)got;
+    }
+    if (parallel) *parallel = pz.parallel() ? 1 : 0;
+    if (accepted) *accepted = pz.chunks_accepted();
+    if (serial_stretches) *serial_stretches = pz.serial_stretches();
+  } catch (const std::exception& e) { return fail(std::string("rsm_debug_pgunzip: ") + e.what()); }
   return 0;
 }
 
@@ -1139,7 +1182,8 @@ int rsm_gpu_align_pair(const char* file1, const char* file2, const rsm_gpu_devic
     swb_ctx* c = context_for(dev ? dev->ordinal : 0);
     if (!c) return 1;
     std::lock_guard<std::mutex> use(g_use_mu[dev ? dev->ordinal : 0]);
-    FastqReader r1, r2; if (r1.open(file1) || r2.open(file2)) return 1;
+    const unsigned spare = std::min<unsigned>((std::max(2u, std::thread::hardware_concurrency()) - 2) / 2, kMaxInflateThreads);   // two files, this thread
+    FastqReader r1, r2; if (r1.open(file1, spare) || r2.open(file2, spare)) return 1;
     bool eof1 = false, eof2 = false; std::vector<swb_result> res;
     while (!eof1 && !eof2) {
       if (r1.next_chunk(chunk ? chunk : 1, 0, b1, o1, &eof1) || r2.next_chunk(chunk ? chunk : 1, 0, b2, o2, &eof2)) return 1;
@@ -1412,8 +1456,10 @@ int rsm_process_full_wgs_dataset(const rsm_gpu_device* device, rsm_alignment_res
       std::vector<size_t> mine;
       for (size_t t = w; t < todo.size(); t += n_workers) mine.push_back(todo[t]);
       if (mine.empty()) return;
-      wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes, readers_per_file, order.size(),
-                          std::thread::hardware_concurrency() >= 2 * todo.size() + n_workers);
+      // plain .gz files: the cores left over once every file has its parsing thread and every GPU its consumer, dealt evenly
+      const size_t hc = std::thread::hardware_concurrency(), taken = todo.size() + n_workers;
+      const unsigned spare = hc > taken ? (unsigned)std::min<size_t>((hc - taken) / todo.size(), kMaxInflateThreads) : 0u;
+      wgs_device_pipeline(mine, files, total, chunk, chunk_bases, &devs[ord], ctx, ref.size(), window_len, &outcomes, readers_per_file, order.size(), spare);
       stamp("a device's files done");
     });
   }
