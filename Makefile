@@ -36,6 +36,11 @@ build/inflate_bench: tools/inflate_bench.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)
 	mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ tools/inflate_bench.cu $(CSRC)/swb_fastq_kernels.cu -lz
 
+# host gzip readers alone (serial, zlib, several threads per file): no GPU, no nvcc
+build/gunzip_bench: tools/gunzip_bench.cpp $(CSRC)/host_gunzip.h $(CSRC)/host_pgunzip.h
+	mkdir -p build
+	g++ -O2 -std=c++17 -pthread -o $@ tools/gunzip_bench.cpp -lz
+
 oracle:
 	$(MAKE) -C oracle
 
