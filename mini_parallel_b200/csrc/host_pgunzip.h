@@ -476,9 +476,18 @@ class ParallelGunzip {
         if (found) spec_decode(*T, base_, size_, p, until, kMaxSyms, *R);
         if (!R->clean) { R->sym.release(); R->n = 0; }
       } catch (const std::exception&) { if (R) { R->clean = false; R->sym.release(); } }
-      { std::lock_guard<std::mutex> lk(mu_); spec_[k] = std::move(R); spec_state_[k] = 2; }
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (k < consumer_chunk_) recycle(R);                  // the chain went past this chunk while it was being decoded
+        spec_[k] = std::move(R); spec_state_[k] = 2;
+      }
       cv_done_.notify_all();
     }
+  }
+  void recycle(std::unique_ptr<SpecChunk>& R)               // mu_ held: the symbol buffer back to the pool, the chunk gone
+  {
+    if (R && R->sym.p && sym_pool_.size() < pool_cap()) sym_pool_.push_back(std::move(R->sym));
+    R.reset();
   }
   size_t pool_cap() const { return 2 * (size_t)threads_ + 4; }
   bool can_spec() const { return spec_on_ && next_spec_ < n_chunks_ && next_spec_ < consumer_chunk_ + 2 * (uint64_t)threads_ + 2 && queued_bytes_ < kMaxQueued; }
@@ -507,11 +516,15 @@ class ParallelGunzip {
       uint64_t target = (j + 1) * cbits_;
       {
         std::lock_guard<std::mutex> lk(mu_);
-        if (consumer_chunk_ != j) { consumer_chunk_ = j; if (next_spec_ < j) next_spec_ = j; cv_work_.notify_all(); }
+        if (consumer_chunk_ != j) {
+          for (uint64_t k = consumer_chunk_; k < j; ++k) recycle(spec_[k]);      // chunks the chain has passed (a block may span several)
+          consumer_chunk_ = j; if (next_spec_ < j) next_spec_ = j;
+          cv_work_.notify_all();
+        }
         if (spec_state_[j] != 2) return;                    // not there yet
         if (spec_[j] && spec_[j]->clean && spec_[j]->start_bit >= pos_) {
           if (spec_[j]->start_bit == pos_) R = std::move(spec_[j]); else target = spec_[j]->start_bit;
-        } else spec_[j].reset();                            // nothing found, or it started behind the known text: of no use
+        } else recycle(spec_[j]);                           // nothing found, or it started behind the known text: of no use
       }
       if (R && hist_ < kWin && reaches_before_start(*R)) R.reset();      // a match beyond the start of the member: the serial decoder reports it
       if (R) { accept(std::move(R)); misses_ = 0; continue; }
@@ -607,8 +620,8 @@ class ParallelGunzip {
     push_last(Seg::END);                                    // NEED_INPUT with the whole file in hand: it is truncated -- an early end
   }
 
-  static constexpr size_t kSlab = 4 << 20, kMaxSyms = 256u << 20;
-  static constexpr uint64_t kMaxQueued = 512ull << 20;
+  static constexpr size_t kSlab = 4 << 20, kMaxSyms = 48u << 20;      // a chunk that inflates to more than 48 M symbols is left to the serial decoder
+  static constexpr uint64_t kMaxQueued = 256ull << 20;                  // text waiting for the reader: the chain and the workers pause beyond it
   static constexpr unsigned kMaxMisses = 32;
   unsigned threads_ = 1;
   uint64_t chunk_ = 1 << 20, cbits_ = 8 << 20, n_chunks_ = 0;
