@@ -332,8 +332,12 @@ class ParallelGunzip {
     chain_done_ = false; fb_active_ = false;
     err_.clear(); failed_ = false; ended_ = false; cur_pos_ = 0;
     crc_run_ = 0; isize_run_ = 0; n_accepted_ = 0; n_fallbacks_ = 0;
-    try { for (unsigned t = 0; t < threads_; ++t) pool_.emplace_back([this] { worker(); }); }
-    catch (const std::exception&) { if (pool_.empty()) { close(); use_serial_ = true; return serial_.open(path); } }
+    // a worker's decoder state and look-up table are allocated here, where a failure can still send the file to the serial reader
+    try {
+      kits_.clear();
+      for (unsigned t = 0; t < threads_; ++t) { kits_.emplace_back(new Kit); kits_.back()->lut.assign(65536, 0); for (int i = 0; i < 256; ++i) kits_.back()->lut[i] = (uint8_t)i; }
+      for (unsigned t = 0; t < threads_; ++t) { Kit* kit = kits_[t].get(); pool_.emplace_back([this, kit] { worker(*kit); }); }
+    } catch (const std::exception&) { if (pool_.empty()) { close(); use_serial_ = true; return serial_.open(path); } }     // (fewer threads than asked for: carry on)
     return true;
   }
 
@@ -345,6 +349,7 @@ class ParallelGunzip {
       for (auto& t : pool_) t.join();
       pool_.clear();
     }
+    kits_.clear();
     segs_.clear(); resolve_q_.clear(); spec_.clear(); spec_state_.clear(); sym_pool_.clear(); data_pool_.clear();
     unmap();
     serial_.close();
@@ -354,6 +359,13 @@ class ParallelGunzip {
   long read(uint8_t* dst, size_t cap)
   {
     if (use_serial_) return serial_.read(dst, cap);
+    try { return read_chain(dst, cap); }
+    catch (const std::exception&) { err_ = "out of memory"; failed_ = true; return -1; }       // (a buffer could not be had: nothing else throws in here)
+  }
+
+ private:
+  long read_chain(uint8_t* dst, size_t cap)
+  {
     size_t got = 0;
     while (got < cap) {
       if (failed_) return got ? (long)got : -1;
@@ -418,11 +430,11 @@ class ParallelGunzip {
   }
 
   // ---- workers: resolve tasks first, then the next chunk to decode ahead of the chain ----
-  void worker()
+  struct Kit { Inflater inf; std::vector<uint8_t> lut; };   // one per worker: decoder tables (150 KB: not on a thread's stack) and the resolve table
+  void worker(Kit& kit)
   {
-    std::unique_ptr<Inflater> T(new Inflater);               // (its tables are 150 KB: not on a thread's stack)
-    std::vector<uint8_t> lut(65536, 0);
-    for (int i = 0; i < 256; ++i) lut[i] = (uint8_t)i;
+    Inflater* const T = &kit.inf;
+    std::vector<uint8_t>& lut = kit.lut;
     for (;;) {
       Seg* job = nullptr; uint64_t k = 0;
       RawBuf<uint16_t> spare_sym;                             // buffers go round (fresh ones cost a page fault per 4 KiB)
@@ -631,7 +643,7 @@ class ParallelGunzip {
   uint64_t first_data_bit_ = 0;
   // shared with the workers (mu_)
   std::mutex mu_; std::condition_variable cv_work_, cv_done_;
-  std::vector<std::thread> pool_;
+  std::vector<std::thread> pool_; std::vector<std::unique_ptr<Kit>> kits_;
   std::vector<std::unique_ptr<SpecChunk>> spec_; std::vector<uint8_t> spec_state_;      // 0 untouched, 1 being decoded, 2 done
   uint64_t next_spec_ = 0, consumer_chunk_ = 0, queued_bytes_ = 0;
   std::deque<Seg*> resolve_q_;
