@@ -98,3 +98,37 @@ def test_repr_c_structs_match_the_header():
     assert "typedef struct { int32_t start_i, start_j; uint32_t cigar_len; uint32_t status; uint64_t cigar_off; } swb_alignment;" in h
     assert fields("SwbBgzfBlock") == [("in_off", "u64"), ("in_len", "u32"), ("out_len", "u32")]
     assert re.search(r"typedef struct \{ uint64_t in_off; uint32_t in_len; uint32_t out_len; \} swb_bgzf_block;", h)
+
+
+def _ctypes_shape(t):
+    """ctypes type -> ("ptr",) or ("int", size in bytes) / ("float", size)"""
+    import ctypes
+    if t is None:
+        return ("void",)
+    if t in (ctypes.c_void_p, ctypes.c_char_p) or isinstance(t, type) and issubclass(t, (ctypes._Pointer, ctypes._CFuncPtr)):
+        return ("ptr",)
+    if t in (ctypes.c_double, ctypes.c_float):
+        return ("float", ctypes.sizeof(t))
+    return ("int", ctypes.sizeof(t))
+
+
+_WIDTH = {"i32": ("int", 4), "u32": ("int", 4), "i64": ("int", 8), "u64": ("int", 8), "usize": ("int", 8), "f64": ("float", 8), "f32": ("float", 4),
+          "i8": ("int", 1), "u8": ("int", 1), "void": ("void",)}
+
+
+def _c_shape(ct):
+    depth, _, base = ct
+    return ("ptr",) if depth else _WIDTH[base]
+
+
+def test_ctypes_signatures_match_the_header():
+    """The Python view (mini_parallel_b200/_lib.py SIGNATURES) against the same header: arity, pointer-ness and scalar widths."""
+    from mini_parallel_b200 import _lib
+    c = c_functions()
+    for name, (restype, argtypes) in _lib.SIGNATURES.items():
+        assert name in c, name
+        cret, cps = c[name]
+        assert len(cps) == len(argtypes), f"{name}: {len(cps)} parameters in the header, {len(argtypes)} in _lib.py"
+        assert _c_shape(cret) == _ctypes_shape(restype), f"{name}: return type"
+        for k, (cp, a) in enumerate(zip(cps, argtypes)):
+            assert _c_shape(cp) == _ctypes_shape(a), f"{name} parameter {k}: {cp} in the header, {a} in _lib.py"
