@@ -1,0 +1,48 @@
+"""bench.py's contract on the side that runs without a GPU: the CPU arm (`--impl reference`) prints exactly one JSON line with
+the keys the driver reads, on the same workload string as the GPU arm; under torchrun only rank 0 works and prints; and the GPU
+arm refuses to run without a device instead of falling back to anything."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, env=e, cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_line():
+    p = run(["--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "1", "--pairs", "20000"])
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "GCUPS" and d["unit"] == "GCUPS" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("BASELINE.json configs[1]") and d["config"]["pairs_per_gpu"] == 20000
+    # the GPU arm names its workload with the same function: the driver compares the two strings
+    sys.path.insert(0, ROOT)
+    import bench
+    class A:
+        dist, ref_bases = 0, 16_000_000
+    assert bench.workload_config(A, 8, 20000)["workload"] == d["config"]["workload"]
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    p = run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1", "--pairs", "1000"], {"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_gpu_arm_refuses_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        return
+    p = run(["--steps", "1", "--warmup", "1", "--pairs", "1000", "--no-aux"])
+    assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
+    assert not [l for l in p.stdout.splitlines() if l.startswith("{")]          # no number without a GPU
