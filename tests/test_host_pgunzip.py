@@ -98,6 +98,11 @@ def test_multi_member_header_fields_and_trailing_garbage(tmp_path):
     same_as_serial(tmp_path, "multi.gz", multi, raw)
     same_as_serial(tmp_path, "garbage.gz", multi + b"\x00\x00trailing bytes that are not a member", raw)
     same_as_serial(tmp_path, "garbage2.gz", multi + b"\x1f", raw, chunks=(4096,))
+    # a header longer than several chunks (FNAME + FCOMMENT): the first chunks hold no deflate data at all
+    long_hdr = bytearray(gz(b, 6)); long_hdr[3] |= 8 | 16
+    long_hdr = bytes(long_hdr[:10]) + b"n" * 3000 + b"\x00" + b"c" * 5000 + b"\x00" + bytes(long_hdr[10:])
+    same_as_serial(tmp_path, "long_header.gz", long_hdr, b, chunks=(512, 2048))
+    same_as_serial(tmp_path, "long_header_twice.gz", named + long_hdr, a + b, chunks=(512,))
     # BGZF-like: every block is a member of its own, all blocks final -- nothing for the block finder, all of it serial
     same_as_serial(tmp_path, "bgzf_like.gz", b"".join(gz(a[k:k + 60000], 1) for k in range(0, len(a), 60000)), a, chunks=(4096, 65536))
     # not gzip at all / tiny: the serial reader's business
