@@ -5,7 +5,7 @@ NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 CSRC      := mini_parallel_b200/csrc
 LIB       := mini_parallel_b200/libswb200.so
 
-all: $(LIB) variants build/rustseq_mini build/issue_rate_bench build/cell_loop_bench build/inflate_bench oracle
+all: $(LIB) variants build/rustseq_mini build/issue_rate_bench build/cell_loop_bench build/inflate_bench build/gunzip_bench oracle
 
 $(LIB): $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp $(CSRC)/swb_kernels.cuh $(CSRC)/swb_inflate.cuh $(CSRC)/host_gunzip.h $(CSRC)/host_pgunzip.h include/swb200.h include/rustseq_host.h
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/swb_kernels.cu $(CSRC)/swb_fastq_kernels.cu $(CSRC)/swb_traceback.cu $(CSRC)/swb_capi.cu $(CSRC)/rustseq_host.cpp -lz
