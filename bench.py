@@ -190,6 +190,21 @@ def checksum64(out_i32, first_index):
     return int(h.sum().item()) & ((1 << 64) - 1)
 
 
+# configs[2] at full size on the CPU checker: the checksum64 of ITS results over all 100 M pairs (tests/tools/checksum_config2_cpu.py,
+# profiles/config2_full_checksum_cpu_r02.json).  The GPU leg's checksum equal to it = full-population parity for configs[2].
+CONFIG2_CPU_CHECKSUM = {(100_000_000, 0, 150, 500): "5ec5834cd0ec6b2a"}
+
+
+def annotate_strong(res, total, dist_, rl, wl):
+    """Adds the CPU checker's full-size checksum beside the GPU's, where one is on record for this exact workload."""
+    ref = CONFIG2_CPU_CHECKSUM.get((int(total), int(dist_), int(rl), int(wl)))
+    if ref is not None:
+        res["cpu_checker_checksum64"] = ref
+        res["cpu_checker_checksum_source"] = "profiles/config2_full_checksum_cpu_r02.json (tests/tools/checksum_config2_cpu.py: oracle/sw_simd.c over all pairs)"
+        res["equals_cpu_checker_on_all_pairs"] = res.get("checksum64") == ref
+    return res
+
+
 def leg_strong(args, eng, dev, rank, world, barrier, reduce_scalars):
     """BASELINE.json configs[2]: 100 M reads (one lane-equivalent, aligner.rs:214-215 counts 51.8 M per lane file) sharded
     over the ranks -- STRONG scaling: the total is fixed, every rank scores total/N pairs in device-resident slices.  Timed:
@@ -250,13 +265,18 @@ def leg_strong(args, eng, dev, rank, world, barrier, reduce_scalars):
     csum_all = (int(parts[0]) + (int(parts[1]) << 32)) & ((1 << 64) - 1)
     del d_q, d_r, d_qo, d_ro, d_out
     cells = float(total) * rl * wl
-    return {"workload": f"BASELINE.json configs[2]: {total} synthetic {rl} bp reads vs {wl} bp windows, one lane-equivalent, sharded over {world} GPU(s)",
+    res = {"workload": f"BASELINE.json configs[2]: {total} synthetic {rl} bp reads vs {wl} bp windows, one lane-equivalent, sharded over {world} GPU(s)",
             "scaling": "strong", "pairs_total": total, "pairs_per_gpu": (total + world - 1) // world, "slice_pairs": sl,
             "score_ms_max_over_ranks": round(ms, 3), "gcups": round(cells / (ms * 1e-3) / 1e9, 1), "reads_per_s": round(total / (ms * 1e-3), 1),
             "score_ms_by_library_events_this_rank": round(lib_ms, 3), "wall_s_with_generation_and_checks": round(wall, 3),
             "checksum64": f"{csum_all:016x}", "checksum_is": "wrapping sum over ALL pairs of hash(pair index, score, end_i, end_j): equal at every N",
             "mean_score": round(parts[2] / total, 3), "oracle_checked_pairs": int(parts[3]), "oracle_checked_pairs_per_rank": checked,
             "oracle_equal": parts[4] == 0.0, "gpu_launches": int(parts[5])}
+    try:
+        annotate_strong(res, total, args.dist, rl, wl)
+    except Exception:                                       # an annotation never costs the line
+        pass
+    return res
 
 
 def leg_long(args, eng, dev):

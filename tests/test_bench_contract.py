@@ -46,3 +46,19 @@ def test_gpu_arm_refuses_without_a_device():
     p = run(["--steps", "1", "--warmup", "1", "--pairs", "1000", "--no-aux"])
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
     assert not [l for l in p.stdout.splitlines() if l.startswith("{")]          # no number without a GPU
+
+
+def test_config2_checksum_annotation():
+    """The strong-scaling leg puts the CPU checker's full-size checksum beside the GPU's for the exact workload it was computed on
+    (and only for that one); the constant is the one on record under profiles/."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rec = json.load(open(os.path.join(ROOT, "profiles", "config2_full_checksum_cpu_r02.json")))
+    assert rec["pairs"] == 100_000_000 and rec["equal"] is True
+    assert bench.CONFIG2_CPU_CHECKSUM[(100_000_000, 0, 150, 500)] == rec["checksum64"] == rec["gpu_checksum64"]
+    r = bench.annotate_strong({"checksum64": rec["checksum64"]}, 100_000_000, 0, 150, 500)
+    assert r["equals_cpu_checker_on_all_pairs"] is True and r["cpu_checker_checksum64"] == rec["checksum64"]
+    r = bench.annotate_strong({"checksum64": "0" * 16}, 100_000_000, 0, 150, 500)
+    assert r["equals_cpu_checker_on_all_pairs"] is False
+    r = bench.annotate_strong({"checksum64": rec["checksum64"]}, 50_000_000, 0, 150, 500)       # another workload: no claim
+    assert "equals_cpu_checker_on_all_pairs" not in r
