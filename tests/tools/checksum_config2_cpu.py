@@ -38,31 +38,34 @@ def checksum64(res, first_index):
 
 
 def one_slice(job):
-    first, n, dist = job
+    first, n, dist, rl, wl = job
     import oracle_lib as ol
     from mini_parallel_b200 import synth
-    q, qo, r, ro = synth.make_pairs(first, n, RL, WL, dist)
+    q, qo, r, ro = synth.make_pairs(first, n, rl, wl, dist)
     res = ol.batch(q, np.asarray(qo, dtype=np.uint64), r, np.asarray(ro, dtype=np.uint64), threads=1, simd=True)
-    return checksum64(res, first), int(res["score"].sum(dtype=np.int64)), n
+    plain = int(res["score"].sum(dtype=np.int64)) + int(res["end_i"].sum(dtype=np.int64)) + int(res["end_j"].sum(dtype=np.int64))
+    return checksum64(res, first), int(res["score"].sum(dtype=np.int64)), n, plain
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--pairs", type=int, default=100_000_000)
     ap.add_argument("--dist", type=int, default=0)
+    ap.add_argument("--read", type=int, default=RL, help="other shapes of the same generator (tools/probe_rows128.py records the plain sum)")
+    ap.add_argument("--window", type=int, default=WL)
     ap.add_argument("--expect", default="", help="the GPU's checksum64 (hex) from the bench line")
     ap.add_argument("--procs", type=int, default=os.cpu_count() or 1)
     args = ap.parse_args()
-    jobs = [(a, min(SLICE, args.pairs - a), args.dist) for a in range(0, args.pairs, SLICE)]
-    t0, csum, ssum, done = time.time(), 0, 0, 0
+    jobs = [(a, min(SLICE, args.pairs - a), args.dist, args.read, args.window) for a in range(0, args.pairs, SLICE)]
+    t0, csum, ssum, done, plain = time.time(), 0, 0, 0, 0
     with mpc.get_context("fork").Pool(args.procs) as pool:
-        for k, (c, s_, n) in enumerate(pool.imap_unordered(one_slice, jobs, chunksize=1)):
-            csum = (csum + c) & ((1 << 64) - 1); ssum += s_; done += n
+        for k, (c, s_, n, pl) in enumerate(pool.imap_unordered(one_slice, jobs, chunksize=1)):
+            csum = (csum + c) & ((1 << 64) - 1); ssum += s_; done += n; plain += pl
             if (k + 1) % 100 == 0:
                 print(f"  {done} pairs, {time.time() - t0:.0f} s", file=sys.stderr, flush=True)
-    out = {"workload": f"BASELINE.json configs[2]: {args.pairs} synthetic {RL} bp reads vs {WL} bp windows (SURVEY.md 8d generator, distribution {args.dist})",
+    out = {"workload": f"{'BASELINE.json configs[2]: ' if (args.read, args.window) == (RL, WL) else ''}{args.pairs} synthetic {args.read} bp reads vs {args.window} bp windows (SURVEY.md 8d generator, distribution {args.dist})",
            "checker": "oracle/sw_simd.c (CPU SIMD port, bit-exact with the scalar restatement)", "pairs": done, "checksum64": f"{csum:016x}",
-           "mean_score": round(ssum / max(done, 1), 3), "seconds": round(time.time() - t0, 1), "procs": args.procs}
+           "sum_of_score_end_i_end_j": plain, "mean_score": round(ssum / max(done, 1), 3), "seconds": round(time.time() - t0, 1), "procs": args.procs}
     if args.expect:
         out["gpu_checksum64"] = args.expect.lower()
         out["equal"] = out["checksum64"] == args.expect.lower()
