@@ -14,6 +14,8 @@ import pytest
 from mini_parallel_b200 import aligner
 from test_host_gunzip import ACGT, fastq, gz
 
+pytestmark = pytest.mark.timeout(900)       # threads and condition variables: a lost wake-up must fail a test, not hang the suite
+
 
 OUT_CAP = 64 << 20          # every text of this file fits (the hooks' default is 64 x the compressed size: too little for a file of zeros)
 
