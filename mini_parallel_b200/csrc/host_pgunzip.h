@@ -18,6 +18,9 @@
 //     every error and every early end is either the serial decoder's own or the replay of a clean decode from a certain
 //     position: behaviour at the edges is GunzipStream's (= gzread's) by construction, and tests/test_host_pgunzip.py holds
 //     the two against each other on every kind of stream, chunk sizes down to 512 bytes, and mutated files.
+//   * a file that begins with a BGZF member needs neither markers nor a block finder: a member's size stands in its header and
+//     it has no history.  The workers inflate runs of whole members into bytes (CRC-32 and ISIZE of every member checked by
+//     the worker) and the chain takes a run when it starts at the header it stands in front of; everything else as above.
 // Files that are not regular files, not gzip, or smaller than three chunks go to GunzipStream unchanged.
 #pragma once
 #include "host_gunzip.h"
@@ -52,7 +55,57 @@ struct SpecChunk {
   uint64_t start_bit = 0, end_bit = 0;
   RawBuf<uint16_t> sym;            // kWin marker slots, then the n symbols
   size_t n = 0;
+  // A run of BGZF members instead (bgzf_run): whole members from the header at start_byte to the header at end_byte, inflated
+  // to n BYTES in `bytes`, every member's CRC-32 and ISIZE checked by the worker.  No markers: a member has no history.
+  bool bgzf_run = false;
+  uint64_t start_byte = 0, end_byte = 0, members = 0;
+  RawBuf<uint8_t> bytes;
 };
+
+// The member header bgzip writes: 1f 8b 08 04, MTIME XFL OS, XLEN = 6, 'B' 'C' 02 00, BSIZE (member size - 1).  (BGZF allows other
+// extra subfields beside BC; files that carry them are simply not recognised here and take the serial reader.)
+static inline bool bgzf_header_at(const uint8_t* base, uint64_t size, uint64_t p, uint64_t* next)
+{
+  if (p + 18 + 8 > size) return false;
+  const uint8_t* h = base + p;
+  if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || h[3] != 4 || h[10] != 6 || h[11] != 0 || h[12] != 'B' || h[13] != 'C' || h[14] != 2 || h[15] != 0) return false;
+  const uint64_t total = ((uint64_t)h[16] | ((uint64_t)h[17] << 8)) + 1;
+  if (total < 18 + 2 + 8 || p + total > size) return false;
+  *next = p + total;
+  return true;
+}
+
+// Inflate the BGZF members from the header at `first` up to the first member that starts at or after `limit` (or that does not
+// check out: the run ends in front of it).  R.clean = at least one member, all of them with the right CRC-32 and length.
+static inline void bgzf_run_decode(Inflater& T, const uint8_t* base, uint64_t size, uint64_t first, uint64_t limit, bool verify, SpecChunk& R)
+{
+  R.clean = false; R.bgzf_run = true; R.start_byte = R.end_byte = first; R.n = 0; R.members = 0;
+  uint64_t total = 0, q = first, next = 0, count = 0;
+  while (q < limit && bgzf_header_at(base, size, q, &next)) {              // sizes first: one buffer for the run
+    const uint8_t* t = base + next - 8;
+    const uint32_t isz = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+    if (isz > 65536) break;                                                // not a BGZF member (they hold <= 64 KiB)
+    total += isz; q = next; ++count;
+  }
+  if (!count) return;
+  R.bytes.reserve(total + 512);
+  uint8_t* out = R.bytes.p; uint8_t* const out_end = out + total + 320;
+  q = first;
+  for (uint64_t m = 0; m < count; ++m) {
+    bgzf_header_at(base, size, q, &next);
+    const uint8_t* t = base + next - 8;
+    const uint32_t crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    const uint32_t isz = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+    T.reset();
+    const uint8_t* in = base + q + 18; uint8_t* o = out;
+    const Inflater::Result r = T.run(in, t, true, o, out_end, 0);
+    const bool ok = r == Inflater::DONE && in - (T.bitcnt >> 3) == t && (uint64_t)(o - out) == isz && (!verify || crc32_update(0u, out, isz) == crc);
+    if (!ok) break;                                                        // the serial reader will say what is wrong with this member
+    out += isz; q = next; ++R.members;
+  }
+  if (!R.members) return;
+  R.n = (size_t)(out - R.bytes.p); R.end_byte = q; R.clean = true;
+}
 
 // Is bit p the start of a non-final dynamic block whose three codes are acceptable to zlib?  On success T holds its tables.
 static inline bool dynamic_header_at(Inflater& T, const uint8_t* base, uint64_t size, uint64_t p)
@@ -329,6 +382,11 @@ class ParallelGunzip {
     next_spec_ = 0; consumer_chunk_ = 0; stop_ = false; spec_on_ = true; misses_ = 0;
     segs_.clear(); resolve_q_.clear(); queued_bytes_ = 0;
     pos_ = first_data_bit_ = (uint64_t)(data - base_) * 8; hist_ = 0; win_.assign(kWin, 0);
+    // A file that begins with a BGZF member is taken for BGZF: the workers then inflate runs of whole members (no block finder, no
+    // markers: a member's size is in its header and it has no history), and the chain starts in front of the first header.
+    uint64_t next0 = 0;
+    bgzf_ = bgzf_header_at(base_, size_, 0, &next0);
+    at_boundary_ = bgzf_; hdr_byte_ = 0;
     chain_done_ = false; fb_active_ = false;
     err_.clear(); failed_ = false; ended_ = false; cur_pos_ = 0;
     crc_run_ = 0; isize_run_ = 0; n_accepted_ = 0; n_fallbacks_ = 0;
@@ -375,7 +433,7 @@ class ParallelGunzip {
       Seg& s = *segs_.front();
       if (!s.ready.load(std::memory_order_acquire)) { wait_for_progress(); continue; }
       if (s.kind == Seg::DATA) {
-        if (cur_pos_ == 0 && s.n) { crc_run_ = (uint32_t)crc32_combine(crc_run_, s.crc, (z_off_t)s.n); isize_run_ += (uint32_t)s.n; }
+        if (cur_pos_ == 0 && s.n && !s.verified) { crc_run_ = (uint32_t)crc32_combine(crc_run_, s.crc, (z_off_t)s.n); isize_run_ += (uint32_t)s.n; }
         const size_t n = std::min(cap - got, s.n - cur_pos_);
         if (n) memcpy(dst + got, s.data.p + cur_pos_, n);
         got += n; cur_pos_ += n;
@@ -405,6 +463,7 @@ class ParallelGunzip {
     std::unique_ptr<SpecChunk> src; std::vector<uint8_t> win;       // DATA still to be resolved by a worker: symbols + the window in front of them
     uint32_t isize = 0; int trailer_bytes = 0;                      // MEMBER_END (crc = the trailer's)
     std::string msg;                                                // ERROR
+    bool verified = false;                                          // DATA of a BGZF run: whole members, their CRC-32 / ISIZE already checked
   };
 
   void unmap() { if (base_) munmap((void*)base_, size_); base_ = nullptr; }
@@ -422,7 +481,7 @@ class ParallelGunzip {
   void wait_for_progress()
   {
     std::unique_lock<std::mutex> lk(mu_);
-    const uint64_t j = pos_ / cbits_;
+    const uint64_t j = chain_chunk();
     cv_done_.wait(lk, [&] {
       if (!segs_.empty() && segs_.front()->ready.load(std::memory_order_acquire)) return true;
       return !chain_done_ && !fb_active_ && j < n_chunks_ && spec_state_[j] == 2 && queued_bytes_ < kMaxQueued;
@@ -483,10 +542,17 @@ class ParallelGunzip {
         R->sym = std::move(spare_sym);
         const uint64_t from = k * cbits_, until = std::min((k + 1) * cbits_, size_ * 8);
         uint64_t p = from; bool found = false;
-        if (k == 0) { p = first_data_bit_; found = p < until; }      // the first member's data: a certain start, whatever its block type
-        else for (; p < until; ++p) if (dynamic_header_at(*T, base_, size_, p)) { found = true; break; }
-        if (found) spec_decode(*T, base_, size_, p, until, kMaxSyms, *R);
-        if (!R->clean) { R->sym.release(); R->n = 0; }
+        if (bgzf_) {                                                  // the first member header in the chunk, then whole members
+          uint64_t next = 0;
+          for (p = from >> 3; p < (until >> 3); ++p) if (base_[p] == 0x1f && bgzf_header_at(base_, size_, p, &next)) { found = true; break; }
+          if (found) bgzf_run_decode(*T, base_, size_, p, until >> 3, verify_, *R);
+          if (!R->clean) { R->bytes.release(); R->n = 0; }
+        } else {
+          if (k == 0) { p = first_data_bit_; found = p < until; }      // the first member's data: a certain start, whatever its block type
+          else for (; p < until; ++p) if (dynamic_header_at(*T, base_, size_, p)) { found = true; break; }
+          if (found) spec_decode(*T, base_, size_, p, until, kMaxSyms, *R);
+          if (!R->clean) { R->sym.release(); R->n = 0; }
+        }
       } catch (const std::exception&) { if (R) { R->clean = false; R->sym.release(); } }
       {
         std::lock_guard<std::mutex> lk(mu_);
@@ -499,6 +565,7 @@ class ParallelGunzip {
   void recycle(std::unique_ptr<SpecChunk>& R)               // mu_ held: the symbol buffer back to the pool, the chunk gone
   {
     if (R && R->sym.p && sym_pool_.size() < pool_cap()) sym_pool_.push_back(std::move(R->sym));
+    if (R && R->bytes.p && data_pool_.size() < pool_cap()) data_pool_.push_back(std::move(R->bytes));
     R.reset();
   }
   size_t pool_cap() const { return 2 * (size_t)threads_ + 4; }
@@ -522,17 +589,31 @@ class ParallelGunzip {
       if (chain_done_) return;
       if (queued_bytes_ >= kMaxQueued) return;              // the reader is behind: nothing more until it has caught up
       if (fb_active_) { fallback_step(); continue; }
+      if (at_boundary_) {                                   // in front of a member header (or of the end of the file)
+        if (hdr_byte_ >= size_) { push_last(Seg::END); return; }
+        if (bgzf_ && spec_on_) {
+          const uint64_t jb = chain_chunk();
+          std::unique_ptr<SpecChunk> run;
+          {
+            std::lock_guard<std::mutex> lk(mu_);
+            move_consumer_to(jb);
+            if (spec_state_[jb] != 2) return;               // not there yet
+            if (spec_[jb] && spec_[jb]->clean && spec_[jb]->bgzf_run && spec_[jb]->start_byte == hdr_byte_) run = std::move(spec_[jb]);
+            else if (!(spec_[jb] && spec_[jb]->clean && spec_[jb]->bgzf_run && spec_[jb]->start_byte > hdr_byte_)) recycle(spec_[jb]);
+          }
+          if (run) { accept_run(std::move(run)); misses_ = 0; continue; }
+          if (++misses_ >= kMaxMisses) { std::lock_guard<std::mutex> lk(mu_); spec_on_ = false; }
+        }
+        enter_member();                                     // this member through the serial decoder
+        continue;
+      }
       const uint64_t j = pos_ / cbits_;
-      if (j >= n_chunks_ || !spec_on_) { start_fallback(~0ull); continue; }
+      if (j >= n_chunks_ || !spec_on_ || bgzf_) { start_fallback(~0ull); continue; }     // (BGZF: to the member's end; the next run may fit again)
       std::unique_ptr<SpecChunk> R;
       uint64_t target = (j + 1) * cbits_;
       {
         std::lock_guard<std::mutex> lk(mu_);
-        if (consumer_chunk_ != j) {
-          for (uint64_t k = consumer_chunk_; k < j; ++k) recycle(spec_[k]);      // chunks the chain has passed (a block may span several)
-          consumer_chunk_ = j; if (next_spec_ < j) next_spec_ = j;
-          cv_work_.notify_all();
-        }
+        move_consumer_to(j);
         if (spec_state_[j] != 2) return;                    // not there yet
         if (spec_[j] && spec_[j]->clean && spec_[j]->start_bit >= pos_) {
           if (spec_[j]->start_bit == pos_) R = std::move(spec_[j]); else target = spec_[j]->start_bit;
@@ -543,6 +624,36 @@ class ParallelGunzip {
       if (++misses_ >= kMaxMisses) { std::lock_guard<std::mutex> lk(mu_); spec_on_ = false; }     // not a file this scheme suits (BGZF, fixed codes, ...)
       start_fallback(target);
     }
+  }
+
+  uint64_t chain_chunk() const { return std::min((at_boundary_ ? hdr_byte_ * 8 : pos_) / cbits_, n_chunks_ ? n_chunks_ - 1 : 0); }
+  void move_consumer_to(uint64_t j)                         // mu_ held
+  {
+    if (consumer_chunk_ == j) return;
+    for (uint64_t k = consumer_chunk_; k < j; ++k) recycle(spec_[k]);      // chunks the chain has passed (a block may span several)
+    consumer_chunk_ = j; if (next_spec_ < j) next_spec_ = j;
+    cv_work_.notify_all();
+  }
+
+  void accept_run(std::unique_ptr<SpecChunk> R)             // whole BGZF members, checked by the worker: their text as it is
+  {
+    ++n_accepted_;
+    std::unique_ptr<Seg> s(new Seg);
+    s->kind = Seg::DATA; s->n = R->n; s->data = std::move(R->bytes); s->verified = true; s->ready.store(true);
+    hdr_byte_ = R->end_byte; hist_ = 0;
+    push(std::move(s));
+  }
+
+  // the member header at hdr_byte_: its deflate data is where the chain goes on (or the file ends here, as GunzipStream sees it)
+  void enter_member()
+  {
+    const uint8_t* p = base_ + hdr_byte_; const uint8_t* e = base_ + size_;
+    if (e - p < 2 || p[0] != 0x1f || p[1] != 0x8b) { push_last(Seg::END); return; }      // nothing, or bytes that are not a member: ignored
+    const uint8_t* data = nullptr; const char* why = nullptr;
+    const int r = parse_gzip_header(p, e, &data, &why);
+    if (r == 0) { push_last(Seg::END); return; }            // truncated inside a header: an early end
+    if (r < 0) { push_last(Seg::ERROR, why); return; }
+    pos_ = (uint64_t)(data - base_) * 8; hist_ = 0; at_boundary_ = false;
   }
 
   bool reaches_before_start(const SpecChunk& R) const
@@ -590,13 +701,7 @@ class ParallelGunzip {
     if (left >= 8) s->isize = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
     push(std::move(s));
     if (left < 8) { chain_done_ = true; return; }
-    const uint8_t* p = t + 8; const uint8_t* e = base_ + size_;
-    if (e - p < 2 || p[0] != 0x1f || p[1] != 0x8b) { push_last(Seg::END); return; }      // nothing, or bytes that are not a member: ignored
-    const uint8_t* data = nullptr; const char* why = nullptr;
-    const int r = parse_gzip_header(p, e, &data, &why);
-    if (r == 0) { push_last(Seg::END); return; }            // truncated inside a header: an early end
-    if (r < 0) { push_last(Seg::ERROR, why); return; }
-    pos_ = (uint64_t)(data - base_) * 8; hist_ = 0;
+    at_boundary_ = true; hdr_byte_ = tb + 8;                // (pump goes on from there: a BGZF run, or enter_member())
   }
 
   // ---- the serial decoder on the caller's thread, one slab of output per step, until a block boundary >= target ----
@@ -653,6 +758,7 @@ class ParallelGunzip {
   std::deque<std::unique_ptr<Seg>> segs_;
   uint64_t pos_ = 0, hist_ = 0; std::vector<uint8_t> win_; uint8_t scratch_[kWin];
   bool chain_done_ = false, fb_active_ = false, failed_ = false, ended_ = false;
+  bool bgzf_ = false, at_boundary_ = false; uint64_t hdr_byte_ = 0;      // BGZF file; the chain stands in front of the member header at hdr_byte_
   unsigned misses_ = 0;
   Inflater fb_inf_; const uint8_t* fb_in_ = nullptr; std::vector<uint8_t> fb_buf_;
   size_t cur_pos_ = 0; uint32_t crc_run_ = 0, isize_run_ = 0;

@@ -116,6 +116,37 @@ def test_multi_member_header_fields_and_trailing_garbage(tmp_path):
         assert (got, gf) == (exp, ef), name
 
 
+def test_bgzf_files_run_as_whole_members(tmp_path):
+    """A file that begins with a BGZF member is read as BGZF: the decoder threads inflate runs of whole members (sizes from the
+    headers, CRC-32 and length of every member checked by the thread, no markers), the chain takes a run when it starts at
+    the header it stands in front of; anything else -- a member that fails its check, a plain member in between, a
+    truncated tail -- goes member by member through the serial decoder, and the runs pick up again behind it."""
+    from mini_parallel_b200 import bgzf
+    rng = np.random.default_rng(29)
+    raw = fastq(rng, 9000, "noisy")
+    whole = bgzf.compress(raw, 1, 65280, eof=True)
+    infos = same_as_serial(tmp_path, "b.gz", whole, raw, chunks=(512, 30_000, 200_000), threads=(2, 5))
+    assert all(i["parallel"] and i["accepted"] >= 3 and i["serial_stretches"] == 0 for i in infos), infos
+    # two bgzip files joined (an empty EOF member in the middle), small members, another level
+    joined = bgzf.compress(raw[:700_000], 1, 65280, eof=True) + bgzf.compress(raw[700_000:], 6, 9_000, eof=True)
+    infos = same_as_serial(tmp_path, "bb.gz", joined, raw, chunks=(4096, 100_000))
+    assert all(i["serial_stretches"] == 0 for i in infos), infos
+    # a plain member between BGZF members, a BGZF tail behind a plain file's worth of data
+    mixed = bgzf.compress(raw[:500_000], 1, 65280, eof=False) + gz(raw[500_000:900_000], 6) + bgzf.compress(raw[900_000:], 1, 65280, eof=True)
+    infos = same_as_serial(tmp_path, "mixed.gz", mixed, raw, chunks=(4096, 50_000))
+    assert all(i["accepted"] >= 2 and i["serial_stretches"] >= 1 for i in infos), infos
+    # truncated inside a member, inside a header, inside a trailer; garbage behind the last member
+    for cut in (len(whole) - 1, len(whole) - 20, len(whole) - 30, len(whole) // 2, len(whole) // 2 + 7, 100_000):
+        same_as_serial(tmp_path, f"bcut{cut}.gz", whole[:cut], chunks=(4096, 60_000), threads=(4,), caps=(1 << 16,))
+    same_as_serial(tmp_path, "bgarbage.gz", whole + b"not a member at all", raw, chunks=(4096, 60_000), threads=(4,), caps=(1 << 16,))
+    # a member with a damaged CRC-32, a damaged ISIZE, damaged deflate data, a damaged BSIZE: the same bytes and the same verdict
+    blocks, _ = bgzf.walk(whole)
+    off, ln, _ = blocks[len(blocks) // 2]                    # payload offset (= member start + 18) and length; the trailer follows it
+    for name, at, x in (("crc", off + ln + 1, 0x10), ("isize", off + ln + 5, 0x01), ("data", off + ln // 2, 0x04), ("bsize", off - 2, 0x20), ("magic", off - 17, 0x01)):
+        bad = bytearray(whole); bad[at] ^= x
+        same_as_serial(tmp_path, f"bbad_{name}.gz", bytes(bad), chunks=(4096, 60_000), threads=(4,), caps=(1 << 16,))
+
+
 def test_truncated_files_end_early_and_corrupt_ones_fail(tmp_path):
     rng = np.random.default_rng(24)
     raw = fastq(rng, 12_000, "noisy")

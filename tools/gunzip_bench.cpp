@@ -55,8 +55,14 @@ int main(int argc, char** argv)
 #ifdef HGZ_HAVE_PARALLEL
   if (threads > 1) {
     double b = 1e30; uint64_t n = 0; uint32_t c = 0;
-    for (int k = 0; k < reps; ++k) { hgz::ParallelGunzip r; r.set_threads((unsigned)threads); double s; if (!run(r, argv[1], &n, &c, &s)) return 1; b = std::min(b, s); }
-    std::printf("hgz::ParallelGunzip %7.1f MB/s  %d threads  %s\n", n / b / 1e6, threads, (n == n0 && c == c0) ? "same bytes" : "DIFFERENT BYTES");
+    unsigned long long acc = 0, ser = 0;
+    for (int k = 0; k < reps; ++k) {
+      hgz::ParallelGunzip r; r.set_threads((unsigned)threads); double s;
+      if (!run(r, argv[1], &n, &c, &s)) return 1;
+      b = std::min(b, s); acc = r.chunks_accepted(); ser = r.serial_stretches();
+    }
+    std::printf("hgz::ParallelGunzip %7.1f MB/s  %d threads  %s  (%llu chunks from the decoder threads, %llu serial stretches)\n", n / b / 1e6, threads,
+                (n == n0 && c == c0) ? "same bytes" : "DIFFERENT BYTES", acc, ser);
     if (n != n0 || c != c0) return 1;
   }
 #else
